@@ -1,0 +1,1318 @@
+// lm_solver.cu -- B200-native Levenberg-Marquardt calibration solve (half (b) of the hot path).
+//
+// Replaces, behind the C ABI of include/ezcalib_b200.h, what the reference obtains from
+// ceres::Solve on the problem built in EZCalibrator::computeCalibration
+// (/root/reference/src/ezcalibrator.cpp:105-229) and runMultiCameraCalib (:631-844):
+// trust-region LM, Cauchy(1) loss, SE3 left-perturbation pose blocks eliminated by a Schur
+// complement onto the <= 12 shared intrinsic columns (Ceres rules: SURVEY.md 8a row B8).
+//
+// Device pipeline per LM iteration (all FP64):
+//   lm_accumulate   one warp per view segment.  Phase 1: one lane per observation evaluates the
+//                   residual + analytic Jacobian (lm_models.cuh), applies the Cauchy corrector and
+//                   stores the weighted row pair [J_pose(6) | r | 0 | J_shared(k)] column-major in
+//                   shared memory.  Phase 2: the same warp re-partitions itself into 4x4 register
+//                   tiles x k-slices of the (8+k)^2 Gram matrix and accumulates [J r]^T [J r] with
+//                   DFMAs from 16-byte shared loads.  Tiles touching the pose rows are flushed per
+//                   view into an 8 x (8+k) "strip" (H_pp, g_p, H_pc, per-view g_c); H_cc tiles stay
+//                   in registers for the whole launch and are reduced once, in fixed order.
+//   lm_schur        one thread per view: Jacobi scaling, LM damping, 6x6 Cholesky, Y = L^-1 W,
+//                   z = L^-1 g; fixed-order reduction of Y^T Y, Y^T z, g_c, |x|^2, gradient norm.
+//   (host)          k x k reduced system (k <= 12): scale, damp, Cholesky, solve  [+ one all-reduce
+//                   of the packed partial system over NVLink when views are sharded over GPUs]
+//   lm_backsub      one thread per view: pose step, candidate pose exp(delta) T, model-cost terms.
+//   lm_cost         one thread per observation: candidate cost  sum 1/2 log(1 + |r|^2).
+// Accept / reject, radius update and termination follow Ceres' TrustRegionMinimizer on the host.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <limits>
+#include <new>
+
+#include "ezc_common.cuh"
+#include "lm_models.cuh"
+
+namespace ezc {
+
+constexpr int kCS = 66;            // shared-memory column stride in doubles (64 rows + 2 pad)
+constexpr int kWarpsPerBlock = 4;  // lm_accumulate block = 128 threads
+constexpr int kMaxK = 12;          // max shared columns (2 focal + 2 pp + 8 dist)
+constexpr int kLYZ = 100;          // per-view Schur record: L(21) Y(6*12) z(6) + pad
+
+// layout of the packed reduction buffer "red1" (doubles)
+constexpr int R1_HCC = 0;                     // [12][12] upper triangle used
+constexpr int R1_COST = 144;                  // cost at x
+constexpr int R1_SCHUR = 145;                 // start of the lm_schur section
+constexpr int R1_SIZE = 256;                   // 145 + S(<=78) b(k) gc(k) xnorm2 nres nused fail gmax
+constexpr int R2_SIZE = 5;                    // g.delta, delta H delta, |step|^2, |cand|^2, cand cost
+
+__host__ __device__ inline int tile_index(int ti, int tj, int NT) { return ti * NT - ti * (ti - 1) / 2 + (tj - ti); }
+
+// -------------------------------------------------------------------------------------------
+struct AccumArgs {
+  const float2* obs;
+  const double* pts;
+  const double* poses;
+  const CamParams* cams;  // per-block cameras (multi-camera solve) or nullptr
+  CamParams cam;
+  int n_blocks, M, period;
+  int seg_len, segs_per_block, n_segs;
+  float wb, hb;
+  int k;
+  int colpos[kMaxK];      // full shared column -> Gram column (8 + active index) or -1
+  double* strips;         // [n_segs][8*DA]
+  double* part;           // [n_warps][16][32]  persistent tiles
+  double* cost_part;      // [n_warps]
+};
+
+template <int MODEL, bool MONO, int NT, bool PER_BLOCK_CAM>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+lm_accumulate_kernel(const AccumArgs a) {
+  constexpr int T = NT * (NT + 1) / 2;
+  constexpr int KS = 32 / T;
+  constexpr int DA = 4 * NT;
+  constexpr int NF = MONO ? 1 : 2;
+  constexpr int KFULL = NF + 2 + num_dist(MODEL);
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* J = smem + warp * (DA * kCS);
+  const int gw = blockIdx.x * kWarpsPerBlock + warp;
+  const int nW = gridDim.x * kWarpsPerBlock;
+
+  for (int i = lane; i < DA * kCS; i += 32) J[i] = 0.0;
+
+  const bool active2 = lane < T * KS;
+  const int t = lane % T, s = lane / T;
+  int ti = 0, tj = 0;
+  {
+    int rem = t, len = NT;
+    while (rem >= len) { rem -= len; ++ti; --len; }
+    tj = ti + rem;
+  }
+  int ca[4], cb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { ca[i] = (i * NT + ti) * kCS; cb[i] = (i * NT + tj) * kCS; }
+
+  double acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+  double cost = 0.0;
+
+  for (int seg = gw; seg < a.n_segs; seg += nW) {
+    const int blk = seg / a.segs_per_block;
+    const int l0 = (seg - blk * a.segs_per_block) * a.seg_len;
+    const int l1 = min(l0 + a.seg_len, a.M);
+    double pose[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) pose[i] = a.poses[(size_t)blk * 7 + i];
+    CamParams cam;
+    if constexpr (PER_BLOCK_CAM) cam = a.cams[blk]; else cam = a.cam;
+    int nvalid = 0;
+
+    for (int c0 = l0; c0 < l1; c0 += 32) {
+      const int n = min(32, l1 - c0);
+      const int nr = (n + 1) & ~1;  // rows are consumed in pairs
+      const int l = c0 + lane;
+      bool valid = false;
+      float2 o = make_float2(-1.f, -1.f);
+      if (lane < n) {
+        o = a.obs[(size_t)blk * a.M + l];
+        valid = (o.x > -0.5f && o.y > -0.5f && o.x < a.wb && o.y < a.hb);
+      }
+      __syncwarp();
+      if (lane < nr) {
+        if (valid) {
+          const double* P = a.pts + (size_t)(l % a.period) * 3;
+          double rx, ry, Jpx[6], Jpy[6], Jcx[12], Jcy[12];
+          residual_jacobian<MODEL, MONO>(cam, pose, P[0], P[1], P[2], (double)o.x, (double)o.y, rx, ry, Jpx, Jpy, Jcx, Jcy);
+          const double ss = rx * rx + ry * ry;
+          // ceres::CauchyLoss(1): rho = log(1+s), rho' = 1/(1+s), rho'' < 0 -> Corrector alpha = 0
+          const double w = sqrt(1.0 / (1.0 + ss));
+          cost += 0.5 * log(1.0 + ss);
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            const int p = ((j & 3) * NT + (j >> 2)) * kCS;
+            J[p + lane] = w * Jpx[j];
+            J[p + 32 + lane] = w * Jpy[j];
+          }
+          {
+            const int p = (2 * NT + 1) * kCS;  // column 6: residual
+            J[p + lane] = w * rx;
+            J[p + 32 + lane] = w * ry;
+          }
+#pragma unroll
+          for (int jf = 0; jf < KFULL; ++jf) {
+            const int c = a.colpos[jf];
+            if (c >= 0) {
+              const int p = ((c & 3) * NT + (c >> 2)) * kCS;
+              J[p + lane] = w * Jcx[jf];
+              J[p + 32 + lane] = w * Jcy[jf];
+            }
+          }
+          ++nvalid;
+        } else {
+          const int ncol = 8 + a.k;
+          for (int c = 0; c < ncol; ++c) {
+            const int p = ((c & 3) * NT + (c >> 2)) * kCS;
+            J[p + lane] = 0.0;
+            J[p + 32 + lane] = 0.0;
+          }
+        }
+      }
+      __syncwarp();
+      if (active2) {
+        const int np = nr >> 1;
+        for (int q = s; q < 2 * np; q += KS) {
+          const int ro = 2 * ((q < np) ? q : (16 + q - np));
+          double2 av[4], bv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            av[i] = *reinterpret_cast<const double2*>(J + ca[i] + ro);
+            bv[i] = *reinterpret_cast<const double2*>(J + cb[i] + ro);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[i * 4 + j] = fma(av[i].x, bv[j].x, acc[i * 4 + j]);
+              acc[i * 4 + j] = fma(av[i].y, bv[j].y, acc[i * 4 + j]);
+            }
+        }
+      }
+    }
+    // ---- flush the per-view tiles (tile rows 0,1) into the strip of this segment
+    __syncwarp();
+    double* F = J;  // alias: F[e*32 + lane]
+    if (active2 && ti <= 1) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) { F[e * 32 + lane] = acc[e]; acc[e] = 0.0; }
+    }
+    for (int m = 16; m >= 1; m >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, m);
+    __syncwarp();
+    double* strip = a.strips + (size_t)seg * (8 * DA);
+    for (int e = lane; e < 8 * DA; e += 32) {
+      const int R = e / DA, Cc = e - R * DA;
+      const int tti = R >> 2, ttj = Cc >> 2;
+      double v = 0.0;
+      if (ttj >= tti) {
+        const int tt = tile_index(tti, ttj, NT);
+        const int ee = (R & 3) * 4 + (Cc & 3);
+        for (int ss = 0; ss < KS; ++ss) v += F[ee * 32 + ss * T + tt];
+      }
+      if (e == 7 * DA + 7) v = (double)nvalid;
+      strip[e] = v;
+    }
+    __syncwarp();
+    // re-zero the aliased region (columns beyond 8+k must stay zero)
+    for (int i = lane; i < 16 * 32; i += 32) F[i] = 0.0;
+  }
+  // ---- persistent tiles (H_cc) and cost of this warp
+  double* pw = a.part + (size_t)gw * 512;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) pw[e * 32 + lane] = acc[e];
+  for (int m = 16; m >= 1; m >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, m);
+  if (lane == 0) a.cost_part[gw] = cost;
+}
+
+// Sum the per-segment strips of a block (only when a block is split into several segments).
+__global__ void lm_strip_reduce_kernel(const double* __restrict__ seg_strips, int segs_per_block, int strip_len,
+                                       double* __restrict__ blk_strips) {
+  const int blk = blockIdx.x;
+  for (int e = threadIdx.x; e < strip_len; e += blockDim.x) {
+    double v = 0.0;
+    const double* p = seg_strips + (size_t)blk * segs_per_block * strip_len + e;
+    for (int s = 0; s < segs_per_block; ++s) v += p[(size_t)s * strip_len];
+    blk_strips[(size_t)blk * strip_len + e] = v;
+  }
+}
+
+// Fixed-order reduction of the persistent H_cc tiles and the cost over all warps of lm_accumulate.
+// grid = k(k+1)/2 + 1 blocks of 256 threads.
+__global__ void lm_hcc_reduce_kernel(const double* __restrict__ part, const double* __restrict__ cost_part, int n_warps,
+                                     int NT, int k, double* __restrict__ red1) {
+  __shared__ double sh[256];
+  const int T = NT * (NT + 1) / 2, KS = 32 / T;
+  const int nent = k * (k + 1) / 2;
+  double v = 0.0;
+  int out = R1_COST;
+  if ((int)blockIdx.x < nent) {
+    int a = 0, rem = blockIdx.x, len = k;
+    while (rem >= len) { rem -= len; ++a; --len; }
+    const int b = a + rem;
+    const int R = 8 + a, Cc = 8 + b;
+    const int tt = tile_index(R >> 2, Cc >> 2, NT);
+    const int ee = (R & 3) * 4 + (Cc & 3);
+    for (int w = threadIdx.x; w < n_warps; w += 256)
+      for (int ss = 0; ss < KS; ++ss) v += part[(size_t)w * 512 + ee * 32 + ss * T + tt];
+    out = R1_HCC + a * kMaxK + b;
+  } else {
+    for (int w = threadIdx.x; w < n_warps; w += 256) v += cost_part[w];
+  }
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int m = 128; m >= 1; m >>= 1) {
+    if ((int)threadIdx.x < m) sh[threadIdx.x] += sh[threadIdx.x + m];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) red1[out] = sh[0];
+}
+
+// Generic fixed-order reduction of partial rows: in[nparts][nv] -> out[nv]; values with index >=
+// max_from are max-reduced.  grid = nv blocks of 256 threads.
+__global__ void lm_reduce_rows_kernel(const double* __restrict__ in, int nparts, int nv, int max_from,
+                                      double* __restrict__ out) {
+  __shared__ double sh[256];
+  const int v = blockIdx.x;
+  const bool is_max = v >= max_from;
+  double acc = 0.0;
+  for (int p = threadIdx.x; p < nparts; p += 256) {
+    const double x = in[(size_t)p * nv + v];
+    acc = is_max ? fmax(acc, x) : acc + x;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int m = 128; m >= 1; m >>= 1) {
+    if ((int)threadIdx.x < m) sh[threadIdx.x] = is_max ? fmax(sh[threadIdx.x], sh[threadIdx.x + m]) : sh[threadIdx.x] + sh[threadIdx.x + m];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[v] = sh[0];
+}
+
+// Block-wide fixed-order sum/max of one value per thread; result valid in thread 0.
+__device__ __forceinline__ double block_reduce(double v, bool is_max, double* sh /*[warps]*/) {
+  for (int m = 16; m >= 1; m >>= 1) {
+    const double o = __shfl_xor_sync(0xffffffffu, v, m);
+    v = is_max ? fmax(v, o) : v + o;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double r = sh[0];
+  for (int w = 1; w < nw; ++w) r = is_max ? fmax(r, sh[w]) : r + sh[w];
+  return r;
+}
+
+// -------------------------------------------------------------------------------------------
+struct SchurArgs {
+  const double* strips;   // [n_blocks][8*DA]
+  const double* poses;
+  int n_blocks, DA, k;
+  double radius, min_diag, max_diag;
+  int first;              // compute the Jacobi scaling of the pose columns (iteration 0 of a Solve)
+  int reuse_diag;
+  int undamped;           // covariance mode: no scaling, no damping
+  double* scale_p;        // [n_blocks][6]
+  double* diag_p;         // [n_blocks][6]
+  double* lyz;            // [n_blocks][kLYZ]
+  double* part;           // [grid][nv]
+  int nv;                 // nS + 2k + 4 (+1 max)
+};
+
+__global__ void __launch_bounds__(128) lm_schur_kernel(const SchurArgs a) {
+  __shared__ double sh[8];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = a.k, DA = a.DA;
+  const bool live = b < a.n_blocks;
+  double Y[6][kMaxK];
+  double z[6];
+  double gc[kMaxK];
+  double L[6][6];
+  double xn2 = 0.0, nres = 0.0, nused = 0.0, fail = 0.0, gmax = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    z[i] = 0.0;
+    for (int c = 0; c < kMaxK; ++c) Y[i][c] = 0.0;
+  }
+  for (int c = 0; c < kMaxK; ++c) gc[c] = 0.0;
+  if (live) {
+    const double* st = a.strips + (size_t)b * 8 * DA;
+    const double cnt = st[7 * DA + 7];
+    double sc[6], g[6];
+    double H[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int j = i; j < 6; ++j) { H[i][j] = st[i * DA + j]; H[j][i] = H[i][j]; }
+      g[i] = st[i * DA + 6];
+    }
+    for (int c = 0; c < k; ++c) gc[c] = st[6 * DA + 8 + c];
+    if (a.undamped) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) sc[i] = 1.0;
+    } else if (a.first) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { sc[i] = 1.0 / (1.0 + sqrt(H[i][i])); a.scale_p[(size_t)b * 6 + i] = sc[i]; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) sc[i] = a.scale_p[(size_t)b * 6 + i];
+    }
+    double lm2[6];
+    if (a.undamped) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) lm2[i] = 0.0;
+    } else if (!a.reuse_diag) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double d = fmin(fmax(sc[i] * sc[i] * H[i][i], a.min_diag), a.max_diag);
+        a.diag_p[(size_t)b * 6 + i] = d;
+        lm2[i] = d / a.radius;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) lm2[i] = a.diag_p[(size_t)b * 6 + i] / a.radius;
+    }
+    // V = S H S + D^2 ; Cholesky (lower)
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      double d = sc[j] * sc[j] * H[j][j] + lm2[j];
+#pragma unroll
+      for (int m = 0; m < j; ++m) d -= L[j][m] * L[j][m];
+      if (!(d > 0.0)) { ok = false; d = 1.0; }
+      d = sqrt(d);
+      L[j][j] = d;
+      const double id = 1.0 / d;
+#pragma unroll
+      for (int i = j + 1; i < 6; ++i) {
+        double sacc = sc[i] * sc[j] * H[i][j];
+#pragma unroll
+        for (int m = 0; m < j; ++m) sacc -= L[i][m] * L[j][m];
+        L[i][j] = sacc * id;
+      }
+    }
+    if (cnt > 0.0 && !ok) fail = 1.0;
+    // z = L^-1 (s g) ; Y = L^-1 (s W)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double sacc = sc[i] * g[i];
+#pragma unroll
+      for (int m = 0; m < i; ++m) sacc -= L[i][m] * z[m];
+      z[i] = sacc / L[i][i];
+    }
+    for (int c = 0; c < k; ++c) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        double sacc = sc[i] * st[i * DA + 8 + c];
+#pragma unroll
+        for (int m = 0; m < i; ++m) sacc -= L[i][m] * Y[m][c];
+        Y[i][c] = sacc / L[i][i];
+      }
+    }
+    double* rec = a.lyz + (size_t)b * kLYZ;
+    {
+      int q = 0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) rec[q++] = L[i][j];
+      for (int i = 0; i < 6; ++i) for (int c = 0; c < k; ++c) rec[21 + i * kMaxK + c] = Y[i][c];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) rec[93 + i] = z[i];
+    }
+    if (cnt > 0.0) {
+      nres = cnt; nused = 1.0;
+      const double* x = a.poses + (size_t)b * 7;
+      double ng[6], out[7];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) ng[i] = -g[i];
+      se3_plus(x, ng, out);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) { xn2 += x[i] * x[i]; gmax = fmax(gmax, fabs(x[i] - out[i])); }
+    }
+  }
+  // ---- block reduction, fixed order
+  double* pout = a.part + (size_t)blockIdx.x * a.nv;
+  int q = 0;
+  for (int c = 0; c < k; ++c)
+    for (int c2 = c; c2 < k; ++c2) {
+      double v = 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) v += Y[i][c] * Y[i][c2];
+      v = block_reduce(v, false, sh);
+      if (threadIdx.x == 0) pout[q] = v;
+      ++q;
+    }
+  for (int c = 0; c < k; ++c) {
+    double v = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v += Y[i][c] * z[i];
+    v = block_reduce(v, false, sh);
+    if (threadIdx.x == 0) pout[q] = v;
+    ++q;
+  }
+  for (int c = 0; c < k; ++c) {
+    const double v = block_reduce(gc[c], false, sh);
+    if (threadIdx.x == 0) pout[q] = v;
+    ++q;
+  }
+  {
+    double v = block_reduce(xn2, false, sh);  if (threadIdx.x == 0) pout[q] = v;  ++q;
+    v = block_reduce(nres, false, sh);        if (threadIdx.x == 0) pout[q] = v;  ++q;
+    v = block_reduce(nused, false, sh);       if (threadIdx.x == 0) pout[q] = v;  ++q;
+    v = block_reduce(fail, false, sh);        if (threadIdx.x == 0) pout[q] = v;  ++q;
+    v = block_reduce(gmax, true, sh);         if (threadIdx.x == 0) pout[q] = v;  ++q;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+struct BacksubArgs {
+  const double* strips;
+  const double* poses;
+  double* cand_poses;
+  const double* scale_p;
+  const double* lyz;
+  int n_blocks, DA, k;
+  double uc[kMaxK];      // s_c * yhat_c  (delta_c = -uc)
+  double* step_p;        // [n_blocks][6] tangent step actually applied
+  double* part;          // [grid][4]
+};
+
+__global__ void __launch_bounds__(128) lm_backsub_kernel(const BacksubArgs a) {
+  __shared__ double sh[8];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = a.k, DA = a.DA;
+  double gd = 0.0, dHd = 0.0, step2 = 0.0, cn2 = 0.0;
+  if (b < a.n_blocks) {
+    const double* st = a.strips + (size_t)b * 8 * DA;
+    const double* rec = a.lyz + (size_t)b * kLYZ;
+    const double* x = a.poses + (size_t)b * 7;
+    double* xc = a.cand_poses + (size_t)b * 7;
+    const double cnt = st[7 * DA + 7];
+    if (cnt > 0.0) {
+      double L[6][6], tt[6], y[6], d[6];
+      {
+        int q = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j <= i; ++j) L[i][j] = rec[q++];
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        double sacc = rec[93 + i];
+        for (int c = 0; c < k; ++c) sacc -= rec[21 + i * kMaxK + c] * a.uc[c];
+        tt[i] = sacc;
+      }
+#pragma unroll
+      for (int i = 5; i >= 0; --i) {
+        double sacc = tt[i];
+#pragma unroll
+        for (int m = i + 1; m < 6; ++m) sacc -= L[m][i] * y[m];
+        y[i] = sacc / L[i][i];
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { d[i] = -y[i] * a.scale_p[(size_t)b * 6 + i]; a.step_p[(size_t)b * 6 + i] = d[i]; }
+      double out[7];
+      se3_plus(x, d, out);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) { xc[i] = out[i]; const double e = x[i] - out[i]; step2 += e * e; cn2 += out[i] * out[i]; }
+      // model cost terms in unscaled space: g.delta and delta^T H delta (pose-pose + 2 pose-shared)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        gd += st[i * DA + 6] * d[i];
+        double hrow = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) hrow += ((i <= j) ? st[i * DA + j] : st[j * DA + i]) * d[j];
+        double wrow = 0.0;
+        for (int c = 0; c < k; ++c) wrow += st[i * DA + 8 + c] * (-a.uc[c]);
+        dHd += d[i] * (hrow + 2.0 * wrow);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 7; ++i) xc[i] = x[i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) a.step_p[(size_t)b * 6 + i] = 0.0;
+    }
+  }
+  double* pout = a.part + (size_t)blockIdx.x * 4;
+  double v = block_reduce(gd, false, sh);    if (threadIdx.x == 0) pout[0] = v;
+  v = block_reduce(dHd, false, sh);          if (threadIdx.x == 0) pout[1] = v;
+  v = block_reduce(step2, false, sh);        if (threadIdx.x == 0) pout[2] = v;
+  v = block_reduce(cn2, false, sh);          if (threadIdx.x == 0) pout[3] = v;
+}
+
+// -------------------------------------------------------------------------------------------
+struct CostArgs {
+  const float2* obs;
+  const double* pts;
+  const double* poses;
+  const CamParams* cams;
+  CamParams cam;
+  long long n_obs;  // n_blocks * M
+  int M, period;
+  float wb, hb;
+  double* part;     // [grid]
+};
+
+template <int MODEL, bool MONO, bool PER_BLOCK_CAM>
+__global__ void __launch_bounds__(256) lm_cost_kernel(const CostArgs a) {
+  __shared__ double sh[8];
+  double cost = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_obs; i += (long long)gridDim.x * blockDim.x) {
+    const float2 o = a.obs[i];
+    if (!(o.x > -0.5f && o.y > -0.5f && o.x < a.wb && o.y < a.hb)) continue;
+    const int blk = (int)(i / a.M);
+    const int l = (int)(i - (long long)blk * a.M);
+    const double* P = a.pts + (size_t)(l % a.period) * 3;
+    double rx, ry;
+    if constexpr (PER_BLOCK_CAM) residual<MODEL, MONO>(a.cams[blk], a.poses + (size_t)blk * 7, P[0], P[1], P[2], (double)o.x, (double)o.y, rx, ry);
+    else residual<MODEL, MONO>(a.cam, a.poses + (size_t)blk * 7, P[0], P[1], P[2], (double)o.x, (double)o.y, rx, ry);
+    cost += 0.5 * log(1.0 + (rx * rx + ry * ry));
+  }
+  const double v = block_reduce(cost, false, sh);
+  if (threadIdx.x == 0) a.part[blockIdx.x] = v;
+}
+
+// Per-block RMSE of the plain reprojection error: one warp per block (view).
+template <int MODEL, bool MONO, bool PER_BLOCK_CAM>
+__global__ void __launch_bounds__(128) lm_rmse_kernel(const CostArgs a, int n_blocks, double* __restrict__ rmse) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_blocks) return;
+  double acc = 0.0;
+  int n = 0;
+  for (int l = lane; l < a.M; l += 32) {
+    const float2 o = a.obs[(size_t)w * a.M + l];
+    if (!(o.x > -0.5f && o.y > -0.5f && o.x < a.wb && o.y < a.hb)) continue;
+    const double* P = a.pts + (size_t)(l % a.period) * 3;
+    double rx, ry;
+    if constexpr (PER_BLOCK_CAM) residual<MODEL, MONO>(a.cams[w], a.poses + (size_t)w * 7, P[0], P[1], P[2], (double)o.x, (double)o.y, rx, ry);
+    else residual<MODEL, MONO>(a.cam, a.poses + (size_t)w * 7, P[0], P[1], P[2], (double)o.x, (double)o.y, rx, ry);
+    const double nrm = sqrt(rx * rx + ry * ry);  // (px_obs - px_proj).norm()
+    acc += nrm * nrm;
+    ++n;
+  }
+  for (int m = 16; m >= 1; m >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, m); n += __shfl_xor_sync(0xffffffffu, n, m); }
+  if (lane == 0) rmse[w] = n > 0 ? sqrt(acc / (double)n) : DBL_MAX;
+}
+
+// Single-observation debug kernel (test hook behind ezc_lm_residual_jacobian).
+template <int MODEL, bool MONO>
+__global__ void lm_single_obs_kernel(CamParams cam, const double* __restrict__ in /*pose7 wpt3 u v*/, double* __restrict__ out) {
+  constexpr int NF = MONO ? 1 : 2;
+  constexpr int KFULL = NF + 2 + num_dist(MODEL);
+  double rx, ry, Jpx[6], Jpy[6], Jcx[12], Jcy[12];
+  residual_jacobian<MODEL, MONO>(cam, in, in[7], in[8], in[9], in[10], in[11], rx, ry, Jpx, Jpy, Jcx, Jcy);
+  constexpr int D = KFULL + 6;
+  out[0] = rx; out[1] = ry;
+  for (int j = 0; j < KFULL; ++j) { out[2 + j] = Jcx[j]; out[2 + D + j] = Jcy[j]; }
+  for (int j = 0; j < 6; ++j) { out[2 + KFULL + j] = Jpx[j]; out[2 + D + KFULL + j] = Jpy[j]; }
+}
+
+// ------------------------------------------------------------------------------------------
+// Dispatch tables
+// ------------------------------------------------------------------------------------------
+typedef void (*AccumFn)(const AccumArgs);
+typedef void (*CostFn)(const CostArgs);
+typedef void (*RmseFn)(const CostArgs, int, double*);
+typedef void (*SingleFn)(CamParams, const double*, double*);
+
+template <int MODEL, bool MONO>
+static AccumFn accum_fn(int NT, bool per_block) {
+  if (per_block) {
+    switch (NT) { case 2: return lm_accumulate_kernel<MODEL, MONO, 2, true>; default: return nullptr; }
+  }
+  switch (NT) {
+    case 2: return lm_accumulate_kernel<MODEL, MONO, 2, false>;
+    case 3: return lm_accumulate_kernel<MODEL, MONO, 3, false>;
+    case 4: return lm_accumulate_kernel<MODEL, MONO, 4, false>;
+    case 5: return lm_accumulate_kernel<MODEL, MONO, 5, false>;
+  }
+  return nullptr;
+}
+
+#define EZC_MODEL_SWITCH(model, mono, EXPR)                                         \
+  switch ((model) * 2 + ((mono) ? 1 : 0)) {                                         \
+    case 0: { constexpr int MD = RAD1; constexpr bool MN = false; EXPR; } break;    \
+    case 1: { constexpr int MD = RAD1; constexpr bool MN = true; EXPR; } break;     \
+    case 2: { constexpr int MD = RAD2; constexpr bool MN = false; EXPR; } break;    \
+    case 3: { constexpr int MD = RAD2; constexpr bool MN = true; EXPR; } break;     \
+    case 4: { constexpr int MD = RAD3; constexpr bool MN = false; EXPR; } break;    \
+    case 5: { constexpr int MD = RAD3; constexpr bool MN = true; EXPR; } break;     \
+    case 6: { constexpr int MD = RADTAN4; constexpr bool MN = false; EXPR; } break; \
+    case 7: { constexpr int MD = RADTAN4; constexpr bool MN = true; EXPR; } break;  \
+    case 8: { constexpr int MD = RADTAN5; constexpr bool MN = false; EXPR; } break; \
+    case 9: { constexpr int MD = RADTAN5; constexpr bool MN = true; EXPR; } break;  \
+    case 10: { constexpr int MD = RADTAN8; constexpr bool MN = false; EXPR; } break;\
+    case 11: { constexpr int MD = RADTAN8; constexpr bool MN = true; EXPR; } break; \
+    case 12: { constexpr int MD = KB4; constexpr bool MN = false; EXPR; } break;    \
+    case 13: { constexpr int MD = KB4; constexpr bool MN = true; EXPR; } break;     \
+    default: break;                                                                 \
+  }
+
+static AccumFn get_accum(int model, bool mono, int NT, bool per_block) {
+  AccumFn f = nullptr;
+  EZC_MODEL_SWITCH(model, mono, (f = accum_fn<MD, MN>(NT, per_block)));
+  return f;
+}
+static CostFn get_cost(int model, bool mono, bool per_block) {
+  CostFn f = nullptr;
+  EZC_MODEL_SWITCH(model, mono, (f = per_block ? lm_cost_kernel<MD, MN, true> : lm_cost_kernel<MD, MN, false>));
+  return f;
+}
+static RmseFn get_rmse(int model, bool mono, bool per_block) {
+  RmseFn f = nullptr;
+  EZC_MODEL_SWITCH(model, mono, (f = per_block ? lm_rmse_kernel<MD, MN, true> : lm_rmse_kernel<MD, MN, false>));
+  return f;
+}
+static SingleFn get_single(int model, bool mono) {
+  SingleFn f = nullptr;
+  EZC_MODEL_SWITCH(model, mono, (f = lm_single_obs_kernel<MD, MN>));
+  return f;
+}
+
+// Dense in-place Cholesky / solve for the k x k reduced system (host, k <= 12).
+static bool host_cholesky(double* A, int n) {
+  for (int j = 0; j < n; ++j) {
+    double d = A[j * n + j];
+    for (int m = 0; m < j; ++m) d -= A[j * n + m] * A[j * n + m];
+    if (!(d > 0.0)) return false;
+    d = std::sqrt(d);
+    A[j * n + j] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double s = A[i * n + j];
+      for (int m = 0; m < j; ++m) s -= A[i * n + m] * A[j * n + m];
+      A[i * n + j] = s / d;
+    }
+  }
+  return true;
+}
+static void host_chol_solve(const double* L, int n, double* b) {
+  for (int i = 0; i < n; ++i) { double s = b[i]; for (int m = 0; m < i; ++m) s -= L[i * n + m] * b[m]; b[i] = s / L[i * n + i]; }
+  for (int i = n - 1; i >= 0; --i) { double s = b[i]; for (int m = i + 1; m < n; ++m) s -= L[m * n + i] * b[m]; b[i] = s / L[i * n + i]; }
+}
+
+}  // namespace ezc
+
+using namespace ezc;
+
+// ============================================================================================
+// Solver object
+// ============================================================================================
+struct ezc_lm_solver {
+  ezc_context* ctx = nullptr;
+  ezc_lm_problem prob{};
+  int nf = 1, nd = 1, kfull = 4;
+  bool per_block_cam = false;
+  const float2* d_obs = nullptr;
+  const double* d_pts = nullptr;
+  DevBuf obs_buf, pts_buf;
+  DevBuf poses[2];
+  DevBuf cams[2];            // per-block CamParams (multi-camera) x / candidate
+  CamParams cam{}, cam_cand{};
+  std::vector<CamParams> h_cams;
+  int cur = 0;
+  int seg_len = 0, segs_per_block = 1, n_segs = 0;
+  int acc_grid = 0, acc_warps = 0;
+  DevBuf seg_strips, blk_strips, part, cost_part, scale_p, diag_p, lyz, step_p;
+  DevBuf part2, part3, part4, red1, red2, gmaxbuf, rmse, dbg;
+  HostPinned h_red;
+  int cost_grid = 0;
+  // state of the current variable pattern
+  int k = 0, NT = 2, DA = 8;
+  int cols[kMaxK];
+  int colpos[kMaxK];
+  bool have_params = false;
+};
+
+namespace {
+
+ezc_status launch_check(ezc_context* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("kernel launch failed (%s): %s", what, cudaGetErrorString(e));
+    return EZC_ERR_CUDA;
+  }
+  ctx->kernel_launches++;
+  return EZC_OK;
+}
+
+void setup_pattern(ezc_lm_solver* s, int opt_focal, int opt_pp, int opt_dist) {
+  int k = 0;
+  for (int j = 0; j < kMaxK; ++j) s->colpos[j] = -1;
+  if (!s->per_block_cam) {
+    if (opt_focal) for (int i = 0; i < s->nf; ++i) s->cols[k++] = i;
+    if (opt_pp) for (int i = 0; i < 2; ++i) s->cols[k++] = s->nf + i;
+    if (opt_dist) for (int i = 0; i < s->nd; ++i) s->cols[k++] = s->nf + 2 + i;
+  }
+  s->k = k;
+  for (int c = 0; c < k; ++c) s->colpos[s->cols[c]] = 8 + c;
+  s->NT = (8 + k + 3) / 4;
+  if (s->NT < 2) s->NT = 2;
+  s->DA = 4 * s->NT;
+}
+
+double* shared_param(CamParams& c, int nf, int j) {
+  if (j < nf) return &c.focal[j];
+  if (j < nf + 2) return &c.pp[j - nf];
+  return &c.dist[j - nf - 2];
+}
+
+ezc_status alloc_state(ezc_lm_solver* s) {
+  ezc_context* ctx = s->ctx;
+  const int nb = s->prob.n_blocks, M = s->prob.obs_per_block;
+  // segments: a block (view) is processed by one warp unless it is large (multi-camera solve)
+  s->seg_len = M <= 1024 ? M : 512;
+  s->segs_per_block = (M + s->seg_len - 1) / s->seg_len;
+  s->n_segs = nb * s->segs_per_block;
+  const int max_blocks = ctx->sm_count * 4;
+  s->acc_grid = std::max(1, std::min((s->n_segs + kWarpsPerBlock - 1) / kWarpsPerBlock, max_blocks));
+  s->acc_warps = s->acc_grid * kWarpsPerBlock;
+  const size_t strip_max = 8 * 20;
+  EZC_CUDA(s->seg_strips.reserve(sizeof(double) * strip_max * s->n_segs));
+  if (s->segs_per_block > 1) EZC_CUDA(s->blk_strips.reserve(sizeof(double) * strip_max * nb));
+  EZC_CUDA(s->part.reserve(sizeof(double) * 512 * s->acc_warps));
+  EZC_CUDA(s->cost_part.reserve(sizeof(double) * s->acc_warps));
+  EZC_CUDA(s->poses[0].reserve(sizeof(double) * 7 * std::max(nb, 1)));
+  EZC_CUDA(s->poses[1].reserve(sizeof(double) * 7 * std::max(nb, 1)));
+  EZC_CUDA(s->scale_p.reserve(sizeof(double) * 6 * std::max(nb, 1)));
+  EZC_CUDA(s->diag_p.reserve(sizeof(double) * 6 * std::max(nb, 1)));
+  EZC_CUDA(s->step_p.reserve(sizeof(double) * 6 * std::max(nb, 1)));
+  EZC_CUDA(s->lyz.reserve(sizeof(double) * kLYZ * std::max(nb, 1)));
+  const int g2 = (nb + 127) / 128 + 1;
+  EZC_CUDA(s->part2.reserve(sizeof(double) * 128 * g2));
+  EZC_CUDA(s->part3.reserve(sizeof(double) * 4 * g2));
+  s->cost_grid = std::max(1, std::min((int)(((long long)nb * M + 255) / 256), ctx->sm_count * 8));
+  EZC_CUDA(s->part4.reserve(sizeof(double) * s->cost_grid));
+  EZC_CUDA(s->red1.reserve(sizeof(double) * R1_SIZE));
+  EZC_CUDA(s->red2.reserve(sizeof(double) * 8));
+  EZC_CUDA(s->gmaxbuf.reserve(sizeof(double) * 2));
+  EZC_CUDA(s->rmse.reserve(sizeof(double) * std::max(nb, 1)));
+  EZC_CUDA(s->dbg.reserve(sizeof(double) * 64));
+  EZC_CUDA(s->h_red.reserve(sizeof(double) * (R1_SIZE + 16)));
+  if (s->per_block_cam) {
+    EZC_CUDA(s->cams[0].reserve(sizeof(CamParams) * std::max(nb, 1)));
+    EZC_CUDA(s->cams[1].reserve(sizeof(CamParams) * std::max(nb, 1)));
+  }
+  return EZC_OK;
+}
+
+ezc_status create_common(ezc_context* ctx, const ezc_lm_problem* p, bool device_ptrs, ezc_lm_solver** out) {
+  EZC_CHECK(ctx && p && out, EZC_ERR_INVALID, "ezc_lm_create: null argument");
+  *out = nullptr;
+  EZC_CHECK(p->model >= 0 && p->model < NUM_MODELS, EZC_ERR_INVALID, "ezc_lm_create: unknown model %d", p->model);
+  EZC_CHECK(p->n_blocks >= 0 && p->obs_per_block > 0 && p->pts_period > 0, EZC_ERR_INVALID, "ezc_lm_create: bad sizes");
+  EZC_CHECK(p->n_blocks == 0 || (p->obs && p->pts), EZC_ERR_INVALID, "ezc_lm_create: null data pointer");
+  EZC_CUDA(cudaSetDevice(ctx->device));
+  ezc_lm_solver* s = new (std::nothrow) ezc_lm_solver();
+  EZC_CHECK(s, EZC_ERR_INVALID, "out of host memory");
+  s->ctx = ctx;
+  s->prob = *p;
+  s->nf = p->use_mono_focal ? 1 : 2;
+  s->nd = num_dist(p->model);
+  s->kfull = s->nf + 2 + s->nd;
+  s->per_block_cam = p->cams_per_block != 0;
+  ezc_status st = alloc_state(s);
+  if (st != EZC_OK) { delete s; return st; }
+  const size_t n_obs = (size_t)p->n_blocks * p->obs_per_block;
+  if (device_ptrs) {
+    s->d_obs = reinterpret_cast<const float2*>(p->obs);
+    s->d_pts = p->pts;
+  } else {
+    cudaError_t e = s->obs_buf.reserve(std::max<size_t>(n_obs, 1) * sizeof(float2));
+    if (e == cudaSuccess) e = s->pts_buf.reserve((size_t)p->pts_period * 3 * sizeof(double));
+    if (e == cudaSuccess && n_obs) e = cudaMemcpyAsync(s->obs_buf.p, p->obs, n_obs * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->pts_buf.p, p->pts, (size_t)p->pts_period * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { set_error("ezc_lm_create: upload failed: %s", cudaGetErrorString(e)); delete s; return EZC_ERR_CUDA; }
+    s->d_obs = s->obs_buf.as<float2>();
+    s->d_pts = s->pts_buf.as<double>();
+  }
+  *out = s;
+  return EZC_OK;
+}
+
+// lm_accumulate (+ strip reduce + H_cc reduce) at the CURRENT parameters.
+ezc_status run_accumulate(ezc_lm_solver* s) {
+  ezc_context* ctx = s->ctx;
+  AccumArgs a{};
+  a.obs = s->d_obs; a.pts = s->d_pts; a.poses = s->poses[s->cur].as<double>();
+  a.cams = s->per_block_cam ? s->cams[s->cur].as<CamParams>() : nullptr;
+  a.cam = s->cam;
+  a.n_blocks = s->prob.n_blocks; a.M = s->prob.obs_per_block; a.period = s->prob.pts_period;
+  a.seg_len = s->seg_len; a.segs_per_block = s->segs_per_block; a.n_segs = s->n_segs;
+  a.wb = (float)s->prob.img_w - 0.5f; a.hb = (float)s->prob.img_h - 0.5f;
+  a.k = s->k;
+  for (int j = 0; j < kMaxK; ++j) a.colpos[j] = s->colpos[j];
+  a.strips = s->seg_strips.as<double>();
+  a.part = s->part.as<double>();
+  a.cost_part = s->cost_part.as<double>();
+  AccumFn fn = get_accum(s->prob.model, s->prob.use_mono_focal != 0, s->NT, s->per_block_cam);
+  EZC_CHECK(fn, EZC_ERR_INVALID, "no accumulate kernel for this configuration");
+  const size_t smem = sizeof(double) * kWarpsPerBlock * s->DA * kCS;
+  if (s->n_segs > 0) {
+    fn<<<s->acc_grid, kWarpsPerBlock * 32, smem, ctx->stream>>>(a);
+    if (ezc_status st = launch_check(ctx, "lm_accumulate")) return st;
+    if (s->segs_per_block > 1) {
+      lm_strip_reduce_kernel<<<s->prob.n_blocks, 160, 0, ctx->stream>>>(s->seg_strips.as<double>(), s->segs_per_block,
+                                                                         8 * s->DA, s->blk_strips.as<double>());
+      if (ezc_status st = launch_check(ctx, "lm_strip_reduce")) return st;
+    }
+  } else {
+    EZC_CUDA(cudaMemsetAsync(s->part.p, 0, sizeof(double) * 512 * s->acc_warps, ctx->stream));
+    EZC_CUDA(cudaMemsetAsync(s->cost_part.p, 0, sizeof(double) * s->acc_warps, ctx->stream));
+  }
+  lm_hcc_reduce_kernel<<<s->k * (s->k + 1) / 2 + 1, 256, 0, ctx->stream>>>(s->part.as<double>(), s->cost_part.as<double>(),
+                                                                           s->acc_warps, s->NT, s->k, s->red1.as<double>());
+  return launch_check(ctx, "lm_hcc_reduce");
+}
+
+const double* block_strips(const ezc_lm_solver* s) {
+  return s->segs_per_block > 1 ? s->blk_strips.as<double>() : s->seg_strips.as<double>();
+}
+
+ezc_status run_schur(ezc_lm_solver* s, double radius, bool first, bool reuse, bool undamped, double min_diag, double max_diag) {
+  ezc_context* ctx = s->ctx;
+  const int nb = s->prob.n_blocks;
+  const int k = s->k;
+  const int nS = k * (k + 1) / 2;
+  const int nv = nS + 2 * k + 5;
+  SchurArgs a{};
+  a.strips = block_strips(s); a.poses = s->poses[s->cur].as<double>();
+  a.n_blocks = nb; a.DA = s->DA; a.k = k;
+  a.radius = radius; a.min_diag = min_diag; a.max_diag = max_diag;
+  a.first = first; a.reuse_diag = reuse; a.undamped = undamped;
+  a.scale_p = s->scale_p.as<double>(); a.diag_p = s->diag_p.as<double>(); a.lyz = s->lyz.as<double>();
+  a.part = s->part2.as<double>(); a.nv = nv;
+  const int grid = std::max(1, (nb + 127) / 128);
+  lm_schur_kernel<<<grid, 128, 0, ctx->stream>>>(a);
+  if (ezc_status st = launch_check(ctx, "lm_schur")) return st;
+  // sums -> red1[R1_SCHUR ..], max (gradient) -> gmaxbuf
+  lm_reduce_rows_kernel<<<nv, 256, 0, ctx->stream>>>(s->part2.as<double>(), grid, nv, nv - 1, s->red1.as<double>() + R1_SCHUR);
+  return launch_check(ctx, "lm_reduce_rows");
+}
+
+ezc_status allreduce(ezc_lm_solver* s, double* dev, int count, int op) {
+  ezc_context* ctx = s->ctx;
+  if (ctx->world > 1 && ctx->allreduce) ctx->allreduce(ctx->allreduce_user, dev, count, op, ctx->stream);
+  return EZC_OK;
+}
+
+ezc_status upload_cams(ezc_lm_solver* s, int which) {
+  if (!s->per_block_cam || s->prob.n_blocks == 0) return EZC_OK;
+  EZC_CUDA(cudaMemcpyAsync(s->cams[which].p, s->h_cams.data(), sizeof(CamParams) * s->prob.n_blocks, cudaMemcpyHostToDevice, s->ctx->stream));
+  return EZC_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+extern "C" {
+
+int32_t ezc_num_dist(int32_t model) { return (model >= 0 && model < NUM_MODELS) ? num_dist(model) : -1; }
+
+void ezc_lm_default_options(ezc_lm_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->opt_focal = o->opt_pp = o->opt_dist = 1;
+  o->max_num_iterations = 1000;  // /root/reference/src/ezcalibrator.cpp:172
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->max_num_consecutive_invalid_steps = 5;
+}
+
+ezc_status ezc_lm_create(ezc_context* ctx, const ezc_lm_problem* problem, ezc_lm_solver** out) {
+  return create_common(ctx, problem, false, out);
+}
+ezc_status ezc_lm_create_device(ezc_context* ctx, const ezc_lm_problem* problem, ezc_lm_solver** out) {
+  return create_common(ctx, problem, true, out);
+}
+void ezc_lm_destroy(ezc_lm_solver* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  delete s;
+}
+
+ezc_status ezc_lm_set_params(ezc_lm_solver* s, const double* focal, const double* pp, const double* dist, const double* poses) {
+  EZC_CHECK(s && focal && pp && dist && (poses || s->prob.n_blocks == 0), EZC_ERR_INVALID, "ezc_lm_set_params: null argument");
+  EZC_CUDA(cudaSetDevice(s->ctx->device));
+  const int nb = s->prob.n_blocks;
+  if (s->per_block_cam) {
+    s->h_cams.assign(nb, CamParams{});
+    for (int b = 0; b < nb; ++b) {
+      for (int i = 0; i < s->nf; ++i) s->h_cams[b].focal[i] = focal[b * s->nf + i];
+      if (s->nf == 1) s->h_cams[b].focal[1] = focal[b];
+      for (int i = 0; i < 2; ++i) s->h_cams[b].pp[i] = pp[b * 2 + i];
+      for (int i = 0; i < s->nd; ++i) s->h_cams[b].dist[i] = dist[b * s->nd + i];
+    }
+    if (ezc_status st = upload_cams(s, 0)) return st;
+    if (ezc_status st = upload_cams(s, 1)) return st;
+  } else {
+    s->cam = CamParams{};
+    for (int i = 0; i < s->nf; ++i) s->cam.focal[i] = focal[i];
+    if (s->nf == 1) s->cam.focal[1] = focal[0];
+    s->cam.pp[0] = pp[0]; s->cam.pp[1] = pp[1];
+    for (int i = 0; i < s->nd; ++i) s->cam.dist[i] = dist[i];
+  }
+  s->cur = 0;
+  if (nb) EZC_CUDA(cudaMemcpyAsync(s->poses[0].p, poses, sizeof(double) * 7 * nb, cudaMemcpyHostToDevice, s->ctx->stream));
+  EZC_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  s->have_params = true;
+  return EZC_OK;
+}
+
+ezc_status ezc_lm_get_params(ezc_lm_solver* s, double* focal, double* pp, double* dist, double* poses) {
+  EZC_CHECK(s && s->have_params, EZC_ERR_INVALID, "ezc_lm_get_params: no parameters set");
+  EZC_CUDA(cudaSetDevice(s->ctx->device));
+  const int nb = s->prob.n_blocks;
+  if (s->per_block_cam) {
+    for (int b = 0; b < nb; ++b) {
+      if (focal) for (int i = 0; i < s->nf; ++i) focal[b * s->nf + i] = s->h_cams[b].focal[i];
+      if (pp) for (int i = 0; i < 2; ++i) pp[b * 2 + i] = s->h_cams[b].pp[i];
+      if (dist) for (int i = 0; i < s->nd; ++i) dist[b * s->nd + i] = s->h_cams[b].dist[i];
+    }
+  } else {
+    if (focal) for (int i = 0; i < s->nf; ++i) focal[i] = s->cam.focal[i];
+    if (pp) { pp[0] = s->cam.pp[0]; pp[1] = s->cam.pp[1]; }
+    if (dist) for (int i = 0; i < s->nd; ++i) dist[i] = s->cam.dist[i];
+  }
+  if (poses && nb) {
+    EZC_CUDA(cudaMemcpyAsync(poses, s->poses[s->cur].p, sizeof(double) * 7 * nb, cudaMemcpyDeviceToHost, s->ctx->stream));
+    EZC_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  }
+  return EZC_OK;
+}
+
+ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summary* summary) {
+  EZC_CHECK(s && opt && summary, EZC_ERR_INVALID, "ezc_lm_solve: null argument");
+  EZC_CHECK(s->have_params, EZC_ERR_INVALID, "ezc_lm_solve: call ezc_lm_set_params first");
+  ezc_context* ctx = s->ctx;
+  EZC_CUDA(cudaSetDevice(ctx->device));
+  std::memset(summary, 0, sizeof(*summary));
+  setup_pattern(s, opt->opt_focal, opt->opt_pp, opt->opt_dist);
+  const int k = s->k, nf = s->nf, nb = s->prob.n_blocks;
+  const int nS = k * (k + 1) / 2;
+  double* h = s->h_red.as<double>();
+
+  double scale_c[kMaxK], diag_c[kMaxK], Hcc[kMaxK * kMaxK], gc[kMaxK];
+  double radius = opt->initial_trust_region_radius, decrease_factor = 2.0;
+  bool reuse_diagonal = false, first = true, last_successful = false;
+  double x_cost = 0.0, x_norm = 0.0;
+  int iter = 0, n_success = 1, n_invalid = 0, termination = 3;
+  int n_jac = 0, n_lin = 0;
+  int trace_pending = -1;
+
+  auto record = [&](int it, double cost, int flag) {
+    if (it < opt->trace_capacity) {
+      if (opt->trace_cost) opt->trace_cost[it] = cost;
+      if (opt->trace_radius) opt->trace_radius[it] = radius;
+      if (opt->trace_flag) opt->trace_flag[it] = flag;
+    }
+  };
+
+  if (ezc_status st = run_accumulate(s)) return st;
+  ++n_jac;
+  bool fresh_jacobian = true;
+
+  for (;;) {
+    if (iter >= opt->max_num_iterations) { termination = 3; break; }
+    if (radius <= opt->min_trust_region_radius) { termination = 4; break; }
+    // ---- per-view Schur pieces for the current radius; packed partial system -> host
+    if (ezc_status st = run_schur(s, radius, first, reuse_diagonal, false, opt->min_lm_diagonal, opt->max_lm_diagonal)) return st;
+    ++n_lin;
+    const int n1 = R1_SCHUR + nS + 2 * k + 4;
+    allreduce(s, s->red1.as<double>(), n1, 0);
+    allreduce(s, s->red1.as<double>() + n1, 1, 1);
+    EZC_CUDA(cudaMemcpyAsync(h, s->red1.p, sizeof(double) * (n1 + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double* hs = h + R1_SCHUR;
+    const double* Ssum = hs;
+    const double* bsum = hs + nS;
+    const double* gcs = hs + nS + k;
+    const double xn2_p = hs[nS + 2 * k + 0];
+    const double nres = hs[nS + 2 * k + 1];
+    const double fail = hs[nS + 2 * k + 3];
+    const double gmax_p = hs[nS + 2 * k + 4];
+    if (fresh_jacobian) {
+      x_cost = h[R1_COST];
+      for (int a = 0; a < k; ++a) for (int b = a; b < k; ++b) Hcc[a * k + b] = Hcc[b * k + a] = h[R1_HCC + a * kMaxK + b];
+      for (int c = 0; c < k; ++c) gc[c] = gcs[c];
+      if (first) {
+        summary->initial_cost = x_cost;
+        summary->n_residual_blocks = (int)nres;
+        if (!std::isfinite(x_cost)) {
+          summary->iterations = 0; summary->num_successful = 0; summary->termination = 5;
+          summary->final_cost = x_cost; summary->jacobian_evaluations = n_jac; summary->linear_solves = n_lin;
+          set_error("ezc_lm_solve: non-finite cost at the starting point");
+          return EZC_ERR_NUMERIC;
+        }
+        for (int c = 0; c < k; ++c) scale_c[c] = 1.0 / (1.0 + std::sqrt(Hcc[c * k + c]));
+        double xs = xn2_p;
+        for (int c = 0; c < k; ++c) { const double v = *shared_param(s->cam, nf, s->cols[c]); xs += v * v; }
+        x_norm = std::sqrt(xs);
+        record(0, x_cost, 0);
+      } else if (trace_pending >= 0) {
+        record(trace_pending, x_cost, 1);
+      }
+      trace_pending = -1;
+      fresh_jacobian = false;
+    }
+    first = false;
+    // gradient tolerance (checked only after a successful step, like Ceres)
+    double gmax = gmax_p;
+    for (int c = 0; c < k; ++c) gmax = std::max(gmax, std::fabs(gc[c]));
+    if (last_successful && gmax <= opt->gradient_tolerance) { termination = 2; break; }
+    ++iter;
+
+    // ---- reduced system on the host
+    if (!reuse_diagonal)
+      for (int c = 0; c < k; ++c)
+        diag_c[c] = std::min(std::max(scale_c[c] * scale_c[c] * Hcc[c * k + c], opt->min_lm_diagonal), opt->max_lm_diagonal);
+    reuse_diagonal = true;
+    bool solver_ok = (fail == 0.0);
+    double uc[kMaxK] = {0}, dc[kMaxK] = {0};
+    if (solver_ok && k > 0) {
+      double S[kMaxK * kMaxK], rhs[kMaxK];
+      int q = 0;
+      for (int a = 0; a < k; ++a)
+        for (int b = a; b < k; ++b) {
+          const double v = scale_c[a] * scale_c[b] * (Hcc[a * k + b] - Ssum[q]);
+          S[a * k + b] = S[b * k + a] = v;
+          ++q;
+        }
+      for (int c = 0; c < k; ++c) {
+        S[c * k + c] += diag_c[c] / radius;
+        rhs[c] = scale_c[c] * (gc[c] - bsum[c]);
+      }
+      if (!host_cholesky(S, k)) solver_ok = false;
+      else {
+        host_chol_solve(S, k, rhs);  // yhat_c
+        for (int c = 0; c < k; ++c) { uc[c] = scale_c[c] * rhs[c]; dc[c] = -uc[c]; if (!std::isfinite(uc[c])) solver_ok = false; }
+      }
+    }
+    bool step_valid = false;
+    double model_cost_change = 0.0, cand_cost = 0.0, step2 = 0.0, cn2 = 0.0;
+    if (solver_ok) {
+      BacksubArgs ba{};
+      ba.strips = block_strips(s); ba.poses = s->poses[s->cur].as<double>(); ba.cand_poses = s->poses[1 - s->cur].as<double>();
+      ba.scale_p = s->scale_p.as<double>(); ba.lyz = s->lyz.as<double>();
+      ba.n_blocks = nb; ba.DA = s->DA; ba.k = k;
+      for (int c = 0; c < kMaxK; ++c) ba.uc[c] = uc[c];
+      ba.step_p = s->step_p.as<double>(); ba.part = s->part3.as<double>();
+      const int grid = std::max(1, (nb + 127) / 128);
+      lm_backsub_kernel<<<grid, 128, 0, ctx->stream>>>(ba);
+      if (ezc_status st = launch_check(ctx, "lm_backsub")) return st;
+      lm_reduce_rows_kernel<<<4, 256, 0, ctx->stream>>>(s->part3.as<double>(), grid, 4, 4, s->red2.as<double>());
+      if (ezc_status st = launch_check(ctx, "lm_reduce_rows")) return st;
+      // candidate shared parameters
+      s->cam_cand = s->cam;
+      for (int c = 0; c < k; ++c) *shared_param(s->cam_cand, nf, s->cols[c]) += dc[c];
+      if (nf == 1) s->cam_cand.focal[1] = s->cam_cand.focal[0];
+      CostArgs ca{};
+      ca.obs = s->d_obs; ca.pts = s->d_pts; ca.poses = s->poses[1 - s->cur].as<double>();
+      ca.cams = s->per_block_cam ? s->cams[s->cur].as<CamParams>() : nullptr;
+      ca.cam = s->cam_cand;
+      ca.n_obs = (long long)nb * s->prob.obs_per_block; ca.M = s->prob.obs_per_block; ca.period = s->prob.pts_period;
+      ca.wb = (float)s->prob.img_w - 0.5f; ca.hb = (float)s->prob.img_h - 0.5f;
+      ca.part = s->part4.as<double>();
+      CostFn cf = get_cost(s->prob.model, s->prob.use_mono_focal != 0, s->per_block_cam);
+      cf<<<s->cost_grid, 256, 0, ctx->stream>>>(ca);
+      if (ezc_status st = launch_check(ctx, "lm_cost")) return st;
+      lm_reduce_rows_kernel<<<1, 256, 0, ctx->stream>>>(s->part4.as<double>(), s->cost_grid, 1, 1, s->red2.as<double>() + 4);
+      if (ezc_status st = launch_check(ctx, "lm_reduce_rows")) return st;
+      allreduce(s, s->red2.as<double>(), R2_SIZE, 0);
+      EZC_CUDA(cudaMemcpyAsync(h, s->red2.p, sizeof(double) * R2_SIZE, cudaMemcpyDeviceToHost, ctx->stream));
+      EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+      double gd = h[0], dHd = h[1];
+      step2 = h[2]; cn2 = h[3]; cand_cost = h[4];
+      for (int a = 0; a < k; ++a) {
+        gd += gc[a] * dc[a];
+        double row = 0.0;
+        for (int b = 0; b < k; ++b) row += Hcc[a * k + b] * dc[b];
+        dHd += dc[a] * row;
+        step2 += dc[a] * dc[a];
+        const double v = *shared_param(s->cam_cand, nf, s->cols[a]);
+        cn2 += v * v;
+      }
+      // model_cost_change = -(J step)^T (f + J step / 2) = -g.delta - delta^T H delta / 2
+      model_cost_change = -gd - 0.5 * dHd;
+      step_valid = model_cost_change > 0.0;
+      if (!std::isfinite(cand_cost)) cand_cost = std::numeric_limits<double>::max();
+    }
+    if (!step_valid) {
+      ++n_invalid;
+      if (n_invalid >= opt->max_num_consecutive_invalid_steps) { record(iter, x_cost, 3); termination = 5; break; }
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;  // StepIsInvalid == StepRejected(0)
+      record(iter, x_cost, 3);
+      last_successful = false;
+      continue;
+    }
+    n_invalid = 0;
+    const double step_norm = std::sqrt(step2);
+    if (step_norm <= opt->parameter_tolerance * (x_norm + opt->parameter_tolerance)) { record(iter, x_cost, 2); termination = 1; break; }
+    const double cost_change = x_cost - cand_cost;
+    if (std::fabs(cost_change) <= opt->function_tolerance * x_cost) { record(iter, x_cost, 2); termination = 0; break; }
+    double rel = (cand_cost >= std::numeric_limits<double>::max()) ? std::numeric_limits<double>::lowest() : cost_change / model_cost_change;
+    if (rel > opt->min_relative_decrease) {
+      s->cam = s->cam_cand;
+      s->cur = 1 - s->cur;
+      x_norm = std::sqrt(cn2);
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
+      radius = std::min(opt->max_trust_region_radius, radius);
+      decrease_factor = 2.0; reuse_diagonal = false;
+      ++n_success;
+      last_successful = true;
+      x_cost = cand_cost;  // replaced by the re-evaluated cost when the new Jacobian arrives
+      record(iter, x_cost, 1);
+      trace_pending = iter;
+      if (ezc_status st = run_accumulate(s)) return st;
+      ++n_jac;
+      fresh_jacobian = true;
+    } else {
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      last_successful = false;
+      record(iter, x_cost, 2);
+    }
+  }
+  if (fresh_jacobian) {
+    // the loop ended right after an accepted step (max iterations): fetch the re-evaluated cost
+    EZC_CUDA(cudaMemcpyAsync(h, s->red1.as<double>() + R1_COST, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->world == 1) x_cost = h[0];
+  }
+  summary->iterations = iter + 1;
+  summary->num_successful = n_success;
+  summary->termination = termination;
+  summary->final_cost = x_cost;
+  summary->jacobian_evaluations = n_jac;
+  summary->linear_solves = n_lin;
+  return EZC_OK;
+}
+
+ezc_status ezc_lm_frame_rmse(ezc_lm_solver* s, double* rmse_out) {
+  EZC_CHECK(s && rmse_out && s->have_params, EZC_ERR_INVALID, "ezc_lm_frame_rmse: bad argument");
+  ezc_context* ctx = s->ctx;
+  EZC_CUDA(cudaSetDevice(ctx->device));
+  const int nb = s->prob.n_blocks;
+  if (nb == 0) return EZC_OK;
+  CostArgs ca{};
+  ca.obs = s->d_obs; ca.pts = s->d_pts; ca.poses = s->poses[s->cur].as<double>();
+  ca.cams = s->per_block_cam ? s->cams[s->cur].as<CamParams>() : nullptr;
+  ca.cam = s->cam;
+  ca.n_obs = (long long)nb * s->prob.obs_per_block; ca.M = s->prob.obs_per_block; ca.period = s->prob.pts_period;
+  ca.wb = (float)s->prob.img_w - 0.5f; ca.hb = (float)s->prob.img_h - 0.5f;
+  RmseFn rf = get_rmse(s->prob.model, s->prob.use_mono_focal != 0, s->per_block_cam);
+  const int grid = (nb * 32 + 127) / 128;
+  rf<<<grid, 128, 0, ctx->stream>>>(ca, nb, s->rmse.as<double>());
+  if (ezc_status st = launch_check(ctx, "lm_rmse")) return st;
+  EZC_CUDA(cudaMemcpyAsync(rmse_out, s->rmse.p, sizeof(double) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return EZC_OK;
+}
+
+ezc_status ezc_lm_covariance(ezc_lm_solver* s, double* cov_out) {
+  EZC_CHECK(s && cov_out && s->have_params, EZC_ERR_INVALID, "ezc_lm_covariance: bad argument");
+  EZC_CHECK(!s->per_block_cam, EZC_ERR_INVALID, "ezc_lm_covariance: shared intrinsics only");
+  ezc_context* ctx = s->ctx;
+  EZC_CUDA(cudaSetDevice(ctx->device));
+  setup_pattern(s, 1, 1, 1);
+  const int k = s->k, nS = k * (k + 1) / 2;
+  if (ezc_status st = run_accumulate(s)) return st;
+  if (ezc_status st = run_schur(s, 1.0, false, false, true, 0.0, 0.0)) return st;
+  const int n1 = R1_SCHUR + nS + 2 * k + 4;
+  allreduce(s, s->red1.as<double>(), n1, 0);
+  double* h = s->h_red.as<double>();
+  EZC_CUDA(cudaMemcpyAsync(h, s->red1.p, sizeof(double) * n1, cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  double S[kMaxK * kMaxK];
+  int q = 0;
+  for (int a = 0; a < k; ++a)
+    for (int b = a; b < k; ++b) { S[a * k + b] = S[b * k + a] = h[R1_HCC + a * kMaxK + b] - h[R1_SCHUR + q]; ++q; }
+  EZC_CHECK(host_cholesky(S, k), EZC_ERR_NUMERIC, "ezc_lm_covariance: reduced system is rank deficient");
+  for (int c = 0; c < k; ++c) {
+    double col[kMaxK] = {0};
+    col[c] = 1.0;
+    host_chol_solve(S, k, col);
+    for (int a = 0; a < k; ++a) cov_out[a * k + c] = col[a];
+  }
+  return EZC_OK;
+}
+
+ezc_status ezc_lm_mono(ezc_context* ctx, const ezc_lm_problem* problem, double* focal, double* pp, double* dist,
+                       double* poses, double* frame_rmse_out, ezc_lm_summary summaries[3]) {
+  EZC_CHECK(ctx && problem && focal && pp && dist && poses && summaries, EZC_ERR_INVALID, "ezc_lm_mono: null argument");
+  ezc_lm_solver* s = nullptr;
+  ezc_status st = ezc_lm_create(ctx, problem, &s);
+  if (st != EZC_OK) return st;
+  st = ezc_lm_set_params(s, focal, pp, dist, poses);
+  ezc_lm_options o;
+  ezc_lm_default_options(&o);
+  // stage 1: focal + poses ; stage 2: + distortion ; stage 3: + principal point
+  // (/root/reference/src/ezcalibrator.cpp:192-223)
+  const int masks[3][3] = {{1, 0, 0}, {1, 0, 1}, {1, 1, 1}};
+  for (int i = 0; i < 3 && st == EZC_OK; ++i) {
+    o.opt_focal = masks[i][0]; o.opt_pp = masks[i][1]; o.opt_dist = masks[i][2];
+    st = ezc_lm_solve(s, &o, &summaries[i]);
+  }
+  if (st == EZC_OK && frame_rmse_out) st = ezc_lm_frame_rmse(s, frame_rmse_out);
+  if (st == EZC_OK) st = ezc_lm_get_params(s, focal, pp, dist, poses);
+  ezc_lm_destroy(s);
+  return st;
+}
+
+ezc_status ezc_lm_residual_jacobian(ezc_context* ctx, int32_t model, int32_t mono, const double* focal, const double* pp,
+                                    const double* dist, const double* pose7, const double* wpt3, double u, double v,
+                                    double* r, double* J) {
+  EZC_CHECK(ctx && focal && pp && dist && pose7 && wpt3 && r && J, EZC_ERR_INVALID, "ezc_lm_residual_jacobian: null argument");
+  EZC_CHECK(model >= 0 && model < NUM_MODELS, EZC_ERR_INVALID, "unknown model %d", model);
+  EZC_CUDA(cudaSetDevice(ctx->device));
+  const int nf = mono ? 1 : 2, nd = num_dist(model);
+  CamParams cam{};
+  for (int i = 0; i < nf; ++i) cam.focal[i] = focal[i];
+  if (nf == 1) cam.focal[1] = focal[0];
+  cam.pp[0] = pp[0]; cam.pp[1] = pp[1];
+  for (int i = 0; i < nd; ++i) cam.dist[i] = dist[i];
+  double in[12];
+  for (int i = 0; i < 7; ++i) in[i] = pose7[i];
+  for (int i = 0; i < 3; ++i) in[7 + i] = wpt3[i];
+  in[10] = u; in[11] = v;
+  DevBuf buf;
+  EZC_CUDA(buf.reserve(sizeof(double) * 96));
+  double* d = buf.as<double>();
+  EZC_CUDA(cudaMemcpyAsync(d, in, sizeof(in), cudaMemcpyHostToDevice, ctx->stream));
+  get_single(model, mono != 0)<<<1, 1, 0, ctx->stream>>>(cam, d, d + 16);
+  if (ezc_status st = launch_check(ctx, "lm_single_obs")) return st;
+  const int D = nf + 2 + nd + 6;
+  double out[2 + 2 * 18];
+  EZC_CUDA(cudaMemcpyAsync(out, d + 16, sizeof(double) * (2 + 2 * D), cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  r[0] = out[0]; r[1] = out[1];
+  for (int i = 0; i < 2 * D; ++i) J[i] = out[2 + i];
+  return EZC_OK;
+}
+
+ezc_status ezc_lm_normal_equations(ezc_lm_solver* s, int32_t opt_focal, int32_t opt_pp, int32_t opt_dist, double* H_cc,
+                                   double* g_c, double* H_pp, double* H_pc, double* g_p, double* cost) {
+  EZC_CHECK(s && s->have_params, EZC_ERR_INVALID, "ezc_lm_normal_equations: bad argument");
+  ezc_context* ctx = s->ctx;
+  EZC_CUDA(cudaSetDevice(ctx->device));
+  setup_pattern(s, opt_focal, opt_pp, opt_dist);
+  const int k = s->k, nb = s->prob.n_blocks, DA = s->DA, nS = k * (k + 1) / 2;
+  if (ezc_status st = run_accumulate(s)) return st;
+  if (ezc_status st = run_schur(s, 1.0, false, false, true, 0.0, 0.0)) return st;
+  std::vector<double> h(R1_SIZE), st((size_t)nb * 8 * DA);
+  EZC_CUDA(cudaMemcpyAsync(h.data(), s->red1.p, sizeof(double) * R1_SIZE, cudaMemcpyDeviceToHost, ctx->stream));
+  if (nb) EZC_CUDA(cudaMemcpyAsync(st.data(), block_strips(s), sizeof(double) * st.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (cost) *cost = h[R1_COST];
+  if (H_cc) for (int a = 0; a < k; ++a) for (int b = a; b < k; ++b) H_cc[a * k + b] = H_cc[b * k + a] = h[R1_HCC + a * kMaxK + b];
+  if (g_c) for (int c = 0; c < k; ++c) g_c[c] = h[R1_SCHUR + nS + k + c];
+  for (int b = 0; b < nb; ++b) {
+    const double* sp = &st[(size_t)b * 8 * DA];
+    if (H_pp) for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) H_pp[b * 36 + i * 6 + j] = H_pp[b * 36 + j * 6 + i] = sp[i * DA + j];
+    if (g_p) for (int i = 0; i < 6; ++i) g_p[b * 6 + i] = sp[i * DA + 6];
+    if (H_pc) for (int i = 0; i < 6; ++i) for (int c = 0; c < k; ++c) H_pc[((size_t)b * 6 + i) * k + c] = sp[i * DA + 8 + c];
+  }
+  return EZC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+/* ezcalib_b200.h -- C ABI of the B200-native EZCalib hot path.
+ *
+ * The reference (ferreram/ezcalib) has no FFI layer: its hot path sits behind C++ interfaces
+ * (CalibDetector, DistParam, IntrinsicsParam, AutoDiffLocalLeftSE3) that ezcalibrator.cpp and
+ * camera.cpp program against.  Each entry point below names the reference call it replaces;
+ * INTEGRATION.md shows the binding a maintainer adds on the reference side.
+ *
+ * Conventions: plain C, POD only; caller owns every host buffer; the library owns device memory
+ * behind opaque handles; in/out arrays are overwritten only on success; every function returns an
+ * ezc_status and never aborts (the reference exit(-1)s; see SURVEY.md 8b "Error conventions").
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * EZC_ERR_CUDA.
+ */
+#ifndef EZCALIB_B200_H_
+#define EZCALIB_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  EZC_OK = 0,
+  EZC_ERR_INVALID = 1,   /* bad argument */
+  EZC_ERR_CUDA = 2,      /* CUDA runtime failure (incl. no device) */
+  EZC_ERR_NUMERIC = 3,   /* non-finite cost at the starting point (Ceres: FAILURE) */
+  EZC_ERR_CAPACITY = 4   /* an internal per-image capacity was exceeded */
+} ezc_status;
+
+typedef struct ezc_context ezc_context;
+
+/* Collective hook: all-reduce `count` doubles IN PLACE in DEVICE memory, enqueued on `stream`.
+ * op: 0 = sum, 1 = max.  Production: torch.distributed (NCCL over NVLink); tests: gloo. */
+typedef void (*ezc_allreduce_fn)(void* user, void* device_buf, int32_t count, int32_t op, void* stream);
+
+ezc_status ezc_create(int32_t device, ezc_context** out);
+void ezc_destroy(ezc_context* ctx);
+/* Thread-local message of the last failure on this thread. */
+const char* ezc_last_error(void);
+/* Run all work of this context on an existing cudaStream_t (e.g. torch's current stream). */
+ezc_status ezc_set_stream(ezc_context* ctx, void* cuda_stream);
+/* View-sharded multi-GPU: each rank owns a contiguous slice of the pose blocks. */
+ezc_status ezc_set_allreduce(ezc_context* ctx, ezc_allreduce_fn fn, void* user, int32_t rank, int32_t world);
+/* Number of kernels of this library launched on the context so far (bench.py "gpu_launches"). */
+uint64_t ezc_kernel_launches(const ezc_context* ctx);
+ezc_status ezc_synchronize(ezc_context* ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * Half (b): Levenberg-Marquardt calibration solve.
+ * Replaces the ceres::Problem built in EZCalibrator::computeCalibration
+ * (/root/reference/src/ezcalibrator.cpp:105-229) and runMultiCameraCalib (:631-844), the
+ * cost functions from DistParam::createCeresCostFunction (/root/reference/include/dist_models/
+ * dist_model_base.hpp:73-74) and the AutoDiffLocalLeftSE3 manifold
+ * (/root/reference/include/ceres_params/se3_param.hpp:12-41).
+ * ---------------------------------------------------------------------------------------- */
+
+/* dist_model ids, in the order of Camera::setupInitialDistortion (/root/reference/src/camera.cpp:67-94) */
+enum { EZC_RAD1 = 0, EZC_RAD2 = 1, EZC_RAD3 = 2, EZC_RADTAN4 = 3, EZC_RADTAN5 = 4, EZC_RADTAN8 = 5, EZC_KB4 = 6 };
+
+/* Number of distortion coefficients of a model (DistParam::getNumberOfParameters), -1 if unknown. */
+int32_t ezc_num_dist(int32_t model);
+
+typedef struct {
+  int32_t model;             /* EZC_RAD1 .. EZC_KB4 */
+  int32_t use_mono_focal;    /* 1: one focal, 0: fx,fy */
+  int32_t n_blocks;          /* SE3 blocks owned by THIS rank: views (mono) or extrinsics (multi-cam) */
+  int32_t obs_per_block;     /* observations per block; mono: number of target points */
+  int32_t pts_period;        /* 3-D point of local observation l is pts[l % pts_period] */
+  int32_t cams_per_block;    /* 0: one shared (focal,pp,dist); 1: one constant set per block (multi-cam) */
+  double img_w, img_h;       /* IntrinsicsParam::isPointInImage bounds (calib_models.hpp:107-115) */
+  const double* pts;         /* [pts_period][3] */
+  const float* obs;          /* [n_blocks][obs_per_block][2]; cv::Point2f; (-1,-1) = missing */
+  int32_t n_blocks_global;   /* total blocks over all ranks (== n_blocks when world == 1) */
+} ezc_lm_problem;
+
+typedef struct {
+  int32_t opt_focal, opt_pp, opt_dist;   /* which shared blocks are variable (SetParameterBlockConstant) */
+  int32_t max_num_iterations;            /* reference: 1000 (ezcalibrator.cpp:172) */
+  double function_tolerance;             /* Ceres defaults below */
+  double gradient_tolerance;
+  double parameter_tolerance;
+  double initial_trust_region_radius;
+  double max_trust_region_radius;
+  double min_trust_region_radius;
+  double min_relative_decrease;
+  double min_lm_diagonal, max_lm_diagonal;
+  int32_t max_num_consecutive_invalid_steps;
+  int32_t trace_capacity;                /* entries available in the three trace arrays (may be 0) */
+  double* trace_cost;                    /* per iteration: cost after the iteration */
+  double* trace_radius;                  /*                trust-region radius */
+  int32_t* trace_flag;                   /* 0 iteration zero, 1 successful, 2 unsuccessful, 3 invalid */
+} ezc_lm_options;
+
+typedef struct {
+  int32_t iterations;        /* iteration summaries incl. iteration 0 (ceres Summary::iterations.size()) */
+  int32_t num_successful;    /* incl. iteration 0 */
+  int32_t termination;       /* 0 function tol, 1 parameter tol, 2 gradient tol, 3 max iterations,
+                                4 min radius, 5 failure */
+  int32_t n_residual_blocks;
+  double initial_cost, final_cost;
+  int32_t jacobian_evaluations;
+  int32_t linear_solves;
+} ezc_lm_summary;
+
+typedef struct ezc_lm_solver ezc_lm_solver;
+
+/* Ceres 2.2.0 defaults + the reference's max_num_iterations = 1000; all shared blocks variable. */
+void ezc_lm_default_options(ezc_lm_options* opt);
+
+/* Upload observations / points (HOST pointers) and allocate the device state. */
+ezc_status ezc_lm_create(ezc_context* ctx, const ezc_lm_problem* problem, ezc_lm_solver** out);
+/* Same, but problem->pts / problem->obs are DEVICE pointers that the solver borrows (no copy). */
+ezc_status ezc_lm_create_device(ezc_context* ctx, const ezc_lm_problem* problem, ezc_lm_solver** out);
+void ezc_lm_destroy(ezc_lm_solver* s);
+
+/* focal[1|2], pp[2], dist[nd] (or [n_blocks][..] when cams_per_block), poses[n_blocks][7] = qx qy qz qw tx ty tz
+ * (Sophus::SE3d::data() order).  HOST pointers. */
+ezc_status ezc_lm_set_params(ezc_lm_solver* s, const double* focal, const double* pp, const double* dist,
+                             const double* poses);
+ezc_status ezc_lm_get_params(ezc_lm_solver* s, double* focal, double* pp, double* dist, double* poses);
+
+/* One ceres::Solve(options, &problem, &summary) on the device-resident state. */
+ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summary* summary);
+
+/* Per-block RMS reprojection error, CalibFrame::rmse_err (/root/reference/src/ezcalibrator.cpp:236-274).
+ * Blocks without in-image observation get DBL_MAX.  rmse_out: HOST [n_blocks]. */
+ezc_status ezc_lm_frame_rmse(ezc_lm_solver* s, double* rmse_out);
+
+/* Covariance of the shared parameters (ceres::Covariance on focal, pp, dist;
+ * /root/reference/src/ezcalibrator.cpp:293-331).  cov_out: HOST [k][k] row-major, k = nf+2+nd. */
+ezc_status ezc_lm_covariance(ezc_lm_solver* s, double* cov_out);
+
+/* The whole of EZCalibrator::computeCalibration's optimisation: 3 staged solves
+ * (focal+poses; +dist; +pp) and the per-frame RMSE.  All pointers HOST; host<->device copies inside. */
+ezc_status ezc_lm_mono(ezc_context* ctx, const ezc_lm_problem* problem, double* focal, double* pp, double* dist,
+                       double* poses, double* frame_rmse_out, ezc_lm_summary summaries[3]);
+
+/* Debug / test entry: raw residual r[2] and Jacobian J[2][nf+2+nd+6] (columns focal|pp|dist|pose6) of one
+ * observation, evaluated by the same device code the solver uses. */
+ezc_status ezc_lm_residual_jacobian(ezc_context* ctx, int32_t model, int32_t use_mono_focal, const double* focal,
+                                    const double* pp, const double* dist, const double* pose7, const double* wpt3,
+                                    double u, double v, double* r, double* J);
+
+/* Debug / test entry: robustified normal equations at the current parameters for the given
+ * variable pattern.  H_cc[k*k], g_c[k], per block H_pp[36], H_pc[6*k], g_p[6]; cost.  HOST pointers. */
+ezc_status ezc_lm_normal_equations(ezc_lm_solver* s, int32_t opt_focal, int32_t opt_pp, int32_t opt_dist,
+                                   double* H_cc, double* g_c, double* H_pp, double* H_pc, double* g_p, double* cost);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EZCALIB_B200_H_ */

@@ -1,0 +1,166 @@
+"""GPU parity tests of the LM half against the CPU oracle (oracle/lm_oracle.cpp, "restated Ceres").
+
+Tolerances (BASELINE.json north_star): final intrinsics/distortion <= 1e-6 relative, RMS reprojection
+error <= 1e-6 px.  Residual/Jacobian/normal-equation blocks are held to ~1e-11 relative (analytic
+Jacobian on the GPU vs Jet autodiff in the oracle, both FP64).
+"""
+import numpy as np
+import pytest
+
+from ezcalib_b200 import synth
+from oracle import lm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(m, mono) for m in synth.MODELS for mono in (True, False)]
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.max(np.abs(a - b) / (np.abs(b) + 1e-300)) if a.size else 0.0
+
+
+@pytest.mark.parametrize("model,mono", CASES)
+def test_residual_jacobian_matches_jets(ctx, model, mono):
+    from ezcalib_b200 import lm
+    rng = np.random.default_rng(7)
+    mid = synth.MODEL_ID[model]
+    nd = synth.NUM_DIST[mid]
+    for trial in range(8):
+        focal = np.array([800.0 + 50 * rng.standard_normal()] if mono else [800.0, 812.0])
+        pp = np.array([640.0, 500.0]) + rng.standard_normal(2)
+        dist = np.array(synth.GT_DIST[model]) * (1 + 0.1 * rng.standard_normal(nd))
+        q = rng.standard_normal(4); q /= np.linalg.norm(q)
+        pose = np.concatenate([q * 0 + synth.quat_from_rotvec(0.4 * rng.standard_normal(3)), [0.05, -0.03, 0.9]])
+        wpt = np.array([0.2 * rng.standard_normal(), 0.2 * rng.standard_normal(), 1.0])
+        u, v = 600.0 + rng.standard_normal(), 480.0 + rng.standard_normal()
+        r0, J0 = O.residual_jacobian(mid, mono, focal, pp, dist, pose, wpt, u, v)
+        r1, J1 = lm.residual_jacobian(ctx, mid, mono, focal, pp, dist, pose, wpt, u, v)
+        assert np.allclose(r1, r0, rtol=1e-12, atol=1e-10)
+        scale = np.abs(J0).max()
+        assert np.max(np.abs(J1 - J0)) <= 1e-11 * scale, (model, mono, np.max(np.abs(J1 - J0)), scale)
+
+
+def _oracle_normal_equations(P, mid, focal, pp, dist, poses, cols):
+    nv, npts = P.obs.shape[:2]
+    nf = 1 if P.mono else 2
+    kfull = nf + 2 + len(dist)
+    k = len(cols)
+    Hcc, gc = np.zeros((k, k)), np.zeros(k)
+    Hpp, Hpc, gp = np.zeros((nv, 6, 6)), np.zeros((nv, 6, k)), np.zeros((nv, 6))
+    cost = 0.0
+    for b in range(nv):
+        for j in range(npts):
+            u, v = P.obs[b, j]
+            if not (u > -0.5 and v > -0.5 and u < np.float32(P.width) - np.float32(0.5) and v < np.float32(P.height) - np.float32(0.5)):
+                continue
+            r, J = O.residual_jacobian(mid, P.mono, focal, pp, dist, poses[b], P.target[j], float(u), float(v))
+            s = r @ r
+            w = np.sqrt(1.0 / (1.0 + s))
+            cost += 0.5 * np.log(1.0 + s)
+            r = w * r; J = w * J
+            Jc, Jp = J[:, cols], J[:, kfull:]
+            Hcc += Jc.T @ Jc; gc += Jc.T @ r
+            Hpp[b] += Jp.T @ Jp; Hpc[b] += Jp.T @ Jc; gp[b] += Jp.T @ r
+    return dict(Hcc=Hcc, gc=gc, Hpp=Hpp, Hpc=Hpc, gp=gp, cost=cost)
+
+
+@pytest.mark.parametrize("model,mono,mask", [("radtan5", True, (1, 0, 0)), ("radtan5", True, (1, 0, 1)),
+                                             ("radtan8", False, (1, 1, 1)), ("kannalabrandt", True, (1, 1, 1)),
+                                             ("rad1", False, (1, 1, 1)), ("radtan4", True, (0, 1, 1))])
+def test_normal_equations_match_oracle(ctx, model, mono, mask):
+    from ezcalib_b200 import lm
+    mid = synth.MODEL_ID[model]
+    tgt = synth.chessboard_target(7, 10, 0.05)
+    P = synth.make_lm_problem(model, mono, 9, tgt, 1280, 1024, seed=11, drop_fraction=0.1)
+    P.obs[3] = -1.0  # a view without any observation
+    nf = 1 if mono else 2
+    dist = np.array(synth.GT_DIST[model]) * 0.9
+    cols = ([*range(nf)] if mask[0] else []) + ([nf, nf + 1] if mask[1] else []) + ([nf + 2 + i for i in range(len(dist))] if mask[2] else [])
+    ref = _oracle_normal_equations(P, mid, P.focal_init, P.pp_init, dist, P.poses_init, cols)
+    s = lm.LmSolver(ctx, mid, mono, P.obs, P.target, P.width, P.height)
+    s.set_params(P.focal_init, P.pp_init, dist, P.poses_init)
+    got = s.normal_equations(*mask)
+    s.close()
+    assert abs(got["cost"] - ref["cost"]) <= 1e-12 * ref["cost"]
+    for key in ("Hcc", "gc", "Hpp", "Hpc", "gp"):
+        scale = np.abs(ref[key]).max() + 1e-300
+        assert np.max(np.abs(got[key] - ref[key])) <= 2e-11 * scale, (key, np.max(np.abs(got[key] - ref[key])) / scale)
+
+
+@pytest.mark.parametrize("model,mono", CASES)
+def test_three_stage_solve_parity(ctx, model, mono):
+    """cfg1 geometry (9x6 inner corners, 50 views 1280x1024): same iterate sequence as the oracle."""
+    from ezcalib_b200 import lm
+    mid = synth.MODEL_ID[model]
+    tgt = synth.chessboard_target(7, 10, 0.05)
+    P = synth.make_lm_problem(model, mono, 50, tgt, 1280, 1024)
+    f0, pp0, d0, poses0, rmse0, ss0 = O.solve_mono(mid, mono, P.obs, P.target, P.width, P.height, P.focal_init, P.pp_init,
+                                                   P.dist_init, P.poses_init)
+    f1, pp1, d1, poses1, rmse1, ss1 = lm.lm_mono(ctx, mid, mono, P.obs, P.target, P.width, P.height, P.focal_init,
+                                                 P.pp_init, P.dist_init, P.poses_init)
+    for a, b in zip(ss0, ss1):
+        assert a["iterations"] == b["iterations"], (ss0, ss1)
+        assert a["termination"] == b["termination"]
+        assert a["n_residual_blocks"] == b["n_residual_blocks"]
+        assert abs(a["final_cost"] - b["final_cost"]) <= 1e-9 * abs(a["final_cost"])
+    assert _rel(f1, f0) <= 1e-6
+    assert _rel(pp1, pp0) <= 1e-6
+    assert np.max(np.abs(d1 - d0) / np.maximum(np.abs(d0), 1e-3)) <= 1e-6
+    assert np.max(np.abs(rmse1 - rmse0)) <= 1e-6
+    assert np.max(np.abs(poses1 - poses0)) <= 1e-6
+
+
+def test_trace_matches_oracle_and_ragged_views(ctx):
+    """AprilGrid-like problem with missing corners: per-iteration accept/reject flags, radius and cost."""
+    from ezcalib_b200 import lm
+    model, mono = "radtan8", True
+    mid = synth.MODEL_ID[model]
+    tgt = synth.aprilgrid_target(6, 6, 0.06, 0.3)
+    P = synth.make_lm_problem(model, mono, 37, tgt, 2448, 2048, seed=5, drop_fraction=0.2)
+    P.obs[0] = -1.0
+    P.obs[17, 5:] = -1.0  # a view with only 5 corners
+    res0 = O.solve(mid, mono, P.obs, P.target, P.width, P.height, P.focal_init, P.pp_init, P.dist_init, P.poses_init,
+                   opt_focal=True, opt_pp=False, opt_dist=False)
+    s = lm.LmSolver(ctx, mid, mono, P.obs, P.target, P.width, P.height)
+    s.set_params(P.focal_init, P.pp_init, P.dist_init, P.poses_init)
+    summ, tr = s.solve(True, False, False, trace=True)
+    f1, pp1, d1, poses1 = s.get_params()
+    s.close()
+    f0, pp0, d0, poses0, s0, tr0 = res0
+    assert summ["iterations"] == s0["iterations"]
+    assert np.array_equal(tr["flag"], tr0["flag"])
+    assert np.allclose(tr["radius"], tr0["radius"], rtol=1e-7)
+    assert np.allclose(tr["cost"], tr0["cost"], rtol=1e-9)
+    assert _rel(f1, f0) <= 1e-8
+    assert np.array_equal(poses1[0], P.poses_init[0])  # untouched: no observation in this view
+    assert np.max(np.abs(poses1 - poses0)) <= 1e-7
+
+
+def test_covariance_matches_dense_inverse(ctx):
+    from ezcalib_b200 import lm
+    model, mono = "radtan5", True
+    mid = synth.MODEL_ID[model]
+    tgt = synth.chessboard_target(7, 10, 0.05)
+    P = synth.make_lm_problem(model, mono, 12, tgt, 1280, 1024, seed=3)
+    s = lm.LmSolver(ctx, mid, mono, P.obs, P.target, P.width, P.height)
+    dist = np.array(synth.GT_DIST[model])
+    s.set_params(P.gt["focal"], P.gt["pp"], dist, P.gt["poses"])
+    ne = s.normal_equations(1, 1, 1)
+    cov = s.covariance()
+    s.close()
+    k, nb = ne["Hcc"].shape[0], ne["Hpp"].shape[0]
+    H = np.zeros((k + 6 * nb, k + 6 * nb))
+    H[:k, :k] = ne["Hcc"]
+    for b in range(nb):
+        sl = slice(k + 6 * b, k + 6 * b + 6)
+        H[sl, sl] = ne["Hpp"][b]
+        H[sl, :k] = ne["Hpc"][b]
+        H[:k, sl] = ne["Hpc"][b].T
+    ref = np.linalg.inv(H)[:k, :k]
+    assert np.max(np.abs(cov - ref) / np.sqrt(np.outer(np.diag(ref), np.diag(ref)))) <= 1e-7
+
+
+def test_no_device_message_is_loud():
+    from ezcalib_b200 import _lib
+    assert _lib.lib().ezc_num_dist(5) == 8
