@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native EZCalib hot path.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line.  A "step" is one Levenberg-Marquardt iteration (linear solve of the Schur-reduced system,
+candidate evaluation, accept/reject and -- when accepted -- the Jacobian / normal-equation build at
+the new point) over the cfg5 workload of BASELINE.json: 10,000,080 observations per GPU
+(69,445 views x 144 AprilGrid corners), for each of the 7 distortion models (mono focal).
+
+  value   = 10M-observation LM iterations per second, whole job, inputs resident in HBM
+            (observations processed per second / 10,000,080; aggregate over the 7 models)
+  e2e     = the same through the host-buffer C ABI (ezc_lm_create + set_params + solve + get_params):
+            pinned host buffers, H2D of observations/poses and D2H of the results inside the timed region
+  roofline= the dominant kernel (lm_accumulate) against the FP64 DFMA peak measured in the same run
+  cpu_baseline = the CPU oracle ("restated Ceres", oracle/lm_oracle.cpp) on a bounded sample
+
+`--impl reference` times the reference's CPU path: Ceres itself is not available in this image
+(SURVEY.md 8c), so this is the oracle port with all host threads on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_VIEWS_10M = 69445
+N_PTS = 144
+OBS_10M = N_VIEWS_10M * N_PTS  # 10,000,080
+IMG_W, IMG_H = 2448, 2048
+BENCH_MODELS = ("rad1", "rad2", "rad3", "radtan4", "radtan5", "radtan8", "kannalabrandt")
+
+# Algorithmic FLOPs per observation of one LM evaluation (DESIGN.md "LM roofline"): residual +
+# analytic Jacobian + Cauchy weight (F_rj, counted from lm_models.cuh) plus the Gram accumulation
+# 4*(d(d+1)/2 + d) + 4 with d = 6 + k, k = nf + 2 + nd.
+F_RJ = {"rad1": 165, "rad2": 171, "rad3": 179, "radtan4": 203, "radtan5": 211, "radtan8": 262, "kannalabrandt": 231}
+
+
+def flops_per_obs(model: str, mono: bool = True) -> int:
+    from ezcalib_b200 import synth
+    nd = synth.NUM_DIST[synth.MODEL_ID[model]]
+    k = (1 if mono else 2) + 2 + nd
+    d = 6 + k
+    return F_RJ[model] + 4 * (d * (d + 1) // 2 + d) + 4
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_problem(model: str, n_views: int, seed_offset: int = 0):
+    from ezcalib_b200 import synth
+    tgt = synth.aprilgrid_target(6, 6, 0.06, 0.3)
+    return synth.make_lm_problem(model, True, n_views, tgt, IMG_W, IMG_H, seed=synth.MASTER_SEED + seed_offset,
+                                 roll_range=np.pi)
+
+
+def measured_peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            pass
+    return {}
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def run_cpu(args, models, n_views_sample: int, as_reference: bool):
+    from ezcalib_b200 import synth
+    from oracle import lm_oracle as O
+    cores = host_cores()
+    tot_iters, tot_time = 0, 0.0
+    detail = {}
+    for mi, model in enumerate(models):
+        P = make_problem(model, n_views_sample, seed_offset=mi)
+        mid = synth.MODEL_ID[model]
+        # warm-up: one short solve
+        O.solve(mid, True, P.obs, P.target, P.width, P.height, P.focal_init, P.pp_init, P.dist_init, P.poses_init,
+                max_iterations=max(1, args.warmup), threads=cores, trace=False)
+        t0 = time.perf_counter()
+        res = O.solve(mid, True, P.obs, P.target, P.width, P.height, P.focal_init, P.pp_init, P.dist_init, P.poses_init,
+                      max_iterations=args.steps, threads=cores, trace=False)
+        dt = time.perf_counter() - t0
+        iters = res[4]["iterations"] - 1
+        tot_iters += iters
+        tot_time += dt
+        detail[model] = round(iters / dt * (n_views_sample * N_PTS) / OBS_10M, 6)
+    value = tot_iters / tot_time * (n_views_sample * N_PTS) / OBS_10M
+    sample = f"{n_views_sample} views x {N_PTS} pts = {n_views_sample * N_PTS} obs per model, {len(models)} models, {args.steps} LM iterations each (oracle stops early if it converges)"
+    return value, tot_time / max(tot_iters, 1) * 1e3, dict(value=value, unit="LM iters/s (10M obs)", cores=cores, kind="port",
+                                                           sample=sample, per_model=detail)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from ezcalib_b200 import lm, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream()
+    ctx = lm.Context(local_rank, stream=stream.cuda_stream)
+
+    tensors = {}
+
+    class _Arr:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+    def allreduce(ptr, count, op, strm):
+        key = (ptr, count)
+        t = tensors.get(key)
+        if t is None:
+            t = torch.as_tensor(_Arr(ptr, count), device=f"cuda:{local_rank}")
+            tensors[key] = t
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM)
+
+    if world > 1:
+        ctx.set_allreduce(allreduce, rank, world)
+
+    models = BENCH_MODELS if not args.models else tuple(args.models.split(","))
+    n_views = args.views
+    K, W = args.steps, args.warmup
+    fixed = dict(function_tolerance=-1.0, parameter_tolerance=-1.0, gradient_tolerance=-1.0)  # never terminate early: exactly K iterations
+
+    # ---- per-model device-resident timing (inputs already in HBM) and e2e (host buffers)
+    peak_fp64 = ctx.measure_fp64_peak()
+    sampler = ClockSampler(local_rank)
+    dev_ms, e2e_ms, jac_evals, detail = 0.0, 0.0, 0, {}
+    h2d_bytes = d2h_bytes = 0
+    launches0 = None
+    acc_ms_total, acc_flops_total = 0.0, 0.0
+    sampler.start()
+    for mi, model in enumerate(models):
+        P = make_problem(model, n_views, seed_offset=mi + 100 * rank)
+        mid = synth.MODEL_ID[model]
+        # pinned host copies (what a caller of the C ABI holds)
+        obs_pin = torch.from_numpy(P.obs).pin_memory()
+        poses_pin = torch.from_numpy(P.poses_init).pin_memory()
+        # -------- device-resident: observations uploaded once, outside the timed region
+        obs_dev = obs_pin.cuda(non_blocking=True)
+        pts_dev = torch.from_numpy(P.target).cuda()
+        solver = lm.LmSolver(ctx, mid, True, obs_dev.data_ptr(), pts_dev.data_ptr(), P.width, P.height, pts_period=N_PTS,
+                             device_ptrs=True, n_blocks=n_views, obs_per_block=N_PTS, n_blocks_global=n_views * world)
+        solver.set_params(P.focal_init, P.pp_init, P.dist_init, P.poses_init)
+        solver.solve(max_num_iterations=max(W, 3), **fixed)          # warm-up iterations (untimed)
+        solver.set_params(P.focal_init, P.pp_init, P.dist_init, P.poses_init)
+        if launches0 is None:
+            launches0 = ctx.kernel_launches()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        summ, _ = solver.solve(max_num_iterations=K, **fixed)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        iters = summ["iterations"] - 1
+        assert iters == K, f"{model}: ran {iters} iterations instead of {K} ({summ})"
+        dev_ms += ms
+        jac_evals += summ["jacobian_evaluations"]
+        detail[model] = {"ms_per_iter": round(ms / K, 4), "jacobian_evals": summ["jacobian_evaluations"],
+                         "accepted": summ["num_successful"] - 1}
+        # -------- dominant kernel alone (roofline): the Jacobian / normal-equation build
+        acc_ms = time_accumulate(ctx, solver, stream, reps=5)
+        acc_ms_total += acc_ms
+        acc_flops_total += flops_per_obs(model) * float(summ["n_residual_blocks"]) / max(world, 1)
+        detail[model]["accumulate_ms"] = round(acc_ms, 4)
+        solver.close()
+        del obs_dev
+        # -------- e2e: host buffers through the public C ABI, copies inside the timed region
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        s2 = lm.LmSolver(ctx, mid, True, obs_pin.numpy(), P.target, P.width, P.height, n_blocks_global=n_views * world)
+        s2.set_params(P.focal_init, P.pp_init, P.dist_init, poses_pin.numpy())
+        summ2, _ = s2.solve(max_num_iterations=K, **fixed)
+        out = s2.get_params()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms2], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms2 = float(t.item())
+        e2e_ms += ms2
+        h2d_bytes += P.obs.nbytes + P.poses_init.nbytes + P.target.nbytes + 8 * 12
+        d2h_bytes += out[3].nbytes + 8 * 12 + K * 8 * 261
+        s2.close()
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches() - (launches0 or 0)
+
+    total_steps = K * len(models)
+    obs_scale = (n_views * N_PTS * world) / OBS_10M
+    value = total_steps / (dev_ms * 1e-3) * obs_scale
+    e2e_value = total_steps / (e2e_ms * 1e-3) * obs_scale
+    achieved = acc_flops_total / (acc_ms_total * 1e-3) / 1e12
+    line = {
+        "metric": "LM iters/s (10M obs)", "value": round(value, 3), "unit": "LM iters/s (10M obs)",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(dev_ms / total_steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg5 LM-only sweep: %d views x %d pts = %d observations per GPU, 7 dist_models (mono focal), "
+                               "stage-3 pattern (focal+pp+dist+poses), Cauchy loss; value aggregates the 7 models" % (n_views, N_PTS, n_views * N_PTS),
+                   "models": list(models), "per_model": detail, "l2": "inputs (80 MB obs + 89 MB strips per model) exceed L2 only partly; "
+                   "each iteration rewrites 89 MB of per-view strips + 55 MB Schur records between reads",
+                   "jacobian_evaluations": jac_evals},
+        "e2e": {"value": round(e2e_value, 3), "unit": "LM iters/s (10M obs)",
+                "h2d_bytes_per_step": int(h2d_bytes / total_steps), "d2h_bytes_per_step": int(d2h_bytes / total_steps)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "fp64", "achieved": round(achieved, 3), "peak": round(peak_fp64, 3), "unit": "TFLOP/s",
+                     "frac": round(achieved / peak_fp64, 4) if peak_fp64 else None, "traffic": None,
+                     "kernel": "lm_accumulate_kernel", "peak_source": "DFMA microbenchmark measured in this run "
+                     "(MEASURED_PEAKS.json has no FP64 figure; hbm_gbs there = %s)" % measured_peaks().get("hbm_gbs")},
+    }
+    if rank == 0:
+        if not args.no_cpu and world >= 1:
+            v, ms_cpu, cb = run_cpu(argparse.Namespace(steps=min(K, 10), warmup=1), ("radtan5",), args.cpu_views, False)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def time_accumulate(ctx, solver, stream, reps=5) -> float:
+    """Average duration (ms) of the Jacobian/normal-equation build alone, CUDA events on the launch stream."""
+    import torch
+    solver.normal_equations(1, 1, 1)  # warm
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    from ezcalib_b200 import _lib
+    import ctypes as C
+    best = []
+    for _ in range(reps):
+        e0.record(stream)
+        _lib.check(_lib.lib().ezc_lm_accumulate_only(solver._h, 1, 1, 1), "ezc_lm_accumulate_only")
+        e1.record(stream)
+        torch.cuda.synchronize()
+        best.append(e0.elapsed_time(e1))
+    del C
+    return float(np.mean(best))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--models", default="")
+    ap.add_argument("--views", type=int, default=N_VIEWS_10M)
+    ap.add_argument("--cpu-views", type=int, default=20000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        if rank != 0:
+            return
+        models = BENCH_MODELS if not args.models else tuple(args.models.split(","))
+        a2 = argparse.Namespace(steps=args.steps, warmup=args.warmup)
+        value, ms, cb = run_cpu(a2, models, args.cpu_views, True)
+        line = {"impl": "reference", "metric": "LM iters/s (10M obs)", "value": round(value, 6), "unit": "LM iters/s (10M obs)",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "cfg5 LM-only sweep (bounded CPU sample, scaled to 10M observations): " + cb["sample"],
+                           "note": "Ceres 2.2.0 is not installable here (no source, no network): this is the restated-Ceres oracle port with all host threads"},
+                "cpu_baseline": cb,
+                "e2e": {"value": round(value, 6), "unit": "LM iters/s (10M obs)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

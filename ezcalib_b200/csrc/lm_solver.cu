@@ -1290,6 +1290,13 @@ ezc_status ezc_lm_residual_jacobian(ezc_context* ctx, int32_t model, int32_t mon
   return EZC_OK;
 }
 
+ezc_status ezc_lm_accumulate_only(ezc_lm_solver* s, int32_t opt_focal, int32_t opt_pp, int32_t opt_dist) {
+  EZC_CHECK(s && s->have_params, EZC_ERR_INVALID, "ezc_lm_accumulate_only: bad argument");
+  EZC_CUDA(cudaSetDevice(s->ctx->device));
+  setup_pattern(s, opt_focal, opt_pp, opt_dist);
+  return run_accumulate(s);
+}
+
 ezc_status ezc_lm_normal_equations(ezc_lm_solver* s, int32_t opt_focal, int32_t opt_pp, int32_t opt_dist, double* H_cc,
                                    double* g_c, double* H_pp, double* H_pc, double* g_p, double* cost) {
   EZC_CHECK(s && s->have_params, EZC_ERR_INVALID, "ezc_lm_normal_equations: bad argument");

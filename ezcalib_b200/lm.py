@@ -47,6 +47,11 @@ class Context:
     def kernel_launches(self) -> int:
         return int(_lib.lib().ezc_kernel_launches(self._h))
 
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double()
+        check(_lib.lib().ezc_measure_fp64_peak(self._h, C.byref(v)), "ezc_measure_fp64_peak")
+        return float(v.value)
+
     def synchronize(self):
         check(_lib.lib().ezc_synchronize(self._h), "ezc_synchronize")
 

@@ -45,6 +45,8 @@ ezc_status ezc_set_allreduce(ezc_context* ctx, ezc_allreduce_fn fn, void* user, 
 /* Number of kernels of this library launched on the context so far (bench.py "gpu_launches"). */
 uint64_t ezc_kernel_launches(const ezc_context* ctx);
 ezc_status ezc_synchronize(ezc_context* ctx);
+/* Roofline denominator for the FP64-bound LM kernels: DFMA-saturating microbenchmark (TFLOP/s). */
+ezc_status ezc_measure_fp64_peak(ezc_context* ctx, double* tflops_out);
 
 /* ------------------------------------------------------------------------------------------
  * Half (b): Levenberg-Marquardt calibration solve.
@@ -146,6 +148,10 @@ ezc_status ezc_lm_residual_jacobian(ezc_context* ctx, int32_t model, int32_t use
  * variable pattern.  H_cc[k*k], g_c[k], per block H_pp[36], H_pc[6*k], g_p[6]; cost.  HOST pointers. */
 ezc_status ezc_lm_normal_equations(ezc_lm_solver* s, int32_t opt_focal, int32_t opt_pp, int32_t opt_dist,
                                    double* H_cc, double* g_c, double* H_pp, double* H_pc, double* g_p, double* cost);
+
+/* Bench / profiling entry: enqueue ONLY the Jacobian + normal-equation build (lm_accumulate and its
+ * fixed-order reductions) at the current parameters, asynchronously on the context stream. */
+ezc_status ezc_lm_accumulate_only(ezc_lm_solver* s, int32_t opt_focal, int32_t opt_pp, int32_t opt_dist);
 
 #ifdef __cplusplus
 }
