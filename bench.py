@@ -197,6 +197,7 @@ def run_gpu(args):
 
     # ---- per-model device-resident timing (inputs already in HBM) and e2e (host buffers)
     peak_fp64 = ctx.measure_fp64_peak()
+    peak_dmma = ctx.measure_dmma_peak()
     sampler = ClockSampler(local_rank)
     dev_ms, e2e_ms, jac_evals, detail = 0.0, 0.0, 0, {}
     h2d_bytes = d2h_bytes = 0
@@ -290,7 +291,7 @@ def run_gpu(args):
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": round(achieved, 3), "peak": round(peak_fp64, 3), "unit": "TFLOP/s",
                      "frac": round(achieved / peak_fp64, 4) if peak_fp64 else None, "traffic": None,
-                     "kernel": "lm_accumulate_kernel", "peak_source": "DFMA microbenchmark measured in this run "
+                     "kernel": "lm_accumulate_kernel", "dmma_peak_tflops": round(peak_dmma, 3), "peak_source": "DFMA microbenchmark measured in this run "
                      "(MEASURED_PEAKS.json has no FP64 figure; hbm_gbs there = %s)" % measured_peaks().get("hbm_gbs")},
     }
     if rank == 0:

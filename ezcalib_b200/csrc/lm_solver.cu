@@ -33,7 +33,7 @@
 
 namespace ezc {
 
-constexpr int kCS = 66;            // shared-memory column stride in doubles (64 rows + 2 pad)
+constexpr int kCS = 68;            // shared-memory column stride in doubles (64 rows + 4 pad: conflict-free MMA fragment loads)
 constexpr int kWarpsPerBlock = 4;  // lm_accumulate block = 128 threads
 constexpr int kMaxK = 12;          // max shared columns (2 focal + 2 pp + 8 dist)
 constexpr int kLYZ = 100;          // per-view Schur record: L(21) Y(6*12) z(6) + pad
@@ -64,12 +64,18 @@ struct AccumArgs {
   double* cost_part;      // [n_warps]
 };
 
-template <int MODEL, bool MONO, int NT, bool PER_BLOCK_CAM>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// FP64 tensor-core MMA (DMMA): D(8x8) += A(8x4, row) * B(4x8, col).  Fragments: a = A[lane>>2][lane&3],
+// b = B[lane&3][lane>>2], c0/c1 = C[lane>>2][2*(lane&3) + {0,1}].
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int MODEL, bool MONO, int CG, bool PER_BLOCK_CAM>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 lm_accumulate_kernel(const AccumArgs a) {
-  constexpr int T = NT * (NT + 1) / 2;
-  constexpr int KS = 32 / T;
-  constexpr int DA = 4 * NT;
+  constexpr int DA = 8 * CG;
+  constexpr int NTILE = CG * (CG + 1) / 2;
   constexpr int NF = MONO ? 1 : 2;
   constexpr int KFULL = NF + 2 + num_dist(MODEL);
   extern __shared__ __align__(16) double smem[];
@@ -80,21 +86,11 @@ lm_accumulate_kernel(const AccumArgs a) {
 
   for (int i = lane; i < DA * kCS; i += 32) J[i] = 0.0;
 
-  const bool active2 = lane < T * KS;
-  const int t = lane % T, s = lane / T;
-  int ti = 0, tj = 0;
-  {
-    int rem = t, len = NT;
-    while (rem >= len) { rem -= len; ++ti; --len; }
-    tj = ti + rem;
-  }
-  int ca[4], cb[4];
+  // fragment addressing: column (8g + lane>>2), row (row0 + lane&3)
+  const int fr = (lane >> 2) * kCS + (lane & 3);
+  double acc[NTILE][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { ca[i] = (i * NT + ti) * kCS; cb[i] = (i * NT + tj) * kCS; }
-
-  double acc[16];
-#pragma unroll
-  for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+  for (int t = 0; t < NTILE; ++t) acc[t][0] = acc[t][1] = 0.0;
   double cost = 0.0;
 
   for (int seg = gw; seg < a.n_segs; seg += nW) {
@@ -110,7 +106,7 @@ lm_accumulate_kernel(const AccumArgs a) {
 
     for (int c0 = l0; c0 < l1; c0 += 32) {
       const int n = min(32, l1 - c0);
-      const int nr = (n + 1) & ~1;  // rows are consumed in pairs
+      const int nr = (n + 3) & ~3;  // rows are consumed four at a time (MMA k = 4)
       const int l = c0 + lane;
       bool valid = false;
       float2 o = make_float2(-1.f, -1.f);
@@ -130,85 +126,58 @@ lm_accumulate_kernel(const AccumArgs a) {
           cost += 0.5 * log(1.0 + ss);
 #pragma unroll
           for (int j = 0; j < 6; ++j) {
-            const int p = ((j & 3) * NT + (j >> 2)) * kCS;
-            J[p + lane] = w * Jpx[j];
-            J[p + 32 + lane] = w * Jpy[j];
+            J[j * kCS + lane] = w * Jpx[j];
+            J[j * kCS + 32 + lane] = w * Jpy[j];
           }
-          {
-            const int p = (2 * NT + 1) * kCS;  // column 6: residual
-            J[p + lane] = w * rx;
-            J[p + 32 + lane] = w * ry;
-          }
+          J[6 * kCS + lane] = w * rx;
+          J[6 * kCS + 32 + lane] = w * ry;
 #pragma unroll
           for (int jf = 0; jf < KFULL; ++jf) {
             const int c = a.colpos[jf];
             if (c >= 0) {
-              const int p = ((c & 3) * NT + (c >> 2)) * kCS;
-              J[p + lane] = w * Jcx[jf];
-              J[p + 32 + lane] = w * Jcy[jf];
+              J[c * kCS + lane] = w * Jcx[jf];
+              J[c * kCS + 32 + lane] = w * Jcy[jf];
             }
           }
           ++nvalid;
         } else {
           const int ncol = 8 + a.k;
           for (int c = 0; c < ncol; ++c) {
-            const int p = ((c & 3) * NT + (c >> 2)) * kCS;
-            J[p + lane] = 0.0;
-            J[p + 32 + lane] = 0.0;
+            J[c * kCS + lane] = 0.0;
+            J[c * kCS + 32 + lane] = 0.0;
           }
         }
       }
       __syncwarp();
-      if (active2) {
-        const int np = nr >> 1;
-        for (int q = s; q < 2 * np; q += KS) {
-          const int ro = 2 * ((q < np) ? q : (16 + q - np));
-          double2 av[4], bv[4];
+      // ---- Gram update on the FP64 tensor cores: [J r]^T [J r], 8x8 tiles, 4 rows per MMA
+      const int ks = nr >> 2;
+      for (int j = 0; j < 2 * ks; ++j) {
+        const int row0 = 4 * ((j < ks) ? j : (8 + j - ks));
+        double f[CG];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            av[i] = *reinterpret_cast<const double2*>(J + ca[i] + ro);
-            bv[i] = *reinterpret_cast<const double2*>(J + cb[i] + ro);
-          }
+        for (int g = 0; g < CG; ++g) f[g] = J[g * 8 * kCS + fr + row0];
+        int t = 0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+        for (int gi = 0; gi < CG; ++gi)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              acc[i * 4 + j] = fma(av[i].x, bv[j].x, acc[i * 4 + j]);
-              acc[i * 4 + j] = fma(av[i].y, bv[j].y, acc[i * 4 + j]);
-            }
-        }
+          for (int gj = gi; gj < CG; ++gj) { dmma_m8n8k4(acc[t][0], acc[t][1], f[gi], f[gj]); ++t; }
       }
     }
-    // ---- flush the per-view tiles (tile rows 0,1) into the strip of this segment
-    __syncwarp();
-    double* F = J;  // alias: F[e*32 + lane]
-    if (active2 && ti <= 1) {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) { F[e * 32 + lane] = acc[e]; acc[e] = 0.0; }
-    }
+    // ---- per-view tiles (tile row 0: pose rows, residual row 6, count row 7) -> strip of this segment
     for (int m = 16; m >= 1; m >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, m);
-    __syncwarp();
     double* strip = a.strips + (size_t)seg * (8 * DA);
-    for (int e = lane; e < 8 * DA; e += 32) {
-      const int R = e / DA, Cc = e - R * DA;
-      const int tti = R >> 2, ttj = Cc >> 2;
-      double v = 0.0;
-      if (ttj >= tti) {
-        const int tt = tile_index(tti, ttj, NT);
-        const int ee = (R & 3) * 4 + (Cc & 3);
-        for (int ss = 0; ss < KS; ++ss) v += F[ee * 32 + ss * T + tt];
-      }
-      if (e == 7 * DA + 7) v = (double)nvalid;
-      strip[e] = v;
+#pragma unroll
+    for (int gj = 0; gj < CG; ++gj) {
+      double2 v = make_double2(acc[gj][0], acc[gj][1]);
+      if (gj == 0 && lane == 31) v.y = (double)nvalid;  // element (7,7)
+      *reinterpret_cast<double2*>(strip + (lane >> 2) * DA + gj * 8 + 2 * (lane & 3)) = v;
+      acc[gj][0] = acc[gj][1] = 0.0;
     }
-    __syncwarp();
-    // re-zero the aliased region (columns beyond 8+k must stay zero)
-    for (int i = lane; i < 16 * 32; i += 32) F[i] = 0.0;
   }
   // ---- persistent tiles (H_cc) and cost of this warp
-  double* pw = a.part + (size_t)gw * 512;
+  double* pw = a.part + (size_t)gw * 384;
 #pragma unroll
-  for (int e = 0; e < 16; ++e) pw[e * 32 + lane] = acc[e];
+  for (int t = 0; t < NTILE; ++t) *reinterpret_cast<double2*>(pw + t * 64 + lane * 2) = make_double2(acc[t][0], acc[t][1]);
   for (int m = 16; m >= 1; m >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, m);
   if (lane == 0) a.cost_part[gw] = cost;
 }
@@ -228,9 +197,8 @@ __global__ void lm_strip_reduce_kernel(const double* __restrict__ seg_strips, in
 // Fixed-order reduction of the persistent H_cc tiles and the cost over all warps of lm_accumulate.
 // grid = k(k+1)/2 + 1 blocks of 256 threads.
 __global__ void lm_hcc_reduce_kernel(const double* __restrict__ part, const double* __restrict__ cost_part, int n_warps,
-                                     int NT, int k, double* __restrict__ red1) {
+                                     int CG, int k, double* __restrict__ red1) {
   __shared__ double sh[256];
-  const int T = NT * (NT + 1) / 2, KS = 32 / T;
   const int nent = k * (k + 1) / 2;
   double v = 0.0;
   int out = R1_COST;
@@ -239,10 +207,9 @@ __global__ void lm_hcc_reduce_kernel(const double* __restrict__ part, const doub
     while (rem >= len) { rem -= len; ++a; --len; }
     const int b = a + rem;
     const int R = 8 + a, Cc = 8 + b;
-    const int tt = tile_index(R >> 2, Cc >> 2, NT);
-    const int ee = (R & 3) * 4 + (Cc & 3);
-    for (int w = threadIdx.x; w < n_warps; w += 256)
-      for (int ss = 0; ss < KS; ++ss) v += part[(size_t)w * 512 + ee * 32 + ss * T + tt];
+    const int tt = tile_index(R >> 3, Cc >> 3, CG);
+    const int off = tt * 64 + ((R & 7) * 4 + ((Cc & 7) >> 1)) * 2 + (Cc & 1);
+    for (int w = threadIdx.x; w < n_warps; w += 256) v += part[(size_t)w * 384 + off];
     out = R1_HCC + a * kMaxK + b;
   } else {
     for (int w = threadIdx.x; w < n_warps; w += 256) v += cost_part[w];
@@ -610,13 +577,12 @@ typedef void (*SingleFn)(CamParams, const double*, double*);
 template <int MODEL, bool MONO>
 static AccumFn accum_fn(int NT, bool per_block) {
   if (per_block) {
-    switch (NT) { case 2: return lm_accumulate_kernel<MODEL, MONO, 2, true>; default: return nullptr; }
+    switch (NT) { case 1: return lm_accumulate_kernel<MODEL, MONO, 1, true>; default: return nullptr; }
   }
   switch (NT) {
+    case 1: return lm_accumulate_kernel<MODEL, MONO, 1, false>;
     case 2: return lm_accumulate_kernel<MODEL, MONO, 2, false>;
     case 3: return lm_accumulate_kernel<MODEL, MONO, 3, false>;
-    case 4: return lm_accumulate_kernel<MODEL, MONO, 4, false>;
-    case 5: return lm_accumulate_kernel<MODEL, MONO, 5, false>;
   }
   return nullptr;
 }
@@ -737,9 +703,8 @@ void setup_pattern(ezc_lm_solver* s, int opt_focal, int opt_pp, int opt_dist) {
   }
   s->k = k;
   for (int c = 0; c < k; ++c) s->colpos[s->cols[c]] = 8 + c;
-  s->NT = (8 + k + 3) / 4;
-  if (s->NT < 2) s->NT = 2;
-  s->DA = 4 * s->NT;
+  s->NT = (8 + k + 7) / 8;  // 8-column groups of the Gram matrix (MMA tiles)
+  s->DA = 8 * s->NT;
 }
 
 double* shared_param(CamParams& c, int nf, int j) {
@@ -758,10 +723,10 @@ ezc_status alloc_state(ezc_lm_solver* s) {
   const int max_blocks = ctx->sm_count * 4;
   s->acc_grid = std::max(1, std::min((s->n_segs + kWarpsPerBlock - 1) / kWarpsPerBlock, max_blocks));
   s->acc_warps = s->acc_grid * kWarpsPerBlock;
-  const size_t strip_max = 8 * 20;
+  const size_t strip_max = 8 * 24;
   EZC_CUDA(s->seg_strips.reserve(sizeof(double) * strip_max * s->n_segs));
   if (s->segs_per_block > 1) EZC_CUDA(s->blk_strips.reserve(sizeof(double) * strip_max * nb));
-  EZC_CUDA(s->part.reserve(sizeof(double) * 512 * s->acc_warps));
+  EZC_CUDA(s->part.reserve(sizeof(double) * 384 * s->acc_warps));
   EZC_CUDA(s->cost_part.reserve(sizeof(double) * s->acc_warps));
   EZC_CUDA(s->poses[0].reserve(sizeof(double) * 7 * std::max(nb, 1)));
   EZC_CUDA(s->poses[1].reserve(sizeof(double) * 7 * std::max(nb, 1)));
@@ -840,16 +805,17 @@ ezc_status run_accumulate(ezc_lm_solver* s) {
   AccumFn fn = get_accum(s->prob.model, s->prob.use_mono_focal != 0, s->NT, s->per_block_cam);
   EZC_CHECK(fn, EZC_ERR_INVALID, "no accumulate kernel for this configuration");
   const size_t smem = sizeof(double) * kWarpsPerBlock * s->DA * kCS;
+  if (smem > 48 * 1024) EZC_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (s->n_segs > 0) {
     fn<<<s->acc_grid, kWarpsPerBlock * 32, smem, ctx->stream>>>(a);
     if (ezc_status st = launch_check(ctx, "lm_accumulate")) return st;
     if (s->segs_per_block > 1) {
-      lm_strip_reduce_kernel<<<s->prob.n_blocks, 160, 0, ctx->stream>>>(s->seg_strips.as<double>(), s->segs_per_block,
+      lm_strip_reduce_kernel<<<s->prob.n_blocks, 192, 0, ctx->stream>>>(s->seg_strips.as<double>(), s->segs_per_block,
                                                                          8 * s->DA, s->blk_strips.as<double>());
       if (ezc_status st = launch_check(ctx, "lm_strip_reduce")) return st;
     }
   } else {
-    EZC_CUDA(cudaMemsetAsync(s->part.p, 0, sizeof(double) * 512 * s->acc_warps, ctx->stream));
+    EZC_CUDA(cudaMemsetAsync(s->part.p, 0, sizeof(double) * 384 * s->acc_warps, ctx->stream));
     EZC_CUDA(cudaMemsetAsync(s->cost_part.p, 0, sizeof(double) * s->acc_warps, ctx->stream));
   }
   lm_hcc_reduce_kernel<<<s->k * (s->k + 1) / 2 + 1, 256, 0, ctx->stream>>>(s->part.as<double>(), s->cost_part.as<double>(),

@@ -52,6 +52,11 @@ class Context:
         check(_lib.lib().ezc_measure_fp64_peak(self._h, C.byref(v)), "ezc_measure_fp64_peak")
         return float(v.value)
 
+    def measure_dmma_peak(self) -> float:
+        v = C.c_double()
+        check(_lib.lib().ezc_measure_dmma_peak(self._h, C.byref(v)), "ezc_measure_dmma_peak")
+        return float(v.value)
+
     def synchronize(self):
         check(_lib.lib().ezc_synchronize(self._h), "ezc_synchronize")
 

@@ -47,6 +47,8 @@ uint64_t ezc_kernel_launches(const ezc_context* ctx);
 ezc_status ezc_synchronize(ezc_context* ctx);
 /* Roofline denominator for the FP64-bound LM kernels: DFMA-saturating microbenchmark (TFLOP/s). */
 ezc_status ezc_measure_fp64_peak(ezc_context* ctx, double* tflops_out);
+/* Same for the FP64 tensor-core path (mma.sync m8n8k4 f64) used by the Gram accumulation. */
+ezc_status ezc_measure_dmma_peak(ezc_context* ctx, double* tflops_out);
 
 /* ------------------------------------------------------------------------------------------
  * Half (b): Levenberg-Marquardt calibration solve.
