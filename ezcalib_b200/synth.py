@@ -278,3 +278,122 @@ def make_lm_problem(model: str, mono: bool, n_views: int, target: np.ndarray, wi
                      obs=np.ascontiguousarray(obs), poses_init=np.ascontiguousarray(poses_init), focal_init=focal0,
                      pp_init=np.array([cx0, cy0]), dist_init=np.zeros(NUM_DIST[MODEL_ID[model]]),
                      gt=dict(focal=(fx_gt,) if mono else (fx_gt, fy_gt), pp=(cx_gt, cy_gt), dist=d_gt, poses=poses))
+
+
+# ----------------------------------------------------------------------------- synthetic renders
+def undistort(model: str, xd: np.ndarray, yd: np.ndarray, d, iters: int = 12) -> tuple[np.ndarray, np.ndarray]:
+    """Invert `distort` by Newton iterations with a central-difference Jacobian (the scheme of
+    DistParam::undistortCamPoint, /root/reference/include/dist_models/dist_model_base.hpp:33-71)."""
+    x, y = xd.copy(), yd.copy()
+    for _ in range(iters):
+        h = 1e-6
+        fx0, fy0 = distort(model, x, y, d)
+        ax, ay = distort(model, x + h, y, d)
+        bx, by = distort(model, x - h, y, d)
+        cx_, cy_ = distort(model, x, y + h, d)
+        dx_, dy_ = distort(model, x, y - h, d)
+        j00, j10 = (ax - bx) / (2 * h), (ay - by) / (2 * h)
+        j01, j11 = (cx_ - dx_) / (2 * h), (cy_ - dy_) / (2 * h)
+        ex, ey = fx0 - xd, fy0 - yd
+        det = j00 * j11 - j01 * j10
+        x = x - (j11 * ex - j01 * ey) / det
+        y = y - (-j10 * ex + j00 * ey) / det
+    return x, y
+
+
+def chessboard_pattern(nb_rows: int, nb_cols: int, square_size: float):
+    """White(1)/black(0) lookup on the target plane for the board whose inner corners are
+    chessboard_target(...): squares span x in [-nb_cols*sq, 0], y in [0, nb_rows*sq]; the corner
+    square next to target point 0 is black (cv::findChessboardCorners orders from a black corner)."""
+    sq = square_size
+
+    def fn(X, Y):
+        j = np.floor(-X / sq).astype(np.int64)
+        i = np.floor(Y / sq).astype(np.int64)
+        inside = (i >= 0) & (i < nb_rows) & (j >= 0) & (j < nb_cols)
+        black = ((i + (nb_cols - 1 - j)) % 2 == 0)
+        return np.where(inside & black, 0.0, 1.0)
+    return fn
+
+
+def aprilgrid_pattern(nb_rows: int, nb_cols: int, tag_size: float, tag_space: float, codes: np.ndarray):
+    """AprilGrid (Kalibr layout, 36h11, 2-cell black border): tag id = r*nb_cols + c at
+    offset (c*off, -r*off); the tag spans x in [0,s], y in [-s,0]; data bit i (MSB first) is row-major from
+    the top-left cell, 1 = white."""
+    s = tag_size
+    off = s * (1.0 + tag_space)
+    cs = s / 10.0
+    bits = np.zeros((nb_rows * nb_cols, 10, 10), dtype=np.float64)
+    for t in range(nb_rows * nb_cols):
+        code = int(codes[t])
+        for idx in range(36):
+            bits[t, 2 + idx // 6, 2 + idx % 6] = (code >> (35 - idx)) & 1
+
+    def fn(X, Y):
+        c = np.floor(X / off).astype(np.int64)
+        r = np.floor(-Y / off + 1e-12).astype(np.int64)
+        # tag (r,c) covers y in [-r*off - s, -r*off]
+        r = np.floor((-Y) / off).astype(np.int64)
+        lx = X - c * off
+        ly = Y + r * off            # in (-off, 0]
+        inside = (c >= 0) & (c < nb_cols) & (r >= 0) & (r < nb_rows) & (lx >= 0) & (lx < s) & (ly > -s) & (ly <= 0)
+        cx_ = np.clip(np.floor(lx / cs).astype(np.int64), 0, 9)
+        ry = np.clip(np.floor((ly + s) / cs).astype(np.int64), 0, 9)
+        tid = np.clip(r * nb_cols + c, 0, nb_rows * nb_cols - 1)
+        return np.where(inside, bits[tid, ry, cx_], 1.0)
+    return fn
+
+
+def gaussian_blur_np(img: np.ndarray, sigma: float) -> np.ndarray:
+    if sigma <= 0:
+        return img
+    rad = max(1, int(math.ceil(3 * sigma)))
+    xs = np.arange(-rad, rad + 1)
+    k = np.exp(-xs * xs / (2 * sigma * sigma))
+    k /= k.sum()
+    pad = np.pad(img, rad, mode="edge")
+    tmp = sum(k[i] * pad[:, i:i + img.shape[1]] for i in range(2 * rad + 1))
+    out = sum(k[i] * tmp[i:i + img.shape[0], :] for i in range(2 * rad + 1))
+    return out
+
+
+def render_view(pattern_fn, model: str, fx: float, fy: float, cx: float, cy: float, d, pose: np.ndarray, width: int,
+                height: int, rng: np.random.Generator | None = None, ss: int = 4, blur_sigma: float = 0.8,
+                noise_sigma: float = 2.0, black: float = 20.0, white: float = 235.0) -> np.ndarray:
+    """Supersampled (ss x ss) area-sampled u8 render of a planar target (z_w = 1) through the camera model."""
+    q = pose[:4]
+    t = pose[4:]
+    Rm = np.array([quat_rotate(q, e) for e in np.eye(3)]).T  # columns = R e_i
+    # target-plane coordinates on the lattice of pixel CORNERS (u = i - 0.5); the sub-samples inside a
+    # pixel interpolate them bilinearly (the map is smooth: error << 1e-3 px)
+    u = np.arange(width + 1, dtype=np.float64)[None, :] - 0.5
+    v = np.arange(height + 1, dtype=np.float64)[:, None] - 0.5
+    xd = np.broadcast_to((u - cx) / fx, (height + 1, width + 1)).copy()
+    yd = np.broadcast_to((v - cy) / fy, (height + 1, width + 1)).copy()
+    x, y = undistort(model, xd, yd, d, iters=8)
+    # ray lambda*(x,y,1) = R p_w + t with p_w.z = 1  ->  p_w = R^T (lambda ray - t)
+    r2x, r2y, r2z = Rm[0, 2], Rm[1, 2], Rm[2, 2]
+    num = 1.0 + (r2x * t[0] + r2y * t[1] + r2z * t[2])
+    den = r2x * x + r2y * y + r2z
+    lam = num / den
+    px, py, pz = lam * x - t[0], lam * y - t[1], lam - t[2]
+    Xc = Rm[0, 0] * px + Rm[1, 0] * py + Rm[2, 0] * pz
+    Yc = Rm[0, 1] * px + Rm[1, 1] * py + Rm[2, 1] * pz
+    behind = (lam <= 0)
+    Xc = np.where(behind, 1e9, Xc)
+    Yc = np.where(behind, 1e9, Yc)
+    acc = np.zeros((height, width))
+    X00, X01, X10, X11 = Xc[:-1, :-1], Xc[:-1, 1:], Xc[1:, :-1], Xc[1:, 1:]
+    Y00, Y01, Y10, Y11 = Yc[:-1, :-1], Yc[:-1, 1:], Yc[1:, :-1], Yc[1:, 1:]
+    for a in range(ss):
+        wa = (a + 0.5) / ss
+        for b in range(ss):
+            wb = (b + 0.5) / ss
+            X = (1 - wb) * ((1 - wa) * X00 + wa * X01) + wb * ((1 - wa) * X10 + wa * X11)
+            Y = (1 - wb) * ((1 - wa) * Y00 + wa * Y01) + wb * ((1 - wa) * Y10 + wa * Y11)
+            acc += pattern_fn(X, Y)
+    img = black + (white - black) * acc / (ss * ss)
+    img = gaussian_blur_np(img, blur_sigma)
+    if noise_sigma > 0 and rng is not None:
+        img = img + rng.normal(0.0, noise_sigma, size=img.shape)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)

@@ -51,6 +51,34 @@ ezc_status ezc_measure_fp64_peak(ezc_context* ctx, double* tflops_out);
 ezc_status ezc_measure_dmma_peak(ezc_context* ctx, double* tflops_out);
 
 /* ------------------------------------------------------------------------------------------
+ * Half (a): batched calibration-target detection.
+ * ---------------------------------------------------------------------------------------- */
+
+/* A batch of 8-bit gray images of identical size: what cv::imread(path, IMREAD_GRAYSCALE) yields in
+ * EZCalibrator::runCalibration (/root/reference/src/ezcalibrator.cpp:44).  row_stride / image_stride in
+ * bytes; 0 means densely packed. */
+typedef struct {
+  const uint8_t* data;
+  int32_t n_images, width, height;
+  int64_t row_stride, image_stride;
+} ezc_image_batch;
+
+typedef struct ezc_images ezc_images;
+
+/* Copy a HOST batch into HBM (the detectors then work on the device-resident copy). */
+ezc_status ezc_images_upload(ezc_context* ctx, const ezc_image_batch* host_batch, ezc_images** out);
+/* Borrow a batch that already lives in DEVICE memory (batch->data is a device pointer). */
+ezc_status ezc_images_wrap_device(ezc_context* ctx, const ezc_image_batch* device_batch, ezc_images** out);
+void ezc_images_destroy(ezc_images* imgs);
+
+/* cv::cornerSubPix(img, corners, Size(win_w,win_h), Size(-1,-1), {COUNT+EPS, max_iter, eps}) for n corners;
+ * corner i lies in image image_index[i].  Replaces /root/reference/include/target_detectors/
+ * chessboard_detector.hpp:39-40 and aprilgrid_detector.hpp:52-53 (win 5x5, 100 iterations, eps 0.05).
+ * corners: HOST float [n][2], refined in place.  Corners must lie inside the image (OpenCV asserts it). */
+ezc_status ezc_corner_subpix(ezc_context* ctx, const ezc_images* imgs, float* corners, const int32_t* image_index,
+                             int32_t n, int32_t win_w, int32_t win_h, int32_t max_iter, double eps);
+
+/* ------------------------------------------------------------------------------------------
  * Half (b): Levenberg-Marquardt calibration solve.
  * Replaces the ceres::Problem built in EZCalibrator::computeCalibration
  * (/root/reference/src/ezcalibrator.cpp:105-229) and runMultiCameraCalib (:631-844), the
