@@ -1,0 +1,1248 @@
+// apriltag.cu -- batched AprilGrid detection on the GPU (half (a), AprilGrid path).
+//
+// Replaces AprilTagCalibDetector::detectTarget (/root/reference/include/target_detectors/aprilgrid_detector.hpp:30-71)
+// = AprilTags::TagDetector::extractTags (/root/reference/thirdparty/ethz_apriltag2/src/TagDetector.cc:40-586)
+// + per-tag cv::cornerSubPix + scatter into 4*nb_tags corner slots.
+//
+// Not a port: the reference walks one image at a time through std::vector / std::map / pointer lists on one
+// core.  Here a whole batch of images resident in HBM goes through data-parallel stages, and every stage is
+// arranged so that its result is IDENTICAL to the reference's sequential semantics (float32 operation order
+// included; this translation unit is compiled with -fmad=false and uses bit-exact libm restatements):
+//   1  u8 -> float, 3-tap Gaussian blur (with the reference's border quirk), gradient magnitude / atan2
+//   2  compaction of the pixels above the gradient threshold (raster order == compact order)
+//   3  edge emission in generation order (count, scan, scatter)
+//   4  connected components of the edge graph (lock-free union-find); edges of different components never
+//      interact in Edge::mergeEdges, so the reference's single sequential sweep over the cost-sorted edge
+//      list factorises into one independent sequential sweep PER COMPONENT
+//   5  stable radix sort of the edges by (component, cost) -- generation order inside equal keys
+//   6  one thread per component: the exact union-find / span-merge sweep of Edge.cc:69-117
+//   7  stable radix sort of the clustered pixels by representative (== std::map order, raster inside)
+//   8  one thread per cluster: weighted line fit, segment orientation vote (float32 sums in raster order)
+//   9  10-px spatial hash, child lists, depth-4 quad search, tag decoding, de-duplication, cornerSubPix
+// Stages 4-6 are what removes the reference's serial bottleneck (~1e6 dependent union-find steps per image).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+#include "images.cuh"
+#include "libm_exact.cuh"
+#include "scan_sort.cuh"
+#include "tag36h11.cuh"
+
+namespace ezc {
+
+// ---- constants of the reference ------------------------------------------------------------
+__device__ __constant__ float c_filt[3];           // Gaussian::makeGaussianFilter(0.8, 3), computed on the host
+constexpr float kMinMag = 0.004f;                  // Edge::minMag          (Edge.cc:8)
+constexpr float kThetaThresh = 100.f;              // Edge::thetaThresh     (Edge.cc:11)
+constexpr float kMagThresh = 1200.f;               // Edge::magThresh       (Edge.cc:12)
+constexpr int kMinSegmentSize = 4;                 // Segment::minimumSegmentSize (Segment.h:14)
+constexpr float kMinLineLength = 4.f;              // Segment::minimumLineLength  (Segment.cc:6)
+constexpr int kMinEdgeLength = 6;                  // Quad::minimumEdgeLength (Quad.h:22)
+constexpr float kMaxQuadAspect = 32.f;             // Quad::maxQuadAspectRatio (Quad.cc:11)
+constexpr float kPiF = 3.14159274101257324f;       // (float)M_PI
+
+__device__ __forceinline__ float max_edge_cost() { return 30.f * kPiF / 180.f; }  // Edge.cc:9
+
+// MathUtil::mod2pi (MathUtil.h:30-38)
+__device__ __forceinline__ float mod2pi(float vin) {
+  const float twopi = 2 * kPiF;
+  const float twopi_inv = 1.f / (2.f * kPiF);
+  const float absv = fabsf(vin);
+  const float q = absv * twopi_inv + 0.5f;
+  const int qi = (int)q;
+  const float r = absv - qi * twopi;
+  return (vin < 0) ? -r : r;
+}
+__device__ __forceinline__ float mod2pi_ref(float ref, float v) { return ref + mod2pi(v - ref); }
+__device__ __forceinline__ float dist2d(float ax, float ay, float bx, float by) {
+  const float dx = ax - bx, dy = ay - by;
+  return sqrtf(dx * dx + dy * dy);
+}
+__device__ __forceinline__ float fminr(float a, float b) { return (b < a) ? b : a; }  // std::min
+__device__ __forceinline__ float fmaxr(float a, float b) { return (a < b) ? b : a; }  // std::max
+
+// ---- stage 1: preprocessing -----------------------------------------------------------------
+// Horizontal pass of FloatImage::filterFactoredCentered (FloatImage.cc:46-52 -> Gaussian.cc:33-69).
+// NOTE the reference compares ABSOLUTE offsets (aoff + i) against (alen + j): rows y >= 1 therefore get
+// unfiltered border columns, and row 1 reads the last pixel of row 0.  Reproduced as is.
+__global__ void at_blur_h_kernel(const uint8_t* __restrict__ img, long long pitch, long long istride, int W, int H,
+                                 int n_img, float* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long N = (long long)W * H;
+  if (gid >= N * n_img) return;
+  const int im = (int)(gid / N);
+  const int p = (int)(gid - (long long)im * N);
+  const int y = p / W, x = p - y * W;
+  const uint8_t* I = img + (long long)im * istride;
+  auto px = [&](int xx, int yy) -> float { return (float)((double)I[(long long)yy * pitch + xx] / 255.); };
+  const float f0 = c_filt[0], f1 = c_filt[1], f2 = c_filt[2];
+  double acc = 0;
+  if (x >= 2 && x <= W - 2) {
+    acc += (double)(px(x + 1, y) * f0); acc += (double)(px(x, y) * f1); acc += (double)(px(x - 1, y) * f2);
+  } else if (y == 0) {
+    if (x == 0) { acc += (double)(px(1, 0) * f0); acc += (double)(px(0, 0) * f1); acc += (double)(px(0, 0) * f2); }
+    else if (x == 1) { acc += (double)(px(2, 0) * f0); acc += (double)(px(1, 0) * f1); acc += (double)(px(0, 0) * f2); }
+    else { acc += (double)(px(W - 1, 0) * f0); acc += (double)(px(W - 1, 0) * f1); acc += (double)(px(W - 2, 0) * f2); }
+  } else if (y == 1 && x == 0) {
+    acc += (double)(px(0, 1) * f0); acc += (double)(px(0, 1) * f1); acc += (double)(px(W - 1, 0) * f2);
+  } else {
+    const float a = (x == W - 1) ? px(W - 1, y) : px(0, y);  // columns 0,1 replicate in(0,y); column W-1 in(W-1,y)
+    acc += (double)(a * f0); acc += (double)(a * f1); acc += (double)(a * f2);
+  }
+  out[gid] = (float)acc;
+}
+
+// Vertical pass (true replicated border: the column is copied out with aoff = 0).
+__global__ void at_blur_v_kernel(const float* __restrict__ r, int W, int H, int n_img, float* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long N = (long long)W * H;
+  if (gid >= N * n_img) return;
+  const int im = (int)(gid / N);
+  const int p = (int)(gid - (long long)im * N);
+  const int y = p / W, x = p - y * W;
+  const float* R = r + (long long)im * N;
+  const float f0 = c_filt[0], f1 = c_filt[1], f2 = c_filt[2];
+  const int yp = min(y + 1, H - 1), ym = max(y - 1, 0);
+  double acc = 0;
+  acc += (double)(R[(long long)yp * W + x] * f0);
+  acc += (double)(R[(long long)y * W + x] * f1);
+  acc += (double)(R[(long long)ym * W + x] * f2);
+  out[gid] = (float)acc;
+}
+
+// Gradient (TagDetector.cc:155-169): interior pixels only; border stays 0.  Also emits the activity flag
+// of stage 2: x < W-1, y < H-1, mag >= minMag (TagDetector.cc:214-219).
+__global__ void at_gradient_kernel(const float* __restrict__ seg, int W, int H, int n_img, float* __restrict__ theta,
+                                   float* __restrict__ mag, int* __restrict__ flag) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long N = (long long)W * H;
+  if (gid >= N * n_img) return;
+  const int im = (int)(gid / N);
+  const int p = (int)(gid - (long long)im * N);
+  const int y = p / W, x = p - y * W;
+  float th = 0.f, mg = 0.f;
+  if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
+    const float* S = seg + (long long)im * N;
+    const float Ix = S[p + 1] - S[p - 1];
+    const float Iy = S[p + W] - S[p - W];
+    mg = Ix * Ix + Iy * Iy;
+    th = fd_atan2f(Iy, Ix);
+  }
+  theta[gid] = th;
+  mag[gid] = mg;
+  flag[gid] = (x + 1 < W && y + 1 < H && mg >= kMinMag) ? 1 : 0;
+}
+
+// ---- stage 2: compaction -----------------------------------------------------------------------
+// cidx[] holds the exclusive scan of the flags == compact id of every active pixel (raster order preserved).
+__global__ void at_compact_kernel(const int* __restrict__ cidx, const float* __restrict__ theta, const float* __restrict__ mag,
+                                  long long total, int W, int H, int n_active, int* __restrict__ apix,
+                                  float* __restrict__ a_theta, float* __restrict__ a_mag, int* __restrict__ parent,
+                                  int* __restrict__ setsize, float* __restrict__ tmin, float* __restrict__ tmax,
+                                  float* __restrict__ mmin, float* __restrict__ mmax) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const long long N = (long long)W * H;
+  const int p = (int)(gid % N);
+  const int y = p / W, x = p - y * W;
+  const float mg = mag[gid];
+  if (!(x + 1 < W && y + 1 < H && mg >= kMinMag)) return;
+  const int c = cidx[gid];
+  const float th = theta[gid];
+  apix[c] = (int)gid;  // global dense index (image * N + pixel); sub-batches are sized to keep it < 2^31
+  a_theta[c] = th; a_mag[c] = mg;
+  parent[c] = c; setsize[c] = 1;
+  tmin[c] = th; tmax[c] = th; mmin[c] = mg; mmax[c] = mg;
+  (void)n_active;
+}
+
+// ---- stage 3: edges (Edge.cc:14-67) ------------------------------------------------------------------
+__device__ __forceinline__ int edge_cost(float theta0, float theta1, float mag1) {
+  if (mag1 < kMinMag) return -1;
+  const float thetaErr = fabsf(mod2pi(theta1 - theta0));
+  if (thetaErr > max_edge_cost()) return -1;
+  const float normErr = thetaErr / max_edge_cost();
+  return (int)(normErr * 100);
+}
+
+template <bool EMIT>
+__global__ void at_edges_kernel(const int* __restrict__ apix, const float* __restrict__ theta, const float* __restrict__ mag,
+                                const int* __restrict__ cidx, int n_active, int W, int H, int* __restrict__ ecount,
+                                const int* __restrict__ eoff, int* __restrict__ eA, int* __restrict__ eB,
+                                uint8_t* __restrict__ ecost) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_active) return;
+  const long long g = apix[c];
+  const long long N = (long long)W * H;
+  const int p = (int)(g % N);
+  const int y = p / W, x = p - y * W;
+  const float th0 = theta[g];
+  int n = 0;
+  int o = EMIT ? eoff[c] : 0;
+  auto consider = [&](long long gn) {
+    const int cost = edge_cost(th0, theta[gn], mag[gn]);
+    if (cost >= 0) {
+      if (EMIT) { eA[o] = c; eB[o] = cidx[gn]; ecost[o] = (uint8_t)cost; ++o; }
+      ++n;
+    }
+  };
+  consider(g + 1);          // horizontal
+  consider(g + W);          // vertical
+  consider(g + W + 1);      // downward diagonal
+  if (x != 0) consider(g + W - 1);  // upward diagonal
+  if (!EMIT) ecount[c] = n;
+}
+
+// ---- stage 4: connected components of the edge graph ------------------------------------------------
+__device__ __forceinline__ int ccl_find(const int* L, int x) {
+  int p = L[x];
+  while (p != x) { x = p; p = L[x]; }
+  return x;
+}
+__global__ void at_ccl_init_kernel(int* L, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) L[i] = i;
+}
+__global__ void at_ccl_union_kernel(int* L, const int* __restrict__ eA, const int* __restrict__ eB, int n_edges) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  int a = eA[e], b = eB[e];
+  bool done = false;
+  while (!done) {
+    a = ccl_find(L, a);
+    b = ccl_find(L, b);
+    if (a < b) { const int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+    else if (b < a) { const int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+    else done = true;
+  }
+}
+__global__ void at_ccl_flatten_kernel(int* L, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) L[i] = ccl_find(L, i);
+}
+
+// ---- stage 5: sort functors --------------------------------------------------------------------------
+struct DigitCost {
+  const uint8_t* cost;
+  __device__ int operator()(uint32_t e) const { return cost[e]; }
+};
+struct DigitLabelOfEdge {
+  const int* label; const int* eA; int shift;
+  __device__ int operator()(uint32_t e) const { return (label[eA[e]] >> shift) & 255; }
+};
+struct DigitArray {
+  const int* key; int shift;
+  __device__ int operator()(uint32_t v) const { return (key[v] >> shift) & 255; }
+};
+__global__ void at_iota_kernel(uint32_t* v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (uint32_t)i;
+}
+// flag[i] = 1 where key(order[i]) differs from key(order[i-1])
+__global__ void at_boundary_kernel(const uint32_t* __restrict__ order, int n, const int* __restrict__ key,
+                                   const int* __restrict__ via, int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = via ? key[via[order[i]]] : key[order[i]];
+  int f = 1;
+  if (i > 0) { const int kp = via ? key[via[order[i - 1]]] : key[order[i - 1]]; f = (k != kp); }
+  flag[i] = f;
+}
+__global__ void at_starts_kernel(const int* __restrict__ flag_scan, const int* __restrict__ total, int n, int* __restrict__ starts) {
+  // flag_scan = exclusive scan of boundary flags; element i is a segment start iff scan[i+1] != scan[i]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = flag_scan[i];
+  const int nx = (i + 1 < n) ? flag_scan[i + 1] : *total;
+  if (nx != s) starts[s] = i;
+  if (i == n - 1) starts[*total] = n;
+}
+
+// ---- stage 6: the sequential merge sweep, one thread per component (Edge.cc:69-117) -----------------------
+__device__ __forceinline__ int uf_find(int* parent, int x) {
+  int root = x;
+  while (parent[root] != root) root = parent[root];
+  while (parent[x] != root) { const int nx = parent[x]; parent[x] = root; x = nx; }  // path compression (UnionFindSimple.cc:6-18)
+  return root;
+}
+
+__global__ void at_merge_kernel(const uint32_t* __restrict__ order, const int* __restrict__ starts, int n_comp,
+                                const int* __restrict__ eA, const int* __restrict__ eB, int* __restrict__ parent,
+                                int* __restrict__ setsize, float* __restrict__ tmin, float* __restrict__ tmax,
+                                float* __restrict__ mmin, float* __restrict__ mmax) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_comp) return;
+  const int beg = starts[c], end = starts[c + 1];
+  for (int i = beg; i < end; ++i) {
+    const uint32_t e = order[i];
+    const int ida = uf_find(parent, eA[e]);
+    const int idb = uf_find(parent, eB[e]);
+    if (ida == idb) continue;
+    const int sza = setsize[ida], szb = setsize[idb];
+    const float tmina = tmin[ida], tmaxa = tmax[ida];
+    const float tminb = tmin[idb], tmaxb = tmax[idb];
+    const float costa = (tmaxa - tmina);
+    const float costb = (tmaxb - tminb);
+    const float bshift = mod2pi_ref((tmina + tmaxa) / 2, (tminb + tmaxb) / 2) - (tminb + tmaxb) / 2;
+    const float tminab = fminr(tmina, tminb + bshift);
+    float tmaxab = fmaxr(tmaxa, tmaxb + bshift);
+    if (tmaxab - tminab > 2 * kPiF) tmaxab = tminab + 2 * kPiF;
+    const float mmina = mmin[ida], mmaxa = mmax[ida], mminb = mmin[idb], mmaxb = mmax[idb];
+    const float mminab = fminr(mmina, mminb);
+    const float mmaxab = fmaxr(mmaxa, mmaxb);
+    const float costab = (tmaxab - tminab);
+    if (costab <= (fminr(costa, costb) + kThetaThresh / (sza + szb)) &&
+        (mmaxab - mminab) <= fminr(mmaxa - mmina, mmaxb - mminb) + kMagThresh / (sza + szb)) {
+      int idab;  // UnionFindSimple::connectNodes (UnionFindSimple.cc:25-44)
+      if (sza > szb) { parent[idb] = ida; setsize[ida] = sza + szb; idab = ida; }
+      else { parent[ida] = idb; setsize[idb] = szb + sza; idab = idb; }
+      tmin[idab] = tminab; tmax[idab] = tmaxab;
+      mmin[idab] = mminab; mmax[idab] = mmaxab;
+    }
+  }
+}
+
+// ---- stage 7: clusters ---------------------------------------------------------------------------
+__global__ void at_rep_kernel(const int* __restrict__ parent, const int* __restrict__ setsize, int n_active, int* __restrict__ rep,
+                              int* __restrict__ keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_active) return;
+  int r = i;
+  while (parent[r] != r) r = parent[r];
+  rep[i] = r;
+  keep[i] = setsize[r] >= kMinSegmentSize ? 1 : 0;  // TagDetector.cc:248
+}
+__global__ void at_keep_compact_kernel(const int* __restrict__ keep_scan, const int* __restrict__ rep, const int* __restrict__ setsize,
+                                       int n_active, uint32_t* __restrict__ list) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_active) return;
+  if (setsize[rep[i]] >= kMinSegmentSize) list[keep_scan[i]] = (uint32_t)i;
+}
+
+// ---- stage 8: line fit per cluster (GLine2D.cc:54-87, GLineSegment2D.cc:9-24, TagDetector.cc:265-325) ---------
+struct Segment {
+  float x0, y0, x1, y1, theta, length;
+  int image;
+  int pad;
+};
+
+__global__ void at_fit_kernel(const uint32_t* __restrict__ pts, const int* __restrict__ cstart, int n_clusters,
+                              const int* __restrict__ apix, const float* __restrict__ a_theta, const float* __restrict__ a_mag,
+                              int W, int H, Segment* __restrict__ segs, int* __restrict__ valid) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_clusters) return;
+  const int beg = cstart[c], end = cstart[c + 1];
+  const long long N = (long long)W * H;
+  float mXX = 0, mYY = 0, mXY = 0, mX = 0, mY = 0, n = 0;
+  for (int i = beg; i < end; ++i) {
+    const int a = pts[i];
+    const int p = (int)(apix[a] % N);
+    const float y = (float)(p / W), x = (float)(p % W);
+    const float alpha = a_mag[a];
+    mY += y * alpha;
+    mX += x * alpha;
+    mYY += y * y * alpha;
+    mXX += x * x * alpha;
+    mXY += x * y * alpha;
+    n += alpha;
+  }
+  const float Ex = mX / n, Ey = mY / n;
+  const float Cxx = mXX / n - (mX / n) * (mX / n);
+  const float Cyy = mYY / n - (mY / n) * (mY / n);
+  const float Cxy = mXY / n - (mX / n) * (mY / n);
+  const float phi = 0.5f * fd_atan2f(-2 * Cxy, (Cyy - Cxx));
+  float dx = -gl_sinf(phi), dy = gl_cosf(phi);
+  float px = Ex, py = Ey;
+  // GLine2D::normalizeSlope
+  {
+    const float mag = sqrtf(dx * dx + dy * dy);
+    dx /= mag; dy /= mag;
+  }
+  float maxc = -INFINITY, minc = INFINITY;
+  for (int i = beg; i < end; ++i) {
+    const int a = pts[i];
+    const int p = (int)(apix[a] % N);
+    const float y = (float)(p / W), x = (float)(p % W);
+    const float coord = x * dx + y * dy;
+    maxc = fmaxr(maxc, coord);
+    minc = fminr(minc, coord);
+  }
+  // GLine2D::normalizeP
+  {
+    const float dotprod = -dy * px + dx * py;
+    px = -dy * dotprod; py = dx * dotprod;
+  }
+  const float p0x = px + minc * dx, p0y = py + minc * dy;
+  const float p1x = px + maxc * dx, p1y = py + maxc * dy;
+  const float length = dist2d(p0x, p0y, p1x, p1y);
+  Segment s;
+  s.image = (int)(apix[pts[beg]] / N);
+  s.pad = 0;
+  if (length < kMinLineLength) { valid[c] = 0; s.x0 = s.y0 = s.x1 = s.y1 = s.theta = s.length = 0; segs[c] = s; return; }
+  const float sdy = p1y - p0y, sdx = p1x - p0x;
+  float theta = fd_atan2f(sdy, sdx);
+  float flip = 0, noflip = 0;
+  for (int i = beg; i < end; ++i) {
+    const int a = pts[i];
+    const float err = mod2pi(a_theta[a] - theta);
+    if (err < 0) noflip += a_mag[a]; else flip += a_mag[a];
+  }
+  if (flip > noflip) theta = theta + kPiF;
+  const float dot = sdx * gl_cosf(theta) + sdy * gl_sinf(theta);
+  if (dot > 0) { s.x0 = p1x; s.y0 = p1y; s.x1 = p0x; s.y1 = p0y; }
+  else { s.x0 = p0x; s.y0 = p0y; s.x1 = p1x; s.y1 = p1y; }
+  s.theta = theta; s.length = length;
+  segs[c] = s;
+  valid[c] = 1;
+}
+
+__global__ void at_seg_compact_kernel(const Segment* __restrict__ in, const int* __restrict__ valid, const int* __restrict__ vscan,
+                                      int n, Segment* __restrict__ out, int* __restrict__ img_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !valid[i]) return;
+  out[vscan[i]] = in[i];
+  atomicAdd(&img_count[in[i].image], 1);
+}
+
+// ---- stage 9a: spatial hash (Gridder.h) + children (TagDetector.cc:344-388) ---------------------------------
+struct GridDims { int gw, gh; };
+__host__ __device__ inline GridDims grid_dims(int W, int H) {
+  GridDims g;
+  g.gw = (int)(((float)W - 0.f) / 10.f + 1);
+  g.gh = (int)(((float)H - 0.f) / 10.f + 1);
+  return g;
+}
+__global__ void at_cell_count_kernel(const Segment* __restrict__ segs, int n, int W, int H, int* __restrict__ cell_of,
+                                     int* __restrict__ cell_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const GridDims g = grid_dims(W, H);
+  const int ix = (int)((segs[i].x0 - 0.f) / 10.f);
+  const int iy = (int)((segs[i].y0 - 0.f) / 10.f);
+  int cell = -1;
+  if (ix >= 0 && iy >= 0 && ix < g.gw && iy < g.gh) {
+    cell = (segs[i].image * g.gh + iy) * g.gw + ix;
+    atomicAdd(&cell_count[cell], 1);
+  }
+  cell_of[i] = cell;
+}
+__global__ void at_cell_fill_kernel(const int* __restrict__ cell_of, int n, const int* __restrict__ cell_start, int* __restrict__ cell_fill,
+                                    int* __restrict__ cell_items) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int cell = cell_of[i];
+  if (cell < 0) return;
+  cell_items[cell_start[cell] + atomicAdd(&cell_fill[cell], 1)] = i;
+}
+// LIFO order of Gridder::add: later (higher index) segments come first in a cell's list.
+__global__ void at_cell_sort_kernel(const int* __restrict__ cell_start, const int* __restrict__ cell_count, int n_cells,
+                                    int* __restrict__ cell_items) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const int b = cell_start[c], m = cell_count[c];
+  for (int i = 1; i < m; ++i) {
+    const int v = cell_items[b + i];
+    int j = i - 1;
+    while (j >= 0 && cell_items[b + j] < v) { cell_items[b + j + 1] = cell_items[b + j]; --j; }
+    cell_items[b + j + 1] = v;
+  }
+}
+
+// GLine2D::intersectionWith for lines through (ax0,ay0)-(ax1,ay1) and (bx0,by0)-(bx1,by1); returns false if parallel
+__device__ __forceinline__ bool line_intersect(float ax0, float ay0, float ax1, float ay1, float bx0, float by0, float bx1,
+                                               float by1, float& ox, float& oy) {
+  const float dx = ax1 - ax0, dy = ay1 - ay0;
+  const float ldx = bx1 - bx0, ldy = by1 - by0;
+  const float m00 = dx, m01 = -ldx, m10 = dy, m11 = -ldy;
+  const float det = m00 * m11 - m01 * m10;
+  if (fabs((double)det) < 1e-10) { ox = -1; oy = 0; return false; }
+  const float i00 = m11 / det;
+  const float i01 = -m01 / det;
+  const float b00 = bx0 - ax0;
+  const float b10 = by0 - ay0;
+  const float x00 = i00 * b00 + i01 * b10;
+  ox = dx * x00 + ax0;
+  oy = dy * x00 + ay0;
+  return true;
+}
+
+template <bool EMIT>
+__global__ void at_children_kernel(const Segment* __restrict__ segs, int n, int W, int H, const int* __restrict__ cell_start,
+                                   const int* __restrict__ cell_count, const int* __restrict__ cell_items,
+                                   int* __restrict__ ccount, const int* __restrict__ coff, int* __restrict__ children) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Segment P = segs[i];
+  const GridDims g = grid_dims(W, H);
+  const float range = 0.5f * P.length;
+  int ix0 = (int)((P.x1 - range - 0.f) / 10.f), iy0 = (int)((P.y1 - range - 0.f) / 10.f);
+  int ix1 = (int)((P.x1 + range - 0.f) / 10.f), iy1 = (int)((P.y1 + range - 0.f) / 10.f);
+  ix0 = min(g.gw - 1, max(0, ix0)); ix1 = min(g.gw - 1, max(0, ix1));
+  iy0 = min(g.gh - 1, max(0, iy0)); iy1 = min(g.gh - 1, max(0, iy1));
+  int cnt = 0;
+  int o = EMIT ? coff[i] : 0;
+  for (int iy = iy0; iy <= iy1; ++iy)
+    for (int ix = ix0; ix <= ix1; ++ix) {
+      const int cell = (P.image * g.gh + iy) * g.gw + ix;
+      const int b = cell_start[cell], m = cell_count[cell];
+      for (int q = 0; q < m; ++q) {
+        const int ci = cell_items[b + q];
+        const Segment C = segs[ci];
+        if (mod2pi(C.theta - P.theta) > 0) continue;
+        float px, py;
+        line_intersect(P.x0, P.y0, P.x1, P.y1, C.x0, C.y0, C.x1, C.y1, px, py);
+        if (px == -1) continue;
+        const float parentDist = dist2d(px, py, P.x1, P.y1);
+        const float childDist = dist2d(px, py, C.x0, C.y0);
+        if (fmaxr(parentDist, childDist) > P.length) continue;
+        if (EMIT) children[o++] = ci;
+        ++cnt;
+      }
+    }
+  if (!EMIT) ccount[i] = cnt;
+}
+
+// ---- stage 9b: quad search (Quad.cc:52-157) --------------------------------------------------------------
+struct QuadRec {
+  float p[4][2];
+  float perimeter;
+  int image;
+};
+
+__device__ bool make_quad(const Segment* __restrict__ segs, const int path[5], QuadRec& q) {
+  float p[4][2];
+  float perim = 0;
+  bool bad = false;
+  for (int i = 0; i < 4; ++i) {
+    const Segment A = segs[path[i]], B = segs[path[i + 1]];
+    line_intersect(A.x0, A.y0, A.x1, A.y1, B.x0, B.y0, B.x1, B.y1, p[i][0], p[i][1]);
+    perim += A.length;
+    if (p[i][0] == -1) bad = true;
+  }
+  if (!bad) {
+    const float t0 = fd_atan2f(p[1][1] - p[0][1], p[1][0] - p[0][0]);
+    const float t1 = fd_atan2f(p[2][1] - p[1][1], p[2][0] - p[1][0]);
+    const float t2 = fd_atan2f(p[3][1] - p[2][1], p[3][0] - p[2][0]);
+    const float t3 = fd_atan2f(p[0][1] - p[3][1], p[0][0] - p[3][0]);
+    const float ttheta = mod2pi(t1 - t0) + mod2pi(t2 - t1) + mod2pi(t3 - t2) + mod2pi(t0 - t3);
+    if (ttheta < -7 || ttheta > -5) bad = true;
+  }
+  if (!bad) {
+    const float d0 = dist2d(p[0][0], p[0][1], p[1][0], p[1][1]);
+    const float d1 = dist2d(p[1][0], p[1][1], p[2][0], p[2][1]);
+    const float d2 = dist2d(p[2][0], p[2][1], p[3][0], p[3][1]);
+    const float d3 = dist2d(p[3][0], p[3][1], p[0][0], p[0][1]);
+    const float d4 = dist2d(p[0][0], p[0][1], p[2][0], p[2][1]);
+    const float d5 = dist2d(p[1][0], p[1][1], p[3][0], p[3][1]);
+    if (d0 < kMinEdgeLength || d1 < kMinEdgeLength || d2 < kMinEdgeLength || d3 < kMinEdgeLength || d4 < kMinEdgeLength ||
+        d5 < kMinEdgeLength)
+      bad = true;
+    const float dmax = fmaxr(fmaxr(d0, d1), fmaxr(d2, d3));
+    const float dmin = fminr(fminr(d0, d1), fminr(d2, d3));
+    if (dmax > dmin * kMaxQuadAspect) bad = true;
+  }
+  if (bad) return false;
+  for (int i = 0; i < 4; ++i) { q.p[i][0] = p[i][0]; q.p[i][1] = p[i][1]; }
+  q.perimeter = perim;
+  q.image = segs[path[0]].image;
+  return true;
+}
+
+template <bool EMIT>
+__global__ void at_quads_kernel(const Segment* __restrict__ segs, int n, const int* __restrict__ coff, const int* __restrict__ children,
+                                int* __restrict__ qcount, const int* __restrict__ qoff, QuadRec* __restrict__ quads) {
+  const int s0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s0 >= n) return;
+  int path[5];
+  path[0] = s0;
+  const float th0 = segs[s0].theta;
+  int cnt = 0;
+  int o = EMIT ? qoff[s0] : 0;
+  // depth-first over children lists, depth 4 (iterative form of Quad::search)
+  for (int a = coff[s0]; a < coff[s0 + 1]; ++a) {
+    const int c1 = children[a];
+    if (segs[c1].theta > th0) continue;
+    path[1] = c1;
+    for (int b = coff[c1]; b < coff[c1 + 1]; ++b) {
+      const int c2 = children[b];
+      if (segs[c2].theta > th0) continue;
+      path[2] = c2;
+      for (int c = coff[c2]; c < coff[c2 + 1]; ++c) {
+        const int c3 = children[c];
+        if (segs[c3].theta > th0) continue;
+        path[3] = c3;
+        for (int d = coff[c3]; d < coff[c3 + 1]; ++d) {
+          const int c4 = children[d];
+          if (segs[c4].theta > th0) continue;
+          path[4] = c4;
+          if (c4 != s0) continue;
+          QuadRec q;
+          if (make_quad(segs, path, q)) {
+            if (EMIT) quads[o++] = q;
+            ++cnt;
+          }
+        }
+      }
+    }
+  }
+  if (!EMIT) qcount[s0] = cnt;
+}
+
+// ---- stage 9c: decode (TagDetector.cc:432-532, GrayModel.cc, TagFamily.cc:45-112) -------------------------------
+struct Detection {
+  float p[4][2];
+  float cxy[2];
+  float perimeter;
+  int id, hamming, rotation, good, image;
+  unsigned long long obs_code;
+};
+
+struct GrayModelD {
+  double A[4][4];
+  double b[4];
+  double v[4];
+  int nobs;
+  __device__ void init() {
+    for (int i = 0; i < 4; ++i) { b[i] = 0; v[i] = 0; for (int j = 0; j < 4; ++j) A[i][j] = 0; }
+    nobs = 0;
+  }
+  __device__ void add(float x, float y, float gray) {
+    const float xy = x * y;
+    A[0][0] += x * x; A[0][1] += x * y; A[0][2] += x * xy; A[0][3] += x;
+    A[1][1] += y * y; A[1][2] += y * xy; A[1][3] += y;
+    A[2][2] += xy * xy; A[2][3] += xy;
+    A[3][3] += 1;
+    b[0] += x * gray; b[1] += y * gray; b[2] += xy * gray; b[3] += gray;
+    nobs++;
+  }
+  // cofactor inverse as Eigen's compute_inverse_size4 (scalar path); invertible iff |det| > 1e-12
+  __device__ void compute() {
+    if (nobs >= 6) {
+      for (int i = 0; i < 4; ++i) for (int j = i + 1; j < 4; ++j) A[j][i] = A[i][j];
+      double res[4][4];
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+          const int i1 = (i + 1) & 3, i2 = (i + 2) & 3, i3 = (i + 3) & 3;
+          const int j1 = (j + 1) & 3, j2 = (j + 2) & 3, j3 = (j + 3) & 3;
+          const double h0 = A[i1][j1] * (A[i2][j2] * A[i3][j3] - A[i2][j3] * A[i3][j2]);
+          const double h1 = A[i2][j1] * (A[i3][j2] * A[i1][j3] - A[i3][j3] * A[i1][j2]);
+          const double h2 = A[i3][j1] * (A[i1][j2] * A[i2][j3] - A[i1][j3] * A[i2][j2]);
+          const double cof = h0 + h1 + h2;
+          res[j][i] = ((i + j) & 1) ? -cof : cof;
+        }
+      double det = 0;
+      for (int i = 0; i < 4; ++i) det += A[i][0] * res[0][i];
+      if (fabs(det) > 1e-12) {
+        for (int i = 0; i < 4; ++i) {
+          double s = (res[i][0] / det) * b[0];
+          for (int k = 1; k < 4; ++k) s += (res[i][k] / det) * b[k];
+          v[i] = s;
+        }
+        return;
+      }
+    }
+    v[0] = v[1] = v[2] = 0;
+    v[3] = b[3] / nobs;
+  }
+  __device__ float interp(float x, float y) const { return (float)(v[0] * x + v[1] * y + v[2] * x * y + v[3]); }
+};
+
+// Quad::interpolate with INTERPOLATE defined (Quad.cc:37-50)
+__device__ __forceinline__ void quad_interp01(const QuadRec& q, float x01, float y01, float& ox, float& oy) {
+  const float x = 2 * x01 - 1, y = 2 * y01 - 1;
+  const float kx = (float)((double)x + 1.);  // (x+1.) is a double expression, narrowed to the vector's Scalar
+  const float p01x = q.p[1][0] - q.p[0][0], p01y = q.p[1][1] - q.p[0][1];
+  const float p32x = q.p[2][0] - q.p[3][0], p32y = q.p[2][1] - q.p[3][1];
+  const float r1x = q.p[0][0] + (p01x * kx) / 2.f, r1y = q.p[0][1] + (p01y * kx) / 2.f;
+  const float r2x = q.p[3][0] + (p32x * kx) / 2.f, r2y = q.p[3][1] + (p32y * kx) / 2.f;
+  const float ky = y + 1;
+  ox = r1x + ((r2x - r1x) * ky) / 2.f;
+  oy = r1y + ((r2y - r1y) * ky) / 2.f;
+}
+
+__device__ __forceinline__ unsigned long long rotate90(unsigned long long w, int d) {
+  unsigned long long wr = 0;
+  for (int r = d - 1; r >= 0; r--)
+    for (int c = 0; c < d; c++) {
+      const int b = r + d * c;
+      wr = wr << 1;
+      if ((w & (1ULL << b)) != 0) wr |= 1;
+    }
+  return wr;
+}
+
+// exact homography through (-1,-1),(1,-1),(1,1),(-1,1) -> quad points minus the optical centre; only used to
+// find which quad corner is nearest to H*(-1,-1) after the decoded rotation (TagDetector.cc:496-524)
+__device__ void homography4(const float dst[4][2], double H[3][3]) {
+  const double sx[4] = {-1, 1, 1, -1}, sy[4] = {-1, -1, 1, 1};
+  double A[8][9];
+  for (int i = 0; i < 4; ++i) {
+    const double x = sx[i], y = sy[i], u = dst[i][0], v = dst[i][1];
+    const double r0[9] = {x, y, 1, 0, 0, 0, -u * x, -u * y, u};
+    const double r1[9] = {0, 0, 0, x, y, 1, -v * x, -v * y, v};
+    for (int k = 0; k < 9; ++k) { A[2 * i][k] = r0[k]; A[2 * i + 1][k] = r1[k]; }
+  }
+  for (int c = 0; c < 8; ++c) {
+    int p = c;
+    for (int r = c + 1; r < 8; ++r) if (fabs(A[r][c]) > fabs(A[p][c])) p = r;
+    if (p != c) for (int k = 0; k < 9; ++k) { const double t = A[p][k]; A[p][k] = A[c][k]; A[c][k] = t; }
+    const double piv = A[c][c];
+    for (int r = 0; r < 8; ++r) {
+      if (r == c || piv == 0.0) continue;
+      const double f = A[r][c] / piv;
+      for (int k = c; k < 9; ++k) A[r][k] -= f * A[c][k];
+    }
+  }
+  double h[9];
+  for (int i = 0; i < 8; ++i) h[i] = A[i][i] != 0.0 ? A[i][8] / A[i][i] : 0.0;
+  h[8] = 1.0;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) H[i][j] = h[i * 3 + j];
+}
+
+__global__ void at_decode_kernel(const QuadRec* __restrict__ quads, int n, const uint8_t* __restrict__ imgs, long long pitch,
+                                 long long istride, int W, int H, int img0, Detection* __restrict__ dets) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= n) return;
+  const QuadRec q = quads[qi];
+  const uint8_t* I = imgs + (long long)(img0 + q.image) * istride;
+  auto fim = [&](int x, int y) -> float { return (float)((double)I[(long long)y * pitch + x] / 255.); };
+  const int dd = 2 * 2 + 6;  // 2*blackBorder + dimension
+  GrayModelD black, white;
+  black.init(); white.init();
+  for (int iy = -1; iy <= dd; iy++) {
+    const float y = (iy + 0.5f) / dd;
+    for (int ix = -1; ix <= dd; ix++) {
+      const float x = (ix + 0.5f) / dd;
+      float px, py;
+      quad_interp01(q, x, y, px, py);
+      const int irx = (int)((double)px + 0.5);
+      const int iry = (int)((double)py + 0.5);
+      if (irx < 0 || irx >= W || iry < 0 || iry >= H) continue;
+      const float v = fim(irx, iry);
+      if (iy == -1 || iy == dd || ix == -1 || ix == dd) white.add(x, y, v);
+      else if (iy == 0 || iy == (dd - 1) || ix == 0 || ix == (dd - 1)) black.add(x, y, v);
+    }
+  }
+  black.compute(); white.compute();
+  bool bad = false;
+  unsigned long long tagCode = 0;
+  for (int iy = 5; iy >= 0; iy--) {
+    const float y = (2 + iy + 0.5f) / dd;
+    for (int ix = 0; ix < 6; ix++) {
+      const float x = (2 + ix + 0.5f) / dd;
+      float px, py;
+      quad_interp01(q, x, y, px, py);
+      const int irx = (int)((double)px + 0.5);
+      const int iry = (int)((double)py + 0.5);
+      if (irx < 0 || irx >= W || iry < 0 || iry >= H) { bad = true; continue; }
+      const float threshold = (black.interp(x, y) + white.interp(x, y)) * 0.5f;
+      const float v = fim(irx, iry);
+      tagCode = tagCode << 1;
+      if (v > threshold) tagCode |= 1;
+    }
+  }
+  Detection d;
+  d.good = 0; d.id = -1; d.hamming = 0; d.rotation = 0; d.image = q.image; d.obs_code = tagCode;
+  d.perimeter = q.perimeter; d.cxy[0] = d.cxy[1] = 0;
+  for (int i = 0; i < 4; ++i) { d.p[i][0] = q.p[i][0]; d.p[i][1] = q.p[i][1]; }
+  if (!bad) {
+    // TagFamily::decode: min Hamming over 587 codes x 4 rotations, first minimum in (id, rot) order wins
+    unsigned long long rc[4];
+    rc[0] = tagCode; rc[1] = rotate90(rc[0], 6); rc[2] = rotate90(rc[1], 6); rc[3] = rotate90(rc[2], 6);
+    int bestId = -1, bestH = 0x7fffffff, bestRot = 0;
+    for (int id = 0; id < kNumTag36h11; ++id) {
+      const unsigned long long code = c_tag36h11[id];
+      for (int rot = 0; rot < 4; ++rot) {
+        const int hd = __popcll(rc[rot] ^ code);
+        if (hd < bestH) { bestH = hd; bestRot = rot; bestId = id; }
+      }
+    }
+    d.id = bestId; d.hamming = bestH; d.rotation = bestRot;
+    d.good = (bestH <= 1) ? 1 : 0;  // errorRecoveryBits = 1
+    // homography (optical centre = (W/2, H/2) as ints) rotated by the decoded rotation
+    const float cx = (float)(W / 2), cy = (float)(H / 2);
+    float dst[4][2];
+    for (int i = 0; i < 4; ++i) { dst[i][0] = q.p[i][0] - cx; dst[i][1] = q.p[i][1] - cy; }
+    double Hm[3][3];
+    homography4(dst, Hm);
+    const float c = gl_cosf(bestRot * kPiF / 2);
+    const float s = gl_sinf(bestRot * kPiF / 2);
+    double R[3][3] = {{c, -s, 0}, {s, c, 0}, {0, 0, 1}};
+    double T[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) { double a = Hm[i][0] * R[0][j]; a += Hm[i][1] * R[1][j]; a += Hm[i][2] * R[2][j]; T[i][j] = a; }
+    // TagDetection::interpolate(-1,-1)
+    float blx = 0, bly = 0;
+    {
+      const float x = -1, y = -1;
+      const float z = (float)(T[2][0] * x + T[2][1] * y + T[2][2]);
+      if (z != 0) {
+        blx = (float)((T[0][0] * x + T[0][1] * y + T[0][2]) / z + cx);
+        bly = (float)((T[1][0] * x + T[1][1] * y + T[1][2]) / z + cy);
+      }
+    }
+    int bestR = -1;
+    float bestDist = FLT_MAX;
+    for (int i = 0; i < 4; ++i) {
+      const float dist = dist2d(blx, bly, q.p[i][0], q.p[i][1]);
+      if (dist < bestDist) { bestDist = dist; bestR = i; }
+    }
+    for (int i = 0; i < 4; ++i) { d.p[i][0] = q.p[(i + bestR) % 4][0]; d.p[i][1] = q.p[(i + bestR) % 4][1]; }
+    if (d.good) quad_interp01(q, 0.5f, 0.5f, d.cxy[0], d.cxy[1]);
+  }
+  dets[qi] = d;
+}
+
+// ---- stage 9d: de-duplication per image (TagDetector.cc:547-580) and output assembly -------------------------
+__device__ bool overlaps_too_much(const Detection& a, const Detection& b) {
+  const float radius = (dist2d(a.p[0][0], a.p[0][1], a.p[1][0], a.p[1][1]) + dist2d(a.p[1][0], a.p[1][1], a.p[2][0], a.p[2][1]) +
+                        dist2d(a.p[2][0], a.p[2][1], a.p[3][0], a.p[3][1]) + dist2d(a.p[3][0], a.p[3][1], a.p[0][0], a.p[0][1]) +
+                        dist2d(b.p[0][0], b.p[0][1], b.p[1][0], b.p[1][1]) + dist2d(b.p[1][0], b.p[1][1], b.p[2][0], b.p[2][1]) +
+                        dist2d(b.p[2][0], b.p[2][1], b.p[3][0], b.p[3][1]) + dist2d(b.p[3][0], b.p[3][1], b.p[0][0], b.p[0][1])) /
+                       16.0f;
+  const float dist = dist2d(a.cxy[0], a.cxy[1], b.cxy[0], b.cxy[1]);
+  return dist < radius;
+}
+
+// one thread per image; quads of image i are dets[qstart[i] .. qstart[i+1]); the surviving detections are
+// written back, in the reference's order, to the front of the same range; ngood[i] = their number.
+__global__ void at_dedup_kernel(Detection* __restrict__ dets, const int* __restrict__ qstart, int n_img, int* __restrict__ ngood) {
+  const int im = blockIdx.x * blockDim.x + threadIdx.x;
+  if (im >= n_img) return;
+  const int beg = qstart[im], end = qstart[im + 1];
+  int ng = 0;
+  for (int i = beg; i < end; ++i) {
+    const Detection t = dets[i];
+    if (!t.good) continue;
+    bool newFeature = true;
+    for (int o = 0; o < ng; ++o) {
+      Detection& other = dets[beg + o];
+      if (t.id != other.id || !overlaps_too_much(t, other)) continue;
+      newFeature = false;
+      if (t.hamming > other.hamming) continue;
+      if (t.hamming < other.hamming || t.perimeter > other.perimeter) other = t;
+    }
+    if (newFeature) { dets[beg + ng] = t; ++ng; }
+  }
+  ngood[im] = ng;
+}
+
+// gather the corners to refine: detections with id < nb_tags whose 4 corners all lie inside the image
+// (cv::cornerSubPix asserts that; the reference would throw otherwise)
+__global__ void at_gather_corners_kernel(const Detection* __restrict__ dets, const int* __restrict__ qstart, const int* __restrict__ ngood,
+                                         int n_img, int nb_tags, int W, int H, int img0, float2* __restrict__ corners,
+                                         int* __restrict__ cimg, int* __restrict__ refine_flag) {
+  const int im = blockIdx.x, t = threadIdx.x;
+  if (im >= n_img) return;
+  const int beg = qstart[im];
+  for (int k = t; k < ngood[im]; k += blockDim.x) {
+    const Detection& d = dets[beg + k];
+    bool inside = true;
+    for (int i = 0; i < 4; ++i)
+      inside = inside && (d.p[i][0] >= 0 && d.p[i][0] < (float)W && d.p[i][1] >= 0 && d.p[i][1] < (float)H);
+    const int flag = (d.id < nb_tags && inside) ? 1 : 0;
+    refine_flag[beg + k] = flag;
+    for (int i = 0; i < 4; ++i) {
+      // corners that are not refined still occupy a slot (clamped inside so that the kernel may run on them)
+      float2 c = make_float2(d.p[i][0], d.p[i][1]);
+      if (!flag) c = make_float2(fminf(fmaxf(c.x, 0.f), (float)(W - 1)), fminf(fmaxf(c.y, 0.f), (float)(H - 1)));
+      corners[(size_t)(beg + k) * 4 + i] = c;
+      cimg[(size_t)(beg + k) * 4 + i] = img0 + im;
+    }
+  }
+}
+
+// aprilgrid_detector.hpp:35-70: slots pre-filled with (-1,-1), detections scattered in order (later overwrite)
+__global__ void at_scatter_kernel(const Detection* __restrict__ dets, const int* __restrict__ qstart, const int* __restrict__ ngood,
+                                  const float2* __restrict__ refined, const int* __restrict__ refine_flag, int n_img, int nb_tags,
+                                  float2* __restrict__ out_corners, int* __restrict__ out_ndet, uint8_t* __restrict__ out_success) {
+  const int im = blockIdx.x;
+  if (im >= n_img) return;
+  float2* oc = out_corners + (size_t)im * 4 * nb_tags;
+  for (int k = threadIdx.x; k < 4 * nb_tags; k += blockDim.x) oc[k] = make_float2(-1.f, -1.f);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int beg = qstart[im], ng = ngood[im];
+    for (int k = 0; k < ng; ++k) {
+      const Detection& d = dets[beg + k];
+      if (d.id >= nb_tags) continue;
+      for (int i = 0; i < 4; ++i)
+        oc[d.id * 4 + i] = refine_flag[beg + k] ? refined[(size_t)(beg + k) * 4 + i] : make_float2(d.p[i][0], d.p[i][1]);
+    }
+    out_ndet[im] = ng;
+    const int threshold = (nb_tags / 2) - 1;
+    out_success[im] = ng > threshold ? 1 : 0;
+  }
+}
+
+__global__ void at_image_starts_kernel(const int* __restrict__ counts, int n_img, int* __restrict__ starts) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int s = 0;
+    for (int i = 0; i < n_img; ++i) { starts[i] = s; s += counts[i]; }
+    starts[n_img] = s;
+  }
+}
+__global__ void at_quad_image_count_kernel(const QuadRec* __restrict__ quads, int n, int* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&counts[quads[i].image], 1);
+}
+
+}  // namespace ezc
+
+using namespace ezc;
+
+// ============================================================================================
+// Host orchestration
+// ============================================================================================
+struct ezc_apriltag_debug {
+  // optional stage products of the LAST image processed (tests only)
+  std::vector<float> theta, mag;
+  std::vector<int> edges;      // (cost, pixelA, pixelB) triples in the order the merge sweep consumed them
+  std::vector<int> rep, size;  // per pixel (dense), -1 for inactive pixels
+  std::vector<float> segments; // x0,y0,x1,y1,theta,length
+  std::vector<float> quads;    // 4 corners + perimeter
+};
+
+namespace {
+
+struct Pools {
+  DevBuf fr, seg, theta, mag, cidx, scan_tmp, total;
+  DevBuf apix, a_theta, a_mag, parent, setsize, tmin, tmax, mmin, mmax, ecount, label;
+  DevBuf eA, eB, ecost, order0, order1, flags, starts;
+  DevBuf rep, keep, plist0, plist1, cstart, segs_raw, seg_valid, segs, img_count, seg_start;
+  DevBuf cell_of, cell_count, cell_start, cell_fill, cell_items, ccount, children;
+  DevBuf qcount, quads, dets, qimg_count, qstart, ngood, corners, cimg, refine_flag;
+  SortTemp sort;
+  HostPinned h;
+};
+
+#define AT_LAUNCH(kernel, n, ...)                                                     \
+  do {                                                                                \
+    if ((n) > 0) {                                                                    \
+      const long long _n = (n);                                                       \
+      kernel<<<(unsigned)((_n + 255) / 256), 256, 0, ctx->stream>>>(__VA_ARGS__);     \
+      EZC_CUDA(cudaGetLastError());                                                   \
+      ctx->kernel_launches++;                                                         \
+    }                                                                                 \
+  } while (0)
+
+ezc_status read_int(ezc_context* ctx, const int* d, int* h_out, Pools& P) {
+  EZC_CUDA(cudaMemcpyAsync(P.h.p, d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  *h_out = *P.h.as<int>();
+  return EZC_OK;
+}
+
+int bits_for(int n) { int b = 1; while ((1LL << b) < n) ++b; return b; }
+
+// Process images [img0, img0 + nb) of the batch.
+ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, int nb, int nb_tags, Pools& P,
+                             float2* d_out_corners, int* d_out_ndet, uint8_t* d_out_success, ezc_apriltag_debug* dbg) {
+  const int W = imgs->width, H = imgs->height;
+  const long long N = (long long)W * H;
+  const long long total = N * nb;
+  const uint8_t* d_img = imgs->d + (long long)img0 * imgs->image_stride;
+  EZC_CUDA(P.fr.reserve(sizeof(float) * total));
+  EZC_CUDA(P.seg.reserve(sizeof(float) * total));
+  EZC_CUDA(P.theta.reserve(sizeof(float) * total));
+  EZC_CUDA(P.mag.reserve(sizeof(float) * total));
+  EZC_CUDA(P.cidx.reserve(sizeof(int) * total));
+  EZC_CUDA(P.total.reserve(sizeof(int) * 16));
+  EZC_CUDA(P.h.reserve(4096));
+  int* d_tot = P.total.as<int>();
+
+  // ---- 1: preprocessing
+  AT_LAUNCH(at_blur_h_kernel, total, d_img, imgs->pitch, imgs->image_stride, W, H, nb, P.fr.as<float>());
+  AT_LAUNCH(at_blur_v_kernel, total, P.fr.as<float>(), W, H, nb, P.seg.as<float>());
+  AT_LAUNCH(at_gradient_kernel, total, P.seg.as<float>(), W, H, nb, P.theta.as<float>(), P.mag.as<float>(), P.cidx.as<int>());
+  // ---- 2: compaction
+  if (ezc_status st = exclusive_scan_i32(ctx, P.cidx.as<int>(), P.cidx.as<int>(), total, P.scan_tmp, d_tot)) return st;
+  int nA = 0;
+  if (ezc_status st = read_int(ctx, d_tot, &nA, P)) return st;
+  const size_t cap = (size_t)std::max(nA, 1);
+  EZC_CUDA(P.apix.reserve(sizeof(int) * cap)); EZC_CUDA(P.a_theta.reserve(sizeof(float) * cap)); EZC_CUDA(P.a_mag.reserve(sizeof(float) * cap));
+  EZC_CUDA(P.parent.reserve(sizeof(int) * cap)); EZC_CUDA(P.setsize.reserve(sizeof(int) * cap));
+  EZC_CUDA(P.tmin.reserve(sizeof(float) * cap)); EZC_CUDA(P.tmax.reserve(sizeof(float) * cap));
+  EZC_CUDA(P.mmin.reserve(sizeof(float) * cap)); EZC_CUDA(P.mmax.reserve(sizeof(float) * cap));
+  EZC_CUDA(P.ecount.reserve(sizeof(int) * (cap + 1))); EZC_CUDA(P.label.reserve(sizeof(int) * cap));
+  EZC_CUDA(P.rep.reserve(sizeof(int) * cap)); EZC_CUDA(P.keep.reserve(sizeof(int) * (cap + 1)));
+  AT_LAUNCH(at_compact_kernel, total, P.cidx.as<int>(), P.theta.as<float>(), P.mag.as<float>(), total, W, H, nA, P.apix.as<int>(),
+            P.a_theta.as<float>(), P.a_mag.as<float>(), P.parent.as<int>(), P.setsize.as<int>(), P.tmin.as<float>(),
+            P.tmax.as<float>(), P.mmin.as<float>(), P.mmax.as<float>());
+  // ---- 3: edges
+  AT_LAUNCH(at_edges_kernel<false>, nA, P.apix.as<int>(), P.theta.as<float>(), P.mag.as<float>(), P.cidx.as<int>(), nA, W, H,
+            P.ecount.as<int>(), nullptr, nullptr, nullptr, nullptr);
+  if (ezc_status st = exclusive_scan_i32(ctx, P.ecount.as<int>(), P.ecount.as<int>(), nA, P.scan_tmp, d_tot)) return st;
+  int nE = 0;
+  if (ezc_status st = read_int(ctx, d_tot, &nE, P)) return st;
+  const size_t ecap = (size_t)std::max(nE, 1);
+  EZC_CUDA(P.eA.reserve(sizeof(int) * ecap)); EZC_CUDA(P.eB.reserve(sizeof(int) * ecap)); EZC_CUDA(P.ecost.reserve(ecap));
+  EZC_CUDA(P.order0.reserve(sizeof(uint32_t) * ecap)); EZC_CUDA(P.order1.reserve(sizeof(uint32_t) * ecap));
+  EZC_CUDA(P.flags.reserve(sizeof(int) * (std::max(ecap, cap) + 1)));
+  AT_LAUNCH(at_edges_kernel<true>, nA, P.apix.as<int>(), P.theta.as<float>(), P.mag.as<float>(), P.cidx.as<int>(), nA, W, H,
+            nullptr, P.ecount.as<int>(), P.eA.as<int>(), P.eB.as<int>(), P.ecost.as<uint8_t>());
+  // ---- 4: connected components of the edge graph
+  AT_LAUNCH(at_ccl_init_kernel, nA, P.label.as<int>(), nA);
+  AT_LAUNCH(at_ccl_union_kernel, nE, P.label.as<int>(), P.eA.as<int>(), P.eB.as<int>(), nE);
+  AT_LAUNCH(at_ccl_flatten_kernel, nA, P.label.as<int>(), nA);
+  // ---- 5: stable sort of the edges by (component, cost)
+  uint32_t* o0 = P.order0.as<uint32_t>();
+  uint32_t* o1 = P.order1.as<uint32_t>();
+  AT_LAUNCH(at_iota_kernel, nE, o0, nE);
+  if (ezc_status st = radix_pass(ctx, o0, o1, nE, DigitCost{P.ecost.as<uint8_t>()}, P.sort)) return st;
+  std::swap(o0, o1);
+  for (int shift = 0; shift < bits_for(std::max(nA, 2)); shift += 8) {
+    if (ezc_status st = radix_pass(ctx, o0, o1, nE, DigitLabelOfEdge{P.label.as<int>(), P.eA.as<int>(), shift}, P.sort)) return st;
+    std::swap(o0, o1);
+  }
+  // component boundaries -> starts
+  int nComp = 0;
+  if (nE > 0) {
+    AT_LAUNCH(at_boundary_kernel, nE, o0, nE, P.label.as<int>(), P.eA.as<int>(), P.flags.as<int>());
+    if (ezc_status st = exclusive_scan_i32(ctx, P.flags.as<int>(), P.flags.as<int>(), nE, P.scan_tmp, d_tot)) return st;
+    if (ezc_status st = read_int(ctx, d_tot, &nComp, P)) return st;
+    EZC_CUDA(P.starts.reserve(sizeof(int) * ((size_t)nComp + 2)));
+    AT_LAUNCH(at_starts_kernel, nE, P.flags.as<int>(), d_tot, nE, P.starts.as<int>());
+    // ---- 6: merge sweep
+    AT_LAUNCH(at_merge_kernel, nComp, o0, P.starts.as<int>(), nComp, P.eA.as<int>(), P.eB.as<int>(), P.parent.as<int>(),
+              P.setsize.as<int>(), P.tmin.as<float>(), P.tmax.as<float>(), P.mmin.as<float>(), P.mmax.as<float>());
+  }
+  if (dbg && nb == 1) {
+    dbg->theta.resize(N); dbg->mag.resize(N);
+    EZC_CUDA(cudaMemcpyAsync(dbg->theta.data(), P.theta.p, sizeof(float) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    EZC_CUDA(cudaMemcpyAsync(dbg->mag.data(), P.mag.p, sizeof(float) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int> apix(nA), eA(nE), eB(nE), par(nA), ssz(nA);
+    std::vector<uint8_t> ec(nE);
+    std::vector<uint32_t> ord(nE);
+    if (nA) {
+      EZC_CUDA(cudaMemcpyAsync(apix.data(), P.apix.p, sizeof(int) * nA, cudaMemcpyDeviceToHost, ctx->stream));
+      EZC_CUDA(cudaMemcpyAsync(par.data(), P.parent.p, sizeof(int) * nA, cudaMemcpyDeviceToHost, ctx->stream));
+      EZC_CUDA(cudaMemcpyAsync(ssz.data(), P.setsize.p, sizeof(int) * nA, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (nE) {
+      EZC_CUDA(cudaMemcpyAsync(eA.data(), P.eA.p, sizeof(int) * nE, cudaMemcpyDeviceToHost, ctx->stream));
+      EZC_CUDA(cudaMemcpyAsync(eB.data(), P.eB.p, sizeof(int) * nE, cudaMemcpyDeviceToHost, ctx->stream));
+      EZC_CUDA(cudaMemcpyAsync(ec.data(), P.ecost.p, nE, cudaMemcpyDeviceToHost, ctx->stream));
+      EZC_CUDA(cudaMemcpyAsync(ord.data(), o0, sizeof(uint32_t) * nE, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+    dbg->edges.resize((size_t)nE * 3);
+    for (int i = 0; i < nE; ++i) { const uint32_t e = ord[i]; dbg->edges[3 * i] = ec[e]; dbg->edges[3 * i + 1] = apix[eA[e]]; dbg->edges[3 * i + 2] = apix[eB[e]]; }
+    dbg->rep.assign(N, -1); dbg->size.assign(N, 1);
+    for (int i = 0; i < nA; ++i) { int r = i; while (par[r] != r) r = par[r]; dbg->rep[apix[i]] = apix[r]; dbg->size[apix[i]] = ssz[r]; }
+  }
+  // ---- 7: clusters = pixels grouped by representative (ascending), raster order inside
+  AT_LAUNCH(at_rep_kernel, nA, P.parent.as<int>(), P.setsize.as<int>(), nA, P.rep.as<int>(), P.keep.as<int>());
+  if (ezc_status st = exclusive_scan_i32(ctx, P.keep.as<int>(), P.keep.as<int>(), nA, P.scan_tmp, d_tot)) return st;
+  int nK = 0;
+  if (ezc_status st = read_int(ctx, d_tot, &nK, P)) return st;
+  const size_t kcap = (size_t)std::max(nK, 1);
+  EZC_CUDA(P.plist0.reserve(sizeof(uint32_t) * kcap)); EZC_CUDA(P.plist1.reserve(sizeof(uint32_t) * kcap));
+  uint32_t* l0 = P.plist0.as<uint32_t>();
+  uint32_t* l1 = P.plist1.as<uint32_t>();
+  AT_LAUNCH(at_keep_compact_kernel, nA, P.keep.as<int>(), P.rep.as<int>(), P.setsize.as<int>(), nA, l0);
+  for (int shift = 0; shift < bits_for(std::max(nA, 2)); shift += 8) {
+    if (ezc_status st = radix_pass(ctx, l0, l1, nK, DigitArray{P.rep.as<int>(), shift}, P.sort)) return st;
+    std::swap(l0, l1);
+  }
+  int nC = 0;
+  if (nK > 0) {
+    EZC_CUDA(P.flags.reserve(sizeof(int) * (kcap + 1)));
+    AT_LAUNCH(at_boundary_kernel, nK, l0, nK, P.rep.as<int>(), (const int*)nullptr, P.flags.as<int>());
+    if (ezc_status st = exclusive_scan_i32(ctx, P.flags.as<int>(), P.flags.as<int>(), nK, P.scan_tmp, d_tot)) return st;
+    if (ezc_status st = read_int(ctx, d_tot, &nC, P)) return st;
+    EZC_CUDA(P.cstart.reserve(sizeof(int) * ((size_t)nC + 2)));
+    AT_LAUNCH(at_starts_kernel, nK, P.flags.as<int>(), d_tot, nK, P.cstart.as<int>());
+  }
+  // ---- 8: line fits -> segments
+  const size_t ccap = (size_t)std::max(nC, 1);
+  EZC_CUDA(P.segs_raw.reserve(sizeof(Segment) * ccap)); EZC_CUDA(P.seg_valid.reserve(sizeof(int) * (ccap + 1)));
+  EZC_CUDA(P.img_count.reserve(sizeof(int) * ((size_t)nb + 1))); EZC_CUDA(P.seg_start.reserve(sizeof(int) * ((size_t)nb + 2)));
+  AT_LAUNCH(at_fit_kernel, nC, l0, P.cstart.as<int>(), nC, P.apix.as<int>(), P.a_theta.as<float>(), P.a_mag.as<float>(), W, H,
+            P.segs_raw.as<Segment>(), P.seg_valid.as<int>());
+  EZC_CUDA(P.keep.reserve(sizeof(int) * (ccap + 1)));
+  int* vscan = P.keep.as<int>();
+  if (ezc_status st = exclusive_scan_i32(ctx, P.seg_valid.as<int>(), vscan, nC, P.scan_tmp, d_tot)) return st;
+  int nS = 0;
+  if (ezc_status st = read_int(ctx, d_tot, &nS, P)) return st;
+  const size_t scap = (size_t)std::max(nS, 1);
+  EZC_CUDA(P.segs.reserve(sizeof(Segment) * scap));
+  EZC_CUDA(cudaMemsetAsync(P.img_count.p, 0, sizeof(int) * (nb + 1), ctx->stream));
+  AT_LAUNCH(at_seg_compact_kernel, nC, P.segs_raw.as<Segment>(), P.seg_valid.as<int>(), vscan, nC, P.segs.as<Segment>(), P.img_count.as<int>());
+  // ---- 9a: spatial hash + children
+  const GridDims gd = grid_dims(W, H);
+  const int n_cells = gd.gw * gd.gh * nb;
+  EZC_CUDA(P.cell_of.reserve(sizeof(int) * scap)); EZC_CUDA(P.cell_count.reserve(sizeof(int) * ((size_t)n_cells + 1)));
+  EZC_CUDA(P.cell_start.reserve(sizeof(int) * ((size_t)n_cells + 1))); EZC_CUDA(P.cell_fill.reserve(sizeof(int) * ((size_t)n_cells + 1)));
+  EZC_CUDA(P.cell_items.reserve(sizeof(int) * scap)); EZC_CUDA(P.ccount.reserve(sizeof(int) * (scap + 1)));
+  EZC_CUDA(P.qcount.reserve(sizeof(int) * (scap + 1)));
+  EZC_CUDA(cudaMemsetAsync(P.cell_count.p, 0, sizeof(int) * (n_cells + 1), ctx->stream));
+  EZC_CUDA(cudaMemsetAsync(P.cell_fill.p, 0, sizeof(int) * (n_cells + 1), ctx->stream));
+  AT_LAUNCH(at_cell_count_kernel, nS, P.segs.as<Segment>(), nS, W, H, P.cell_of.as<int>(), P.cell_count.as<int>());
+  if (ezc_status st = exclusive_scan_i32(ctx, P.cell_count.as<int>(), P.cell_start.as<int>(), n_cells, P.scan_tmp, nullptr)) return st;
+  AT_LAUNCH(at_cell_fill_kernel, nS, P.cell_of.as<int>(), nS, P.cell_start.as<int>(), P.cell_fill.as<int>(), P.cell_items.as<int>());
+  AT_LAUNCH(at_cell_sort_kernel, n_cells, P.cell_start.as<int>(), P.cell_count.as<int>(), n_cells, P.cell_items.as<int>());
+  AT_LAUNCH(at_children_kernel<false>, nS, P.segs.as<Segment>(), nS, W, H, P.cell_start.as<int>(), P.cell_count.as<int>(),
+            P.cell_items.as<int>(), P.ccount.as<int>(), nullptr, nullptr);
+  EZC_CUDA(cudaMemsetAsync(P.ccount.as<int>() + nS, 0, sizeof(int), ctx->stream));
+  if (ezc_status st = exclusive_scan_i32(ctx, P.ccount.as<int>(), P.ccount.as<int>(), nS + 1, P.scan_tmp, d_tot)) return st;
+  int nCh = 0;
+  if (ezc_status st = read_int(ctx, d_tot, &nCh, P)) return st;
+  EZC_CUDA(P.children.reserve(sizeof(int) * (size_t)std::max(nCh, 1)));
+  AT_LAUNCH(at_children_kernel<true>, nS, P.segs.as<Segment>(), nS, W, H, P.cell_start.as<int>(), P.cell_count.as<int>(),
+            P.cell_items.as<int>(), nullptr, P.ccount.as<int>(), P.children.as<int>());
+  // ---- 9b: quads
+  AT_LAUNCH(at_quads_kernel<false>, nS, P.segs.as<Segment>(), nS, P.ccount.as<int>(), P.children.as<int>(), P.qcount.as<int>(), nullptr, nullptr);
+  if (ezc_status st = exclusive_scan_i32(ctx, P.qcount.as<int>(), P.qcount.as<int>(), nS, P.scan_tmp, d_tot)) return st;
+  int nQ = 0;
+  if (ezc_status st = read_int(ctx, d_tot, &nQ, P)) return st;
+  const size_t qcap = (size_t)std::max(nQ, 1);
+  EZC_CUDA(P.quads.reserve(sizeof(QuadRec) * qcap)); EZC_CUDA(P.dets.reserve(sizeof(Detection) * qcap));
+  EZC_CUDA(P.qimg_count.reserve(sizeof(int) * ((size_t)nb + 1))); EZC_CUDA(P.qstart.reserve(sizeof(int) * ((size_t)nb + 2)));
+  EZC_CUDA(P.ngood.reserve(sizeof(int) * ((size_t)nb + 1)));
+  EZC_CUDA(P.corners.reserve(sizeof(float2) * qcap * 4)); EZC_CUDA(P.cimg.reserve(sizeof(int) * qcap * 4));
+  EZC_CUDA(P.refine_flag.reserve(sizeof(int) * qcap));
+  AT_LAUNCH(at_quads_kernel<true>, nS, P.segs.as<Segment>(), nS, P.ccount.as<int>(), P.children.as<int>(), nullptr, P.qcount.as<int>(),
+            P.quads.as<QuadRec>());
+  // ---- 9c: decode
+  AT_LAUNCH(at_decode_kernel, nQ, P.quads.as<QuadRec>(), nQ, imgs->d, imgs->pitch, imgs->image_stride, W, H, img0, P.dets.as<Detection>());
+  // ---- 9d: per-image ranges, de-dup, sub-pixel refinement, scatter
+  EZC_CUDA(cudaMemsetAsync(P.qimg_count.p, 0, sizeof(int) * (nb + 1), ctx->stream));
+  AT_LAUNCH(at_quad_image_count_kernel, nQ, P.quads.as<QuadRec>(), nQ, P.qimg_count.as<int>());
+  at_image_starts_kernel<<<1, 1, 0, ctx->stream>>>(P.qimg_count.as<int>(), nb, P.qstart.as<int>());
+  ctx->kernel_launches++;
+  AT_LAUNCH(at_dedup_kernel, nb, P.dets.as<Detection>(), P.qstart.as<int>(), nb, P.ngood.as<int>());
+  EZC_CUDA(cudaMemsetAsync(P.refine_flag.p, 0, sizeof(int) * qcap, ctx->stream));
+  if (nQ > 0) {
+    // the slots of non-surviving detections are never read, but cornerSubPix runs over the whole array:
+    // give them a harmless in-image position
+    EZC_CUDA(cudaMemsetAsync(P.corners.p, 0, sizeof(float2) * qcap * 4, ctx->stream));
+    EZC_CUDA(cudaMemsetAsync(P.cimg.p, 0, sizeof(int) * qcap * 4, ctx->stream));
+    at_gather_corners_kernel<<<nb, 64, 0, ctx->stream>>>(P.dets.as<Detection>(), P.qstart.as<int>(), P.ngood.as<int>(), nb, nb_tags, W, H, img0,
+                                                          P.corners.as<float2>(), P.cimg.as<int>(), P.refine_flag.as<int>());
+    EZC_CUDA(cudaGetLastError());
+    ctx->kernel_launches++;
+    // aprilgrid_detector.hpp:52-53
+    if (ezc_status st = subpix_device(ctx, imgs, P.corners.as<float2>(), P.cimg.as<int>(), nQ * 4, 5, 5, 100, 0.05)) return st;
+  }
+  at_scatter_kernel<<<nb, 64, 0, ctx->stream>>>(P.dets.as<Detection>(), P.qstart.as<int>(), P.ngood.as<int>(), P.corners.as<float2>(),
+                                                 P.refine_flag.as<int>(), nb, nb_tags, d_out_corners + (size_t)img0 * 4 * nb_tags,
+                                                 d_out_ndet + img0, d_out_success + img0);
+  EZC_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  if (dbg && nb == 1) {
+    std::vector<Segment> hs(nS);
+    std::vector<QuadRec> hq(nQ);
+    if (nS) EZC_CUDA(cudaMemcpyAsync(hs.data(), P.segs.p, sizeof(Segment) * nS, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nQ) EZC_CUDA(cudaMemcpyAsync(hq.data(), P.quads.p, sizeof(QuadRec) * nQ, cudaMemcpyDeviceToHost, ctx->stream));
+    EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+    dbg->segments.resize((size_t)nS * 6);
+    for (int i = 0; i < nS; ++i) { float* o = &dbg->segments[(size_t)i * 6]; o[0] = hs[i].x0; o[1] = hs[i].y0; o[2] = hs[i].x1; o[3] = hs[i].y1; o[4] = hs[i].theta; o[5] = hs[i].length; }
+    dbg->quads.resize((size_t)nQ * 9);
+    for (int i = 0; i < nQ; ++i) { float* o = &dbg->quads[(size_t)i * 9]; for (int k = 0; k < 4; ++k) { o[2 * k] = hq[i].p[k][0]; o[2 * k + 1] = hq[i].p[k][1]; } o[8] = hq[i].perimeter; }
+  }
+  return EZC_OK;
+}
+
+void init_filter() {
+  // Gaussian::makeGaussianFilter(0.8f, 3)  (Gaussian.cc:8-31)
+  const float sigma = 0.8f;
+  const int n = 3;
+  float f[3];
+  const double inv_variance = 1. / (2 * sigma * sigma);
+  float sum = 0;
+  for (int i = 0; i < n; i++) {
+    const int j = i - n / 2;
+    f[i] = (float)std::exp(-j * j * inv_variance);
+    sum += f[i];
+  }
+  for (int i = 0; i < n; i++) f[i] /= sum;
+  cudaMemcpyToSymbol(c_filt, f, sizeof(f));
+}
+
+}  // namespace
+
+extern "C" {
+
+ezc_status ezc_detect_aprilgrid_batch(ezc_context* ctx, const ezc_images* imgs, int32_t nb_rows, int32_t nb_cols,
+                                      float* corners_out, int32_t* n_detections_out, uint8_t* success_out,
+                                      int32_t max_images_in_flight) {
+  EZC_CHECK(ctx && imgs && corners_out && n_detections_out && success_out, EZC_ERR_INVALID, "ezc_detect_aprilgrid_batch: null argument");
+  EZC_CHECK(nb_rows > 0 && nb_cols > 0, EZC_ERR_INVALID, "ezc_detect_aprilgrid_batch: bad grid size");
+  EZC_CHECK(imgs->width >= 4 && imgs->height >= 4, EZC_ERR_INVALID, "ezc_detect_aprilgrid_batch: image too small");
+  EZC_CUDA(cudaSetDevice(ctx->device));
+  const int nb_tags = nb_rows * nb_cols;
+  const int n = imgs->n;
+  if (n == 0) return EZC_OK;
+  init_filter();
+  const long long N = (long long)imgs->width * imgs->height;
+  // sub-batch: dense indices must stay below 2^31 and the working set (~40 B/px dense + compact pools) bounded
+  int sub = (int)std::max<long long>(1, std::min<long long>((1LL << 30) / N, 4LL * 1024 * 1024 * 1024 / (N * 24)));
+  if (max_images_in_flight > 0) sub = std::min(sub, max_images_in_flight);
+  sub = std::min(sub, n);
+  Pools P;
+  ezc::DevBuf d_corners, d_ndet, d_succ;
+  EZC_CUDA(d_corners.reserve(sizeof(float2) * (size_t)n * 4 * nb_tags));
+  EZC_CUDA(d_ndet.reserve(sizeof(int) * (size_t)n));
+  EZC_CUDA(d_succ.reserve((size_t)n));
+  for (int i0 = 0; i0 < n; i0 += sub) {
+    const int nb = std::min(sub, n - i0);
+    if (ezc_status st = process_sub_batch(ctx, imgs, i0, nb, nb_tags, P, d_corners.as<float2>(), d_ndet.as<int>(), d_succ.as<uint8_t>(), nullptr))
+      return st;
+  }
+  EZC_CUDA(cudaMemcpyAsync(corners_out, d_corners.p, sizeof(float2) * (size_t)n * 4 * nb_tags, cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaMemcpyAsync(n_detections_out, d_ndet.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaMemcpyAsync(success_out, d_succ.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return EZC_OK;
+}
+
+// Test hook: run ONE image and return the stage products (counts first, then data through getters).
+ezc_status ezc_apriltag_debug_run(ezc_context* ctx, const ezc_images* imgs, int32_t image, int32_t nb_rows, int32_t nb_cols,
+                                  ezc_apriltag_debug** out, float* corners_out, int32_t* n_detections_out, uint8_t* success_out) {
+  EZC_CHECK(ctx && imgs && out && image >= 0 && image < imgs->n, EZC_ERR_INVALID, "ezc_apriltag_debug_run: bad argument");
+  EZC_CUDA(cudaSetDevice(ctx->device));
+  init_filter();
+  const int nb_tags = nb_rows * nb_cols;
+  Pools P;
+  ezc::DevBuf d_corners, d_ndet, d_succ;
+  EZC_CUDA(d_corners.reserve(sizeof(float2) * (size_t)imgs->n * 4 * nb_tags));
+  EZC_CUDA(d_ndet.reserve(sizeof(int) * (size_t)imgs->n));
+  EZC_CUDA(d_succ.reserve((size_t)imgs->n));
+  ezc_apriltag_debug* d = new ezc_apriltag_debug();
+  ezc_status st = process_sub_batch(ctx, imgs, image, 1, nb_tags, P, d_corners.as<float2>(), d_ndet.as<int>(), d_succ.as<uint8_t>(), d);
+  if (st != EZC_OK) { delete d; return st; }
+  if (corners_out) EZC_CUDA(cudaMemcpyAsync(corners_out, d_corners.as<float2>() + (size_t)image * 4 * nb_tags, sizeof(float2) * 4 * nb_tags, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_detections_out) EZC_CUDA(cudaMemcpyAsync(n_detections_out, d_ndet.as<int>() + image, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (success_out) EZC_CUDA(cudaMemcpyAsync(success_out, d_succ.as<uint8_t>() + image, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = d;
+  return EZC_OK;
+}
+int32_t ezc_apriltag_debug_count(const ezc_apriltag_debug* d, int32_t what) {
+  if (!d) return 0;
+  switch (what) {
+    case 0: return (int32_t)d->theta.size();
+    case 1: return (int32_t)(d->edges.size() / 3);
+    case 2: return (int32_t)(d->segments.size() / 6);
+    case 3: return (int32_t)(d->quads.size() / 9);
+    default: return 0;
+  }
+}
+ezc_status ezc_apriltag_debug_get(const ezc_apriltag_debug* d, float* theta, float* mag, int32_t* edges, int32_t* rep, int32_t* size,
+                                  float* segments, float* quads) {
+  EZC_CHECK(d, EZC_ERR_INVALID, "ezc_apriltag_debug_get: null");
+  if (theta) std::memcpy(theta, d->theta.data(), sizeof(float) * d->theta.size());
+  if (mag) std::memcpy(mag, d->mag.data(), sizeof(float) * d->mag.size());
+  if (edges) std::memcpy(edges, d->edges.data(), sizeof(int) * d->edges.size());
+  if (rep) std::memcpy(rep, d->rep.data(), sizeof(int) * d->rep.size());
+  if (size) std::memcpy(size, d->size.data(), sizeof(int) * d->size.size());
+  if (segments) std::memcpy(segments, d->segments.data(), sizeof(float) * d->segments.size());
+  if (quads) std::memcpy(quads, d->quads.data(), sizeof(float) * d->quads.size());
+  return EZC_OK;
+}
+void ezc_apriltag_debug_free(ezc_apriltag_debug* d) { delete d; }
+
+}  // extern "C"

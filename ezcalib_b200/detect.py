@@ -68,3 +68,38 @@ def corner_subpix(ctx: Context, imgs: Images, corners, image_index, win=(5, 5), 
     check(_lib.lib().ezc_corner_subpix(ctx.handle, imgs.handle, _p(c), _p(idx), c.shape[0], int(win[0]), int(win[1]),
                                        int(max_iter), float(eps)), "ezc_corner_subpix")
     return c
+
+
+def detect_aprilgrid(ctx: Context, imgs: Images, nb_rows: int, nb_cols: int, max_images_in_flight: int = 0):
+    """AprilTagCalibDetector::detectTarget for every image: returns (success[n] bool, corners[n, 4*nb_tags, 2] float32
+    with (-1,-1) for missing corners, n_detections[n])."""
+    nb_tags = nb_rows * nb_cols
+    corners = np.zeros((imgs.n, 4 * nb_tags, 2), np.float32)
+    ndet = np.zeros(imgs.n, np.int32)
+    succ = np.zeros(imgs.n, np.uint8)
+    check(_lib.lib().ezc_detect_aprilgrid_batch(ctx.handle, imgs.handle, int(nb_rows), int(nb_cols), _p(corners), _p(ndet), _p(succ),
+                                                int(max_images_in_flight)), "ezc_detect_aprilgrid_batch")
+    return succ.astype(bool), corners, ndet
+
+
+def apriltag_debug(ctx: Context, imgs: Images, image: int, nb_rows: int, nb_cols: int) -> dict:
+    """Stage products of the GPU extractTags for one image (tests)."""
+    L = _lib.lib()
+    nb_tags = nb_rows * nb_cols
+    h = C.c_void_p()
+    corners = np.zeros((4 * nb_tags, 2), np.float32)
+    ndet = np.zeros(1, np.int32)
+    succ = np.zeros(1, np.uint8)
+    check(L.ezc_apriltag_debug_run(ctx.handle, imgs.handle, int(image), int(nb_rows), int(nb_cols), C.byref(h), _p(corners), _p(ndet), _p(succ)),
+          "ezc_apriltag_debug_run")
+    try:
+        npx, ne, ns, nq = (L.ezc_apriltag_debug_count(h, k) for k in range(4))
+        theta = np.zeros(npx, np.float32); mag = np.zeros(npx, np.float32)
+        edges = np.zeros((ne, 3), np.int32); rep = np.zeros(npx, np.int32); size = np.zeros(npx, np.int32)
+        segs = np.zeros((ns, 6), np.float32); quads = np.zeros((nq, 9), np.float32)
+        check(L.ezc_apriltag_debug_get(h, _p(theta), _p(mag), _p(edges), _p(rep), _p(size), _p(segs), _p(quads)), "ezc_apriltag_debug_get")
+    finally:
+        L.ezc_apriltag_debug_free(h)
+    shp = (imgs.height, imgs.width)
+    return dict(theta=theta.reshape(shp), mag=mag.reshape(shp), edges=edges, rep=rep.reshape(shp), size=size.reshape(shp),
+                segments=segs, quads=quads, corners=corners, n_detections=int(ndet[0]), success=bool(succ[0]))

@@ -78,6 +78,29 @@ void ezc_images_destroy(ezc_images* imgs);
 ezc_status ezc_corner_subpix(ezc_context* ctx, const ezc_images* imgs, float* corners, const int32_t* image_index,
                              int32_t n, int32_t win_w, int32_t win_h, int32_t max_iter, double eps);
 
+/* AprilTagCalibDetector::detectTarget (/root/reference/include/target_detectors/aprilgrid_detector.hpp:30-71) for
+ * every image of the batch: AprilTags::TagDetector(tagCodes36h11).extractTags
+ * (/root/reference/thirdparty/ethz_apriltag2/src/TagDetector.cc:40-586), cv::cornerSubPix (5,5)/(100,0.05) on the
+ * 4 corners of every detection with id < nb_rows*nb_cols, scatter into slot id*4+i.
+ * corners_out: HOST float [n_images][4*nb_tags][2], (-1,-1) = not detected;
+ * n_detections_out: HOST [n_images] = vdet.size(); success_out: HOST [n_images] = vdet.size() > nb_tags/2 - 1.
+ * max_images_in_flight <= 0 lets the library size its sub-batches. */
+ezc_status ezc_detect_aprilgrid_batch(ezc_context* ctx, const ezc_images* imgs, int32_t nb_rows, int32_t nb_cols,
+                                      float* corners_out, int32_t* n_detections_out, uint8_t* success_out,
+                                      int32_t max_images_in_flight);
+
+/* Test hooks: stage products of extractTags for ONE image (theta/mag images, merge-order edge list, union-find
+ * representatives, segments, quads), compared stage by stage against the reference objects in tests/. */
+typedef struct ezc_apriltag_debug ezc_apriltag_debug;
+ezc_status ezc_apriltag_debug_run(ezc_context* ctx, const ezc_images* imgs, int32_t image, int32_t nb_rows, int32_t nb_cols,
+                                  ezc_apriltag_debug** out, float* corners_out, int32_t* n_detections_out,
+                                  uint8_t* success_out);
+/* what: 0 pixels, 1 edges, 2 segments, 3 quads */
+int32_t ezc_apriltag_debug_count(const ezc_apriltag_debug* d, int32_t what);
+ezc_status ezc_apriltag_debug_get(const ezc_apriltag_debug* d, float* theta, float* mag, int32_t* edges /*[n][3]*/,
+                                  int32_t* rep, int32_t* size, float* segments /*[n][6]*/, float* quads /*[n][9]*/);
+void ezc_apriltag_debug_free(ezc_apriltag_debug* d);
+
 /* ------------------------------------------------------------------------------------------
  * Half (b): Levenberg-Marquardt calibration solve.
  * Replaces the ceres::Problem built in EZCalibrator::computeCalibration
