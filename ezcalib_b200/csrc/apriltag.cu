@@ -916,7 +916,16 @@ struct Pools {
   DevBuf qcount, quads, dets, qimg_count, qstart, ngood, corners, cimg, refine_flag;
   SortTemp sort;
   HostPinned h;
+  DevBuf out_corners, out_ndet, out_succ;
 };
+
+Pools& get_pools(ezc_context* ctx) {
+  if (!ctx->at_pools) {
+    ctx->at_pools = new Pools();
+    ctx->at_pools_free = [](void* p) { delete static_cast<Pools*>(p); };
+  }
+  return *static_cast<Pools*>(ctx->at_pools);
+}
 
 #define AT_LAUNCH(kernel, n, ...)                                                     \
   do {                                                                                \
@@ -1182,8 +1191,8 @@ ezc_status ezc_detect_aprilgrid_batch(ezc_context* ctx, const ezc_images* imgs, 
   int sub = (int)std::max<long long>(1, std::min<long long>((1LL << 30) / N, 4LL * 1024 * 1024 * 1024 / (N * 24)));
   if (max_images_in_flight > 0) sub = std::min(sub, max_images_in_flight);
   sub = std::min(sub, n);
-  Pools P;
-  ezc::DevBuf d_corners, d_ndet, d_succ;
+  Pools& P = get_pools(ctx);
+  ezc::DevBuf& d_corners = P.out_corners; ezc::DevBuf& d_ndet = P.out_ndet; ezc::DevBuf& d_succ = P.out_succ;
   EZC_CUDA(d_corners.reserve(sizeof(float2) * (size_t)n * 4 * nb_tags));
   EZC_CUDA(d_ndet.reserve(sizeof(int) * (size_t)n));
   EZC_CUDA(d_succ.reserve((size_t)n));

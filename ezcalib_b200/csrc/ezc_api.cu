@@ -44,6 +44,8 @@ ezc_status ezc_create(int32_t device, ezc_context** out) {
 void ezc_destroy(ezc_context* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->at_pools && ctx->at_pools_free) ctx->at_pools_free(ctx->at_pools);
+  if (ctx->cb_pools && ctx->cb_pools_free) ctx->cb_pools_free(ctx->cb_pools);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -77,4 +77,9 @@ struct ezc_context {
   int rank = 0;
   int world = 1;
   uint64_t kernel_launches = 0;
+  // per-context scratch pools of the detection pipelines (kept between calls; freed with the context)
+  void* at_pools = nullptr;
+  void (*at_pools_free)(void*) = nullptr;
+  void* cb_pools = nullptr;
+  void (*cb_pools_free)(void*) = nullptr;
 };

@@ -48,6 +48,19 @@ class Images:
     def handle(self):
         return self._h
 
+    @classmethod
+    def from_handle(cls, ctx, handle, n, height, width):
+        self = cls.__new__(cls)
+        self.ctx, self._h, self._keep = ctx, handle, None
+        self.n, self.height, self.width = int(n), int(height), int(width)
+        return self
+
+    def download(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.n - first if count is None else count
+        out = np.zeros((count, self.height, self.width), np.uint8)
+        check(_lib.lib().ezc_images_download(self.ctx.handle, self._h, int(first), int(count), _p(out)), "ezc_images_download")
+        return out
+
     def close(self):
         if self._h:
             _lib.lib().ezc_images_destroy(self._h)
@@ -103,3 +116,16 @@ def apriltag_debug(ctx: Context, imgs: Images, image: int, nb_rows: int, nb_cols
     shp = (imgs.height, imgs.width)
     return dict(theta=theta.reshape(shp), mag=mag.reshape(shp), edges=edges, rep=rep.reshape(shp), size=size.reshape(shp),
                 segments=segs, quads=quads, corners=corners, n_detections=int(ndet[0]), success=bool(succ[0]))
+
+
+def render_targets(ctx: Context, pattern: str, rows: int, cols: int, size: float, space: float, model_id: int, width: int,
+                   height: int, cams12, poses7, noise_sigma: float = 2.0, seed: int = 20261019) -> Images:
+    """Render synthetic target views straight into HBM (bench / large tests). pattern: 'chessboard' | 'aprilgrid'."""
+    cams = np.ascontiguousarray(cams12, dtype=np.float64).reshape(-1, 12)
+    poses = np.ascontiguousarray(poses7, dtype=np.float64).reshape(-1, 7)
+    assert cams.shape[0] == poses.shape[0]
+    h = C.c_void_p()
+    check(_lib.lib().ezc_render_targets(ctx.handle, 0 if pattern == "chessboard" else 1, int(rows), int(cols), float(size), float(space),
+                                        int(model_id), int(width), int(height), int(poses.shape[0]), _p(cams), _p(poses), float(noise_sigma),
+                                        int(seed), C.byref(h)), "ezc_render_targets")
+    return Images.from_handle(ctx, h, poses.shape[0], height, width)

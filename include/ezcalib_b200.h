@@ -71,6 +71,17 @@ ezc_status ezc_images_upload(ezc_context* ctx, const ezc_image_batch* host_batch
 ezc_status ezc_images_wrap_device(ezc_context* ctx, const ezc_image_batch* device_batch, ezc_images** out);
 void ezc_images_destroy(ezc_images* imgs);
 
+/* Copy images [first, first+count) back to HOST memory (densely packed). */
+ezc_status ezc_images_download(ezc_context* ctx, const ezc_images* imgs, int32_t first, int32_t count, uint8_t* host_out);
+
+/* Synthetic data generator (not part of the reference's path; the reference ships no images): renders n_images views
+ * of a planar target directly into HBM.  pattern 0 = chessboard (rows x cols SQUARES of `size` metres),
+ * 1 = AprilGrid 36h11 (rows x cols tags of `size` metres, gap ratio `space`).  cams12: HOST [n][12] = fx fy cx cy
+ * dist[8] (reference coefficient order); poses7: HOST [n][7] world->camera. */
+ezc_status ezc_render_targets(ezc_context* ctx, int32_t pattern, int32_t rows, int32_t cols, double size, double space,
+                              int32_t model, int32_t width, int32_t height, int32_t n_images, const double* cams12,
+                              const double* poses7, double noise_sigma, uint64_t seed, ezc_images** out);
+
 /* cv::cornerSubPix(img, corners, Size(win_w,win_h), Size(-1,-1), {COUNT+EPS, max_iter, eps}) for n corners;
  * corner i lies in image image_index[i].  Replaces /root/reference/include/target_detectors/
  * chessboard_detector.hpp:39-40 and aprilgrid_detector.hpp:52-53 (win 5x5, 100 iterations, eps 0.05).
