@@ -268,38 +268,70 @@ __device__ __forceinline__ int uf_find(int* parent, int x) {
   return root;
 }
 
-__global__ void at_merge_kernel(const uint32_t* __restrict__ order, const int* __restrict__ starts, int n_comp,
-                                const int* __restrict__ eA, const int* __restrict__ eB, int* __restrict__ parent,
-                                int* __restrict__ setsize, float* __restrict__ tmin, float* __restrict__ tmax,
-                                float* __restrict__ mmin, float* __restrict__ mmax) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per component.  The sweep order is strictly sequential in the reference; what a warp adds is
+// latency hiding that cannot change the result: (A) the 32 lanes look up the current roots of the next 32
+// edges in parallel -- an edge whose end points already share a root can never merge later (sets only grow),
+// so it is dropped; (B) the remaining candidates are replayed one by one, in order, by the whole warp
+// (uniform control flow, lane 0 writes), re-resolving their roots first because an earlier candidate of the
+// same batch may have merged them.
+__device__ __forceinline__ int uf_find_ro(const int* parent, int x) {
+  int p = parent[x];
+  while (p != x) { x = p; p = parent[x]; }
+  return x;
+}
+
+__global__ void __launch_bounds__(256) at_merge_kernel(const uint32_t* __restrict__ order, const int* __restrict__ starts, int n_comp,
+                                                         const int* __restrict__ eA, const int* __restrict__ eB, int* parent,
+                                                         int* setsize, float* tmin, float* tmax, float* mmin, float* mmax) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= n_comp) return;
   const int beg = starts[c], end = starts[c + 1];
-  for (int i = beg; i < end; ++i) {
-    const uint32_t e = order[i];
-    const int ida = uf_find(parent, eA[e]);
-    const int idb = uf_find(parent, eB[e]);
-    if (ida == idb) continue;
-    const int sza = setsize[ida], szb = setsize[idb];
-    const float tmina = tmin[ida], tmaxa = tmax[ida];
-    const float tminb = tmin[idb], tmaxb = tmax[idb];
-    const float costa = (tmaxa - tmina);
-    const float costb = (tmaxb - tminb);
-    const float bshift = mod2pi_ref((tmina + tmaxa) / 2, (tminb + tmaxb) / 2) - (tminb + tmaxb) / 2;
-    const float tminab = fminr(tmina, tminb + bshift);
-    float tmaxab = fmaxr(tmaxa, tmaxb + bshift);
-    if (tmaxab - tminab > 2 * kPiF) tmaxab = tminab + 2 * kPiF;
-    const float mmina = mmin[ida], mmaxa = mmax[ida], mminb = mmin[idb], mmaxb = mmax[idb];
-    const float mminab = fminr(mmina, mminb);
-    const float mmaxab = fmaxr(mmaxa, mmaxb);
-    const float costab = (tmaxab - tminab);
-    if (costab <= (fminr(costa, costb) + kThetaThresh / (sza + szb)) &&
-        (mmaxab - mminab) <= fminr(mmaxa - mmina, mmaxb - mminb) + kMagThresh / (sza + szb)) {
-      int idab;  // UnionFindSimple::connectNodes (UnionFindSimple.cc:25-44)
-      if (sza > szb) { parent[idb] = ida; setsize[ida] = sza + szb; idab = ida; }
-      else { parent[ida] = idb; setsize[idb] = szb + sza; idab = idb; }
-      tmin[idab] = tminab; tmax[idab] = tmaxab;
-      mmin[idab] = mminab; mmax[idab] = mmaxab;
+  for (int i0 = beg; i0 < end; i0 += 32) {
+    const int i = i0 + lane;
+    int ra = 0, rb = 0;
+    if (i < end) {
+      const uint32_t e = order[i];
+      const int a = eA[e], b = eB[e];
+      ra = uf_find_ro(parent, a);
+      rb = uf_find_ro(parent, b);
+      // path shortening (UnionFindSimple compresses too; it never changes a representative)
+      if (parent[a] != ra) parent[a] = ra;
+      if (parent[b] != rb) parent[b] = rb;
+    }
+    unsigned cand = __ballot_sync(0xffffffffu, i < end && ra != rb);
+    __syncwarp();
+    while (cand) {
+      const int l = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const int ida = uf_find_ro(parent, __shfl_sync(0xffffffffu, ra, l));
+      const int idb = uf_find_ro(parent, __shfl_sync(0xffffffffu, rb, l));
+      if (ida != idb) {
+        const int sza = setsize[ida], szb = setsize[idb];
+        const float tmina = tmin[ida], tmaxa = tmax[ida];
+        const float tminb = tmin[idb], tmaxb = tmax[idb];
+        const float mmina = mmin[ida], mmaxa = mmax[ida], mminb = mmin[idb], mmaxb = mmax[idb];
+        const float costa = (tmaxa - tmina);
+        const float costb = (tmaxb - tminb);
+        const float bshift = mod2pi_ref((tmina + tmaxa) / 2, (tminb + tmaxb) / 2) - (tminb + tmaxb) / 2;
+        const float tminab = fminr(tmina, tminb + bshift);
+        float tmaxab = fmaxr(tmaxa, tmaxb + bshift);
+        if (tmaxab - tminab > 2 * kPiF) tmaxab = tminab + 2 * kPiF;
+        const float mminab = fminr(mmina, mminb);
+        const float mmaxab = fmaxr(mmaxa, mmaxb);
+        const float costab = (tmaxab - tminab);
+        if (costab <= (fminr(costa, costb) + kThetaThresh / (sza + szb)) &&
+            (mmaxab - mminab) <= fminr(mmaxa - mmina, mmaxb - mminb) + kMagThresh / (sza + szb)) {
+          if (lane == 0) {
+            int idab;  // UnionFindSimple::connectNodes (UnionFindSimple.cc:25-44)
+            if (sza > szb) { parent[idb] = ida; setsize[ida] = sza + szb; idab = ida; }
+            else { parent[ida] = idb; setsize[idb] = szb + sza; idab = idb; }
+            tmin[idab] = tminab; tmax[idab] = tmaxab;
+            mmin[idab] = mminab; mmax[idab] = mmaxab;
+          }
+        }
+      }
+      __syncwarp();
     }
   }
 }
@@ -1015,7 +1047,7 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
     EZC_CUDA(P.starts.reserve(sizeof(int) * ((size_t)nComp + 2)));
     AT_LAUNCH(at_starts_kernel, nE, P.flags.as<int>(), d_tot, nE, P.starts.as<int>());
     // ---- 6: merge sweep
-    AT_LAUNCH(at_merge_kernel, nComp, o0, P.starts.as<int>(), nComp, P.eA.as<int>(), P.eB.as<int>(), P.parent.as<int>(),
+    AT_LAUNCH(at_merge_kernel, (long long)nComp * 32, o0, P.starts.as<int>(), nComp, P.eA.as<int>(), P.eB.as<int>(), P.parent.as<int>(),
               P.setsize.as<int>(), P.tmin.as<float>(), P.tmax.as<float>(), P.mmin.as<float>(), P.mmax.as<float>());
   }
   if (dbg && nb == 1) {
