@@ -294,6 +294,9 @@ def run_gpu(args):
                      "kernel": "lm_accumulate_kernel", "dmma_peak_tflops": round(peak_dmma, 3), "peak_source": "DFMA microbenchmark measured in this run "
                      "(MEASURED_PEAKS.json has no FP64 figure; hbm_gbs there = %s)" % measured_peaks().get("hbm_gbs")},
     }
+    if not args.no_detect:
+        line["detect"] = run_detect(ctx, args, rank, world, stream)
+        line["gpu_launches"] += line["detect"]["gpu_launches"]
     if rank == 0:
         if not args.no_cpu and world >= 1:
             v, ms_cpu, cb = run_cpu(argparse.Namespace(steps=min(K, 10), warmup=1), ("radtan5",), args.cpu_views, False)
@@ -303,6 +306,92 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------- detection
+DET_W, DET_H, DET_ROWS, DET_COLS = 2448, 2048, 6, 6
+
+
+def run_detect(ctx, args, rank, world, stream):
+    """cfg3-style workload: 6x6 AprilGrid (36h11) views 2448x2048 rendered into HBM, radtan8 camera.
+    Returns the `detect` object of the JSON line (images/s detect+subpix, HBM roofline, reference CPU)."""
+    import torch
+    import torch.distributed as dist
+
+    from ezcalib_b200 import detect, synth
+    n = args.det_images
+    model = "radtan8"
+    mid = synth.MODEL_ID[model]
+    d = synth.GT_DIST[model]
+    f, cx, cy = 2000.0, DET_W / 2 + 3.0, DET_H / 2 - 4.0
+    tgt = synth.aprilgrid_target(DET_ROWS, DET_COLS, 0.06, 0.3)
+    rng = np.random.Generator(np.random.Philox(key=synth.MASTER_SEED + 1000 + rank))
+    poses = synth.sample_poses(rng, n, tgt, model, f, cx, cy, d, DET_W, DET_H, margin=30, tilt_sigma=0.3)
+    cams = np.tile(np.array([f, f, cx, cy] + list(d)), (n, 1))
+    imgs = detect.render_targets(ctx, "aprilgrid", DET_ROWS, DET_COLS, 0.06, 0.3, mid, DET_W, DET_H, cams, poses,
+                                 seed=synth.MASTER_SEED + rank)
+    for _ in range(max(args.warmup, 3) if n <= 64 else 3):
+        succ, corners, ndet = detect.detect_aprilgrid(ctx, imgs, DET_ROWS, DET_COLS)
+    reps = max(1, args.det_reps)
+    l0 = ctx.kernel_launches()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        succ, corners, ndet = detect.detect_aprilgrid(ctx, imgs, DET_ROWS, DET_COLS)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches() - l0
+    # e2e: host (pinned) images -> upload -> detect -> results on the host
+    host = imgs.download(0, n)
+    pin = torch.from_numpy(host).pin_memory()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    im2 = detect.Images(ctx, pin.numpy())
+    s2, c2, n2 = detect.detect_aprilgrid(ctx, im2, DET_ROWS, DET_COLS)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1)
+    im2.close()
+    assert np.array_equal(c2, corners) and np.array_equal(n2, ndet)
+    if world > 1:
+        t = torch.tensor([ms, ms2], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms2 = float(t[0].item()), float(t[1].item())
+    value = n * reps * world / (ms * 1e-3)
+    e2e_value = n * world / (ms2 * 1e-3)
+    alg_bytes = DET_W * DET_H + 8 * 4 * DET_ROWS * DET_COLS
+    peak = measured_peaks().get("hbm_gbs", 6650.0)
+    achieved = value / world * alg_bytes / 1e9
+    out = {"metric": "images/s detect+subpix", "value": round(value, 2), "unit": "images/s", "ms_per_image": round(ms / (n * reps), 4),
+           "config": {"workload": "cfg3-style: %d views %dx%d per GPU, 6x6 AprilGrid 36h11, radtan8, rendered into HBM (inputs %.1f GB > L2)" % (n, DET_W, DET_H, n * DET_W * DET_H / 1e9),
+                      "found": int(succ.sum()), "mean_detections": float(ndet.mean())},
+           "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": int(DET_W * DET_H), "d2h_bytes_per_step": int(8 * 144 + 5)},
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
+                        "traffic": None, "kernel": "whole detection pipeline (no single dominant kernel; see profiles/launches_detect_r01.csv)",
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if measured_peaks().get("hbm_gbs") else "fallback 6650"}}
+    if rank == 0 and not args.no_cpu:
+        from oracle import apriltag_oracle as A
+        k = min(n, args.det_cpu_images)
+        A.detect_target(host[0], DET_ROWS, DET_COLS)
+        t0 = time.perf_counter()
+        same = True
+        for i in range(k):
+            ok, c, nd, _ = A.detect_target(host[i], DET_ROWS, DET_COLS)
+            same = same and bool(ok) == bool(succ[i]) and int(nd) == int(ndet[i]) and np.array_equal(c[:, 0] < 0, corners[i][:, 0] < 0) \
+                and float(np.abs(c - corners[i]).max()) <= 0.01
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": round(k / dt, 3), "unit": "images/s", "cores": host_cores(), "kind": "reference",
+                               "sample": "%d of the same images: the reference's own extractTags (oracle/_ref, OpenMP) + cv2.cornerSubPix, serial image loop like ezcalibrator.cpp:40-59" % k,
+                               "parity_on_sample": bool(same)}
+    imgs.close()
+    return out
 
 
 def time_accumulate(ctx, solver, stream, reps=5) -> float:
@@ -334,6 +423,10 @@ def main():
     ap.add_argument("--views", type=int, default=N_VIEWS_10M)
     ap.add_argument("--cpu-views", type=int, default=20000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-detect", action="store_true")
+    ap.add_argument("--det-images", type=int, default=500)
+    ap.add_argument("--det-reps", type=int, default=2)
+    ap.add_argument("--det-cpu-images", type=int, default=24)
     args = ap.parse_args()
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
