@@ -173,19 +173,8 @@ def run_gpu(args):
     stream = torch.cuda.current_stream()
     ctx = lm.Context(local_rank, stream=stream.cuda_stream)
 
-    tensors = {}
-
-    class _Arr:
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
-
-    def allreduce(ptr, count, op, strm):
-        key = (ptr, count)
-        t = tensors.get(key)
-        if t is None:
-            t = torch.as_tensor(_Arr(ptr, count), device=f"cuda:{local_rank}")
-            tensors[key] = t
-        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM)
+    from ezcalib_b200 import dist as ezdist
+    allreduce = ezdist.make_allreduce(f"cuda:{local_rank}") if world > 1 else None
 
     if world > 1:
         ctx.set_allreduce(allreduce, rank, world)

@@ -164,3 +164,65 @@ def test_covariance_matches_dense_inverse(ctx):
 def test_no_device_message_is_loud():
     from ezcalib_b200 import _lib
     assert _lib.lib().ezc_num_dist(5) == 8
+
+
+def test_view_sharded_solve_matches_single_rank(ctx):
+    """Two ranks (threads, each with its own context/stream on the one GPU) own half of the views each; the packed
+    partial reduced systems are merged through the ezc_set_allreduce callback.  Result must equal the 1-rank solve."""
+    import threading
+
+    import torch
+
+    from ezcalib_b200 import dist as ezdist, lm
+    model, mono = "radtan5", True
+    mid = synth.MODEL_ID[model]
+    tgt = synth.chessboard_target(7, 10, 0.05)
+    P = synth.make_lm_problem(model, mono, 41, tgt, 1280, 1024, seed=21, drop_fraction=0.05)
+    ref = lm.lm_mono(ctx, mid, mono, P.obs, P.target, P.width, P.height, P.focal_init, P.pp_init, P.dist_init, P.poses_init)
+    world = 2
+    barrier = threading.Barrier(world)
+    slots = [None] * world
+    results = [None] * world
+    errors = []
+
+    def rank_main(rank):
+        try:
+            c = lm.Context(0)
+            b, e = ezdist.shard_range(P.obs.shape[0], rank, world)
+
+            def allreduce(ptr, count, op, stream):
+                c.synchronize()
+                t = torch.as_tensor(ezdist._CudaArray(ptr, count), device="cuda:0")
+                slots[rank] = t.cpu().numpy().copy()
+                barrier.wait()
+                tot = np.maximum(slots[0], slots[1]) if op == 1 else slots[0] + slots[1]  # fixed rank order
+                barrier.wait()
+                t.copy_(torch.from_numpy(tot))
+                torch.cuda.synchronize()
+
+            c.set_allreduce(allreduce, rank, world)
+            s = lm.LmSolver(c, mid, mono, P.obs[b:e], P.target, P.width, P.height, n_blocks_global=P.obs.shape[0])
+            s.set_params(P.focal_init, P.pp_init, P.dist_init, P.poses_init[b:e])
+            summ = []
+            for mask in ((1, 0, 0), (1, 0, 1), (1, 1, 1)):
+                summ.append(s.solve(*mask)[0])
+            f, pp, d, poses = s.get_params()
+            results[rank] = (f, pp, d, poses, s.frame_rmse(), summ)
+            s.close(); c.close()
+        except Exception as ex:  # pragma: no cover
+            errors.append(ex)
+            barrier.abort()
+
+    ths = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in ths: t.start()
+    for t in ths: t.join(timeout=300)
+    assert not errors, errors
+    for r in range(world):
+        f, pp, d, poses, rmse, summ = results[r]
+        assert [s["iterations"] for s in summ] == [s["iterations"] for s in ref[5]]
+        assert _rel(f, ref[0]) <= 1e-9 and _rel(pp, ref[1]) <= 1e-9
+        assert np.max(np.abs(d - ref[2])) <= 1e-9
+        b, e = ezdist.shard_range(P.obs.shape[0], r, world)
+        assert np.max(np.abs(poses - ref[3][b:e])) <= 1e-9
+        assert np.max(np.abs(rmse - ref[4][b:e])) <= 1e-9
+    assert np.array_equal(results[0][0], results[1][0])  # both ranks hold identical shared parameters
