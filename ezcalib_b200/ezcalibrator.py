@@ -1,0 +1,138 @@
+"""Host-side orchestration mirroring the reference's EZCalibrator / Camera / CalibFrame
+(/root/reference/include/ezcalibrator.hpp, camera.hpp): frame selection (skip rule), the mono 3-stage calibration and
+the multi-camera extrinsic calibration, expressed over the GPU entry points.  Only bookkeeping happens here."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import lm, synth
+
+
+@dataclass
+class CalibFrame:
+    """camera.hpp:14-33"""
+    img_name: str
+    corners_px: np.ndarray          # [n_pts, 2] float32 (cv::Point2f), (-1,-1) = missing
+    T_world_2_cam: np.ndarray       # [7] qx qy qz qw tx ty tz
+    rmse_err: float = -1.0
+
+
+@dataclass
+class Camera:
+    """camera.hpp:35-69 (state only)."""
+    model: str
+    use_mono_focal: bool
+    width: int
+    height: int
+    focal: np.ndarray
+    pp: np.ndarray
+    dist: np.ndarray
+    frames: list = field(default_factory=list)
+    T_cam0_2_cam: np.ndarray | None = None
+
+
+def replay_skip_rule(found_flags) -> list[int]:
+    """EZCalibrator::runCalibration's image loop (/root/reference/src/ezcalibrator.cpp:39-59): returns the indices of the
+    images the reference would have processed, given the per-image detection result of ALL images (detectTarget is a
+    pure function of the image, so detecting everything in one batch and replaying the rule is equivalent).
+    After a failure the iterator skips nb_consec_bad/2 further images (the reference can step past end(); we stop)."""
+    out = []
+    n = len(found_flags)
+    i = 0
+    bad = 0
+    while i < n:
+        out.append(i)
+        if found_flags[i]:
+            bad = 0
+        else:
+            bad += 1
+            i += bad // 2
+        i += 1
+    return out
+
+
+def compute_calibration(ctx: lm.Context, cam: Camera, target: np.ndarray):
+    """EZCalibrator::computeCalibration's optimisation (ezcalibrator.cpp:105-291): 3 staged solves, parameters written
+    back into the camera / frames, rmse_err filled."""
+    obs = np.stack([f.corners_px for f in cam.frames]).astype(np.float32)
+    poses = np.stack([f.T_world_2_cam for f in cam.frames])
+    f, pp, d, poses, rmse, summ = lm.lm_mono(ctx, synth.MODEL_ID[cam.model], cam.use_mono_focal, obs, target, cam.width,
+                                              cam.height, cam.focal, cam.pp, cam.dist, poses)
+    cam.focal, cam.pp, cam.dist = f, pp, d
+    for fr, p, r in zip(cam.frames, poses, rmse):
+        fr.T_world_2_cam = p
+        fr.rmse_err = float(r)
+    return summ
+
+
+def build_multicam_problem(cameras: list[Camera], target: np.ndarray):
+    """Problem set-up of EZCalibrator::runMultiCameraCalib (ezcalibrator.cpp:631-785): returns
+    (obs [n_cams-1, n_frames0*n_pts, 2], pts [n_frames0*n_pts, 3], init extrinsics [n_cams-1, 7], n_good_pairs).
+    Reproduces the reference's initialisation quirk Q3: the 'median' for camera i is taken over copies of the relative
+    pose of cam0's frame #i (indexed with the CAMERA index, :680)."""
+    cam0 = cameras[0]
+    n_pts = target.shape[0]
+    n0 = len(cam0.frames)
+    pts = np.concatenate([synth.transform(f.T_world_2_cam, target) for f in cam0.frames], axis=0)
+    obs = np.full((len(cameras) - 1, n0 * n_pts, 2), -1.0, np.float32)
+    init = np.zeros((len(cameras) - 1, 7))
+    n_good = 0
+    for i in range(1, len(cameras)):
+        camj = cameras[i]
+        logs = []
+        for _ in range(n0):
+            if i >= n0:
+                raise IndexError("reference indexes cam0.m_v_calib_frames[camera index] out of range (quirk Q3)")
+            f0 = cam0.frames[i]
+            if f0.rmse_err > 1.0:
+                continue
+            for fj in camj.frames:
+                if f0.img_name == fj.img_name:
+                    n_good += 1
+                    logs.append(synth.se3_log(synth.se3_mul(fj.T_world_2_cam, synth.se3_inverse(f0.T_world_2_cam))))
+                    break
+                elif fj.img_name > f0.img_name:
+                    break
+        if not logs:
+            raise IndexError("no usable frame pair for the extrinsic initialisation (the reference reads out of bounds here, :707-713)")
+        logs = np.sort(np.asarray(logs), axis=0)
+        med = logs[len(logs) // 2]
+        init[i - 1] = synth.se3_exp_left(med, np.array([0, 0, 0, 1.0, 0, 0, 0]))
+        for a, f0 in enumerate(cam0.frames):
+            if f0.rmse_err > 1.0:
+                continue
+            for fj in camj.frames:
+                if fj.rmse_err > 1.0:
+                    continue
+                if f0.img_name == fj.img_name:
+                    obs[i - 1, a * n_pts:(a + 1) * n_pts] = fj.corners_px
+                    break
+                elif fj.img_name > f0.img_name:
+                    break
+    return obs, pts, init, n_good
+
+
+def run_multicam_calib(ctx: lm.Context, cameras: list[Camera], target: np.ndarray):
+    """EZCalibrator::runMultiCameraCalib: intrinsics of cameras 1..N-1 frozen, one SE3 block T_ci_c0 per camera, one
+    joint solve (one trust region for all blocks, like the single ceres::Problem of the reference).
+    Limitation of this round: all cameras must share dist_model / use_mono_focal (true for every BASELINE config)."""
+    if len(cameras) < 2:
+        return None
+    m0, mono0 = cameras[1].model, cameras[1].use_mono_focal
+    if any(c.model != m0 or c.use_mono_focal != mono0 for c in cameras[1:]):
+        raise NotImplementedError("mixed distortion models across cameras are not supported yet")
+    obs, pts, init, n_good = build_multicam_problem(cameras, target)
+    cam1 = cameras[1]
+    solver = lm.LmSolver(ctx, synth.MODEL_ID[m0], mono0, obs, pts, cam1.width, cam1.height, pts_period=pts.shape[0], cams_per_block=True)
+    focal = np.concatenate([c.focal for c in cameras[1:]])
+    pp = np.concatenate([c.pp for c in cameras[1:]])
+    dist = np.concatenate([c.dist for c in cameras[1:]])
+    solver.set_params(focal, pp, dist, init)
+    summ, _ = solver.solve(False, False, False)
+    _, _, _, ext = solver.get_params()
+    solver.close()
+    for c, e in zip(cameras[1:], ext):
+        c.T_cam0_2_cam = e
+    return dict(summary=summ, n_good_pairs=n_good, init=init, extrinsics=ext, obs=obs, pts=pts)

@@ -397,3 +397,43 @@ def render_view(pattern_fn, model: str, fx: float, fy: float, cx: float, cy: flo
     if noise_sigma > 0 and rng is not None:
         img = img + rng.normal(0.0, noise_sigma, size=img.shape)
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------- SE3 log / inverse / product
+def se3_inverse(pose: np.ndarray) -> np.ndarray:
+    q = pose[..., :4] * np.array([-1.0, -1.0, -1.0, 1.0])
+    t = -quat_rotate(q, pose[..., 4:])
+    return np.concatenate([q, t], axis=-1)
+
+
+def se3_mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    q = quat_mul(a[..., :4], b[..., :4])
+    q = q / np.linalg.norm(q, axis=-1, keepdims=True)
+    t = a[..., 4:] + quat_rotate(a[..., :4], b[..., 4:])
+    return np.concatenate([q, t], axis=-1)
+
+
+def se3_log(pose: np.ndarray) -> np.ndarray:
+    """Sophus::SE3d::log -> (upsilon, omega) for a single pose [7]."""
+    q = np.asarray(pose[:4], dtype=np.float64)
+    t = np.asarray(pose[4:], dtype=np.float64)
+    n2 = float(q[:3] @ q[:3])
+    n = math.sqrt(n2)
+    w = float(q[3])
+    if n2 < 1e-20:
+        two_atan = 2.0 / w - (2.0 / 3.0) * n2 / (w * w * w)
+        theta = 2.0 * n2 / w if False else two_atan * n
+    else:
+        if abs(w) < 1e-10:
+            two_atan = (math.pi if w >= 0 else -math.pi) / n
+        else:
+            two_atan = 2.0 * math.atan(n / w) / n
+        theta = two_atan * n
+    om = two_atan * q[:3]
+    Om = np.array([[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0]])
+    if abs(theta) < 1e-10:
+        Vinv = np.eye(3) - 0.5 * Om + (1.0 / 12.0) * (Om @ Om)
+    else:
+        half = 0.5 * theta
+        Vinv = np.eye(3) - 0.5 * Om + (1.0 - theta * math.cos(half) / (2.0 * math.sin(half))) / (theta * theta) * (Om @ Om)
+    return np.concatenate([Vinv @ t, om])

@@ -226,3 +226,42 @@ def test_view_sharded_solve_matches_single_rank(ctx):
         assert np.max(np.abs(poses - ref[3][b:e])) <= 1e-9
         assert np.max(np.abs(rmse - ref[4][b:e])) <= 1e-9
     assert np.array_equal(results[0][0], results[1][0])  # both ranks hold identical shared parameters
+
+
+def test_multicam_extrinsics_match_oracle(ctx):
+    """runMultiCameraCalib (ezcalibrator.cpp:631-844): 3-camera rig, frozen intrinsics, 2 SE3 extrinsic blocks."""
+    from ezcalib_b200 import ezcalibrator as E
+    rng = np.random.default_rng(9)
+    model, mono = "kannalabrandt", False
+    mid = synth.MODEL_ID[model]
+    W, H = 1920, 1080
+    tgt = synth.chessboard_target(7, 10, 0.05)
+    d = np.array(synth.GT_DIST[model])
+    f0, cx, cy = 600.0, W / 2 + 4, H / 2 - 3
+    poses0 = synth.sample_poses(np.random.Generator(np.random.Philox(key=3)), 14, tgt, model, f0, cx, cy, d, W, H, margin=250.0, tilt_sigma=0.2)
+    rel = [np.concatenate([synth.quat_from_rotvec(np.array([0.01, -0.02, 0.005])), [-0.12, 0.003, 0.002]]),
+           np.concatenate([synth.quat_from_rotvec(np.array([-0.015, 0.03, 0.01])), [0.11, -0.004, 0.006]])]
+    cams = []
+    for j in range(3):
+        focal = np.array([f0 * (1 + 0.01 * j), f0 * (1.002 + 0.01 * j)])
+        cam = E.Camera(model, mono, W, H, focal, np.array([cx + j, cy - j]), d * (1 + 0.05 * j))
+        for i in range(14):
+            if j > 0 and i in (2 + j, 9):
+                continue  # this camera missed the frame
+            Tj = poses0[i] if j == 0 else synth.se3_mul(rel[j - 1], poses0[i])
+            px = synth.project(model, focal[0], focal[1], cam.pp[0], cam.pp[1], cam.dist, Tj, tgt)
+            px = (px + rng.normal(0, 0.08, px.shape)).astype(np.float32)
+            px[rng.uniform(size=len(px)) < 0.05] = -1.0
+            Tn = synth.se3_exp_left(np.concatenate([rng.normal(0, 0.002, 3), rng.normal(0, 0.004, 3)]), Tj)
+            fr = E.CalibFrame(f"img_{i:04d}.png", px, Tn, rmse_err=0.2 if i != 5 else 1.7)
+            cam.frames.append(fr)
+        cams.append(cam)
+    out = E.run_multicam_calib(ctx, cams, tgt)
+    focal = np.concatenate([c.focal for c in cams[1:]]); pp = np.concatenate([c.pp for c in cams[1:]]); dist = np.concatenate([c.dist for c in cams[1:]])
+    res = O.solve(mid, mono, out["obs"], out["pts"], W, H, focal, pp, dist, out["init"], opt_focal=False, opt_pp=False, opt_dist=False,
+                  pts_period=out["pts"].shape[0], shared_per_block=True)
+    assert out["summary"]["iterations"] == res[4]["iterations"]
+    assert out["summary"]["n_residual_blocks"] == res[4]["n_residual_blocks"] > 1000
+    assert np.max(np.abs(out["extrinsics"] - res[3])) <= 1e-9
+    for j in range(2):  # recovered extrinsics close to the rig's ground truth
+        assert np.max(np.abs(cams[j + 1].T_cam0_2_cam - rel[j])) < 2e-2  # poses of cam0 carry noise
