@@ -1,0 +1,739 @@
+// chessboard.cu -- batched chessboard detection on the GPU (half (a), chessboard path).
+//
+// Replaces ChessboardCalibDetector::detectTarget (/root/reference/include/target_detectors/chessboard_detector.hpp:27-50):
+//   cv::findChessboardCorners(img, Size(nb_cols-1, nb_rows-1), corners,
+//                             ADAPTIVE_THRESH + NORMALIZE_IMAGE + FILTER_QUADS + FAST_CHECK)
+//   + cv::cornerSubPix(img, corners, (5,5), (-1,-1), {COUNT+EPS, 100, 0.05}).
+// The algorithm lives in OpenCV (un-vendored; "OpenCV 3 or 4", README.md:67); it is restated against the OpenCV 4.13
+// behaviour observed in this image (cv2 4.13.0), see cb_logic.h and tests/test_cb_logic.py.
+//
+// Structure: the image-level passes run as data-parallel kernels over the whole batch -- histogram binarisation,
+// 3x3 dilation, white frame, union-find labelling (black 4-connected = the "holes" cv::findContours(RETR_CCOMP) reports,
+// white 8-connected = their parents), one thread per hole for Suzuki border following (CHAIN_APPROX_SIMPLE) and for
+// approxPolyDP/quad filtering -- and the small, irregular quad-graph logic (neighbour linking, grouping, ordering,
+// corner extraction; a few dozen quads) runs with one thread per image from cb_logic.h.  The attempt loop of
+// cv::findChessboardCorners (8 dilations of the histogram-binarised image, then 6 adaptive thresholds x 8 dilations on
+// the equalised image) is driven by the host for all images of the batch in lock-step; images that are done drop out.
+// Known deviation: CALIB_CB_FAST_CHECK is an early-exit heuristic of OpenCV and is not evaluated (an image it would
+// reject goes through the full search and is then rejected by it).
+#include <algorithm>
+#include <vector>
+
+#include "cb_logic.h"
+#include "images.cuh"
+#include "scan_sort.cuh"
+
+namespace ezc {
+
+// ---------------------------------------------------------------------------------------------- histogram binarisation
+__global__ void cb_hist_kernel(const uint8_t* __restrict__ img, long long pitch, long long istride, int W, int H, int* __restrict__ hist) {
+  __shared__ int sh[256];
+  const int im = blockIdx.y;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const long long N = (long long)W * H;
+  const uint8_t* I = img + (long long)im * istride;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(p / W), x = (int)(p - (long long)y * W);
+    atomicAdd(&sh[I[(long long)y * pitch + x]], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) if (sh[i]) atomicAdd(&hist[im * 256 + i], sh[i]);
+}
+
+// icvBinarizationHistogramBased (calibinit.cpp): threshold from the smoothed histogram's maxima; one thread per image
+__global__ void cb_select_threshold_kernel(const int* __restrict__ hist_all, int n_img, int W, int H, int* __restrict__ thresh) {
+  const int im = blockIdx.x * blockDim.x + threadIdx.x;
+  if (im >= n_img) return;
+  const int* hist = hist_all + im * 256;
+  const int max_pix = W * H, max_pix1 = max_pix / 100;
+  int smooth[256], grad[256], maxpos[20];
+  for (int i = 0; i < 256; ++i) {
+    const int lo = i > 0 ? i - 1 : 0, hi = i < 255 ? i + 1 : 255;
+    int s = 0;
+    for (int k = lo; k <= hi; ++k) s += hist[k];
+    smooth[i] = s / 3;
+  }
+  grad[0] = 0; grad[255] = 0;
+  int prev = 0;
+  for (int i = 1; i < 255; ++i) {
+    int g = smooth[i - 1] - smooth[i + 1];
+    if (abs(g) < 100) g = (prev == 0) ? -100 : prev;
+    grad[i] = g;
+    prev = g;
+  }
+  int n = 0;
+  for (int i = 254; i > 2 && n < 20; --i) {
+    if (grad[i - 1] < 0 && grad[i] > 0) {
+      const int s = smooth[i - 1] + smooth[i] + smooth[i + 1];
+      if (!(s < max_pix1 && i < 64)) maxpos[n++] = i;
+    }
+  }
+  int t = 0;
+  if (n == 0) {
+    int acc = 0;
+    for (int i = 0; i < 256; ++i) { acc += hist[i]; if (acc > max_pix / 2) { t = i; break; } }
+  } else if (n == 1) {
+    t = maxpos[0] / 2;
+  } else if (n == 2) {
+    t = (maxpos[0] + maxpos[1]) / 2;
+  } else {
+    int idx_acc = 0, acc = 0;
+    for (int i = 255; i > 0; --i) { acc += hist[i]; if (acc > max_pix / 18) { idx_acc = i; break; } }
+    int idx_bg = 0, bright = maxpos[0];
+    for (int k = 0; k < n - 1; ++k) {
+      idx_bg = k + 1;
+      if (maxpos[k] < idx_acc) break;
+      bright = maxpos[k];
+    }
+    int maxval = hist[maxpos[idx_bg]];
+    if (maxpos[idx_bg] >= 250 && idx_bg + 1 < n) { idx_bg++; maxval = hist[maxpos[idx_bg]]; }
+    for (int k = idx_bg + 1; k < n; ++k) if (hist[maxpos[k]] >= maxval) { maxval = hist[maxpos[k]]; idx_bg = k; }
+    const int dist2 = (bright - maxpos[idx_bg]) / 2;
+    t = bright - dist2;
+  }
+  thresh[im] = t;
+}
+
+__global__ void cb_binarize_kernel(const uint8_t* __restrict__ img, long long pitch, long long istride, int W, int H, int n_img,
+                                   const int* __restrict__ thresh, const int* __restrict__ active, uint8_t* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long N = (long long)W * H;
+  if (gid >= N * n_img) return;
+  const int im = (int)(gid / N);
+  if (active && !active[im]) return;
+  const int p = (int)(gid - (long long)im * N);
+  const int y = p / W, x = p - y * W;
+  const uint8_t v = img[(long long)im * istride + (long long)y * pitch + x];
+  const int t = thresh[im];
+  out[gid] = t > 0 ? (v >= t ? 255 : 0) : v;
+}
+
+// cv::dilate(src, dst, Mat(), Point(-1,-1), 1): 3x3 max, pixels outside the image are ignored
+__global__ void cb_dilate_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int W, int H, int n_img,
+                                 const int* __restrict__ active) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long N = (long long)W * H;
+  if (gid >= N * n_img) return;
+  const int im = (int)(gid / N);
+  if (active && !active[im]) return;
+  const int p = (int)(gid - (long long)im * N);
+  const int y = p / W, x = p - y * W;
+  const uint8_t* S = src + (long long)im * N;
+  uint8_t m = 0;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= H) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= W) continue;
+      const uint8_t v = S[(long long)yy * W + xx];
+      m = v > m ? v : m;
+    }
+  }
+  dst[gid] = m;
+}
+
+// rectangle(img, (0,0), (W-1,H-1), 255, 3, LINE_8): a 3-pixel white frame (checked against cv2)
+__global__ void cb_frame_kernel(uint8_t* __restrict__ img, int W, int H, int n_img, const int* __restrict__ active) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long N = (long long)W * H;
+  if (gid >= N * n_img) return;
+  const int im = (int)(gid / N);
+  if (active && !active[im]) return;
+  const int p = (int)(gid - (long long)im * N);
+  const int y = p / W, x = p - y * W;
+  if (x < 3 || y < 3 || x >= W - 3 || y >= H - 3) img[gid] = 255;
+}
+
+// ---------------------------------------------------------------------------------------------- labelling
+// One union-find over all pixels: black pixels connect 4-way (holes of cv::findContours), white pixels 8-way.
+// label = smallest linear index of the component = its raster-first pixel (where the border following starts).
+__device__ __forceinline__ int cbl_find(const int* L, int x) {
+  int p = L[x];
+  while (p != x) { x = p; p = L[x]; }
+  return x;
+}
+__device__ __forceinline__ void cbl_union(int* L, int a, int b) {
+  bool done = false;
+  while (!done) {
+    a = cbl_find(L, a);
+    b = cbl_find(L, b);
+    if (a < b) { const int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+    else if (b < a) { const int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+    else done = true;
+  }
+}
+__global__ void cb_label_init_kernel(int* __restrict__ L, long long total, long long N, const int* __restrict__ active) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  if (active && !active[gid / N]) return;
+  L[gid] = (int)gid;
+}
+__global__ void cb_label_union_kernel(const uint8_t* __restrict__ bin, int* __restrict__ L, int W, int H, int n_img,
+                                      const int* __restrict__ active) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long N = (long long)W * H;
+  if (gid >= N * n_img) return;
+  const int im = (int)(gid / N);
+  if (active && !active[im]) return;
+  const int p = (int)(gid - (long long)im * N);
+  const int y = p / W, x = p - y * W;
+  const bool white = bin[gid] != 0;
+  if (x + 1 < W && (bin[gid + 1] != 0) == white) cbl_union(L, (int)gid, (int)gid + 1);
+  if (y + 1 < H) {
+    if ((bin[gid + W] != 0) == white) cbl_union(L, (int)gid, (int)gid + W);
+    if (white) {
+      if (x + 1 < W && bin[gid + W + 1] != 0) cbl_union(L, (int)gid, (int)gid + W + 1);
+      if (x > 0 && bin[gid + W - 1] != 0) cbl_union(L, (int)gid, (int)gid + W - 1);
+    }
+  }
+}
+__global__ void cb_label_flatten_kernel(const uint8_t* __restrict__ bin, int* __restrict__ L, long long total, long long N,
+                                        const int* __restrict__ active, int* __restrict__ hole_flag) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  if (active && !active[gid / N]) { hole_flag[gid] = 0; return; }
+  const int r = cbl_find(L, (int)gid);
+  L[gid] = r;
+  hole_flag[gid] = (bin[gid] == 0 && r == (int)gid) ? 1 : 0;  // raster-first pixel of a black component
+}
+__global__ void cb_hole_list_kernel(const int* __restrict__ flag_scan, const uint8_t* __restrict__ bin, const int* __restrict__ L,
+                                    long long total, int* __restrict__ hole_start) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  if (bin[gid] == 0 && L[gid] == (int)gid) hole_start[flag_scan[gid]] = (int)gid;
+}
+
+// ---------------------------------------------------------------------------------------------- border following
+// icvFetchContour for a hole border with CHAIN_APPROX_SIMPLE (contours.cpp): starts at the foreground pixel left of the
+// hole's raster-first pixel, emits a vertex whenever the chain direction changes.
+struct HoleInfo {
+  int start;       // global linear index of the hole's first (black) pixel
+  int n_pts;       // vertices of the simple-approximated border (-1: too long)
+  int minx, miny, maxx, maxy;
+  int parent;      // label of the enclosing white component
+  int offset;      // into the point pool
+  int quad_ok;
+  cb::Pt quad[4];
+};
+
+template <bool STORE>
+__global__ void cb_trace_kernel(const uint8_t* __restrict__ bin, const int* __restrict__ L, int W, int H, int n_holes,
+                                HoleInfo* __restrict__ holes, cb::Pt* __restrict__ pool, int max_pts) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_holes) return;
+  HoleInfo& hi = holes[h];
+  if (STORE && (hi.n_pts <= 0 || hi.offset < 0)) return;
+  const long long N = (long long)W * H;
+  const int im = (int)(hi.start / N);
+  const int p0 = (int)(hi.start - (long long)im * N);
+  const uint8_t* B = bin + (long long)im * N;
+  const int y0 = p0 / W, x0 = p0 % W - 1;  // origin: the white pixel left of the first hole pixel (frame => x0 >= 2)
+  const int DX[8] = {1, 1, 0, -1, -1, -1, 0, 1}, DY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+  auto val = [&](int x, int y) -> bool { return B[(long long)y * W + x] != 0; };
+  int n = 0, minx = x0, maxx = x0, miny = y0, maxy = y0;
+  cb::Pt* out = STORE ? pool + hi.offset : nullptr;
+  int s = 0, s_end = 0;
+  do { s = (s - 1) & 7; } while (!val(x0 + DX[s], y0 + DY[s]) && s != s_end);
+  if (s == s_end && !val(x0 + DX[s], y0 + DY[s])) {
+    if (STORE) out[0] = cb::Pt{x0, y0};
+    n = 1;
+  } else {
+    const int i1x = x0 + DX[s], i1y = y0 + DY[s];
+    int i3x = x0, i3y = y0, prev_s = s ^ 4;
+    int x = x0, y = y0;
+    for (;;) {
+      int i4x, i4y;
+      for (;;) {
+        ++s;
+        i4x = i3x + DX[s & 7]; i4y = i3y + DY[s & 7];
+        if (val(i4x, i4y)) break;
+      }
+      s &= 7;
+      if (s != prev_s) {
+        if (STORE) { if (n < hi.n_pts) out[n] = cb::Pt{x, y}; }
+        ++n;
+        minx = x < minx ? x : minx; maxx = x > maxx ? x : maxx; miny = y < miny ? y : miny; maxy = y > maxy ? y : maxy;
+        prev_s = s;
+      }
+      x += DX[s]; y += DY[s];
+      if (i4x == x0 && i4y == y0 && i3x == i1x && i3y == i1y) break;
+      i3x = i4x; i3y = i4y;
+      s = (s + 4) & 7;
+      if (!STORE && n > max_pts) { n = -1; break; }
+    }
+  }
+  if (!STORE) {
+    hi.n_pts = n;
+    hi.minx = minx; hi.maxx = maxx; hi.miny = miny; hi.maxy = maxy;
+    hi.parent = L[(long long)im * N + (long long)y0 * W + x0];
+    hi.quad_ok = 0;
+    // only contours that can become a quad get storage: bounding rect area >= 25 and a sane vertex count
+    const bool want = n >= 4 && (maxx - minx + 1) * (maxy - miny + 1) >= 25;
+    hi.offset = want ? 0 : -1;
+  }
+}
+__global__ void cb_hole_init_kernel(const int* __restrict__ hole_start, int n_holes, HoleInfo* __restrict__ holes, int* __restrict__ need) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_holes) return;
+  holes[h].start = hole_start[h];
+  holes[h].n_pts = 0; holes[h].offset = -1; holes[h].quad_ok = 0;
+  need[h] = 0;
+}
+__global__ void cb_hole_need_kernel(const HoleInfo* __restrict__ holes, int n_holes, int* __restrict__ need) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_holes) return;
+  need[h] = (holes[h].offset >= 0 && holes[h].n_pts > 0) ? 3 * holes[h].n_pts + 8 : 0;  // contour + 2 approx buffers
+}
+__global__ void cb_hole_offset_kernel(HoleInfo* __restrict__ holes, int n_holes, const int* __restrict__ need_scan) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_holes) return;
+  if (holes[h].offset >= 0) holes[h].offset = need_scan[h];
+}
+// approxPolyDP levels 1..7 + convexity + FILTER_QUADS tests: one thread per hole
+__global__ void cb_quad_kernel(HoleInfo* __restrict__ holes, int n_holes, cb::Pt* __restrict__ pool, int* __restrict__ stack_pool) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_holes) return;
+  HoleInfo& hi = holes[h];
+  if (hi.offset < 0 || hi.n_pts <= 0) return;
+  cb::Pt* c = pool + hi.offset;
+  cb::Pt* ta = c + hi.n_pts + 2;
+  cb::Pt* tb = ta + hi.n_pts + 2;
+  int* stack = stack_pool + (size_t)hi.offset * 2;  // >= 4*n + 16 ints per hole
+  cb::Pt q[4];
+  if (cb::contour_to_quad(c, hi.n_pts, ta, tb, stack, q)) {
+    hi.quad_ok = 1;
+    for (int i = 0; i < 4; ++i) hi.quad[i] = q[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- per-image quad logic
+struct ImageState {
+  int found;            // processQuads succeeded in some attempt
+  int prev_sqr_size;
+  int n_quads;
+  int hole_begin, hole_end;
+};
+
+__global__ void cb_hole_ranges_kernel(const HoleInfo* __restrict__ holes, int n_holes, long long N, int n_img, ImageState* __restrict__ st) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_holes) return;
+  const int im = (int)(holes[h].start / N);
+  if (h == 0 || (int)(holes[h - 1].start / N) != im) st[im].hole_begin = h;
+  if (h == n_holes - 1 || (int)(holes[h + 1].start / N) != im) st[im].hole_end = h + 1;
+}
+
+__global__ void cb_process_kernel(const HoleInfo* __restrict__ holes, ImageState* __restrict__ st, const int* __restrict__ active,
+                                  int n_img, int pw, int ph, int dilations, cb::Work* __restrict__ works, int* __restrict__ scratch,
+                                  cb::Ptf* __restrict__ corners_out) {
+  const int im = blockIdx.x * blockDim.x + threadIdx.x;
+  if (im >= n_img) return;
+  if (!active[im]) return;
+  cb::Work& w = works[im];
+  ImageState& S = st[im];
+  // generateQuads, second half: the parent contour with the most quads wins (CALIB_CB_FILTER_QUADS)
+  int boardIdx = -1, boardCount = 0, total = 0;
+  for (int h = S.hole_begin; h < S.hole_end; ++h) {
+    if (!holes[h].quad_ok) continue;
+    ++total;
+    const int p = holes[h].parent;
+    int cnt = 0;
+    for (int g = S.hole_begin; g <= h; ++g) if (holes[g].quad_ok && holes[g].parent == p) ++cnt;
+    if (boardIdx != p && (boardIdx < 0 || boardCount < cnt)) { boardIdx = p; boardCount = cnt; }
+    else if (boardIdx == p) boardCount = cnt;
+  }
+  w.n_quads = 0;
+  w.max_quads = total * 3 > 2 ? total * 3 : 2;
+  if (w.max_quads > cb::kMaxQuads) w.max_quads = cb::kMaxQuads;
+  w.pw = pw; w.ph = ph;
+  for (int h = S.hole_begin; h < S.hole_end; ++h) {
+    if (!holes[h].quad_ok || holes[h].parent != boardIdx) continue;
+    if (w.n_quads >= w.max_quads) break;
+    cb::add_quad(w, holes[h].quad, dilations);
+  }
+  S.n_quads = w.n_quads;
+  int n_out = 0, prev = S.prev_sqr_size;
+  cb::Ptf* out = corners_out + (size_t)im * pw * ph;
+  // process_quads writes partial corner sets too; keep them in a scratch area and copy on success only
+  cb::Ptf* tmp = reinterpret_cast<cb::Ptf*>(w.hull);
+  const bool ok = cb::process_quads(w, tmp, &n_out, &prev, scratch + (size_t)im * cb::kMaxQuads * 4);
+  S.prev_sqr_size = prev;
+  if (ok) {
+    for (int i = 0; i < pw * ph; ++i) out[i] = tmp[i];
+    S.found = 1;
+  }
+}
+
+// final checks of cv::findChessboardCorners after a successful attempt: board monotony, 8-px border, even/even flip
+__global__ void cb_finalize_kernel(ImageState* __restrict__ st, int n_img, int pw, int ph, int W, int H, cb::Ptf* __restrict__ corners,
+                                   uint8_t* __restrict__ found_out) {
+  const int im = blockIdx.x * blockDim.x + threadIdx.x;
+  if (im >= n_img) return;
+  cb::Ptf* c = corners + (size_t)im * pw * ph;
+  bool found = st[im].found != 0;
+  if (found) found = cb::check_board_monotony(c, pw, ph);
+  if (found) {
+    const int BORDER = 8;
+    for (int k = 0; k < pw * ph; ++k)
+      if (c[k].x <= BORDER || c[k].x > W - BORDER || c[k].y <= BORDER || c[k].y > H - BORDER) { found = false; break; }
+  }
+  if (found && (ph & 1) == 0 && (pw & 1) == 0) {
+    const int last_row = (ph - 1) * pw;
+    const double dy0 = c[last_row].y - c[0].y;
+    if (dy0 < 0) {
+      const int n = pw * ph;
+      for (int i = 0; i < n / 2; i++) { const cb::Ptf t = c[i]; c[i] = c[n - i - 1]; c[n - i - 1] = t; }
+    }
+  }
+  found_out[im] = found ? 1 : 0;
+  if (!found) for (int k = 0; k < pw * ph; ++k) c[k] = cb::Ptf{0.f, 0.f};
+}
+
+// ---------------------------------------------------------------------------------------------- fallback image ops
+// cv::equalizeHist LUT from the histogram (one thread per image)
+__global__ void cb_equalize_lut_kernel(const int* __restrict__ hist_all, int n_img, int total, uint8_t* __restrict__ lut_all) {
+  const int im = blockIdx.x * blockDim.x + threadIdx.x;
+  if (im >= n_img) return;
+  const int* hist = hist_all + im * 256;
+  uint8_t* lut = lut_all + im * 256;
+  int i = 0;
+  while (!hist[i]) ++i;
+  if (hist[i] == total) { for (int k = 0; k < 256; ++k) lut[k] = (uint8_t)i; return; }
+  const float scale = (256 - 1.f) / (total - hist[i]);
+  int sum = 0;
+  for (int k = 0; k <= i; ++k) lut[k] = 0;
+  for (++i; i < 256; ++i) {
+    sum += hist[i];
+    const int v = __float2int_rn(sum * scale);
+    lut[i] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+  }
+}
+__global__ void cb_apply_lut_kernel(const uint8_t* __restrict__ img, long long pitch, long long istride, int W, int H, int n_img,
+                                    const uint8_t* __restrict__ lut, uint8_t* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long N = (long long)W * H;
+  if (gid >= N * n_img) return;
+  const int im = (int)(gid / N);
+  const int p = (int)(gid - (long long)im * N);
+  const int y = p / W, x = p - y * W;
+  out[gid] = lut[im * 256 + img[(long long)im * istride + (long long)y * pitch + x]];
+}
+// cv::adaptiveThreshold(MEAN_C, BINARY): separable box sums with replicated border, per-image block size
+__global__ void cb_box_h_kernel(const uint8_t* __restrict__ src, int W, int H, int n_img, const int* __restrict__ block, int* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long N = (long long)W * H;
+  if (gid >= N * n_img) return;
+  const int im = (int)(gid / N);
+  const int b = block[im];
+  if (b <= 0) return;
+  const int p = (int)(gid - (long long)im * N);
+  const int y = p / W, x = p - y * W;
+  const uint8_t* S = src + (long long)im * N + (long long)y * W;
+  const int r = b / 2;
+  int s = 0;
+  for (int d = -r; d <= r; ++d) s += S[min(W - 1, max(0, x + d))];
+  out[gid] = s;
+}
+__global__ void cb_box_v_thresh_kernel(const uint8_t* __restrict__ src, const int* __restrict__ hs, int W, int H, int n_img,
+                                       const int* __restrict__ block, const int* __restrict__ delta, uint8_t* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long N = (long long)W * H;
+  if (gid >= N * n_img) return;
+  const int im = (int)(gid / N);
+  const int b = block[im];
+  if (b <= 0) return;
+  const int p = (int)(gid - (long long)im * N);
+  const int y = p / W, x = p - y * W;
+  const int* S = hs + (long long)im * N;
+  const int r = b / 2;
+  int s = 0;
+  for (int d = -r; d <= r; ++d) s += S[(long long)min(H - 1, max(0, y + d)) * W + x];
+  const float scale = (float)(1.0 / ((double)b * b));
+  int mean = __float2int_rn((float)s * scale);
+  mean = mean > 255 ? 255 : mean;
+  out[gid] = ((int)src[gid] - mean > -delta[im]) ? 255 : 0;
+}
+__global__ void cb_copy_active_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long N, int n_img, const int* __restrict__ flag) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= N * n_img) return;
+  if (flag[gid / N]) dst[gid] = src[gid];
+}
+__global__ void cb_gather_corners_kernel(const cb::Ptf* __restrict__ corners, const uint8_t* __restrict__ found, int n_img, int npts,
+                                         float2* __restrict__ out, int* __restrict__ img_index) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * npts) return;
+  const int im = i / npts;
+  // images without a board keep a harmless in-image position so that the refinement kernel can run over the batch
+  out[i] = found[im] ? make_float2(corners[i].x, corners[i].y) : make_float2(16.f, 16.f);
+  img_index[i] = im;
+}
+__global__ void cb_scatter_corners_kernel(const float2* __restrict__ refined, const uint8_t* __restrict__ found, int n_img, int npts,
+                                          float2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * npts) return;
+  out[i] = found[i / npts] ? refined[i] : make_float2(0.f, 0.f);
+}
+
+}  // namespace ezc
+
+using namespace ezc;
+
+namespace {
+
+struct CbPools {
+  DevBuf hist, thresh, bin0, bin1, prevbin, eq, lut, labels, flags, scan_tmp, total, hole_start, holes, need, pool, stack_pool;
+  DevBuf works, scratch, state, active, corners, found, block, delta, hsum, sub_corners, sub_idx, refresh;
+  HostPinned h;
+};
+
+CbPools& cb_pools(ezc_context* ctx) {
+  if (!ctx->cb_pools) {
+    ctx->cb_pools = new CbPools();
+    ctx->cb_pools_free = [](void* p) { delete static_cast<CbPools*>(p); };
+  }
+  return *static_cast<CbPools*>(ctx->cb_pools);
+}
+
+#define CB_LAUNCH(kernel, n, ...)                                                     \
+  do {                                                                                \
+    if ((n) > 0) {                                                                    \
+      const long long _n = (n);                                                       \
+      kernel<<<(unsigned)((_n + 255) / 256), 256, 0, ctx->stream>>>(__VA_ARGS__);     \
+      EZC_CUDA(cudaGetLastError());                                                   \
+      ctx->kernel_launches++;                                                         \
+    }                                                                                 \
+  } while (0)
+
+// One attempt for all active images: quads from `bin` (already dilated + framed) -> processQuads.
+ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, int H, int nb, int pw, int ph, int dilations) {
+  const long long N = (long long)W * H, total = N * nb;
+  const int* active = P.active.as<int>();
+  int* d_tot = P.total.as<int>();
+  CB_LAUNCH(cb_label_init_kernel, total, P.labels.as<int>(), total, N, active);
+  CB_LAUNCH(cb_label_union_kernel, total, bin, P.labels.as<int>(), W, H, nb, active);
+  CB_LAUNCH(cb_label_flatten_kernel, total, bin, P.labels.as<int>(), total, N, active, P.flags.as<int>());
+  if (ezc_status st = exclusive_scan_i32(ctx, P.flags.as<int>(), P.flags.as<int>(), total, P.scan_tmp, d_tot)) return st;
+  EZC_CUDA(cudaMemcpyAsync(P.h.p, d_tot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int nH = *P.h.as<int>();
+  ImageState* st = P.state.as<ImageState>();
+  if (nH > 0) {
+    EZC_CUDA(P.hole_start.reserve(sizeof(int) * (size_t)nH));
+    EZC_CUDA(P.holes.reserve(sizeof(HoleInfo) * (size_t)nH));
+    EZC_CUDA(P.need.reserve(sizeof(int) * ((size_t)nH + 1)));
+    // active-only hole list: inactive images have no flags set
+    CB_LAUNCH(cb_hole_list_kernel, total, P.flags.as<int>(), bin, P.labels.as<int>(), total, P.hole_start.as<int>());
+    CB_LAUNCH(cb_hole_init_kernel, nH, P.hole_start.as<int>(), nH, P.holes.as<HoleInfo>(), P.need.as<int>());
+    CB_LAUNCH(cb_trace_kernel<false>, nH, bin, P.labels.as<int>(), W, H, nH, P.holes.as<HoleInfo>(), nullptr, cb::kMaxContourPts);
+    CB_LAUNCH(cb_hole_need_kernel, nH, P.holes.as<HoleInfo>(), nH, P.need.as<int>());
+    if (ezc_status s2 = exclusive_scan_i32(ctx, P.need.as<int>(), P.need.as<int>(), nH, P.scan_tmp, d_tot)) return s2;
+    EZC_CUDA(cudaMemcpyAsync(P.h.p, d_tot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int nPts = *P.h.as<int>();
+    EZC_CUDA(P.pool.reserve(sizeof(cb::Pt) * ((size_t)nPts + 16)));
+    EZC_CUDA(P.stack_pool.reserve(sizeof(int) * 2 * ((size_t)nPts + 16)));
+    CB_LAUNCH(cb_hole_offset_kernel, nH, P.holes.as<HoleInfo>(), nH, P.need.as<int>());
+    CB_LAUNCH(cb_trace_kernel<true>, nH, bin, P.labels.as<int>(), W, H, nH, P.holes.as<HoleInfo>(), P.pool.as<cb::Pt>(), cb::kMaxContourPts);
+    CB_LAUNCH(cb_quad_kernel, nH, P.holes.as<HoleInfo>(), nH, P.pool.as<cb::Pt>(), P.stack_pool.as<int>());
+    CB_LAUNCH(cb_hole_ranges_kernel, nH, P.holes.as<HoleInfo>(), nH, N, nb, st);
+  }
+  CB_LAUNCH(cb_process_kernel, nb, P.holes.as<HoleInfo>(), st, active, nb, pw, ph, dilations, P.works.as<cb::Work>(), P.scratch.as<int>(),
+            P.corners.as<cb::Ptf>());
+  return EZC_OK;
+}
+
+// refresh the host copy of the per-image state; recompute the device `active` flags (= not yet found)
+ezc_status sync_state(ezc_context* ctx, CbPools& P, int nb, std::vector<ImageState>& h_state, std::vector<int>& h_active, bool reset_ranges) {
+  EZC_CUDA(cudaMemcpyAsync(h_state.data(), P.state.p, sizeof(ImageState) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < nb; ++i) {
+    h_active[i] = h_state[i].found ? 0 : 1;
+    if (reset_ranges) { h_state[i].hole_begin = 0; h_state[i].hole_end = 0; }
+  }
+  if (reset_ranges) EZC_CUDA(cudaMemcpyAsync(P.state.p, h_state.data(), sizeof(ImageState) * nb, cudaMemcpyHostToDevice, ctx->stream));
+  EZC_CUDA(cudaMemcpyAsync(P.active.p, h_active.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+  return EZC_OK;
+}
+
+ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, int nb, int pw, int ph, bool final_subpix,
+                            float2* d_corners_out, uint8_t* d_found_out) {
+  CbPools& P = cb_pools(ctx);
+  const int W = imgs->width, H = imgs->height;
+  const long long N = (long long)W * H, total = N * nb;
+  const uint8_t* d_img = imgs->d + (long long)img0 * imgs->image_stride;
+  const int npts = pw * ph;
+  EZC_CUDA(P.hist.reserve(sizeof(int) * 256 * nb)); EZC_CUDA(P.thresh.reserve(sizeof(int) * nb));
+  EZC_CUDA(P.bin0.reserve(total)); EZC_CUDA(P.bin1.reserve(total));
+  EZC_CUDA(P.labels.reserve(sizeof(int) * total)); EZC_CUDA(P.flags.reserve(sizeof(int) * (total + 1)));
+  EZC_CUDA(P.total.reserve(64)); EZC_CUDA(P.h.reserve(4096));
+  EZC_CUDA(P.works.reserve(sizeof(cb::Work) * (size_t)nb)); EZC_CUDA(P.scratch.reserve(sizeof(int) * cb::kMaxQuads * 4 * (size_t)nb));
+  EZC_CUDA(P.state.reserve(sizeof(ImageState) * nb)); EZC_CUDA(P.active.reserve(sizeof(int) * nb));
+  EZC_CUDA(P.corners.reserve(sizeof(cb::Ptf) * (size_t)npts * nb)); EZC_CUDA(P.found.reserve(nb));
+  EZC_CUDA(P.holes.reserve(sizeof(HoleInfo) * 16));
+  std::vector<ImageState> h_state(nb, ImageState{0, 0, 0, 0, 0});
+  std::vector<int> h_active(nb, 1);
+  EZC_CUDA(cudaMemcpyAsync(P.state.p, h_state.data(), sizeof(ImageState) * nb, cudaMemcpyHostToDevice, ctx->stream));
+  EZC_CUDA(cudaMemcpyAsync(P.active.p, h_active.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+  EZC_CUDA(cudaMemsetAsync(P.hist.p, 0, sizeof(int) * 256 * nb, ctx->stream));
+  {
+    dim3 grid(std::max(1, std::min(64, (int)((N + 255) / 256))), nb);
+    cb_hist_kernel<<<grid, 256, 0, ctx->stream>>>(d_img, imgs->pitch, imgs->image_stride, W, H, P.hist.as<int>());
+    EZC_CUDA(cudaGetLastError());
+    ctx->kernel_launches++;
+  }
+  CB_LAUNCH(cb_select_threshold_kernel, nb, P.hist.as<int>(), nb, W, H, P.thresh.as<int>());
+  uint8_t* b0 = P.bin0.as<uint8_t>();
+  uint8_t* b1 = P.bin1.as<uint8_t>();
+  CB_LAUNCH(cb_binarize_kernel, total, d_img, imgs->pitch, imgs->image_stride, W, H, nb, P.thresh.as<int>(), (const int*)nullptr, b0);
+  // ---- phase 1: histogram-binarised image, 8 cumulative dilations (the frame of the previous pass is dilated too)
+  int remaining = nb;
+  for (int dil = 0; dil <= 7 && remaining > 0; ++dil) {
+    CB_LAUNCH(cb_dilate_kernel, total, b0, b1, W, H, nb, P.active.as<int>());
+    std::swap(b0, b1);
+    CB_LAUNCH(cb_frame_kernel, total, b0, W, H, nb, P.active.as<int>());
+    if (ezc_status st = run_attempt(ctx, P, b0, W, H, nb, pw, ph, dil)) return st;
+    if (ezc_status st = sync_state(ctx, P, nb, h_state, h_active, true)) return st;
+    remaining = 0;
+    for (int i = 0; i < nb; ++i) remaining += h_active[i];
+    // the other ping-pong buffer must hold the current image for the images still active: both buffers are kept in
+    // step by always dilating from b0 into b1 for ACTIVE images only (inactive images are never read again)
+  }
+  // ---- phase 2: equalised image, 6 adaptive thresholds x 8 dilations, for the images still without a board
+  const bool phase2_ran = remaining > 0;
+  std::vector<int> h_phase2(h_active);
+  if (remaining > 0) {
+    EZC_CUDA(P.eq.reserve(total)); EZC_CUDA(P.lut.reserve(256 * nb)); EZC_CUDA(P.prevbin.reserve(total));
+    EZC_CUDA(P.block.reserve(sizeof(int) * nb)); EZC_CUDA(P.delta.reserve(sizeof(int) * nb)); EZC_CUDA(P.hsum.reserve(sizeof(int) * total));
+    EZC_CUDA(P.refresh.reserve(sizeof(int) * nb));
+    CB_LAUNCH(cb_equalize_lut_kernel, nb, P.hist.as<int>(), nb, (int)N, P.lut.as<uint8_t>());
+    CB_LAUNCH(cb_apply_lut_kernel, total, d_img, imgs->pitch, imgs->image_stride, W, H, nb, P.lut.as<uint8_t>(), P.eq.as<uint8_t>());
+    std::vector<int> prev_sqr(nb, 0), h_block(nb), h_delta(nb), h_refresh(nb), prev_block(nb);
+    // prev_sqr_size is reset to 0 when the fallback starts
+    for (int i = 0; i < nb; ++i) h_state[i].prev_sqr_size = 0;
+    EZC_CUDA(cudaMemcpyAsync(P.state.p, h_state.data(), sizeof(ImageState) * nb, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* th = P.bin0.as<uint8_t>();       // thresh_img (gets the frame)
+    uint8_t* tmp = P.bin1.as<uint8_t>();
+    uint8_t* prevb = P.prevbin.as<uint8_t>(); // prev_thresh_img (no frame)
+    for (int k = 0; k < 6 && remaining > 0; ++k) {
+      std::fill(prev_block.begin(), prev_block.end(), -1);
+      for (int dil = 0; dil <= 7 && remaining > 0; ++dil) {
+        for (int i = 0; i < nb; ++i) {
+          const int ps = h_state[i].prev_sqr_size;
+          int bs = (int)lrint(ps == 0 ? std::min(W, H) * (k % 2 == 0 ? 0.2 : 0.1) : ps * 2.0);
+          bs |= 1;
+          const bool fresh = h_active[i] && bs != prev_block[i];
+          h_refresh[i] = fresh ? 1 : 0;
+          h_block[i] = fresh ? bs : 0;
+          h_delta[i] = (k / 2) * 5;
+          if (h_active[i]) prev_block[i] = bs;
+        }
+        EZC_CUDA(cudaMemcpyAsync(P.block.p, h_block.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+        EZC_CUDA(cudaMemcpyAsync(P.delta.p, h_delta.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+        EZC_CUDA(cudaMemcpyAsync(P.refresh.p, h_refresh.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+        // images with a new block size: adaptive threshold, then `dil` dilations -> prev_thresh_img
+        bool any_fresh = false, any_old = false;
+        for (int i = 0; i < nb; ++i) { any_fresh |= h_refresh[i] != 0; any_old |= (h_active[i] && !h_refresh[i]); }
+        if (any_fresh) {
+          CB_LAUNCH(cb_box_h_kernel, total, P.eq.as<uint8_t>(), W, H, nb, P.block.as<int>(), P.hsum.as<int>());
+          CB_LAUNCH(cb_box_v_thresh_kernel, total, P.eq.as<uint8_t>(), P.hsum.as<int>(), W, H, nb, P.block.as<int>(), P.delta.as<int>(), tmp);
+          for (int d = 0; d < dil; ++d) {
+            CB_LAUNCH(cb_dilate_kernel, total, tmp, th, W, H, nb, P.refresh.as<int>());
+            CB_LAUNCH(cb_copy_active_kernel, total, th, tmp, N, nb, P.refresh.as<int>());
+          }
+          CB_LAUNCH(cb_copy_active_kernel, total, tmp, prevb, N, nb, P.refresh.as<int>());
+        }
+        if (any_old && dil > 0) {
+          // same block size as before: one more dilation of prev_thresh_img
+          std::vector<int> h_old(nb);
+          for (int i = 0; i < nb; ++i) h_old[i] = (h_active[i] && !h_refresh[i]) ? 1 : 0;
+          EZC_CUDA(cudaMemcpyAsync(P.refresh.p, h_old.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+          CB_LAUNCH(cb_dilate_kernel, total, prevb, tmp, W, H, nb, P.refresh.as<int>());
+          CB_LAUNCH(cb_copy_active_kernel, total, tmp, prevb, N, nb, P.refresh.as<int>());
+        }
+        CB_LAUNCH(cb_copy_active_kernel, total, prevb, th, N, nb, P.active.as<int>());
+        CB_LAUNCH(cb_frame_kernel, total, th, W, H, nb, P.active.as<int>());
+        // no edge-length compensation in the fallback (empirically what cv2 4.13 does: exact on all phase-2 fixtures)
+        if (ezc_status st = run_attempt(ctx, P, th, W, H, nb, pw, ph, 0)) return st;
+        if (ezc_status st = sync_state(ctx, P, nb, h_state, h_active, true)) return st;
+        remaining = 0;
+        for (int i = 0; i < nb; ++i) remaining += h_active[i];
+      }
+    }
+  }
+  // ---- final checks, internal (2,2) refinement on the image the search ended on, then the reference's (5,5) refinement
+  CB_LAUNCH(cb_finalize_kernel, nb, P.state.as<ImageState>(), nb, pw, ph, W, H, P.corners.as<cb::Ptf>(), P.found.as<uint8_t>());
+  EZC_CUDA(P.sub_corners.reserve(sizeof(float2) * (size_t)npts * nb)); EZC_CUDA(P.sub_idx.reserve(sizeof(int) * (size_t)npts * nb));
+  CB_LAUNCH(cb_gather_corners_kernel, (long long)nb * npts, P.corners.as<cb::Ptf>(), P.found.as<uint8_t>(), nb, npts, P.sub_corners.as<float2>(),
+            P.sub_idx.as<int>());
+  // cv::cornerSubPix(img, corners, (2,2), (-1,-1), {EPS+MAX_ITER, 15, 0.1}): `img` is the original image when the board was
+  // found on the histogram-binarised image, the equalised copy when the fallback had to run (NORMALIZE_IMAGE).
+  ezc_images view;
+  view.ctx = ctx; view.n = nb; view.width = W; view.height = H;
+  if (!phase2_ran) {
+    view.d = d_img; view.pitch = imgs->pitch; view.image_stride = imgs->image_stride;
+  } else {
+    // dense "used" image: equalised for the images that entered the fallback, original otherwise (LUT = identity)
+    std::vector<uint8_t> ident(256 * (size_t)nb);
+    for (int i = 0; i < nb; ++i) for (int k = 0; k < 256; ++k) ident[(size_t)i * 256 + k] = (uint8_t)k;
+    std::vector<uint8_t> h_lut(256 * (size_t)nb);
+    EZC_CUDA(cudaMemcpyAsync(h_lut.data(), P.lut.p, 256 * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
+    EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < nb; ++i) if (!h_phase2[i]) std::copy(&ident[(size_t)i * 256], &ident[(size_t)i * 256] + 256, &h_lut[(size_t)i * 256]);
+    EZC_CUDA(cudaMemcpyAsync(P.lut.p, h_lut.data(), 256 * (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
+    CB_LAUNCH(cb_apply_lut_kernel, total, d_img, imgs->pitch, imgs->image_stride, W, H, nb, P.lut.as<uint8_t>(), P.eq.as<uint8_t>());
+    view.d = P.eq.as<uint8_t>(); view.pitch = W; view.image_stride = N;
+  }
+  if (ezc_status st = subpix_device(ctx, &view, P.sub_corners.as<float2>(), P.sub_idx.as<int>(), nb * npts, 2, 2, 15, 0.1)) return st;
+  if (final_subpix) {
+    // chessboard_detector.hpp:39-40 -- on the ORIGINAL image
+    view.d = d_img; view.pitch = imgs->pitch; view.image_stride = imgs->image_stride;
+    if (ezc_status st = subpix_device(ctx, &view, P.sub_corners.as<float2>(), P.sub_idx.as<int>(), nb * npts, 5, 5, 100, 0.05)) return st;
+  }
+  CB_LAUNCH(cb_scatter_corners_kernel, (long long)nb * npts, P.sub_corners.as<float2>(), P.found.as<uint8_t>(), nb, npts,
+            d_corners_out + (size_t)img0 * npts);
+  EZC_CUDA(cudaMemcpyAsync(d_found_out + img0, P.found.p, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+  return EZC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+ezc_status ezc_find_chessboard_corners_batch(ezc_context* ctx, const ezc_images* imgs, int32_t pattern_w, int32_t pattern_h,
+                                             int32_t final_subpix, float* corners_out, uint8_t* found_out, int32_t max_images_in_flight) {
+  EZC_CHECK(ctx && imgs && corners_out && found_out, EZC_ERR_INVALID, "ezc_find_chessboard_corners_batch: null argument");
+  EZC_CHECK(pattern_w > 2 && pattern_h > 2, EZC_ERR_INVALID, "ezc_find_chessboard_corners_batch: both pattern dimensions must be > 2 (OpenCV rule)");
+  EZC_CHECK(pattern_w * pattern_h <= cb::kMaxQuads, EZC_ERR_INVALID, "ezc_find_chessboard_corners_batch: pattern too large");
+  EZC_CHECK(imgs->width >= 16 && imgs->height >= 16, EZC_ERR_INVALID, "ezc_find_chessboard_corners_batch: image too small");
+  EZC_CUDA(cudaSetDevice(ctx->device));
+  const int n = imgs->n;
+  if (n == 0) return EZC_OK;
+  const long long N = (long long)imgs->width * imgs->height;
+  int sub = (int)std::max<long long>(1, std::min<long long>((1LL << 30) / N, 2LL * 1024 * 1024 * 1024 / (N * 16)));
+  sub = std::min(sub, 256);
+  if (max_images_in_flight > 0) sub = std::min(sub, max_images_in_flight);
+  sub = std::min(sub, n);
+  const int npts = pattern_w * pattern_h;
+  ezc::DevBuf d_corners, d_found;
+  EZC_CUDA(d_corners.reserve(sizeof(float2) * (size_t)n * npts));
+  EZC_CUDA(d_found.reserve((size_t)n));
+  for (int i0 = 0; i0 < n; i0 += sub) {
+    const int nb = std::min(sub, n - i0);
+    if (ezc_status st = detect_sub_batch(ctx, imgs, i0, nb, pattern_w, pattern_h, final_subpix != 0, d_corners.as<float2>(), d_found.as<uint8_t>()))
+      return st;
+  }
+  EZC_CUDA(cudaMemcpyAsync(corners_out, d_corners.p, sizeof(float2) * (size_t)n * npts, cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaMemcpyAsync(found_out, d_found.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return EZC_OK;
+}
+
+// ChessboardCalibDetector::detectTarget for every image: nb_rows x nb_cols SQUARES (the reference's constructor
+// arguments), i.e. pattern (nb_cols-1) x (nb_rows-1) inner corners, findChessboardCorners + cornerSubPix (5,5).
+ezc_status ezc_detect_chessboard_batch(ezc_context* ctx, const ezc_images* imgs, int32_t nb_rows, int32_t nb_cols, float* corners_out,
+                                       uint8_t* found_out, int32_t max_images_in_flight) {
+  return ezc_find_chessboard_corners_batch(ctx, imgs, nb_cols - 1, nb_rows - 1, 1, corners_out, found_out, max_images_in_flight);
+}
+
+}  // extern "C"

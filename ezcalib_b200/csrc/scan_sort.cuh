@@ -12,7 +12,7 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;                       // per thread
 constexpr int kScanTile = kScanThreads * kScanItems;  // 2048
 
-__global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(const int* __restrict__ in, long long n, int* __restrict__ sums) {
+static __global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(const int* __restrict__ in, long long n, int* __restrict__ sums) {
   __shared__ int sh[kScanThreads / 32];
   const long long base = (long long)blockIdx.x * kScanTile;
   int v = 0;
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(const int
 }
 
 // single block: in-place exclusive scan of sums[nb]; writes the grand total to *total (if not null)
-__global__ void __launch_bounds__(1024) scan_sums_kernel(int* __restrict__ sums, int nb, int* __restrict__ total) {
+static __global__ void __launch_bounds__(1024) scan_sums_kernel(int* __restrict__ sums, int nb, int* __restrict__ total) {
   __shared__ int sh[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(int* __restrict__ sums,
   if (threadIdx.x == 0 && total) *total = carry;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const int* __restrict__ in, int* __restrict__ out, long long n,
+static __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const int* __restrict__ in, int* __restrict__ out, long long n,
                                                                    const int* __restrict__ sums) {
   __shared__ int sh[kScanThreads / 32];
   const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;

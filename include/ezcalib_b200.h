@@ -89,6 +89,19 @@ ezc_status ezc_render_targets(ezc_context* ctx, int32_t pattern, int32_t rows, i
 ezc_status ezc_corner_subpix(ezc_context* ctx, const ezc_images* imgs, float* corners, const int32_t* image_index,
                              int32_t n, int32_t win_w, int32_t win_h, int32_t max_iter, double eps);
 
+/* ChessboardCalibDetector::detectTarget (/root/reference/include/target_detectors/chessboard_detector.hpp:27-50) for
+ * every image of the batch: cv::findChessboardCorners(img, Size(nb_cols-1, nb_rows-1), ADAPTIVE_THRESH + NORMALIZE_IMAGE +
+ * FILTER_QUADS + FAST_CHECK) followed by cv::cornerSubPix (5,5)/(100,0.05).  nb_rows / nb_cols count SQUARES, like the
+ * reference's constructor.  corners_out: HOST float [n_images][(nb_cols-1)*(nb_rows-1)][2] in OpenCV's corner order
+ * (zeros when not found); found_out: HOST [n_images]. */
+ezc_status ezc_detect_chessboard_batch(ezc_context* ctx, const ezc_images* imgs, int32_t nb_rows, int32_t nb_cols,
+                                       float* corners_out, uint8_t* found_out, int32_t max_images_in_flight);
+/* The same search with an explicit inner-corner pattern; final_subpix = 0 returns what cv::findChessboardCorners itself
+ * returns (after its internal (2,2) refinement), for parity tests against cv2. */
+ezc_status ezc_find_chessboard_corners_batch(ezc_context* ctx, const ezc_images* imgs, int32_t pattern_w, int32_t pattern_h,
+                                             int32_t final_subpix, float* corners_out, uint8_t* found_out,
+                                             int32_t max_images_in_flight);
+
 /* AprilTagCalibDetector::detectTarget (/root/reference/include/target_detectors/aprilgrid_detector.hpp:30-71) for
  * every image of the batch: AprilTags::TagDetector(tagCodes36h11).extractTags
  * (/root/reference/thirdparty/ethz_apriltag2/src/TagDetector.cc:40-586), cv::cornerSubPix (5,5)/(100,0.05) on the

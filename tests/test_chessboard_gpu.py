@@ -1,0 +1,56 @@
+"""GPU: batched chessboard detection against the REAL OpenCV (cv2 is present on the GPU box too) and the committed
+golden vectors: found flag and corner ORDER bit-exact, corners after the reference's cornerSubPix within 0.01 px on
+clean renders (north_star tolerance); heavily degraded fixtures are held to 0.05 px."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "chessboard_golden.npz"))
+NAMES = [str(n) for n in G["names"]]
+BIG = [n for n in NAMES if G[n + "_img"].shape == (480, 640)]
+
+
+def test_batch_raw_corners_match_cv2_golden(ctx):
+    from ezcalib_b200 import detect
+    imgs = detect.Images(ctx, np.stack([G[n + "_img"] for n in BIG]))
+    found, corners = detect.find_chessboard_corners(ctx, imgs, (9, 6), final_subpix=False)
+    imgs.close()
+    for k, n in enumerate(BIG):
+        assert bool(found[k]) == bool(G[n + "_found"]), n
+        if found[k]:
+            d = np.abs(corners[k] - G[n + "_raw"]).max(axis=1)
+            assert (d <= 1e-4).mean() >= 0.9, (n, d.max())
+            if n.startswith("render"):
+                assert d.max() <= 1e-4, (n, d.max())
+
+
+def test_detect_target_matches_reference_calls(ctx):
+    """ChessboardCalibDetector::detectTarget == findChessboardCorners + cornerSubPix(5,5): live cv2 on the same images."""
+    cv2 = pytest.importorskip("cv2")
+    from ezcalib_b200 import detect
+    flags = cv2.CALIB_CB_ADAPTIVE_THRESH + cv2.CALIB_CB_NORMALIZE_IMAGE + cv2.CALIB_CB_FILTER_QUADS + cv2.CALIB_CB_FAST_CHECK
+    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 100, 0.05)
+    imgs = detect.Images(ctx, np.stack([G[n + "_img"] for n in BIG]))
+    found, corners = detect.detect_chessboard(ctx, imgs, 7, 10)   # 7 x 10 squares -> 9 x 6 inner corners
+    imgs.close()
+    for k, n in enumerate(BIG):
+        img = G[n + "_img"]
+        ok, c = cv2.findChessboardCorners(img, (9, 6), flags=flags)
+        assert bool(ok) == bool(found[k]), n
+        if ok:
+            ref = cv2.cornerSubPix(img, c, (5, 5), (-1, -1), crit).reshape(-1, 2)
+            tol = 0.01 if n.startswith("render") else 0.05
+            assert np.abs(corners[k] - ref).max() <= tol, (n, np.abs(corners[k] - ref).max())
+            assert np.abs(corners[k] - G[n + "_final"]).max() <= tol
+        else:
+            assert np.all(corners[k] == 0)
+
+
+def test_small_noise_image_is_rejected(ctx):
+    from ezcalib_b200 import detect
+    imgs = detect.Images(ctx, G["noise_img"])
+    found, corners = detect.detect_chessboard(ctx, imgs, 7, 10)
+    imgs.close()
+    assert not found[0]
