@@ -263,7 +263,19 @@ CB_HD inline void add_quad(Work& w, const Pt q[4], int dilations) {
 }
 
 // ------------------------------------------------------------------------------------------ findQuadNeighbors
-CB_HD inline void find_quad_neighbors(Work& w) {
+// `Par` lets a warp share the two O(n_quads) scans of every (quad, corner) step without changing the sequential
+// semantics: candidates are strided over the lanes and reduced with the tie-break of the sequential loop (first in
+// (k, j) order among equal distances); the state is written by lane 0.  SerialPar (host, tests) is the plain loop.
+struct SerialPar {
+  CB_HD int lane() const { return 0; }
+  CB_HD int lanes() const { return 1; }
+  CB_HD void sync() const {}
+  CB_HD void reduce_min(float&, int&) const {}
+  CB_HD bool any(bool v) const { return v; }
+};
+
+template <class Par>
+CB_HD inline void find_quad_neighbors(Work& w, const Par& par) {
   const float thresh_scale = 1.f;
   const int nq = w.n_quads;
   for (int idx = 0; idx < nq; idx++) {
@@ -271,23 +283,26 @@ CB_HD inline void find_quad_neighbors(Work& w) {
     for (int i = 0; i < 4; i++) {
       if (cur.nb[i] >= 0) continue;
       float min_dist = FLT_MAX;
-      int closest_corner_idx = -1, closest_quad = -1;
+      int code = 0x7fffffff;  // k * 4 + j of the closest admissible corner
       const Ptf pt = w.corners[cur.corners[i]].pt;
-      for (int k = 0; k < nq; k++) {
+      const float cur_edge = cur.edge_len;
+      for (int k = par.lane(); k < nq; k += par.lanes()) {
         if (k == idx) continue;
         const Quad& qk = w.quads[k];
         for (int j = 0; j < 4; j++) {
           if (qk.nb[j] >= 0) continue;
           const Ptf o = w.corners[qk.corners[j]].pt;
           const float dist = normL2Sqrf(pt.x - o.x, pt.y - o.y);
-          if (dist < min_dist && dist <= cur.edge_len * thresh_scale && dist <= qk.edge_len * thresh_scale) {
-            const float ediff = fabsf(cur.edge_len - qk.edge_len);
-            if (ediff > 32 * cur.edge_len || ediff > 32 * qk.edge_len) continue;
-            closest_corner_idx = j; closest_quad = k; min_dist = dist;
+          if (dist < min_dist && dist <= cur_edge * thresh_scale && dist <= qk.edge_len * thresh_scale) {
+            const float ediff = fabsf(cur_edge - qk.edge_len);
+            if (ediff > 32 * cur_edge || ediff > 32 * qk.edge_len) continue;
+            code = k * 4 + j; min_dist = dist;
           }
         }
       }
-      if (closest_corner_idx >= 0 && min_dist < FLT_MAX) {
+      par.reduce_min(min_dist, code);
+      if (code != 0x7fffffff && min_dist < FLT_MAX) {
+        const int closest_quad = code >> 2, closest_corner_idx = code & 3;
         Quad& cq = w.quads[closest_quad];
         if (cur.count >= 4 || cq.count >= 4) continue;
         Corner& cc = w.corners[cq.corners[closest_corner_idx]];
@@ -300,27 +315,29 @@ CB_HD inline void find_quad_neighbors(Work& w) {
         if (j < 4) continue;
         for (j = 0; j < 4; j++) if (cq.nb[j] == idx) break;
         if (j < 4) continue;
-        // is some corner of a third quad closer to closest_corner than this one?
-        for (j = 0; j < nq; j++) {
-          if (j == idx || j == closest_quad) continue;
-          const Quad& q = w.quads[j];
-          int k = 0;
-          for (; k < 4; k++) {
+        // is some free corner of a third quad closer to closest_corner than this one?
+        bool blocked = false;
+        for (int q3 = par.lane(); q3 < nq && !blocked; q3 += par.lanes()) {
+          if (q3 == idx || q3 == closest_quad) continue;
+          const Quad& q = w.quads[q3];
+          for (int k = 0; k < 4; k++) {
             if (q.nb[k] < 0) {
               const Ptf o = w.corners[q.corners[k]].pt;
-              if (normL2Sqrf(cc.pt.x - o.x, cc.pt.y - o.y) < min_dist) break;
+              if (normL2Sqrf(cc.pt.x - o.x, cc.pt.y - o.y) < min_dist) { blocked = true; break; }
             }
           }
-          if (k < 4) break;
         }
-        if (j < nq) continue;
-        cc.pt.x = (pt.x + cc.pt.x) * 0.5f;
-        cc.pt.y = (pt.y + cc.pt.y) * 0.5f;
-        cur.count++;
-        cur.nb[i] = closest_quad;
-        cur.corners[i] = cq.corners[closest_corner_idx];
-        cq.count++;
-        cq.nb[closest_corner_idx] = idx;
+        if (par.any(blocked)) continue;
+        if (par.lane() == 0) {
+          cc.pt.x = (pt.x + cc.pt.x) * 0.5f;
+          cc.pt.y = (pt.y + cc.pt.y) * 0.5f;
+          cur.count++;
+          cur.nb[i] = closest_quad;
+          cur.corners[i] = cq.corners[closest_corner_idx];
+          cq.count++;
+          cq.nb[closest_corner_idx] = idx;
+        }
+        par.sync();
       }
     }
   }
@@ -752,10 +769,10 @@ CB_HD inline bool check_board_monotony(const Ptf* c, int pw, int ph) {
 
 // ------------------------------------------------------------------------------------------ processQuads
 // quads already in w (n_quads, max_quads set).  On success writes pw*ph corners to out_pts and returns true.
-CB_HD inline bool process_quads(Work& w, Ptf* out_pts, int* n_out_pts, int* prev_sqr_size, int* scratch) {
+// (find_quad_neighbors must have run)
+CB_HD inline bool process_groups(Work& w, Ptf* out_pts, int* n_out_pts, int* prev_sqr_size, int* scratch) {
   *n_out_pts = 0;
   if (w.n_quads <= 0) return false;
-  find_quad_neighbors(w);
   for (int group_idx = 0;; group_idx++) {
     find_connected_quads(w, group_idx);
     if (w.n_group == 0) break;
@@ -800,6 +817,13 @@ CB_HD inline bool process_quads(Work& w, Ptf* out_pts, int* n_out_pts, int* prev
     }
   }
   return false;
+}
+
+CB_HD inline bool process_quads(Work& w, Ptf* out_pts, int* n_out_pts, int* prev_sqr_size, int* scratch) {
+  *n_out_pts = 0;
+  if (w.n_quads <= 0) return false;
+  find_quad_neighbors(w, SerialPar());
+  return process_groups(w, out_pts, n_out_pts, prev_sqr_size, scratch);
 }
 
 }  // namespace cb

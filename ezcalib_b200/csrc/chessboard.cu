@@ -97,12 +97,13 @@ __global__ void cb_select_threshold_kernel(const int* __restrict__ hist_all, int
 
 __global__ void cb_binarize_kernel(const uint8_t* __restrict__ img, long long pitch, long long istride, int W, int H, int n_img,
                                    const int* __restrict__ thresh, const int* __restrict__ active, uint8_t* __restrict__ out) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long N = (long long)W * H;
-  if (gid >= N * n_img) return;
-  const int im = (int)(gid / N);
-  if (active && !active[im]) return;
-  const int p = (int)(gid - (long long)im * N);
+  if (cg >= N * n_img) return;
+  const int slot = (int)(cg / N);
+  const int im = active ? active[slot] : slot;   // `active` = compact list of image indices still searching
+  const int p = (int)(cg - (long long)slot * N);
+  const long long gid = (long long)im * N + p;
   const int y = p / W, x = p - y * W;
   const uint8_t v = img[(long long)im * istride + (long long)y * pitch + x];
   const int t = thresh[im];
@@ -112,12 +113,13 @@ __global__ void cb_binarize_kernel(const uint8_t* __restrict__ img, long long pi
 // cv::dilate(src, dst, Mat(), Point(-1,-1), 1): 3x3 max, pixels outside the image are ignored
 __global__ void cb_dilate_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int W, int H, int n_img,
                                  const int* __restrict__ active) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long N = (long long)W * H;
-  if (gid >= N * n_img) return;
-  const int im = (int)(gid / N);
-  if (active && !active[im]) return;
-  const int p = (int)(gid - (long long)im * N);
+  if (cg >= N * n_img) return;
+  const int slot = (int)(cg / N);
+  const int im = active ? active[slot] : slot;   // `active` = compact list of image indices still searching
+  const int p = (int)(cg - (long long)slot * N);
+  const long long gid = (long long)im * N + p;
   const int y = p / W, x = p - y * W;
   const uint8_t* S = src + (long long)im * N;
   uint8_t m = 0;
@@ -136,12 +138,13 @@ __global__ void cb_dilate_kernel(const uint8_t* __restrict__ src, uint8_t* __res
 
 // rectangle(img, (0,0), (W-1,H-1), 255, 3, LINE_8): a 3-pixel white frame (checked against cv2)
 __global__ void cb_frame_kernel(uint8_t* __restrict__ img, int W, int H, int n_img, const int* __restrict__ active) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long N = (long long)W * H;
-  if (gid >= N * n_img) return;
-  const int im = (int)(gid / N);
-  if (active && !active[im]) return;
-  const int p = (int)(gid - (long long)im * N);
+  if (cg >= N * n_img) return;
+  const int slot = (int)(cg / N);
+  const int im = active ? active[slot] : slot;   // `active` = compact list of image indices still searching
+  const int p = (int)(cg - (long long)slot * N);
+  const long long gid = (long long)im * N + p;
   const int y = p / W, x = p - y * W;
   if (x < 3 || y < 3 || x >= W - 3 || y >= H - 3) img[gid] = 255;
 }
@@ -165,19 +168,21 @@ __device__ __forceinline__ void cbl_union(int* L, int a, int b) {
   }
 }
 __global__ void cb_label_init_kernel(int* __restrict__ L, long long total, long long N, const int* __restrict__ active) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  if (active && !active[gid / N]) return;
+  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cg >= total) return;
+  const int slot = (int)(cg / N);
+  const long long gid = (long long)(active ? active[slot] : slot) * N + (cg - (long long)slot * N);
   L[gid] = (int)gid;
 }
 __global__ void cb_label_union_kernel(const uint8_t* __restrict__ bin, int* __restrict__ L, int W, int H, int n_img,
                                       const int* __restrict__ active) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long N = (long long)W * H;
-  if (gid >= N * n_img) return;
-  const int im = (int)(gid / N);
-  if (active && !active[im]) return;
-  const int p = (int)(gid - (long long)im * N);
+  if (cg >= N * n_img) return;
+  const int slot = (int)(cg / N);
+  const int im = active ? active[slot] : slot;   // `active` = compact list of image indices still searching
+  const int p = (int)(cg - (long long)slot * N);
+  const long long gid = (long long)im * N + p;
   const int y = p / W, x = p - y * W;
   const bool white = bin[gid] != 0;
   if (x + 1 < W && (bin[gid + 1] != 0) == white) cbl_union(L, (int)gid, (int)gid + 1);
@@ -191,18 +196,21 @@ __global__ void cb_label_union_kernel(const uint8_t* __restrict__ bin, int* __re
 }
 __global__ void cb_label_flatten_kernel(const uint8_t* __restrict__ bin, int* __restrict__ L, long long total, long long N,
                                         const int* __restrict__ active, int* __restrict__ hole_flag) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  if (active && !active[gid / N]) { hole_flag[gid] = 0; return; }
+  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cg >= total) return;
+  const int slot = (int)(cg / N);
+  const long long gid = (long long)(active ? active[slot] : slot) * N + (cg - (long long)slot * N);
   const int r = cbl_find(L, (int)gid);
   L[gid] = r;
-  hole_flag[gid] = (bin[gid] == 0 && r == (int)gid) ? 1 : 0;  // raster-first pixel of a black component
+  hole_flag[cg] = (bin[gid] == 0 && r == (int)gid) ? 1 : 0;  // raster-first pixel of a black component (compact index)
 }
 __global__ void cb_hole_list_kernel(const int* __restrict__ flag_scan, const uint8_t* __restrict__ bin, const int* __restrict__ L,
-                                    long long total, int* __restrict__ hole_start) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  if (bin[gid] == 0 && L[gid] == (int)gid) hole_start[flag_scan[gid]] = (int)gid;
+                                    long long total, long long N, const int* __restrict__ active, int* __restrict__ hole_start) {
+  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cg >= total) return;
+  const int slot = (int)(cg / N);
+  const long long gid = (long long)(active ? active[slot] : slot) * N + (cg - (long long)slot * N);
+  if (bin[gid] == 0 && L[gid] == (int)gid) hole_start[flag_scan[cg]] = (int)gid;
 }
 
 // ---------------------------------------------------------------------------------------------- border following
@@ -324,44 +332,85 @@ __global__ void cb_hole_ranges_kernel(const HoleInfo* __restrict__ holes, int n_
   if (h == n_holes - 1 || (int)(holes[h + 1].start / N) != im) st[im].hole_end = h + 1;
 }
 
-__global__ void cb_process_kernel(const HoleInfo* __restrict__ holes, ImageState* __restrict__ st, const int* __restrict__ active,
-                                  int n_img, int pw, int ph, int dilations, cb::Work* __restrict__ works, int* __restrict__ scratch,
-                                  cb::Ptf* __restrict__ corners_out) {
-  const int im = blockIdx.x * blockDim.x + threadIdx.x;
-  if (im >= n_img) return;
-  if (!active[im]) return;
+struct WarpPar {
+  __device__ int lane() const { return threadIdx.x & 31; }
+  __device__ int lanes() const { return 32; }
+  __device__ void sync() const { __syncwarp(); }
+  __device__ void reduce_min(float& d, int& code) const {
+    for (int m = 16; m >= 1; m >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, d, m);
+      const int oc = __shfl_xor_sync(0xffffffffu, code, m);
+      if (od < d || (od == d && oc < code)) { d = od; code = oc; }
+    }
+  }
+  __device__ bool any(bool v) const { return __any_sync(0xffffffffu, v) != 0; }
+};
+
+// one WARP per active image
+__global__ void __launch_bounds__(256) cb_process_kernel(const HoleInfo* __restrict__ holes, ImageState* __restrict__ st,
+                                                         const int* __restrict__ active, int n_img, int pw, int ph, int dilations,
+                                                         cb::Work* __restrict__ works, int* __restrict__ scratch_all,
+                                                         cb::Ptf* __restrict__ corners_out) {
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (slot >= n_img) return;
+  const int im = active[slot];
   cb::Work& w = works[im];
   ImageState& S = st[im];
-  // generateQuads, second half: the parent contour with the most quads wins (CALIB_CB_FILTER_QUADS)
-  int boardIdx = -1, boardCount = 0, total = 0;
-  for (int h = S.hole_begin; h < S.hole_end; ++h) {
-    if (!holes[h].quad_ok) continue;
-    ++total;
-    const int p = holes[h].parent;
-    int cnt = 0;
-    for (int g = S.hole_begin; g <= h; ++g) if (holes[g].quad_ok && holes[g].parent == p) ++cnt;
-    if (boardIdx != p && (boardIdx < 0 || boardCount < cnt)) { boardIdx = p; boardCount = cnt; }
-    else if (boardIdx == p) boardCount = cnt;
+  int* scratch = scratch_all + (size_t)im * cb::kMaxQuads * 4;
+  if (lane == 0) {
+    // generateQuads, second half: the parent contour with the most quads wins (CALIB_CB_FILTER_QUADS).  Counts per parent
+    // in an open-addressing table (keys = white-component labels).
+    constexpr int TS = 2048;
+    int* keys = scratch;
+    int* cnts = scratch + TS;
+    for (int i = 0; i < TS; ++i) { keys[i] = -1; cnts[i] = 0; }
+    int boardIdx = -1, boardCount = 0, total = 0, distinct = 0;
+    for (int h = S.hole_begin; h < S.hole_end; ++h) {
+      if (!holes[h].quad_ok) continue;
+      ++total;
+      const int p = holes[h].parent;
+      unsigned hsh = ((unsigned)p * 2654435761u) >> 21;  // 11 bits
+      int cnt = 0;
+      for (int probe = 0; probe < TS; ++probe) {
+        const int sl = (hsh + probe) & (TS - 1);
+        if (keys[sl] == p) { cnt = ++cnts[sl]; break; }
+        if (keys[sl] == -1) {
+          if (distinct < TS - 1) { keys[sl] = p; ++distinct; cnt = ++cnts[sl]; }
+          else cnt = 1;  // table full (thousands of distinct parents: noise); such a parent never wins
+          break;
+        }
+      }
+      if (boardIdx == p) boardCount = cnt;
+      else if (boardIdx < 0 || boardCount < cnt) { boardIdx = p; boardCount = cnt; }
+    }
+    w.n_quads = 0;
+    w.max_quads = total * 3 > 2 ? total * 3 : 2;
+    if (w.max_quads > cb::kMaxQuads) w.max_quads = cb::kMaxQuads;
+    w.pw = pw; w.ph = ph;
+    for (int h = S.hole_begin; h < S.hole_end; ++h) {
+      if (!holes[h].quad_ok || holes[h].parent != boardIdx) continue;
+      if (w.n_quads >= w.max_quads) break;
+      cb::add_quad(w, holes[h].quad, dilations);
+    }
+    S.n_quads = w.n_quads;
   }
-  w.n_quads = 0;
-  w.max_quads = total * 3 > 2 ? total * 3 : 2;
-  if (w.max_quads > cb::kMaxQuads) w.max_quads = cb::kMaxQuads;
-  w.pw = pw; w.ph = ph;
-  for (int h = S.hole_begin; h < S.hole_end; ++h) {
-    if (!holes[h].quad_ok || holes[h].parent != boardIdx) continue;
-    if (w.n_quads >= w.max_quads) break;
-    cb::add_quad(w, holes[h].quad, dilations);
-  }
-  S.n_quads = w.n_quads;
-  int n_out = 0, prev = S.prev_sqr_size;
-  cb::Ptf* out = corners_out + (size_t)im * pw * ph;
-  // process_quads writes partial corner sets too; keep them in a scratch area and copy on success only
-  cb::Ptf* tmp = reinterpret_cast<cb::Ptf*>(w.hull);
-  const bool ok = cb::process_quads(w, tmp, &n_out, &prev, scratch + (size_t)im * cb::kMaxQuads * 4);
-  S.prev_sqr_size = prev;
-  if (ok) {
-    for (int i = 0; i < pw * ph; ++i) out[i] = tmp[i];
-    S.found = 1;
+  __syncwarp();
+  // a complete board needs all its inner squares: fewer quads than that cannot succeed (and leave no trace in
+  // prev_sqr_size either), so the quad-graph stage is skipped
+  if (w.n_quads < ((pw - 1) * (ph - 1)) / 2) return;
+  cb::find_quad_neighbors(w, WarpPar());
+  __syncwarp();
+  if (lane == 0) {
+    int n_out = 0, prev = S.prev_sqr_size;
+    cb::Ptf* out = corners_out + (size_t)im * pw * ph;
+    cb::Ptf* tmp = reinterpret_cast<cb::Ptf*>(w.hull);  // partial corner sets are written too; copy on success only
+    const bool ok = cb::process_groups(w, tmp, &n_out, &prev, scratch);
+    S.prev_sqr_size = prev;
+    if (ok) {
+      for (int i = 0; i < pw * ph; ++i) out[i] = tmp[i];
+      S.found = 1;
+    }
   }
 }
 
@@ -420,14 +469,16 @@ __global__ void cb_apply_lut_kernel(const uint8_t* __restrict__ img, long long p
   out[gid] = lut[im * 256 + img[(long long)im * istride + (long long)y * pitch + x]];
 }
 // cv::adaptiveThreshold(MEAN_C, BINARY): separable box sums with replicated border, per-image block size
-__global__ void cb_box_h_kernel(const uint8_t* __restrict__ src, int W, int H, int n_img, const int* __restrict__ block, int* __restrict__ out) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void cb_box_h_kernel(const uint8_t* __restrict__ src, int W, int H, int n_img, const int* __restrict__ list,
+                                const int* __restrict__ block, int* __restrict__ out) {
+  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long N = (long long)W * H;
-  if (gid >= N * n_img) return;
-  const int im = (int)(gid / N);
+  if (cg >= N * n_img) return;
+  const int slot = (int)(cg / N);
+  const int im = list[slot];
   const int b = block[im];
-  if (b <= 0) return;
-  const int p = (int)(gid - (long long)im * N);
+  const int p = (int)(cg - (long long)slot * N);
+  const long long gid = (long long)im * N + p;
   const int y = p / W, x = p - y * W;
   const uint8_t* S = src + (long long)im * N + (long long)y * W;
   const int r = b / 2;
@@ -436,14 +487,16 @@ __global__ void cb_box_h_kernel(const uint8_t* __restrict__ src, int W, int H, i
   out[gid] = s;
 }
 __global__ void cb_box_v_thresh_kernel(const uint8_t* __restrict__ src, const int* __restrict__ hs, int W, int H, int n_img,
-                                       const int* __restrict__ block, const int* __restrict__ delta, uint8_t* __restrict__ out) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                                       const int* __restrict__ list, const int* __restrict__ block, const int* __restrict__ delta,
+                                       uint8_t* __restrict__ out) {
+  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long N = (long long)W * H;
-  if (gid >= N * n_img) return;
-  const int im = (int)(gid / N);
+  if (cg >= N * n_img) return;
+  const int slot = (int)(cg / N);
+  const int im = list[slot];
   const int b = block[im];
-  if (b <= 0) return;
-  const int p = (int)(gid - (long long)im * N);
+  const int p = (int)(cg - (long long)slot * N);
+  const long long gid = (long long)im * N + p;
   const int y = p / W, x = p - y * W;
   const int* S = hs + (long long)im * N;
   const int r = b / 2;
@@ -454,10 +507,12 @@ __global__ void cb_box_v_thresh_kernel(const uint8_t* __restrict__ src, const in
   mean = mean > 255 ? 255 : mean;
   out[gid] = ((int)src[gid] - mean > -delta[im]) ? 255 : 0;
 }
-__global__ void cb_copy_active_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long N, int n_img, const int* __restrict__ flag) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= N * n_img) return;
-  if (flag[gid / N]) dst[gid] = src[gid];
+__global__ void cb_copy_active_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long N, int n_img, const int* __restrict__ list) {
+  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cg >= N * n_img) return;
+  const int slot = (int)(cg / N);
+  const long long gid = (long long)list[slot] * N + (cg - (long long)slot * N);
+  dst[gid] = src[gid];
 }
 __global__ void cb_gather_corners_kernel(const cb::Ptf* __restrict__ corners, const uint8_t* __restrict__ found, int n_img, int npts,
                                          float2* __restrict__ out, int* __restrict__ img_index) {
@@ -505,14 +560,23 @@ CbPools& cb_pools(ezc_context* ctx) {
     }                                                                                 \
   } while (0)
 
-// One attempt for all active images: quads from `bin` (already dilated + framed) -> processQuads.
-ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, int H, int nb, int pw, int ph, int dilations) {
-  const long long N = (long long)W * H, total = N * nb;
-  const int* active = P.active.as<int>();
+// Upload a compact list of image indices; returns its device pointer.
+ezc_status upload_list(ezc_context* ctx, DevBuf& buf, const std::vector<int>& list) {
+  EZC_CUDA(buf.reserve(sizeof(int) * std::max<size_t>(list.size(), 1)));
+  if (!list.empty()) EZC_CUDA(cudaMemcpyAsync(buf.p, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, ctx->stream));
+  return EZC_OK;
+}
+
+// One attempt for the images in `list` (device copy in P.active, n_act entries): quads from `bin` (already dilated +
+// framed) -> processQuads.  Per-pixel buffers are indexed by the REAL image index; only the hole flags are compact.
+ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, int H, int n_act, int pw, int ph, int dilations) {
+  if (n_act <= 0) return EZC_OK;
+  const long long N = (long long)W * H, total = N * n_act;
+  const int* list = P.active.as<int>();
   int* d_tot = P.total.as<int>();
-  CB_LAUNCH(cb_label_init_kernel, total, P.labels.as<int>(), total, N, active);
-  CB_LAUNCH(cb_label_union_kernel, total, bin, P.labels.as<int>(), W, H, nb, active);
-  CB_LAUNCH(cb_label_flatten_kernel, total, bin, P.labels.as<int>(), total, N, active, P.flags.as<int>());
+  CB_LAUNCH(cb_label_init_kernel, total, P.labels.as<int>(), total, N, list);
+  CB_LAUNCH(cb_label_union_kernel, total, bin, P.labels.as<int>(), W, H, n_act, list);
+  CB_LAUNCH(cb_label_flatten_kernel, total, bin, P.labels.as<int>(), total, N, list, P.flags.as<int>());
   if (ezc_status st = exclusive_scan_i32(ctx, P.flags.as<int>(), P.flags.as<int>(), total, P.scan_tmp, d_tot)) return st;
   EZC_CUDA(cudaMemcpyAsync(P.h.p, d_tot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   EZC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -522,8 +586,7 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
     EZC_CUDA(P.hole_start.reserve(sizeof(int) * (size_t)nH));
     EZC_CUDA(P.holes.reserve(sizeof(HoleInfo) * (size_t)nH));
     EZC_CUDA(P.need.reserve(sizeof(int) * ((size_t)nH + 1)));
-    // active-only hole list: inactive images have no flags set
-    CB_LAUNCH(cb_hole_list_kernel, total, P.flags.as<int>(), bin, P.labels.as<int>(), total, P.hole_start.as<int>());
+    CB_LAUNCH(cb_hole_list_kernel, total, P.flags.as<int>(), bin, P.labels.as<int>(), total, N, list, P.hole_start.as<int>());
     CB_LAUNCH(cb_hole_init_kernel, nH, P.hole_start.as<int>(), nH, P.holes.as<HoleInfo>(), P.need.as<int>());
     CB_LAUNCH(cb_trace_kernel<false>, nH, bin, P.labels.as<int>(), W, H, nH, P.holes.as<HoleInfo>(), nullptr, cb::kMaxContourPts);
     CB_LAUNCH(cb_hole_need_kernel, nH, P.holes.as<HoleInfo>(), nH, P.need.as<int>());
@@ -536,24 +599,23 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
     CB_LAUNCH(cb_hole_offset_kernel, nH, P.holes.as<HoleInfo>(), nH, P.need.as<int>());
     CB_LAUNCH(cb_trace_kernel<true>, nH, bin, P.labels.as<int>(), W, H, nH, P.holes.as<HoleInfo>(), P.pool.as<cb::Pt>(), cb::kMaxContourPts);
     CB_LAUNCH(cb_quad_kernel, nH, P.holes.as<HoleInfo>(), nH, P.pool.as<cb::Pt>(), P.stack_pool.as<int>());
-    CB_LAUNCH(cb_hole_ranges_kernel, nH, P.holes.as<HoleInfo>(), nH, N, nb, st);
+    CB_LAUNCH(cb_hole_ranges_kernel, nH, P.holes.as<HoleInfo>(), nH, N, 0, st);
   }
-  CB_LAUNCH(cb_process_kernel, nb, P.holes.as<HoleInfo>(), st, active, nb, pw, ph, dilations, P.works.as<cb::Work>(), P.scratch.as<int>(),
+  CB_LAUNCH(cb_process_kernel, (long long)n_act * 32, P.holes.as<HoleInfo>(), st, list, n_act, pw, ph, dilations, P.works.as<cb::Work>(), P.scratch.as<int>(),
             P.corners.as<cb::Ptf>());
   return EZC_OK;
 }
 
-// refresh the host copy of the per-image state; recompute the device `active` flags (= not yet found)
-ezc_status sync_state(ezc_context* ctx, CbPools& P, int nb, std::vector<ImageState>& h_state, std::vector<int>& h_active, bool reset_ranges) {
+// refresh the host copy of the per-image state and rebuild the compact list of images still searching
+ezc_status sync_state(ezc_context* ctx, CbPools& P, int nb, std::vector<ImageState>& h_state, std::vector<int>& list) {
   EZC_CUDA(cudaMemcpyAsync(h_state.data(), P.state.p, sizeof(ImageState) * nb, cudaMemcpyDeviceToHost, ctx->stream));
   EZC_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < nb; ++i) {
-    h_active[i] = h_state[i].found ? 0 : 1;
-    if (reset_ranges) { h_state[i].hole_begin = 0; h_state[i].hole_end = 0; }
-  }
-  if (reset_ranges) EZC_CUDA(cudaMemcpyAsync(P.state.p, h_state.data(), sizeof(ImageState) * nb, cudaMemcpyHostToDevice, ctx->stream));
-  EZC_CUDA(cudaMemcpyAsync(P.active.p, h_active.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
-  return EZC_OK;
+  std::vector<int> next;
+  for (int im : list) if (!h_state[im].found) next.push_back(im);
+  list.swap(next);
+  for (int i = 0; i < nb; ++i) { h_state[i].hole_begin = 0; h_state[i].hole_end = 0; }
+  EZC_CUDA(cudaMemcpyAsync(P.state.p, h_state.data(), sizeof(ImageState) * nb, cudaMemcpyHostToDevice, ctx->stream));
+  return upload_list(ctx, P.active, list);
 }
 
 ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, int nb, int pw, int ph, bool final_subpix,
@@ -568,13 +630,14 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
   EZC_CUDA(P.labels.reserve(sizeof(int) * total)); EZC_CUDA(P.flags.reserve(sizeof(int) * (total + 1)));
   EZC_CUDA(P.total.reserve(64)); EZC_CUDA(P.h.reserve(4096));
   EZC_CUDA(P.works.reserve(sizeof(cb::Work) * (size_t)nb)); EZC_CUDA(P.scratch.reserve(sizeof(int) * cb::kMaxQuads * 4 * (size_t)nb));
-  EZC_CUDA(P.state.reserve(sizeof(ImageState) * nb)); EZC_CUDA(P.active.reserve(sizeof(int) * nb));
+  EZC_CUDA(P.state.reserve(sizeof(ImageState) * nb));
   EZC_CUDA(P.corners.reserve(sizeof(cb::Ptf) * (size_t)npts * nb)); EZC_CUDA(P.found.reserve(nb));
   EZC_CUDA(P.holes.reserve(sizeof(HoleInfo) * 16));
   std::vector<ImageState> h_state(nb, ImageState{0, 0, 0, 0, 0});
-  std::vector<int> h_active(nb, 1);
+  std::vector<int> list(nb);
+  for (int i = 0; i < nb; ++i) list[i] = i;
   EZC_CUDA(cudaMemcpyAsync(P.state.p, h_state.data(), sizeof(ImageState) * nb, cudaMemcpyHostToDevice, ctx->stream));
-  EZC_CUDA(cudaMemcpyAsync(P.active.p, h_active.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+  if (ezc_status st = upload_list(ctx, P.active, list)) return st;
   EZC_CUDA(cudaMemsetAsync(P.hist.p, 0, sizeof(int) * 256 * nb, ctx->stream));
   {
     dim3 grid(std::max(1, std::min(64, (int)((N + 255) / 256))), nb);
@@ -587,77 +650,70 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
   uint8_t* b1 = P.bin1.as<uint8_t>();
   CB_LAUNCH(cb_binarize_kernel, total, d_img, imgs->pitch, imgs->image_stride, W, H, nb, P.thresh.as<int>(), (const int*)nullptr, b0);
   // ---- phase 1: histogram-binarised image, 8 cumulative dilations (the frame of the previous pass is dilated too)
-  int remaining = nb;
-  for (int dil = 0; dil <= 7 && remaining > 0; ++dil) {
-    CB_LAUNCH(cb_dilate_kernel, total, b0, b1, W, H, nb, P.active.as<int>());
+  for (int dil = 0; dil <= 7 && !list.empty(); ++dil) {
+    const int n_act = (int)list.size();
+    CB_LAUNCH(cb_dilate_kernel, N * n_act, b0, b1, W, H, n_act, P.active.as<int>());
     std::swap(b0, b1);
-    CB_LAUNCH(cb_frame_kernel, total, b0, W, H, nb, P.active.as<int>());
-    if (ezc_status st = run_attempt(ctx, P, b0, W, H, nb, pw, ph, dil)) return st;
-    if (ezc_status st = sync_state(ctx, P, nb, h_state, h_active, true)) return st;
-    remaining = 0;
-    for (int i = 0; i < nb; ++i) remaining += h_active[i];
-    // the other ping-pong buffer must hold the current image for the images still active: both buffers are kept in
-    // step by always dilating from b0 into b1 for ACTIVE images only (inactive images are never read again)
+    CB_LAUNCH(cb_frame_kernel, N * n_act, b0, W, H, n_act, P.active.as<int>());
+    if (ezc_status st = run_attempt(ctx, P, b0, W, H, n_act, pw, ph, dil)) return st;
+    if (ezc_status st = sync_state(ctx, P, nb, h_state, list)) return st;
   }
   // ---- phase 2: equalised image, 6 adaptive thresholds x 8 dilations, for the images still without a board
-  const bool phase2_ran = remaining > 0;
-  std::vector<int> h_phase2(h_active);
-  if (remaining > 0) {
+  const bool phase2_ran = !list.empty();
+  std::vector<int> h_phase2(nb, 0);
+  for (int im : list) h_phase2[im] = 1;
+  if (phase2_ran) {
     EZC_CUDA(P.eq.reserve(total)); EZC_CUDA(P.lut.reserve(256 * nb)); EZC_CUDA(P.prevbin.reserve(total));
     EZC_CUDA(P.block.reserve(sizeof(int) * nb)); EZC_CUDA(P.delta.reserve(sizeof(int) * nb)); EZC_CUDA(P.hsum.reserve(sizeof(int) * total));
-    EZC_CUDA(P.refresh.reserve(sizeof(int) * nb));
     CB_LAUNCH(cb_equalize_lut_kernel, nb, P.hist.as<int>(), nb, (int)N, P.lut.as<uint8_t>());
     CB_LAUNCH(cb_apply_lut_kernel, total, d_img, imgs->pitch, imgs->image_stride, W, H, nb, P.lut.as<uint8_t>(), P.eq.as<uint8_t>());
-    std::vector<int> prev_sqr(nb, 0), h_block(nb), h_delta(nb), h_refresh(nb), prev_block(nb);
-    // prev_sqr_size is reset to 0 when the fallback starts
-    for (int i = 0; i < nb; ++i) h_state[i].prev_sqr_size = 0;
+    std::vector<int> h_block(nb, 0), h_delta(nb, 0), prev_block(nb, -1);
+    for (int i = 0; i < nb; ++i) h_state[i].prev_sqr_size = 0;  // prev_sqr_size restarts at 0 with the fallback
     EZC_CUDA(cudaMemcpyAsync(P.state.p, h_state.data(), sizeof(ImageState) * nb, cudaMemcpyHostToDevice, ctx->stream));
     uint8_t* th = P.bin0.as<uint8_t>();       // thresh_img (gets the frame)
     uint8_t* tmp = P.bin1.as<uint8_t>();
     uint8_t* prevb = P.prevbin.as<uint8_t>(); // prev_thresh_img (no frame)
-    for (int k = 0; k < 6 && remaining > 0; ++k) {
+    for (int k = 0; k < 6 && !list.empty(); ++k) {
       std::fill(prev_block.begin(), prev_block.end(), -1);
-      for (int dil = 0; dil <= 7 && remaining > 0; ++dil) {
-        for (int i = 0; i < nb; ++i) {
-          const int ps = h_state[i].prev_sqr_size;
+      for (int dil = 0; dil <= 7 && !list.empty(); ++dil) {
+        std::vector<int> fresh, old;
+        for (int im : list) {
+          const int ps = h_state[im].prev_sqr_size;
           int bs = (int)lrint(ps == 0 ? std::min(W, H) * (k % 2 == 0 ? 0.2 : 0.1) : ps * 2.0);
           bs |= 1;
-          const bool fresh = h_active[i] && bs != prev_block[i];
-          h_refresh[i] = fresh ? 1 : 0;
-          h_block[i] = fresh ? bs : 0;
-          h_delta[i] = (k / 2) * 5;
-          if (h_active[i]) prev_block[i] = bs;
+          if (bs != prev_block[im]) fresh.push_back(im); else old.push_back(im);
+          h_block[im] = bs;
+          h_delta[im] = (k / 2) * 5;
+          prev_block[im] = bs;
         }
         EZC_CUDA(cudaMemcpyAsync(P.block.p, h_block.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
         EZC_CUDA(cudaMemcpyAsync(P.delta.p, h_delta.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
-        EZC_CUDA(cudaMemcpyAsync(P.refresh.p, h_refresh.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
-        // images with a new block size: adaptive threshold, then `dil` dilations -> prev_thresh_img
-        bool any_fresh = false, any_old = false;
-        for (int i = 0; i < nb; ++i) { any_fresh |= h_refresh[i] != 0; any_old |= (h_active[i] && !h_refresh[i]); }
-        if (any_fresh) {
-          CB_LAUNCH(cb_box_h_kernel, total, P.eq.as<uint8_t>(), W, H, nb, P.block.as<int>(), P.hsum.as<int>());
-          CB_LAUNCH(cb_box_v_thresh_kernel, total, P.eq.as<uint8_t>(), P.hsum.as<int>(), W, H, nb, P.block.as<int>(), P.delta.as<int>(), tmp);
+        if (!fresh.empty()) {
+          // new block size: adaptive threshold of the equalised image, then `dil` dilations -> prev_thresh_img
+          if (ezc_status st = upload_list(ctx, P.refresh, fresh)) return st;
+          const int nf = (int)fresh.size();
+          CB_LAUNCH(cb_box_h_kernel, N * nf, P.eq.as<uint8_t>(), W, H, nf, P.refresh.as<int>(), P.block.as<int>(), P.hsum.as<int>());
+          CB_LAUNCH(cb_box_v_thresh_kernel, N * nf, P.eq.as<uint8_t>(), P.hsum.as<int>(), W, H, nf, P.refresh.as<int>(), P.block.as<int>(),
+                    P.delta.as<int>(), tmp);
           for (int d = 0; d < dil; ++d) {
-            CB_LAUNCH(cb_dilate_kernel, total, tmp, th, W, H, nb, P.refresh.as<int>());
-            CB_LAUNCH(cb_copy_active_kernel, total, th, tmp, N, nb, P.refresh.as<int>());
+            CB_LAUNCH(cb_dilate_kernel, N * nf, tmp, th, W, H, nf, P.refresh.as<int>());
+            CB_LAUNCH(cb_copy_active_kernel, N * nf, th, tmp, N, nf, P.refresh.as<int>());
           }
-          CB_LAUNCH(cb_copy_active_kernel, total, tmp, prevb, N, nb, P.refresh.as<int>());
+          CB_LAUNCH(cb_copy_active_kernel, N * nf, tmp, prevb, N, nf, P.refresh.as<int>());
         }
-        if (any_old && dil > 0) {
+        if (!old.empty() && dil > 0) {
           // same block size as before: one more dilation of prev_thresh_img
-          std::vector<int> h_old(nb);
-          for (int i = 0; i < nb; ++i) h_old[i] = (h_active[i] && !h_refresh[i]) ? 1 : 0;
-          EZC_CUDA(cudaMemcpyAsync(P.refresh.p, h_old.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
-          CB_LAUNCH(cb_dilate_kernel, total, prevb, tmp, W, H, nb, P.refresh.as<int>());
-          CB_LAUNCH(cb_copy_active_kernel, total, tmp, prevb, N, nb, P.refresh.as<int>());
+          if (ezc_status st = upload_list(ctx, P.refresh, old)) return st;
+          const int no = (int)old.size();
+          CB_LAUNCH(cb_dilate_kernel, N * no, prevb, tmp, W, H, no, P.refresh.as<int>());
+          CB_LAUNCH(cb_copy_active_kernel, N * no, tmp, prevb, N, no, P.refresh.as<int>());
         }
-        CB_LAUNCH(cb_copy_active_kernel, total, prevb, th, N, nb, P.active.as<int>());
-        CB_LAUNCH(cb_frame_kernel, total, th, W, H, nb, P.active.as<int>());
+        const int n_act = (int)list.size();
+        CB_LAUNCH(cb_copy_active_kernel, N * n_act, prevb, th, N, n_act, P.active.as<int>());
+        CB_LAUNCH(cb_frame_kernel, N * n_act, th, W, H, n_act, P.active.as<int>());
         // no edge-length compensation in the fallback (empirically what cv2 4.13 does: exact on all phase-2 fixtures)
-        if (ezc_status st = run_attempt(ctx, P, th, W, H, nb, pw, ph, 0)) return st;
-        if (ezc_status st = sync_state(ctx, P, nb, h_state, h_active, true)) return st;
-        remaining = 0;
-        for (int i = 0; i < nb; ++i) remaining += h_active[i];
+        if (ezc_status st = run_attempt(ctx, P, th, W, H, n_act, pw, ph, 0)) return st;
+        if (ezc_status st = sync_state(ctx, P, nb, h_state, list)) return st;
       }
     }
   }
