@@ -286,6 +286,9 @@ def run_gpu(args):
     if not args.no_detect:
         line["detect"] = run_detect(ctx, args, rank, world, stream)
         line["gpu_launches"] += line["detect"]["gpu_launches"]
+        if world == 1:
+            line["detect_chessboard"] = run_detect_chessboard(ctx, args, rank, world, stream)
+            line["gpu_launches"] += line["detect_chessboard"]["gpu_launches"]
     if rank == 0:
         if not args.no_cpu and world >= 1:
             v, ms_cpu, cb = run_cpu(argparse.Namespace(steps=min(K, 10), warmup=1), ("radtan5",), args.cpu_views, False)
@@ -383,6 +386,62 @@ def run_detect(ctx, args, rank, world, stream):
     return out
 
 
+def run_detect_chessboard(ctx, args, rank, world, stream):
+    """cfg1-style workload: 9x6 chessboard (10x7 squares), 1280x1024 views, radtan5, rendered into HBM."""
+    import torch
+
+    from ezcalib_b200 import detect, synth
+    n, W, H, model = args.cb_images, 1280, 1024, "radtan5"
+    mid = synth.MODEL_ID[model]
+    d = synth.GT_DIST[model]
+    f, cx, cy = 900.0, 645.0, 505.0
+    tgt = synth.chessboard_target(7, 10, 0.05)
+    rng = np.random.Generator(np.random.Philox(key=synth.MASTER_SEED + 2000 + rank))
+    poses = synth.sample_poses(rng, n, tgt, model, f, cx, cy, d, W, H, margin=90, tilt_sigma=0.3)
+    cams = np.tile(np.array([f, f, cx, cy] + list(d) + [0.0] * (8 - len(d))), (n, 1))
+    imgs = detect.render_targets(ctx, "chessboard", 7, 10, 0.05, 0.0, mid, W, H, cams, poses, seed=synth.MASTER_SEED + 7 + rank)
+    for _ in range(3):
+        found, corners = detect.detect_chessboard(ctx, imgs, 7, 10)
+    l0 = ctx.kernel_launches()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record(stream)
+    for _ in range(reps):
+        found, corners = detect.detect_chessboard(ctx, imgs, 7, 10)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    value = n * reps / (ms * 1e-3)
+    alg_bytes = W * H + 8 * 54
+    peak = measured_peaks().get("hbm_gbs", 6650.0)
+    out = {"metric": "images/s detect+subpix (chessboard)", "value": round(value, 2), "unit": "images/s",
+           "config": {"workload": "cfg1-style: %d views %dx%d, 9x6 inner corners, radtan5, rendered into HBM" % (n, W, H), "found": int(found.sum())},
+           "gpu_launches": int(ctx.kernel_launches() - l0),
+           "roofline": {"bound": "hbm", "achieved": round(value * alg_bytes / 1e9, 3), "peak": peak, "unit": "GB/s",
+                        "frac": round(value * alg_bytes / 1e9 / peak, 6), "traffic": None}}
+    if rank == 0 and not args.no_cpu:
+        import cv2
+        flags = cv2.CALIB_CB_ADAPTIVE_THRESH + cv2.CALIB_CB_NORMALIZE_IMAGE + cv2.CALIB_CB_FILTER_QUADS + cv2.CALIB_CB_FAST_CHECK
+        crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 100, 0.05)
+        host = imgs.download(0, n)
+        t0 = time.perf_counter()
+        worst, flags_equal = 0.0, True
+        for i in range(n):
+            ok, c = cv2.findChessboardCorners(host[i], (9, 6), flags=flags)
+            flags_equal = flags_equal and bool(ok) == bool(found[i])
+            if ok:
+                c = cv2.cornerSubPix(host[i], c, (5, 5), (-1, -1), crit).reshape(-1, 2)
+                if found[i]:
+                    worst = max(worst, float(np.abs(c - corners[i]).max()))
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": round(n / dt, 3), "unit": "images/s", "cores": host_cores(), "kind": "reference",
+                               "sample": "all %d images: cv2.findChessboardCorners + cv2.cornerSubPix with the reference's flags (cv2 %s, %d threads)" % (n, cv2.__version__, cv2.getNumThreads()),
+                               "found_flags_equal": bool(flags_equal), "max_corner_diff_px": round(worst, 6)}
+    imgs.close()
+    return out
+
+
 def time_accumulate(ctx, solver, stream, reps=5) -> float:
     """Average duration (ms) of the Jacobian/normal-equation build alone, CUDA events on the launch stream."""
     import torch
@@ -415,6 +474,7 @@ def main():
     ap.add_argument("--no-detect", action="store_true")
     ap.add_argument("--det-images", type=int, default=500)
     ap.add_argument("--det-reps", type=int, default=2)
+    ap.add_argument("--cb-images", type=int, default=50)
     ap.add_argument("--det-cpu-images", type=int, default=24)
     args = ap.parse_args()
     if args.impl == "reference":

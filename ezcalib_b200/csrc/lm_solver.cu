@@ -508,27 +508,7 @@ struct CostArgs {
   long long n_obs;  // n_blocks * M
   int M, period;
   float wb, hb;
-  double* part;     // [grid]
 };
-
-template <int MODEL, bool MONO, bool PER_BLOCK_CAM>
-__global__ void __launch_bounds__(256) lm_cost_kernel(const CostArgs a) {
-  __shared__ double sh[8];
-  double cost = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_obs; i += (long long)gridDim.x * blockDim.x) {
-    const float2 o = a.obs[i];
-    if (!(o.x > -0.5f && o.y > -0.5f && o.x < a.wb && o.y < a.hb)) continue;
-    const int blk = (int)(i / a.M);
-    const int l = (int)(i - (long long)blk * a.M);
-    const double* P = a.pts + (size_t)(l % a.period) * 3;
-    double rx, ry;
-    if constexpr (PER_BLOCK_CAM) residual<MODEL, MONO>(a.cams[blk], a.poses + (size_t)blk * 7, P[0], P[1], P[2], (double)o.x, (double)o.y, rx, ry);
-    else residual<MODEL, MONO>(a.cam, a.poses + (size_t)blk * 7, P[0], P[1], P[2], (double)o.x, (double)o.y, rx, ry);
-    cost += 0.5 * log(1.0 + (rx * rx + ry * ry));
-  }
-  const double v = block_reduce(cost, false, sh);
-  if (threadIdx.x == 0) a.part[blockIdx.x] = v;
-}
 
 // Per-block RMSE of the plain reprojection error: one warp per block (view).
 template <int MODEL, bool MONO, bool PER_BLOCK_CAM>
@@ -570,7 +550,6 @@ __global__ void lm_single_obs_kernel(CamParams cam, const double* __restrict__ i
 // Dispatch tables
 // ------------------------------------------------------------------------------------------
 typedef void (*AccumFn)(const AccumArgs);
-typedef void (*CostFn)(const CostArgs);
 typedef void (*RmseFn)(const CostArgs, int, double*);
 typedef void (*SingleFn)(CamParams, const double*, double*);
 
@@ -609,11 +588,6 @@ static AccumFn accum_fn(int NT, bool per_block) {
 static AccumFn get_accum(int model, bool mono, int NT, bool per_block) {
   AccumFn f = nullptr;
   EZC_MODEL_SWITCH(model, mono, (f = accum_fn<MD, MN>(NT, per_block)));
-  return f;
-}
-static CostFn get_cost(int model, bool mono, bool per_block) {
-  CostFn f = nullptr;
-  EZC_MODEL_SWITCH(model, mono, (f = per_block ? lm_cost_kernel<MD, MN, true> : lm_cost_kernel<MD, MN, false>));
   return f;
 }
 static RmseFn get_rmse(int model, bool mono, bool per_block) {
@@ -670,10 +644,13 @@ struct ezc_lm_solver {
   int cur = 0;
   int seg_len = 0, segs_per_block = 1, n_segs = 0;
   int acc_grid = 0, acc_warps = 0;
-  DevBuf seg_strips, blk_strips, part, cost_part, scale_p, diag_p, lyz, step_p;
-  DevBuf part2, part3, part4, red1, red2, gmaxbuf, rmse, dbg;
+  // strips / packed H_cc+cost are double-buffered: [sb] belongs to the current point, [1-sb] receives the speculative
+  // evaluation at the candidate (which becomes the current one when the step is accepted)
+  DevBuf seg_strips[2], blk_strips[2], red1[2];
+  int sb = 0;
+  DevBuf part, cost_part, scale_p, diag_p, lyz, step_p;
+  DevBuf part2, part3, red2, gmaxbuf, rmse, dbg;
   HostPinned h_red;
-  int cost_grid = 0;
   // state of the current variable pattern
   int k = 0, NT = 2, DA = 8;
   int cols[kMaxK];
@@ -724,8 +701,12 @@ ezc_status alloc_state(ezc_lm_solver* s) {
   s->acc_grid = std::max(1, std::min((s->n_segs + kWarpsPerBlock - 1) / kWarpsPerBlock, max_blocks));
   s->acc_warps = s->acc_grid * kWarpsPerBlock;
   const size_t strip_max = 8 * 24;
-  EZC_CUDA(s->seg_strips.reserve(sizeof(double) * strip_max * s->n_segs));
-  if (s->segs_per_block > 1) EZC_CUDA(s->blk_strips.reserve(sizeof(double) * strip_max * nb));
+  for (int b = 0; b < 2; ++b) {
+    EZC_CUDA(s->seg_strips[b].reserve(sizeof(double) * strip_max * std::max(s->n_segs, 1)));
+    if (s->segs_per_block > 1) EZC_CUDA(s->blk_strips[b].reserve(sizeof(double) * strip_max * nb));
+    EZC_CUDA(s->red1[b].reserve(sizeof(double) * R1_SIZE));
+    EZC_CUDA(cudaMemsetAsync(s->red1[b].p, 0, sizeof(double) * R1_SIZE, ctx->stream));
+  }
   EZC_CUDA(s->part.reserve(sizeof(double) * 384 * s->acc_warps));
   EZC_CUDA(s->cost_part.reserve(sizeof(double) * s->acc_warps));
   EZC_CUDA(s->poses[0].reserve(sizeof(double) * 7 * std::max(nb, 1)));
@@ -737,9 +718,6 @@ ezc_status alloc_state(ezc_lm_solver* s) {
   const int g2 = (nb + 127) / 128 + 1;
   EZC_CUDA(s->part2.reserve(sizeof(double) * 128 * g2));
   EZC_CUDA(s->part3.reserve(sizeof(double) * 4 * g2));
-  s->cost_grid = std::max(1, std::min((int)(((long long)nb * M + 255) / 256), ctx->sm_count * 8));
-  EZC_CUDA(s->part4.reserve(sizeof(double) * s->cost_grid));
-  EZC_CUDA(s->red1.reserve(sizeof(double) * R1_SIZE));
   EZC_CUDA(s->red2.reserve(sizeof(double) * 8));
   EZC_CUDA(s->gmaxbuf.reserve(sizeof(double) * 2));
   EZC_CUDA(s->rmse.reserve(sizeof(double) * std::max(nb, 1)));
@@ -787,19 +765,19 @@ ezc_status create_common(ezc_context* ctx, const ezc_lm_problem* p, bool device_
   return EZC_OK;
 }
 
-// lm_accumulate (+ strip reduce + H_cc reduce) at the CURRENT parameters.
-ezc_status run_accumulate(ezc_lm_solver* s) {
+// lm_accumulate (+ strip reduce + H_cc reduce) at the parameters (poses[pose_idx], cam) into strip / red1 buffer `buf`.
+ezc_status run_accumulate(ezc_lm_solver* s, int pose_idx, const CamParams& cam, int buf) {
   ezc_context* ctx = s->ctx;
   AccumArgs a{};
-  a.obs = s->d_obs; a.pts = s->d_pts; a.poses = s->poses[s->cur].as<double>();
-  a.cams = s->per_block_cam ? s->cams[s->cur].as<CamParams>() : nullptr;
-  a.cam = s->cam;
+  a.obs = s->d_obs; a.pts = s->d_pts; a.poses = s->poses[pose_idx].as<double>();
+  a.cams = s->per_block_cam ? s->cams[0].as<CamParams>() : nullptr;
+  a.cam = cam;
   a.n_blocks = s->prob.n_blocks; a.M = s->prob.obs_per_block; a.period = s->prob.pts_period;
   a.seg_len = s->seg_len; a.segs_per_block = s->segs_per_block; a.n_segs = s->n_segs;
   a.wb = (float)s->prob.img_w - 0.5f; a.hb = (float)s->prob.img_h - 0.5f;
   a.k = s->k;
   for (int j = 0; j < kMaxK; ++j) a.colpos[j] = s->colpos[j];
-  a.strips = s->seg_strips.as<double>();
+  a.strips = s->seg_strips[buf].as<double>();
   a.part = s->part.as<double>();
   a.cost_part = s->cost_part.as<double>();
   AccumFn fn = get_accum(s->prob.model, s->prob.use_mono_focal != 0, s->NT, s->per_block_cam);
@@ -810,8 +788,8 @@ ezc_status run_accumulate(ezc_lm_solver* s) {
     fn<<<s->acc_grid, kWarpsPerBlock * 32, smem, ctx->stream>>>(a);
     if (ezc_status st = launch_check(ctx, "lm_accumulate")) return st;
     if (s->segs_per_block > 1) {
-      lm_strip_reduce_kernel<<<s->prob.n_blocks, 192, 0, ctx->stream>>>(s->seg_strips.as<double>(), s->segs_per_block,
-                                                                         8 * s->DA, s->blk_strips.as<double>());
+      lm_strip_reduce_kernel<<<s->prob.n_blocks, 192, 0, ctx->stream>>>(s->seg_strips[buf].as<double>(), s->segs_per_block,
+                                                                         8 * s->DA, s->blk_strips[buf].as<double>());
       if (ezc_status st = launch_check(ctx, "lm_strip_reduce")) return st;
     }
   } else {
@@ -819,12 +797,12 @@ ezc_status run_accumulate(ezc_lm_solver* s) {
     EZC_CUDA(cudaMemsetAsync(s->cost_part.p, 0, sizeof(double) * s->acc_warps, ctx->stream));
   }
   lm_hcc_reduce_kernel<<<s->k * (s->k + 1) / 2 + 1, 256, 0, ctx->stream>>>(s->part.as<double>(), s->cost_part.as<double>(),
-                                                                           s->acc_warps, s->NT, s->k, s->red1.as<double>());
+                                                                           s->acc_warps, s->NT, s->k, s->red1[buf].as<double>());
   return launch_check(ctx, "lm_hcc_reduce");
 }
 
 const double* block_strips(const ezc_lm_solver* s) {
-  return s->segs_per_block > 1 ? s->blk_strips.as<double>() : s->seg_strips.as<double>();
+  return s->segs_per_block > 1 ? s->blk_strips[s->sb].as<double>() : s->seg_strips[s->sb].as<double>();
 }
 
 ezc_status run_schur(ezc_lm_solver* s, double radius, bool first, bool reuse, bool undamped, double min_diag, double max_diag) {
@@ -844,7 +822,7 @@ ezc_status run_schur(ezc_lm_solver* s, double radius, bool first, bool reuse, bo
   lm_schur_kernel<<<grid, 128, 0, ctx->stream>>>(a);
   if (ezc_status st = launch_check(ctx, "lm_schur")) return st;
   // sums -> red1[R1_SCHUR ..], max (gradient) -> gmaxbuf
-  lm_reduce_rows_kernel<<<nv, 256, 0, ctx->stream>>>(s->part2.as<double>(), grid, nv, nv - 1, s->red1.as<double>() + R1_SCHUR);
+  lm_reduce_rows_kernel<<<nv, 256, 0, ctx->stream>>>(s->part2.as<double>(), grid, nv, nv - 1, s->red1[s->sb].as<double>() + R1_SCHUR);
   return launch_check(ctx, "lm_reduce_rows");
 }
 
@@ -975,7 +953,8 @@ ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summ
     }
   };
 
-  if (ezc_status st = run_accumulate(s)) return st;
+  if (ezc_status st = run_accumulate(s, s->cur, s->cam, s->sb)) return st;
+  allreduce(s, s->red1[s->sb].as<double>(), R1_SCHUR, 0);  // H_cc + cost of this rank's views
   ++n_jac;
   bool fresh_jacobian = true;
 
@@ -986,9 +965,9 @@ ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summ
     if (ezc_status st = run_schur(s, radius, first, reuse_diagonal, false, opt->min_lm_diagonal, opt->max_lm_diagonal)) return st;
     ++n_lin;
     const int n1 = R1_SCHUR + nS + 2 * k + 4;
-    allreduce(s, s->red1.as<double>(), n1, 0);
-    allreduce(s, s->red1.as<double>() + n1, 1, 1);
-    EZC_CUDA(cudaMemcpyAsync(h, s->red1.p, sizeof(double) * (n1 + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    allreduce(s, s->red1[s->sb].as<double>() + R1_SCHUR, n1 - R1_SCHUR, 0);
+    allreduce(s, s->red1[s->sb].as<double>() + n1, 1, 1);
+    EZC_CUDA(cudaMemcpyAsync(h, s->red1[s->sb].p, sizeof(double) * (n1 + 1), cudaMemcpyDeviceToHost, ctx->stream));
     EZC_CUDA(cudaStreamSynchronize(ctx->stream));
     const double* hs = h + R1_SCHUR;
     const double* Ssum = hs;
@@ -1073,20 +1052,15 @@ ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summ
       s->cam_cand = s->cam;
       for (int c = 0; c < k; ++c) *shared_param(s->cam_cand, nf, s->cols[c]) += dc[c];
       if (nf == 1) s->cam_cand.focal[1] = s->cam_cand.focal[0];
-      CostArgs ca{};
-      ca.obs = s->d_obs; ca.pts = s->d_pts; ca.poses = s->poses[1 - s->cur].as<double>();
-      ca.cams = s->per_block_cam ? s->cams[s->cur].as<CamParams>() : nullptr;
-      ca.cam = s->cam_cand;
-      ca.n_obs = (long long)nb * s->prob.obs_per_block; ca.M = s->prob.obs_per_block; ca.period = s->prob.pts_period;
-      ca.wb = (float)s->prob.img_w - 0.5f; ca.hb = (float)s->prob.img_h - 0.5f;
-      ca.part = s->part4.as<double>();
-      CostFn cf = get_cost(s->prob.model, s->prob.use_mono_focal != 0, s->per_block_cam);
-      cf<<<s->cost_grid, 256, 0, ctx->stream>>>(ca);
-      if (ezc_status st = launch_check(ctx, "lm_cost")) return st;
-      lm_reduce_rows_kernel<<<1, 256, 0, ctx->stream>>>(s->part4.as<double>(), s->cost_grid, 1, 1, s->red2.as<double>() + 4);
-      if (ezc_status st = launch_check(ctx, "lm_reduce_rows")) return st;
-      allreduce(s, s->red2.as<double>(), R2_SIZE, 0);
-      EZC_CUDA(cudaMemcpyAsync(h, s->red2.p, sizeof(double) * R2_SIZE, cudaMemcpyDeviceToHost, ctx->stream));
+      // speculative evaluation at the candidate: residuals, Jacobian and normal-equation blocks in one pass.  Its cost
+      // decides acceptance; when the step is accepted (the common case) the blocks are already the next iteration's.
+      const int alt = 1 - s->sb;
+      if (ezc_status st = run_accumulate(s, 1 - s->cur, s->cam_cand, alt)) return st;
+      ++n_jac;
+      allreduce(s, s->red2.as<double>(), 4, 0);
+      allreduce(s, s->red1[alt].as<double>(), R1_SCHUR, 0);
+      EZC_CUDA(cudaMemcpyAsync(h, s->red2.p, sizeof(double) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      EZC_CUDA(cudaMemcpyAsync(h + 4, s->red1[alt].as<double>() + R1_COST, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
       EZC_CUDA(cudaStreamSynchronize(ctx->stream));
       double gd = h[0], dHd = h[1];
       step2 = h[2]; cn2 = h[3]; cand_cost = h[4];
@@ -1121,29 +1095,22 @@ ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summ
     if (rel > opt->min_relative_decrease) {
       s->cam = s->cam_cand;
       s->cur = 1 - s->cur;
+      s->sb = 1 - s->sb;
       x_norm = std::sqrt(cn2);
       radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
       radius = std::min(opt->max_trust_region_radius, radius);
       decrease_factor = 2.0; reuse_diagonal = false;
       ++n_success;
       last_successful = true;
-      x_cost = cand_cost;  // replaced by the re-evaluated cost when the new Jacobian arrives
+      x_cost = cand_cost;
       record(iter, x_cost, 1);
       trace_pending = iter;
-      if (ezc_status st = run_accumulate(s)) return st;
-      ++n_jac;
-      fresh_jacobian = true;
+      fresh_jacobian = true;  // the candidate's blocks (buffer sb) are the current ones now
     } else {
       radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
       last_successful = false;
       record(iter, x_cost, 2);
     }
-  }
-  if (fresh_jacobian) {
-    // the loop ended right after an accepted step (max iterations): fetch the re-evaluated cost
-    EZC_CUDA(cudaMemcpyAsync(h, s->red1.as<double>() + R1_COST, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    EZC_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->world == 1) x_cost = h[0];
   }
   summary->iterations = iter + 1;
   summary->num_successful = n_success;
@@ -1182,12 +1149,12 @@ ezc_status ezc_lm_covariance(ezc_lm_solver* s, double* cov_out) {
   EZC_CUDA(cudaSetDevice(ctx->device));
   setup_pattern(s, 1, 1, 1);
   const int k = s->k, nS = k * (k + 1) / 2;
-  if (ezc_status st = run_accumulate(s)) return st;
+  if (ezc_status st = run_accumulate(s, s->cur, s->cam, s->sb)) return st;
   if (ezc_status st = run_schur(s, 1.0, false, false, true, 0.0, 0.0)) return st;
   const int n1 = R1_SCHUR + nS + 2 * k + 4;
-  allreduce(s, s->red1.as<double>(), n1, 0);
+  allreduce(s, s->red1[s->sb].as<double>(), n1, 0);
   double* h = s->h_red.as<double>();
-  EZC_CUDA(cudaMemcpyAsync(h, s->red1.p, sizeof(double) * n1, cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaMemcpyAsync(h, s->red1[s->sb].p, sizeof(double) * n1, cudaMemcpyDeviceToHost, ctx->stream));
   EZC_CUDA(cudaStreamSynchronize(ctx->stream));
   double S[kMaxK * kMaxK];
   int q = 0;
@@ -1260,7 +1227,7 @@ ezc_status ezc_lm_accumulate_only(ezc_lm_solver* s, int32_t opt_focal, int32_t o
   EZC_CHECK(s && s->have_params, EZC_ERR_INVALID, "ezc_lm_accumulate_only: bad argument");
   EZC_CUDA(cudaSetDevice(s->ctx->device));
   setup_pattern(s, opt_focal, opt_pp, opt_dist);
-  return run_accumulate(s);
+  return run_accumulate(s, s->cur, s->cam, s->sb);
 }
 
 ezc_status ezc_lm_normal_equations(ezc_lm_solver* s, int32_t opt_focal, int32_t opt_pp, int32_t opt_dist, double* H_cc,
@@ -1270,10 +1237,10 @@ ezc_status ezc_lm_normal_equations(ezc_lm_solver* s, int32_t opt_focal, int32_t 
   EZC_CUDA(cudaSetDevice(ctx->device));
   setup_pattern(s, opt_focal, opt_pp, opt_dist);
   const int k = s->k, nb = s->prob.n_blocks, DA = s->DA, nS = k * (k + 1) / 2;
-  if (ezc_status st = run_accumulate(s)) return st;
+  if (ezc_status st = run_accumulate(s, s->cur, s->cam, s->sb)) return st;
   if (ezc_status st = run_schur(s, 1.0, false, false, true, 0.0, 0.0)) return st;
   std::vector<double> h(R1_SIZE), st((size_t)nb * 8 * DA);
-  EZC_CUDA(cudaMemcpyAsync(h.data(), s->red1.p, sizeof(double) * R1_SIZE, cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaMemcpyAsync(h.data(), s->red1[s->sb].p, sizeof(double) * R1_SIZE, cudaMemcpyDeviceToHost, ctx->stream));
   if (nb) EZC_CUDA(cudaMemcpyAsync(st.data(), block_strips(s), sizeof(double) * st.size(), cudaMemcpyDeviceToHost, ctx->stream));
   EZC_CUDA(cudaStreamSynchronize(ctx->stream));
   if (cost) *cost = h[R1_COST];
