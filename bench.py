@@ -344,7 +344,7 @@ def run_detect(ctx, args, rank, world, stream):
         dist.barrier()
     torch.cuda.synchronize()
     e0.record(stream)
-    im2 = detect.Images(ctx, pin.numpy())
+    im2 = detect.Images(ctx, pin.numpy(), async_upload=True)   # copies on a second stream overlap detection of earlier sub-batches
     s2, c2, n2 = detect.detect_aprilgrid(ctx, im2, DET_ROWS, DET_COLS)
     e1.record(stream)
     torch.cuda.synchronize()

@@ -72,6 +72,7 @@ def lib():
         L.ezc_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.ezc_measure_dmma_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.ezc_images_upload.argtypes = [C.c_void_p, C.POINTER(ImageBatchC), C.POINTER(C.c_void_p)]
+        L.ezc_images_upload_async.argtypes = [C.c_void_p, C.POINTER(ImageBatchC), C.POINTER(C.c_void_p)]
         L.ezc_images_wrap_device.argtypes = [C.c_void_p, C.POINTER(ImageBatchC), C.POINTER(C.c_void_p)]
         L.ezc_images_destroy.argtypes = [C.c_void_p]
         L.ezc_corner_subpix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double]
@@ -111,7 +112,7 @@ def check(status: int, what: str = ""):
 # Every symbol include/ezcalib_b200.h declares (checked by tests/test_abi.py).
 EXPORTED_SYMBOLS = [
     "ezc_create", "ezc_destroy", "ezc_last_error", "ezc_set_stream", "ezc_set_allreduce", "ezc_kernel_launches",
-    "ezc_synchronize", "ezc_images_upload", "ezc_images_wrap_device", "ezc_images_destroy", "ezc_corner_subpix", "ezc_images_download", "ezc_render_targets", "ezc_detect_aprilgrid_batch", "ezc_detect_chessboard_batch", "ezc_find_chessboard_corners_batch", "ezc_apriltag_debug_run", "ezc_apriltag_debug_count",
+    "ezc_synchronize", "ezc_images_upload", "ezc_images_upload_async", "ezc_images_wrap_device", "ezc_images_destroy", "ezc_corner_subpix", "ezc_images_download", "ezc_render_targets", "ezc_detect_aprilgrid_batch", "ezc_detect_chessboard_batch", "ezc_find_chessboard_corners_batch", "ezc_apriltag_debug_run", "ezc_apriltag_debug_count",
     "ezc_apriltag_debug_get", "ezc_apriltag_debug_free", "ezc_measure_fp64_peak", "ezc_measure_dmma_peak", "ezc_num_dist", "ezc_lm_default_options", "ezc_lm_create", "ezc_lm_create_device",
     "ezc_lm_destroy", "ezc_lm_set_params", "ezc_lm_get_params", "ezc_lm_solve", "ezc_lm_frame_rmse",
     "ezc_lm_covariance", "ezc_lm_mono", "ezc_lm_residual_jacobian", "ezc_lm_normal_equations", "ezc_lm_accumulate_only",

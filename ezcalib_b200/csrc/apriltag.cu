@@ -985,6 +985,7 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
   const long long N = (long long)W * H;
   const long long total = N * nb;
   const uint8_t* d_img = imgs->d + (long long)img0 * imgs->image_stride;
+  EZC_CUDA(images_wait(ctx, imgs, img0 + nb - 1));  // asynchronous upload: only this sub-batch has to be resident
   EZC_CUDA(P.fr.reserve(sizeof(float) * total));
   EZC_CUDA(P.seg.reserve(sizeof(float) * total));
   EZC_CUDA(P.theta.reserve(sizeof(float) * total));

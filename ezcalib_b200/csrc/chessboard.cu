@@ -624,6 +624,7 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
   const int W = imgs->width, H = imgs->height;
   const long long N = (long long)W * H, total = N * nb;
   const uint8_t* d_img = imgs->d + (long long)img0 * imgs->image_stride;
+  EZC_CUDA(images_wait(ctx, imgs, img0 + nb - 1));
   const int npts = pw * ph;
   EZC_CUDA(P.hist.reserve(sizeof(int) * 256 * nb)); EZC_CUDA(P.thresh.reserve(sizeof(int) * nb));
   EZC_CUDA(P.bin0.reserve(total)); EZC_CUDA(P.bin1.reserve(total));

@@ -44,14 +44,17 @@ ezc_status ezc_create(int32_t device, ezc_context** out) {
 void ezc_destroy(ezc_context* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);  // cached device blocks are handed to other contexts unsynchronised
   if (ctx->at_pools && ctx->at_pools_free) ctx->at_pools_free(ctx->at_pools);
   if (ctx->cb_pools && ctx->cb_pools_free) ctx->cb_pools_free(ctx->cb_pools);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
 ezc_status ezc_set_stream(ezc_context* ctx, void* cuda_stream) {
   EZC_CHECK(ctx != nullptr, EZC_ERR_INVALID, "ezc_set_stream: ctx is null");
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   ctx->own_stream = false;

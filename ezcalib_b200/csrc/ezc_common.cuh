@@ -1,6 +1,9 @@
 // ezc_common.cuh -- context, error plumbing and small device helpers shared by all kernels.
 #pragma once
 #include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -32,16 +35,78 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 // Simple RAII device buffer (cudaMalloc / cudaFree), grow-only.
+// Process-wide cache of device allocations: cudaMalloc/cudaFree cost milliseconds (cudaFree also synchronises the
+// device), which dominated the host-buffer (e2e) calls that create and destroy a solver / image batch per call.
+// Blocks are handed back by ~DevBuf and reused best-fit (<= 25 % slack) by the next reserve().  Reuse is safe without a
+// synchronise as long as producer and consumer run on the same stream (one context = one stream); entry points that
+// destroy objects synchronise their stream first.  Never freed at process exit (the CUDA context may already be gone).
+struct DevCache {
+  std::mutex m;
+  std::multimap<size_t, void*> blocks;
+  size_t bytes = 0;
+  size_t limit = size_t(24) << 30;
+  void* take(size_t want) {
+    std::lock_guard<std::mutex> g(m);
+    auto it = blocks.lower_bound(want);
+    if (it == blocks.end() || it->first > want + want / 4 + 4096) return nullptr;
+    void* p = it->second;
+    bytes -= it->first;
+    last_size = it->first;
+    blocks.erase(it);
+    return p;
+  }
+  size_t last_size = 0;
+  bool give(void* p, size_t sz) {
+    std::lock_guard<std::mutex> g(m);
+    if (bytes + sz > limit) return false;
+    blocks.emplace(sz, p);
+    bytes += sz;
+    return true;
+  }
+  void flush() {
+    std::lock_guard<std::mutex> g(m);
+    for (auto& kv : blocks) cudaFree(kv.second);
+    blocks.clear();
+    bytes = 0;
+  }
+};
+inline DevCache& dev_cache() {
+  static DevCache* c = new DevCache;  // intentionally leaked
+  return *c;
+}
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p && !dev_cache().give(p, cap)) cudaFree(p);
+    p = nullptr; cap = 0;
+  }
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
+    release();
+    DevCache& c = dev_cache();
+    {
+      std::lock_guard<std::mutex> g(c.m);
+      auto it = c.blocks.lower_bound(bytes);
+      if (it != c.blocks.end() && it->first <= bytes + bytes / 4 + 4096) {
+        p = it->second; cap = it->first;
+        c.bytes -= it->first;
+        c.blocks.erase(it);
+        return cudaSuccess;
+      }
+    }
     cudaError_t e = cudaMalloc(&p, bytes);
-    if (e == cudaSuccess) cap = bytes;
+    if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and retry once
+      cudaGetLastError();
+      c.flush();
+      e = cudaMalloc(&p, bytes);
+    }
+    if (e == cudaSuccess) cap = bytes; else p = nullptr;
     return e;
   }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
@@ -82,4 +147,6 @@ struct ezc_context {
   void (*at_pools_free)(void*) = nullptr;
   void* cb_pools = nullptr;
   void (*cb_pools_free)(void*) = nullptr;
+  // second stream for ezc_images_upload_async: H2D copies overlap the detection kernels of earlier sub-batches
+  cudaStream_t copy_stream = nullptr;
 };

@@ -145,10 +145,14 @@ __device__ __forceinline__ void residual(const CamParams& c, const double* __res
 }
 
 // Residual + Jacobian.  Jp[2][6]: pose tangent (upsilon, omega).  Jc[2][NF+2+ND]: [focal | pp | dist].
-template <int MODEL, bool MONO>
-__device__ __forceinline__ void residual_jacobian(const CamParams& c, const double* __restrict__ pose, double px,
-                                                  double py, double pz, double u, double v, double& rx, double& ry,
-                                                  double (&Jpx)[6], double (&Jpy)[6], double (&Jcx)[12], double (&Jcy)[12]) {
+// `wgt` scales every Jacobian entry (the Cauchy corrector sqrt(rho') is applied by the caller through it when WEIGHTED:
+// the residual is evaluated first, the weight derived from it, and the 2x2 / focal factors are scaled once instead of
+// scaling all 2 x (6 + k) entries).
+template <int MODEL, bool MONO, bool WEIGHTED>
+__device__ __forceinline__ void residual_jacobian_w(const CamParams& c, const double* __restrict__ pose, double px,
+                                                    double py, double pz, double u, double v, double& rx, double& ry,
+                                                    double& wgt, double& half_rho,
+                                                    double (&Jpx)[6], double (&Jpy)[6], double (&Jcx)[12], double (&Jcy)[12]) {
   constexpr int NF = MONO ? 1 : 2;
   constexpr int ND = num_dist(MODEL);
   double X, Y, Z;
@@ -161,25 +165,43 @@ __device__ __forceinline__ void residual_jacobian(const CamParams& c, const doub
   const double fx = c.focal[0], fy = MONO ? c.focal[0] : c.focal[1];
   rx = fx * xd + c.pp[0] - u;
   ry = fy * yd + c.pp[1] - v;
-  // d(x,y)/d delta
-  const double g0[6] = {iz, 0.0, -x * iz, -x * y, 1.0 + x * x, -y};
-  const double g1[6] = {0.0, iz, -y * iz, -(1.0 + y * y), x * y, x};
-  const double m00 = fx * a00, m01 = fx * a01, m10 = fy * a10, m11 = fy * a11;
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    Jpx[j] = m00 * g0[j] + m01 * g1[j];
-    Jpy[j] = m10 * g0[j] + m11 * g1[j];
+  double w = 1.0;
+  if constexpr (WEIGHTED) {
+    // ceres::CauchyLoss(1): rho = log(1+s), rho' = 1/(1+s), rho'' < 0 -> Corrector alpha = 0 -> scale by sqrt(rho')
+    const double ss = rx * rx + ry * ry;
+    w = sqrt(1.0 / (1.0 + ss));
+    half_rho = 0.5 * log(1.0 + ss);
   }
+  wgt = w;
+  const double wfx = w * fx, wfy = w * fy;
+  const double m00 = wfx * a00, m01 = wfx * a01, m10 = wfy * a10, m11 = wfy * a11;
+  // d(x,y)/d delta = [[iz, 0, -x iz, -xy, 1+x^2, -y], [0, iz, -y iz, -(1+y^2), xy, x]]
+  const double xy = x * y;
+  Jpx[0] = m00 * iz;               Jpy[0] = m10 * iz;
+  Jpx[1] = m01 * iz;               Jpy[1] = m11 * iz;
+  Jpx[2] = -(Jpx[0] * x + Jpx[1] * y);  Jpy[2] = -(Jpy[0] * x + Jpy[1] * y);
+  Jpx[3] = -(m00 * xy + m01 * (1.0 + y * y));  Jpy[3] = -(m10 * xy + m11 * (1.0 + y * y));
+  Jpx[4] = m00 * (1.0 + x * x) + m01 * xy;     Jpy[4] = m10 * (1.0 + x * x) + m11 * xy;
+  Jpx[5] = m01 * x - m00 * y;      Jpy[5] = m11 * x - m10 * y;
   if constexpr (MONO) {
-    Jcx[0] = xd; Jcy[0] = yd;
+    Jcx[0] = w * xd; Jcy[0] = w * yd;
   } else {
-    Jcx[0] = xd; Jcy[0] = 0.0;
-    Jcx[1] = 0.0; Jcy[1] = yd;
+    Jcx[0] = w * xd; Jcy[0] = 0.0;
+    Jcx[1] = 0.0; Jcy[1] = w * yd;
   }
-  Jcx[NF] = 1.0; Jcy[NF] = 0.0;
-  Jcx[NF + 1] = 0.0; Jcy[NF + 1] = 1.0;
+  Jcx[NF] = w; Jcy[NF] = 0.0;
+  Jcx[NF + 1] = 0.0; Jcy[NF + 1] = w;
 #pragma unroll
-  for (int i = 0; i < ND; ++i) { Jcx[NF + 2 + i] = fx * ddx[i]; Jcy[NF + 2 + i] = fy * ddy[i]; }
+  for (int i = 0; i < ND; ++i) { Jcx[NF + 2 + i] = wfx * ddx[i]; Jcy[NF + 2 + i] = wfy * ddy[i]; }
+}
+
+// unweighted form (tests, debug entry)
+template <int MODEL, bool MONO>
+__device__ __forceinline__ void residual_jacobian(const CamParams& c, const double* __restrict__ pose, double px,
+                                                  double py, double pz, double u, double v, double& rx, double& ry,
+                                                  double (&Jpx)[6], double (&Jpy)[6], double (&Jcx)[12], double (&Jcy)[12]) {
+  double w, hr;
+  residual_jacobian_w<MODEL, MONO, false>(c, pose, px, py, pz, u, v, rx, ry, w, hr, Jpx, Jpy, Jcx, Jcy);
 }
 
 // ---- SE3 exp(delta) * T  (Sophus SE3::exp + group product with normalisation) -------------

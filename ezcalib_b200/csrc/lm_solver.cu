@@ -10,17 +10,19 @@
 //   lm_accumulate   one warp per view segment.  Phase 1: one lane per observation evaluates the
 //                   residual + analytic Jacobian (lm_models.cuh), applies the Cauchy corrector and
 //                   stores the weighted row pair [J_pose(6) | r | 0 | J_shared(k)] column-major in
-//                   shared memory.  Phase 2: the same warp re-partitions itself into 4x4 register
-//                   tiles x k-slices of the (8+k)^2 Gram matrix and accumulates [J r]^T [J r] with
-//                   DFMAs from 16-byte shared loads.  Tiles touching the pose rows are flushed per
-//                   view into an 8 x (8+k) "strip" (H_pp, g_p, H_pc, per-view g_c); H_cc tiles stay
-//                   in registers for the whole launch and are reduced once, in fixed order.
+//                   shared memory.  Phase 2: the (8+k)^2 Gram matrix [J r]^T [J r] is accumulated in
+//                   8x8 tiles on the FP64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA).  Tile row 0
+//                   (pose rows + residual row) is flushed per view into an 8 x 8*CG "strip"
+//                   (H_pp, g_p, H_pc, per-view g_c); H_cc tiles stay in registers for the whole launch
+//                   and are reduced once, in fixed order.  The cost sum comes out of the same pass.
 //   lm_schur        one thread per view: Jacobi scaling, LM damping, 6x6 Cholesky, Y = L^-1 W,
 //                   z = L^-1 g; fixed-order reduction of Y^T Y, Y^T z, g_c, |x|^2, gradient norm.
 //   (host)          k x k reduced system (k <= 12): scale, damp, Cholesky, solve  [+ one all-reduce
 //                   of the packed partial system over NVLink when views are sharded over GPUs]
 //   lm_backsub      one thread per view: pose step, candidate pose exp(delta) T, model-cost terms.
-//   lm_cost         one thread per observation: candidate cost  sum 1/2 log(1 + |r|^2).
+//   lm_accumulate   again, AT THE CANDIDATE, into the alternate half of the double-buffered strips:
+//                   its cost is the candidate cost; on acceptance the buffers are swapped and the next
+//                   iteration's normal equations already exist (speculative evaluation).
 // Accept / reject, radius update and termination follow Ceres' TrustRegionMinimizer on the host.
 #include <algorithm>
 #include <cfloat>
@@ -118,16 +120,14 @@ lm_accumulate_kernel(const AccumArgs a) {
       if (lane < nr) {
         if (valid) {
           const double* P = a.pts + (size_t)(l % a.period) * 3;
-          double rx, ry, Jpx[6], Jpy[6], Jcx[12], Jcy[12];
-          residual_jacobian<MODEL, MONO>(cam, pose, P[0], P[1], P[2], (double)o.x, (double)o.y, rx, ry, Jpx, Jpy, Jcx, Jcy);
-          const double ss = rx * rx + ry * ry;
-          // ceres::CauchyLoss(1): rho = log(1+s), rho' = 1/(1+s), rho'' < 0 -> Corrector alpha = 0
-          const double w = sqrt(1.0 / (1.0 + ss));
-          cost += 0.5 * log(1.0 + ss);
+          double rx, ry, w, half_rho, Jpx[6], Jpy[6], Jcx[12], Jcy[12];
+          residual_jacobian_w<MODEL, MONO, true>(cam, pose, P[0], P[1], P[2], (double)o.x, (double)o.y, rx, ry, w, half_rho, Jpx, Jpy,
+                                                 Jcx, Jcy);
+          cost += half_rho;
 #pragma unroll
           for (int j = 0; j < 6; ++j) {
-            J[j * kCS + lane] = w * Jpx[j];
-            J[j * kCS + 32 + lane] = w * Jpy[j];
+            J[j * kCS + lane] = Jpx[j];
+            J[j * kCS + 32 + lane] = Jpy[j];
           }
           J[6 * kCS + lane] = w * rx;
           J[6 * kCS + 32 + lane] = w * ry;
@@ -135,8 +135,8 @@ lm_accumulate_kernel(const AccumArgs a) {
           for (int jf = 0; jf < KFULL; ++jf) {
             const int c = a.colpos[jf];
             if (c >= 0) {
-              J[c * kCS + lane] = w * Jcx[jf];
-              J[c * kCS + 32 + lane] = w * Jcy[jf];
+              J[c * kCS + lane] = Jcx[jf];
+              J[c * kCS + 32 + lane] = Jcy[jf];
             }
           }
           ++nvalid;
@@ -873,6 +873,7 @@ ezc_status ezc_lm_create_device(ezc_context* ctx, const ezc_lm_problem* problem,
 void ezc_lm_destroy(ezc_lm_solver* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
   delete s;
 }
 

@@ -195,6 +195,7 @@ extern "C" ezc_status ezc_render_targets(ezc_context* ctx, int32_t pattern, int3
 extern "C" ezc_status ezc_images_download(ezc_context* ctx, const ezc_images* imgs, int32_t first, int32_t count, uint8_t* host_out) {
   EZC_CHECK(ctx && imgs && host_out && first >= 0 && count >= 0 && first + count <= imgs->n, EZC_ERR_INVALID, "ezc_images_download: bad argument");
   EZC_CUDA(cudaSetDevice(ctx->device));
+  EZC_CUDA(ezc::images_wait(ctx, imgs, first + count - 1));
   for (int i = 0; i < count; ++i)
     EZC_CUDA(cudaMemcpy2DAsync(host_out + (size_t)i * imgs->width * imgs->height, imgs->width, imgs->d + (size_t)(first + i) * imgs->image_stride,
                                imgs->pitch, imgs->width, imgs->height, cudaMemcpyDeviceToHost, ctx->stream));

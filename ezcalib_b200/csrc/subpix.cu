@@ -7,7 +7,7 @@
 // One warp per corner.  Every iteration the warp (1) samples the (2w+3)x(2h+3) float32 patch around the
 // current estimate with exactly the arithmetic of OpenCV's getRectSubPix_8u32f (its "prev/t" recurrence in
 // the fully-inside case, the replicated-border formulas otherwise; no FMA contraction), (2) accumulates the
-// five gradient moments in FP64 with a fixed-order shuffle tree, (3) solves the 2x2 system and rounds the
+// five gradient moments in FP64 in the reference's sequential order (no FMA contraction: -fmad=false), (3) solves the 2x2 system and rounds the
 // estimate to float32 like cv::Point2f does.
 #include <cmath>
 
@@ -18,6 +18,7 @@ namespace ezc {
 constexpr int kMaxWin = 5;                           // window half-size supported
 constexpr int kMaxPatch = (2 * kMaxWin + 3);         // 13
 constexpr int kSubpixWarps = 4;
+constexpr int kMaxTerms = (2 * kMaxWin + 1) * (2 * kMaxWin + 1);  // 121
 
 struct SubpixArgs {
   const uint8_t* imgs;
@@ -34,10 +35,12 @@ struct SubpixArgs {
 
 __global__ void __launch_bounds__(kSubpixWarps * 32) corner_subpix_kernel(const SubpixArgs a) {
   __shared__ float patch_s[kSubpixWarps][kMaxPatch * kMaxPatch];
+  __shared__ double terms_s[kSubpixWarps][5 * kMaxTerms];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int idx = blockIdx.x * kSubpixWarps + warp;
   if (idx >= a.n) return;
   float* patch = patch_s[warp];
+  double* terms = terms_s[warp];
   const uint8_t* img = a.imgs + (long long)a.image_index[idx] * a.image_stride;
   const int W = a.W, H = a.H;
   const long long pitch = a.pitch;
@@ -117,7 +120,9 @@ __global__ void __launch_bounds__(kSubpixWarps * 32) corner_subpix_kernel(const 
     }
     __syncwarp();
     // ---- gradient moments over the inner iw x ih window
-    double sa = 0, sb = 0, sc = 0, sbb1 = 0, sbb2 = 0;
+    // products in parallel (one element per lane and pass), sums in the reference's SEQUENTIAL raster order
+    // (cornersubpix.cpp: a += gxx; b += gxy; ... inside the i/j loops): lanes 0..4 each own one accumulator.
+    // The TU is compiled with -fmad=false, so no product is contracted into the following add.
     for (int q = lane; q < iw * ih; q += 32) {
       const int i = q / iw, j = q - i * iw;
       const float* sp = patch + (i + 1) * pw + (j + 1);
@@ -126,17 +131,20 @@ __global__ void __launch_bounds__(kSubpixWarps * 32) corner_subpix_kernel(const 
       const double tgy = (double)__fsub_rn(sp[pw], sp[-pw]);
       const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
       const double px = (double)(j - a.ww), py = (double)(i - a.wh);
-      sa += gxx; sb += gxy; sc += gyy;
-      sbb1 += gxx * px + gxy * py;
-      sbb2 += gxy * px + gyy * py;
+      terms[0 * kMaxTerms + q] = gxx;
+      terms[1 * kMaxTerms + q] = gxy;
+      terms[2 * kMaxTerms + q] = gyy;
+      terms[3 * kMaxTerms + q] = gxx * px + gxy * py;
+      terms[4 * kMaxTerms + q] = gxy * px + gyy * py;
     }
-    for (int m = 16; m >= 1; m >>= 1) {
-      sa += __shfl_xor_sync(0xffffffffu, sa, m);
-      sb += __shfl_xor_sync(0xffffffffu, sb, m);
-      sc += __shfl_xor_sync(0xffffffffu, sc, m);
-      sbb1 += __shfl_xor_sync(0xffffffffu, sbb1, m);
-      sbb2 += __shfl_xor_sync(0xffffffffu, sbb2, m);
+    __syncwarp();
+    double acc = 0;
+    if (lane < 5) {
+      const double* tp = terms + lane * kMaxTerms;
+      for (int q = 0; q < iw * ih; ++q) acc += tp[q];
     }
+    const double sa = __shfl_sync(0xffffffffu, acc, 0), sb = __shfl_sync(0xffffffffu, acc, 1), sc = __shfl_sync(0xffffffffu, acc, 2);
+    const double sbb1 = __shfl_sync(0xffffffffu, acc, 3), sbb2 = __shfl_sync(0xffffffffu, acc, 4);
     const double det = sa * sc - sb * sb;
     if (fabs(det) <= 2.220446049250313e-16 * 2.220446049250313e-16) break;
     const double scale = 1.0 / det;
@@ -186,7 +194,7 @@ ezc_status subpix_device(ezc_context* ctx, const ezc_images* imgs, float2* corne
 
 extern "C" {
 
-ezc_status ezc_images_upload(ezc_context* ctx, const ezc_image_batch* b, ezc_images** out) {
+static ezc_status images_upload_impl(ezc_context* ctx, const ezc_image_batch* b, ezc_images** out, bool async) {
   EZC_CHECK(ctx && b && out, EZC_ERR_INVALID, "ezc_images_upload: null argument");
   *out = nullptr;
   EZC_CHECK(b->n_images >= 0 && b->width > 0 && b->height > 0, EZC_ERR_INVALID, "ezc_images_upload: bad sizes");
@@ -199,14 +207,43 @@ ezc_status ezc_images_upload(ezc_context* ctx, const ezc_image_batch* b, ezc_ima
   im->pitch = b->width; im->image_stride = (int64_t)b->width * b->height;
   const size_t bytes = (size_t)std::max<int64_t>(1, im->image_stride * b->n_images);
   cudaError_t e = im->own.reserve(bytes + 64);
-  for (int i = 0; e == cudaSuccess && i < b->n_images; ++i)
-    e = cudaMemcpy2DAsync(im->own.as<uint8_t>() + (size_t)i * im->image_stride, im->pitch, b->data + (size_t)i * ist, row,
-                          b->width, b->height, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaStream_t st = ctx->stream;
+  if (async && e == cudaSuccess && b->n_images > 0) {
+    if (!ctx->copy_stream) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    st = ctx->copy_stream;
+    // ~64 MB per readiness event: fine enough to pipeline, coarse enough to keep the event count small
+    im->chunk = (int)std::max<int64_t>(1, (int64_t(64) << 20) / std::max<int64_t>(1, im->image_stride));
+  }
+  const bool packed = (row == b->width && ist == row * b->height);
+  for (int i = 0; e == cudaSuccess && i < b->n_images;) {
+    const int nb = im->chunk > 0 ? std::min(im->chunk, b->n_images - i) : (packed ? b->n_images : 1);
+    if (packed) {
+      e = cudaMemcpyAsync(im->own.as<uint8_t>() + (size_t)i * im->image_stride, b->data + (size_t)i * ist, (size_t)nb * ist,
+                          cudaMemcpyHostToDevice, st);
+    } else {
+      for (int j = i; e == cudaSuccess && j < i + nb; ++j)
+        e = cudaMemcpy2DAsync(im->own.as<uint8_t>() + (size_t)j * im->image_stride, im->pitch, b->data + (size_t)j * ist, row,
+                              b->width, b->height, cudaMemcpyHostToDevice, st);
+    }
+    if (im->chunk > 0 && e == cudaSuccess) {
+      cudaEvent_t ev;
+      e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      if (e == cudaSuccess) { im->ready.push_back(ev); e = cudaEventRecord(ev, st); }
+    }
+    i += nb;
+  }
+  if (e == cudaSuccess && !async) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { ezc::set_error("ezc_images_upload: %s", cudaGetErrorString(e)); delete im; return EZC_ERR_CUDA; }
   im->d = im->own.as<uint8_t>();
   *out = im;
   return EZC_OK;
+}
+
+ezc_status ezc_images_upload(ezc_context* ctx, const ezc_image_batch* b, ezc_images** out) {
+  return images_upload_impl(ctx, b, out, false);
+}
+ezc_status ezc_images_upload_async(ezc_context* ctx, const ezc_image_batch* b, ezc_images** out) {
+  return images_upload_impl(ctx, b, out, true);
 }
 
 ezc_status ezc_images_wrap_device(ezc_context* ctx, const ezc_image_batch* b, ezc_images** out) {
@@ -224,6 +261,7 @@ ezc_status ezc_images_wrap_device(ezc_context* ctx, const ezc_image_batch* b, ez
 void ezc_images_destroy(ezc_images* im) {
   if (!im) return;
   cudaSetDevice(im->ctx->device);
+  cudaStreamSynchronize(im->ctx->stream);
   delete im;
 }
 
@@ -232,6 +270,7 @@ ezc_status ezc_corner_subpix(ezc_context* ctx, const ezc_images* imgs, float* co
   EZC_CHECK(ctx && imgs && (n == 0 || (corners && image_index)), EZC_ERR_INVALID, "ezc_corner_subpix: null argument");
   EZC_CUDA(cudaSetDevice(ctx->device));
   if (n <= 0) return EZC_OK;
+  EZC_CUDA(ezc::images_wait(ctx, imgs, imgs->n - 1));
   for (int i = 0; i < n; ++i)
     EZC_CHECK(image_index[i] >= 0 && image_index[i] < imgs->n, EZC_ERR_INVALID, "ezc_corner_subpix: image index out of range");
   for (int i = 0; i < n; ++i)  // cv::cornerSubPix asserts Rect(0,0,cols,rows).contains(corner)

@@ -23,7 +23,7 @@ def _p(a):
 class Images:
     """Device-resident batch of u8 gray images [n, H, W]."""
 
-    def __init__(self, ctx: Context, images=None, device_ptr: int | None = None, shape=None):
+    def __init__(self, ctx: Context, images=None, device_ptr: int | None = None, shape=None, async_upload: bool = False):
         self.ctx = ctx
         b = ImageBatchC()
         if device_ptr is not None:
@@ -41,7 +41,8 @@ class Images:
         b.row_stride, b.image_stride = 0, 0
         self.n, self.height, self.width = int(n), int(h), int(w)
         self._h = C.c_void_p()
-        fn = _lib.lib().ezc_images_wrap_device if device_ptr is not None else _lib.lib().ezc_images_upload
+        L = _lib.lib()
+        fn = L.ezc_images_wrap_device if device_ptr is not None else (L.ezc_images_upload_async if async_upload else L.ezc_images_upload)
         check(fn(ctx.handle, C.byref(b), C.byref(self._h)), "ezc_images_upload")
 
     @property

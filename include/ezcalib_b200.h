@@ -67,6 +67,11 @@ typedef struct ezc_images ezc_images;
 
 /* Copy a HOST batch into HBM (the detectors then work on the device-resident copy). */
 ezc_status ezc_images_upload(ezc_context* ctx, const ezc_image_batch* host_batch, ezc_images** out);
+/* The same, but returns as soon as the copies are QUEUED on a second stream; the detectors start on the first
+ * sub-batch while later images are still crossing PCIe (what the reference's loop does implicitly by reading image i+1
+ * after processing image i, ezcalibrator.cpp:40-59).  The host buffer must stay valid and unmodified until the first
+ * call that consumes the whole batch has returned (or ezc_images_destroy); pinned host memory is needed for real overlap. */
+ezc_status ezc_images_upload_async(ezc_context* ctx, const ezc_image_batch* host_batch, ezc_images** out);
 /* Borrow a batch that already lives in DEVICE memory (batch->data is a device pointer). */
 ezc_status ezc_images_wrap_device(ezc_context* ctx, const ezc_image_batch* device_batch, ezc_images** out);
 void ezc_images_destroy(ezc_images* imgs);

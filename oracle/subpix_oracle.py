@@ -27,6 +27,23 @@ def _floor(v: np.float32) -> int:
     return int(math.floor(float(v)))
 
 
+def _expf(x) -> np.float32:
+    """std::exp(float) as the reference's C++ gets it: glibc expf.  numpy's float32 exp is a different (SIMD)
+    implementation and is 1 ulp off for several of the mask arguments (e.g. exp(-1)), which shows up in the last bits
+    of ill-conditioned windows."""
+    global _LIBM
+    if _LIBM is None:
+        import ctypes
+        import ctypes.util
+        _LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        _LIBM.expf.restype = ctypes.c_float
+        _LIBM.expf.argtypes = [ctypes.c_float]
+    return F(_LIBM.expf(float(x)))
+
+
+_LIBM = None
+
+
 def get_rect_subpix_8u32f(img: np.ndarray, win_w: int, win_h: int, cx: np.float32, cy: np.float32) -> np.ndarray:
     """getRectSubPix_8u32f (samplers.cpp): float32 patch win_h x win_w centred at (cx,cy)."""
     H, W = img.shape
@@ -124,10 +141,10 @@ def corner_subpix(img: np.ndarray, corners: np.ndarray, win=(5, 5), max_iter: in
     mask = np.zeros((win_h, win_w), dtype=F)
     for i in range(win_h):
         y = F(F(i - wh) / F(wh))
-        vy = F(np.exp(F(-y * y)))
+        vy = _expf(F(-y * y))
         for j in range(win_w):
             x = F(F(j - ww) / F(ww))
-            mask[i, j] = F(vy * F(np.exp(F(-x * x))))
+            mask[i, j] = F(vy * _expf(F(-x * x)))
     out = np.array(corners, dtype=F, copy=True).reshape(-1, 2)
     iters = np.zeros(len(out), dtype=np.int32)
     py = (np.arange(win_h, dtype=np.float64) - wh)[:, None]
@@ -144,9 +161,12 @@ def corner_subpix(img: np.ndarray, corners: np.ndarray, win=(5, 5), max_iter: in
             gxx = tgx * tgx * m64
             gxy = tgx * tgy * m64
             gyy = tgy * tgy * m64
-            a = gxx.sum(); b = gxy.sum(); c = gyy.sum()
-            bb1 = (gxx * pxv + gxy * py).sum()
-            bb2 = (gxy * pxv + gyy * py).sum()
+            # sequential raster-order accumulation like the reference's scalar loop (np.sum is pairwise: differs in
+            # the last bits, which shows on ill-conditioned windows); cumsum adds strictly left to right
+            seq = lambda x: float(np.cumsum(x.ravel())[-1])
+            a = seq(gxx); b = seq(gxy); c = seq(gyy)
+            bb1 = seq(gxx * pxv + gxy * py)
+            bb2 = seq(gxy * pxv + gyy * py)
             det = a * c - b * b
             if abs(det) <= np.finfo(np.float64).eps ** 2:
                 break

@@ -71,3 +71,24 @@ def test_batch_end_to_end_matches_reference(ctx):
         assert np.array_equal(corners[0][:, 0] < 0, G[name + "_corners"][:, 0] < 0)
         assert np.abs(corners[0] - G[name + "_corners"]).max() <= 0.01
         assert int(ndet[0]) == int(G[name + "_n"]) and bool(succ[0]) == bool(G[name + "_ok"])
+
+
+def test_async_upload_pipelined_sub_batches_identical(ctx):
+    """ezc_images_upload_async + max_images_in_flight=2: copies overlap detection sub-batch by sub-batch;
+    results must equal the synchronous path bit for bit (incl. after the device-allocation cache recycles buffers)."""
+    from ezcalib_b200 import detect
+    name = NAMES[0]
+    img = G[name + "_img"]
+    rows, cols = (int(v) for v in G[name + "_grid"])
+    batch = np.stack([img, img[::-1].copy(), img, np.zeros_like(img), img[:, ::-1].copy(), img, img[::-1].copy()])
+    imgs = detect.Images(ctx, batch)
+    ref = detect.detect_aprilgrid(ctx, imgs, rows, cols)
+    imgs.close()
+    for _ in range(2):
+        im2 = detect.Images(ctx, batch, async_upload=True)
+        got = detect.detect_aprilgrid(ctx, im2, rows, cols, max_images_in_flight=2)
+        back = im2.download()
+        im2.close()
+        assert np.array_equal(back, batch)
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b)
