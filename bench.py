@@ -293,7 +293,7 @@ def run_gpu(args):
         if not args.no_cpu and world >= 1:
             v, ms_cpu, cb = run_cpu(argparse.Namespace(steps=min(K, 10), warmup=1), ("radtan5",), args.cpu_views, False)
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -461,7 +461,29 @@ def time_accumulate(ctx, solver, stream, reps=5) -> float:
     return float(np.mean(best))
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when
+    NCCL_DEBUG is set), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -491,7 +513,7 @@ def main():
                            "note": "Ceres 2.2.0 is not installable here (no source, no network): this is the restated-Ceres oracle port with all host threads"},
                 "cpu_baseline": cb,
                 "e2e": {"value": round(value, 6), "unit": "LM iters/s (10M obs)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
     run_gpu(args)
 
