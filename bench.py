@@ -351,6 +351,16 @@ def run_detect(ctx, args, rank, world, stream):
     ms2 = e0.elapsed_time(e1)
     im2.close()
     assert np.array_equal(c2, corners) and np.array_equal(n2, ndet)
+    # what the PCIe link of this box delivers for the same pinned buffer (context for e2e: it is transfer bound)
+    dst = torch.empty(pin.numel(), dtype=torch.uint8, device="cuda")
+    dst.copy_(pin.view(-1), non_blocking=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    dst.copy_(pin.view(-1), non_blocking=True)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    h2d_gbs = pin.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    del dst
     if world > 1:
         t = torch.tensor([ms, ms2], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -363,7 +373,8 @@ def run_detect(ctx, args, rank, world, stream):
     out = {"metric": "images/s detect+subpix", "value": round(value, 2), "unit": "images/s", "ms_per_image": round(ms / (n * reps), 4),
            "config": {"workload": "cfg3-style: %d views %dx%d per GPU, 6x6 AprilGrid 36h11, radtan8, rendered into HBM (inputs %.1f GB > L2)" % (n, DET_W, DET_H, n * DET_W * DET_H / 1e9),
                       "found": int(succ.sum()), "mean_detections": float(ndet.mean())},
-           "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": int(DET_W * DET_H), "d2h_bytes_per_step": int(8 * 144 + 5)},
+           "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": int(DET_W * DET_H), "d2h_bytes_per_step": int(8 * 144 + 5),
+                   "h2d_link_gbs": round(h2d_gbs, 2), "h2d_bound_images_per_s": round(h2d_gbs * 1e9 / (DET_W * DET_H) * world, 1)},
            "gpu_launches": int(launches),
            "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
                         "traffic": None, "kernel": "whole detection pipeline (no single dominant kernel; see profiles/launches_detect_r01.csv)",

@@ -38,7 +38,7 @@ namespace ezc {
 constexpr int kCS = 68;            // shared-memory column stride in doubles (64 rows + 4 pad: conflict-free MMA fragment loads)
 constexpr int kWarpsPerBlock = 4;  // lm_accumulate block = 128 threads
 constexpr int kMaxK = 12;          // max shared columns (2 focal + 2 pp + 8 dist)
-constexpr int kLYZ = 100;          // per-view Schur record: L(21) Y(6*12) z(6) + pad
+constexpr int kLYZ = 100;          // per-view Schur record: L(21) pad z(6) @22, Y(6*12) @28
 
 // layout of the packed reduction buffer "red1" (doubles)
 constexpr int R1_HCC = 0;                     // [12][12] upper triangle used
@@ -275,37 +275,76 @@ struct SchurArgs {
   int nv;                 // nS + 2k + 4 (+1 max)
 };
 
+constexpr int kXS = 36;            // staging stride (32 rows + 4): == 4 mod 16 -> conflict-free MMA fragment loads
+constexpr int kSchurPart = 3 * 64 + kMaxK + 6;  // per-warp partial: Gram tiles of [Y z], g_c sums, 5 scalars
+
+// One lane per view does the 6x6 work (scaling, damping, Cholesky, forward substitutions); the reduction
+// S = sum_views Y^T Y and Y^T z is a Gram matrix of the stacked rows [Y | z] (6 rows per view) and is accumulated on the
+// FP64 tensor cores: after computing row i of its view, every lane stages it in shared memory and the warp folds the 32
+// rows into persistent 8x8 DMMA tiles.  KC = number of shared columns the instantiation can hold (7 -> one 8-column
+// group [Y(7) z], 12 -> two groups).  z sits in the last column (ZC) of the padded range.
+template <int KC>
 __global__ void __launch_bounds__(128) lm_schur_kernel(const SchurArgs a) {
-  __shared__ double sh[8];
+  constexpr int KG = (KC + 1 + 7) / 8;
+  constexpr int NT = KG * (KG + 1) / 2;
+  constexpr int ZC = 8 * KG - 1;
+  __shared__ double xs_all[4][8 * KG * kXS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* xs = xs_all[warp];
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int k = a.k, DA = a.DA;
   const bool live = b < a.n_blocks;
-  double Y[6][kMaxK];
-  double z[6];
-  double gc[kMaxK];
-  double L[6][6];
+  for (int i = lane; i < 8 * KG * kXS; i += 32) xs[i] = 0.0;
+
+  double Wm[6][KC];   // W rows, overwritten in place by Y rows
+  double H[6][6], g[6], sc[6], lm2[6], L[6][6], z[6], gc[KC];
+  double cnt = 0.0;
   double xn2 = 0.0, nres = 0.0, nused = 0.0, fail = 0.0, gmax = 0.0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
-    z[i] = 0.0;
-    for (int c = 0; c < kMaxK; ++c) Y[i][c] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) H[i][j] = (i == j) ? 1.0 : 0.0;
+    g[i] = 0.0; sc[i] = 1.0; lm2[i] = 0.0;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) Wm[i][c] = 0.0;
   }
-  for (int c = 0; c < kMaxK; ++c) gc[c] = 0.0;
+#pragma unroll
+  for (int c = 0; c < KC; ++c) gc[c] = 0.0;
   if (live) {
     const double* st = a.strips + (size_t)b * 8 * DA;
-    const double cnt = st[7 * DA + 7];
-    double sc[6], g[6];
-    double H[6][6];
+    // 16-byte loads: every 32-byte sector of the strip rows is consumed by two back-to-back loads of the same lane
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
+      const double2* r2 = reinterpret_cast<const double2*>(st + i * DA);
+      double row[8];
 #pragma unroll
-      for (int j = i; j < 6; ++j) { H[i][j] = st[i * DA + j]; H[j][i] = H[i][j]; }
-      g[i] = st[i * DA + 6];
+      for (int j = 0; j < 4; ++j) { const double2 v = r2[j]; row[2 * j] = v.x; row[2 * j + 1] = v.y; }
+#pragma unroll
+      for (int j = i; j < 6; ++j) { H[i][j] = row[j]; H[j][i] = row[j]; }
+      g[i] = row[6];
+#pragma unroll
+      for (int j = 0; j < (KC + 1) / 2; ++j) {
+        if (2 * j < k) {
+          const double2 v = r2[4 + j];
+          Wm[i][2 * j] = v.x;
+          if (2 * j + 1 < KC) Wm[i][2 * j + 1] = v.y;   // zero padding of the strip when 2j+1 == k
+        }
+      }
     }
-    for (int c = 0; c < k; ++c) gc[c] = st[6 * DA + 8 + c];
-    if (a.undamped) {
+    {
+      const double2* r2 = reinterpret_cast<const double2*>(st + 6 * DA);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) sc[i] = 1.0;
+      for (int j = 0; j < (KC + 1) / 2; ++j) {
+        if (2 * j < k) {
+          const double2 v = r2[4 + j];
+          gc[2 * j] = v.x;
+          if (2 * j + 1 < KC) gc[2 * j + 1] = v.y;
+        }
+      }
+    }
+    cnt = st[7 * DA + 7];
+    if (a.undamped) {
+      // sc = 1, lm2 = 0
     } else if (a.first) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) { sc[i] = 1.0 / (1.0 + sqrt(H[i][i])); a.scale_p[(size_t)b * 6 + i] = sc[i]; }
@@ -313,58 +352,81 @@ __global__ void __launch_bounds__(128) lm_schur_kernel(const SchurArgs a) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) sc[i] = a.scale_p[(size_t)b * 6 + i];
     }
-    double lm2[6];
-    if (a.undamped) {
+    if (!a.undamped) {
+      if (!a.reuse_diag) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) lm2[i] = 0.0;
-    } else if (!a.reuse_diag) {
+        for (int i = 0; i < 6; ++i) {
+          const double d = fmin(fmax(sc[i] * sc[i] * H[i][i], a.min_diag), a.max_diag);
+          a.diag_p[(size_t)b * 6 + i] = d;
+          lm2[i] = d / a.radius;
+        }
+      } else {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const double d = fmin(fmax(sc[i] * sc[i] * H[i][i], a.min_diag), a.max_diag);
-        a.diag_p[(size_t)b * 6 + i] = d;
-        lm2[i] = d / a.radius;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) lm2[i] = a.diag_p[(size_t)b * 6 + i] / a.radius;
-    }
-    // V = S H S + D^2 ; Cholesky (lower)
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      double d = sc[j] * sc[j] * H[j][j] + lm2[j];
-#pragma unroll
-      for (int m = 0; m < j; ++m) d -= L[j][m] * L[j][m];
-      if (!(d > 0.0)) { ok = false; d = 1.0; }
-      d = sqrt(d);
-      L[j][j] = d;
-      const double id = 1.0 / d;
-#pragma unroll
-      for (int i = j + 1; i < 6; ++i) {
-        double sacc = sc[i] * sc[j] * H[i][j];
-#pragma unroll
-        for (int m = 0; m < j; ++m) sacc -= L[i][m] * L[j][m];
-        L[i][j] = sacc * id;
+        for (int i = 0; i < 6; ++i) lm2[i] = a.diag_p[(size_t)b * 6 + i] / a.radius;
       }
     }
-    if (cnt > 0.0 && !ok) fail = 1.0;
-    // z = L^-1 (s g) ; Y = L^-1 (s W)
+  }
+  // V = S H S + D^2 ; Cholesky (lower)
+  bool ok = true;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
+  for (int j = 0; j < 6; ++j) {
+    double d = sc[j] * sc[j] * H[j][j] + lm2[j];
+#pragma unroll
+    for (int m = 0; m < j; ++m) d -= L[j][m] * L[j][m];
+    if (!(d > 0.0)) { ok = false; d = 1.0; }
+    d = sqrt(d);
+    L[j][j] = d;
+    const double id = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double sacc = sc[i] * sc[j] * H[i][j];
+#pragma unroll
+      for (int m = 0; m < j; ++m) sacc -= L[i][m] * L[j][m];
+      L[i][j] = sacc * id;
+    }
+  }
+  if (live && cnt > 0.0 && !ok) fail = 1.0;
+
+  double acc[NT][2];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+  const int fr = (lane >> 2) * kXS + (lane & 3);
+  __syncwarp();
+  // row i of z = L^-1 (s g) and Y = L^-1 (s W), staged and folded into the Gram tiles
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const double il = 1.0 / L[i][i];
+    {
       double sacc = sc[i] * g[i];
 #pragma unroll
       for (int m = 0; m < i; ++m) sacc -= L[i][m] * z[m];
-      z[i] = sacc / L[i][i];
+      z[i] = sacc * il;
     }
-    for (int c = 0; c < k; ++c) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        double sacc = sc[i] * st[i * DA + 8 + c];
+    for (int c = 0; c < KC; ++c) {
+      double sacc = sc[i] * Wm[i][c];
 #pragma unroll
-        for (int m = 0; m < i; ++m) sacc -= L[i][m] * Y[m][c];
-        Y[i][c] = sacc / L[i][i];
-      }
+      for (int m = 0; m < i; ++m) sacc -= L[i][m] * Wm[m][c];
+      Wm[i][c] = sacc * il;
+      xs[c * kXS + lane] = Wm[i][c];
     }
+    xs[ZC * kXS + lane] = z[i];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      double f[KG];
+#pragma unroll
+      for (int q = 0; q < KG; ++q) f[q] = xs[q * 8 * kXS + fr + 4 * j];
+      int t = 0;
+#pragma unroll
+      for (int gi = 0; gi < KG; ++gi)
+#pragma unroll
+        for (int gj = gi; gj < KG; ++gj) { dmma_m8n8k4(acc[t][0], acc[t][1], f[gi], f[gj]); ++t; }
+    }
+    __syncwarp();
+  }
+  if (live) {
+    // record for lm_backsub: L(21) | pad | z(6) @22 | Y rows @28 + 12 i   (16-byte aligned rows)
     double* rec = a.lyz + (size_t)b * kLYZ;
     {
       int q = 0;
@@ -372,10 +434,14 @@ __global__ void __launch_bounds__(128) lm_schur_kernel(const SchurArgs a) {
       for (int i = 0; i < 6; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j) rec[q++] = L[i][j];
-      for (int i = 0; i < 6; ++i) for (int c = 0; c < k; ++c) rec[21 + i * kMaxK + c] = Y[i][c];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) rec[93 + i] = z[i];
     }
+#pragma unroll
+    for (int i = 0; i < 6; i += 2) *reinterpret_cast<double2*>(rec + 22 + i) = make_double2(z[i], z[i + 1]);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < (KC + 1) / 2; ++j)
+        if (2 * j < k) *reinterpret_cast<double2*>(rec + 28 + i * kMaxK + 2 * j) = make_double2(Wm[i][2 * j], (2 * j + 1 < KC) ? Wm[i][2 * j + 1] : 0.0);
     if (cnt > 0.0) {
       nres = cnt; nused = 1.0;
       const double* x = a.poses + (size_t)b * 7;
@@ -387,41 +453,71 @@ __global__ void __launch_bounds__(128) lm_schur_kernel(const SchurArgs a) {
       for (int i = 0; i < 7; ++i) { xn2 += x[i] * x[i]; gmax = fmax(gmax, fabs(x[i] - out[i])); }
     }
   }
-  // ---- block reduction, fixed order
-  double* pout = a.part + (size_t)blockIdx.x * a.nv;
-  int q = 0;
-  for (int c = 0; c < k; ++c)
-    for (int c2 = c; c2 < k; ++c2) {
-      double v = 0.0;
+  // ---- per-warp partials (fixed order): Gram tiles, g_c sums, scalars
+  const int gw = blockIdx.x * 4 + warp;
+  double* pw = a.part + (size_t)gw * kSchurPart;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) v += Y[i][c] * Y[i][c2];
-      v = block_reduce(v, false, sh);
-      if (threadIdx.x == 0) pout[q] = v;
-      ++q;
-    }
-  for (int c = 0; c < k; ++c) {
-    double v = 0.0;
+  for (int t = 0; t < NT; ++t) *reinterpret_cast<double2*>(pw + t * 64 + lane * 2) = make_double2(acc[t][0], acc[t][1]);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) v += Y[i][c] * z[i];
-    v = block_reduce(v, false, sh);
-    if (threadIdx.x == 0) pout[q] = v;
-    ++q;
+  for (int c = 0; c < KC; ++c) {
+    double v = gc[c];
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if (lane == 0) pw[192 + c] = v;
   }
-  for (int c = 0; c < k; ++c) {
-    const double v = block_reduce(gc[c], false, sh);
-    if (threadIdx.x == 0) pout[q] = v;
-    ++q;
+  for (int m = 16; m >= 1; m >>= 1) {
+    xn2 += __shfl_xor_sync(0xffffffffu, xn2, m);
+    nres += __shfl_xor_sync(0xffffffffu, nres, m);
+    nused += __shfl_xor_sync(0xffffffffu, nused, m);
+    fail += __shfl_xor_sync(0xffffffffu, fail, m);
+    gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, m));
   }
-  {
-    double v = block_reduce(xn2, false, sh);  if (threadIdx.x == 0) pout[q] = v;  ++q;
-    v = block_reduce(nres, false, sh);        if (threadIdx.x == 0) pout[q] = v;  ++q;
-    v = block_reduce(nused, false, sh);       if (threadIdx.x == 0) pout[q] = v;  ++q;
-    v = block_reduce(fail, false, sh);        if (threadIdx.x == 0) pout[q] = v;  ++q;
-    v = block_reduce(gmax, true, sh);         if (threadIdx.x == 0) pout[q] = v;  ++q;
+  if (lane == 0) {
+    pw[192 + kMaxK + 0] = xn2; pw[192 + kMaxK + 1] = nres; pw[192 + kMaxK + 2] = nused; pw[192 + kMaxK + 3] = fail;
+    pw[192 + kMaxK + 4] = gmax;
   }
 }
 
-// -------------------------------------------------------------------------------------------
+// Fixed-order reduction of the per-warp Schur partials into the packed layout
+//   [S upper triangle (k(k+1)/2) | Y^T z (k) | g_c (k) | |x|^2, n_res, n_used, fail | gmax(max)].
+// grid = nv blocks of 256 threads.
+__global__ void lm_schur_reduce_kernel(const double* __restrict__ part, int n_warps, int k, int KG, double* __restrict__ out) {
+  __shared__ double sh[256];
+  const int nS = k * (k + 1) / 2;
+  const int q = blockIdx.x;
+  const int ZC = 8 * KG - 1;
+  int off;
+  bool is_max = false;
+  if (q < nS + k) {
+    int R, Cc;
+    if (q < nS) {
+      int a = 0, rem = q, len = k;
+      while (rem >= len) { rem -= len; ++a; --len; }
+      R = a; Cc = a + rem;
+    } else {
+      R = q - nS; Cc = ZC;
+    }
+    const int tt = tile_index(R >> 3, Cc >> 3, KG);
+    off = tt * 64 + ((R & 7) * 4 + ((Cc & 7) >> 1)) * 2 + (Cc & 1);
+  } else if (q < nS + 2 * k) {
+    off = 192 + (q - nS - k);
+  } else {
+    off = 192 + kMaxK + (q - nS - 2 * k);
+    is_max = (q - nS - 2 * k) == 4;
+  }
+  double v = 0.0;
+  for (int w = threadIdx.x; w < n_warps; w += 256) {
+    const double x = part[(size_t)w * kSchurPart + off];
+    v = is_max ? fmax(v, x) : v + x;
+  }
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int m = 128; m >= 1; m >>= 1) {
+    if ((int)threadIdx.x < m) sh[threadIdx.x] = is_max ? fmax(sh[threadIdx.x], sh[threadIdx.x + m]) : sh[threadIdx.x] + sh[threadIdx.x + m];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[q] = sh[0];
+}
+
 struct BacksubArgs {
   const double* strips;
   const double* poses;
@@ -456,8 +552,8 @@ __global__ void __launch_bounds__(128) lm_backsub_kernel(const BacksubArgs a) {
       }
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        double sacc = rec[93 + i];
-        for (int c = 0; c < k; ++c) sacc -= rec[21 + i * kMaxK + c] * a.uc[c];
+        double sacc = rec[22 + i];
+        for (int c = 0; c < k; ++c) sacc -= rec[28 + i * kMaxK + c] * a.uc[c];
         tt[i] = sacc;
       }
 #pragma unroll
@@ -716,7 +812,7 @@ ezc_status alloc_state(ezc_lm_solver* s) {
   EZC_CUDA(s->step_p.reserve(sizeof(double) * 6 * std::max(nb, 1)));
   EZC_CUDA(s->lyz.reserve(sizeof(double) * kLYZ * std::max(nb, 1)));
   const int g2 = (nb + 127) / 128 + 1;
-  EZC_CUDA(s->part2.reserve(sizeof(double) * 128 * g2));
+  EZC_CUDA(s->part2.reserve(sizeof(double) * kSchurPart * 4 * g2));
   EZC_CUDA(s->part3.reserve(sizeof(double) * 4 * g2));
   EZC_CUDA(s->red2.reserve(sizeof(double) * 8));
   EZC_CUDA(s->gmaxbuf.reserve(sizeof(double) * 2));
@@ -819,11 +915,12 @@ ezc_status run_schur(ezc_lm_solver* s, double radius, bool first, bool reuse, bo
   a.scale_p = s->scale_p.as<double>(); a.diag_p = s->diag_p.as<double>(); a.lyz = s->lyz.as<double>();
   a.part = s->part2.as<double>(); a.nv = nv;
   const int grid = std::max(1, (nb + 127) / 128);
-  lm_schur_kernel<<<grid, 128, 0, ctx->stream>>>(a);
+  if (k <= 7) lm_schur_kernel<7><<<grid, 128, 0, ctx->stream>>>(a);
+  else lm_schur_kernel<12><<<grid, 128, 0, ctx->stream>>>(a);
   if (ezc_status st = launch_check(ctx, "lm_schur")) return st;
-  // sums -> red1[R1_SCHUR ..], max (gradient) -> gmaxbuf
-  lm_reduce_rows_kernel<<<nv, 256, 0, ctx->stream>>>(s->part2.as<double>(), grid, nv, nv - 1, s->red1[s->sb].as<double>() + R1_SCHUR);
-  return launch_check(ctx, "lm_reduce_rows");
+  // per-warp partials -> red1[R1_SCHUR ..] in fixed order (last value, the gradient max-norm, is max-reduced)
+  lm_schur_reduce_kernel<<<nv, 256, 0, ctx->stream>>>(s->part2.as<double>(), grid * 4, k, k <= 7 ? 1 : 2, s->red1[s->sb].as<double>() + R1_SCHUR);
+  return launch_check(ctx, "lm_schur_reduce");
 }
 
 ezc_status allreduce(ezc_lm_solver* s, double* dev, int count, int op) {
