@@ -179,30 +179,8 @@ CB_HD inline bool is_convex4(const Pt* p) {
 // ------------------------------------------------------------------------------------------ generateQuads (per contour)
 // Returns true and fills q[4] if the hole contour yields an acceptable quadrangle (approxPolyDP levels 1..7 applied
 // twice, convexity, CALIB_CB_FILTER_QUADS size / aspect tests).
-CB_HD inline bool contour_to_quad(const Pt* contour, int n, Pt* tmp_a, Pt* tmp_b, int* stack_buf, Pt q[4]) {
-  // bounding rect area >= 25
-  int minx = contour[0].x, maxx = minx, miny = contour[0].y, maxy = miny;
-  for (int i = 1; i < n; ++i) {
-    minx = contour[i].x < minx ? contour[i].x : minx; maxx = contour[i].x > maxx ? contour[i].x : maxx;
-    miny = contour[i].y < miny ? contour[i].y : miny; maxy = contour[i].y > maxy ? contour[i].y : maxy;
-  }
-  const int min_area = 25;
-  if ((maxx - minx + 1) * (maxy - miny + 1) < min_area) return false;
-  // OpenCV 4.13 behaviour (checked against cv2 vertex by vertex): every level works on the OUTPUT of the previous
-  // level (and each level is applied twice), not on the original contour.
-  int na = n;
-  const Pt* cur = contour;
-  for (int level = 1; level <= kMaxApproxLevel; level++) {
-    int nb = approx_poly_dp_closed(cur, na, tmp_b, (double)(float)level, stack_buf);
-    for (int i = 0; i < nb; ++i) tmp_a[i] = tmp_b[i];
-    na = nb; cur = tmp_a;
-    if (na == 4) break;
-    nb = approx_poly_dp_closed(tmp_a, na, tmp_b, (double)(float)level, stack_buf);
-    for (int i = 0; i < nb; ++i) tmp_a[i] = tmp_b[i];
-    na = nb;
-    if (na == 4) break;
-  }
-  if (na != 4) return false;
+// Convexity + CALIB_CB_FILTER_QUADS tests on a 4-vertex approximation; fills q on success.
+CB_HD inline bool quad_from_4(const Pt* tmp_a, Pt q[4]) {
   if (!is_convex4(tmp_a)) return false;
   for (int i = 0; i < 4; ++i) q[i] = tmp_a[i];
   // CALIB_CB_FILTER_QUADS
@@ -230,8 +208,35 @@ CB_HD inline bool contour_to_quad(const Pt* contour, int n, Pt* tmp_a, Pt* tmp_b
   const double area = a00;
   auto d = [&](int i, int j) { const double dx = q[i].x - q[j].x, dy = q[i].y - q[j].y; return sqrt(dx * dx + dy * dy); };
   const double d1 = d(0, 2), d2 = d(1, 3), d3 = d(0, 1), d4 = d(1, 2);
-  if (!(d3 * 4 > d4 && d4 * 4 > d3 && d3 * d4 < area * 1.5 && area > min_area && d1 >= 0.15 * p && d2 >= 0.15 * p)) return false;
+  if (!(d3 * 4 > d4 && d4 * 4 > d3 && d3 * d4 < area * 1.5 && area > 25 /* min_area */ && d1 >= 0.15 * p && d2 >= 0.15 * p)) return false;
   return true;
+}
+
+CB_HD inline bool contour_to_quad(const Pt* contour, int n, Pt* tmp_a, Pt* tmp_b, int* stack_buf, Pt q[4]) {
+  // bounding rect area >= 25
+  int minx = contour[0].x, maxx = minx, miny = contour[0].y, maxy = miny;
+  for (int i = 1; i < n; ++i) {
+    minx = contour[i].x < minx ? contour[i].x : minx; maxx = contour[i].x > maxx ? contour[i].x : maxx;
+    miny = contour[i].y < miny ? contour[i].y : miny; maxy = contour[i].y > maxy ? contour[i].y : maxy;
+  }
+  const int min_area = 25;
+  if ((maxx - minx + 1) * (maxy - miny + 1) < min_area) return false;
+  // OpenCV 4.13 behaviour (checked against cv2 vertex by vertex): every level works on the OUTPUT of the previous
+  // level (and each level is applied twice), not on the original contour.
+  int na = n;
+  const Pt* cur = contour;
+  for (int level = 1; level <= kMaxApproxLevel; level++) {
+    int nb = approx_poly_dp_closed(cur, na, tmp_b, (double)(float)level, stack_buf);
+    for (int i = 0; i < nb; ++i) tmp_a[i] = tmp_b[i];
+    na = nb; cur = tmp_a;
+    if (na == 4) break;
+    nb = approx_poly_dp_closed(tmp_a, na, tmp_b, (double)(float)level, stack_buf);
+    for (int i = 0; i < nb; ++i) tmp_a[i] = tmp_b[i];
+    na = nb;
+    if (na == 4) break;
+  }
+  if (na != 4) return false;
+  return quad_from_4(tmp_a, q);
 }
 
 // add a quad (generateQuads, second loop)

@@ -20,6 +20,8 @@
 #include <vector>
 
 #include "cb_logic.h"
+#include <cstdlib>
+
 #include "images.cuh"
 #include "scan_sort.cuh"
 
@@ -341,12 +343,13 @@ __global__ void cb_hole_offset_kernel(HoleInfo* __restrict__ holes, int n_holes,
   if (h >= n_holes) return;
   if (holes[h].offset >= 0) holes[h].offset = need_scan[h];
 }
-// approxPolyDP levels 1..7 + convexity + FILTER_QUADS tests: one thread per hole
+// approxPolyDP levels 1..7 + convexity + FILTER_QUADS tests: one thread per hole (contours up to kWarpContour vertices)
+constexpr int kWarpContour = 96;
 __global__ void cb_quad_kernel(HoleInfo* __restrict__ holes, int n_holes, cb::Pt* __restrict__ pool, int* __restrict__ stack_pool) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= n_holes) return;
   HoleInfo& hi = holes[h];
-  if (hi.offset < 0 || hi.n_pts <= 0) return;
+  if (hi.offset < 0 || hi.n_pts <= 0 || hi.n_pts > kWarpContour) return;
   cb::Pt* c = pool + hi.offset;
   cb::Pt* ta = c + hi.n_pts + 2;
   cb::Pt* tb = ta + hi.n_pts + 2;
@@ -355,6 +358,170 @@ __global__ void cb_quad_kernel(HoleInfo* __restrict__ holes, int n_holes, cb::Pt
   if (cb::contour_to_quad(c, hi.n_pts, ta, tb, stack, q)) {
     hi.quad_ok = 1;
     for (int i = 0; i < 4; ++i) hi.quad[i] = q[i];
+  }
+}
+
+// Long contours (noise blobs of the adaptive-threshold attempts run to thousands of vertices): one WARP per hole.  The
+// Douglas-Peucker scans -- "farthest point from the start" and "farthest point from the chord" -- are lane-strided with a
+// (distance, first index) arg-max, i.e. exactly the element the sequential scan of cb::approx_poly_dp_closed keeps (it
+// uses a strict '>' in contour order); the stack discipline and the clean-up pass are unchanged and run on every lane
+// redundantly on lane-uniform data, lane 0 does the writes.
+__device__ __forceinline__ void warp_argmax(double& d, int& ord) {
+  for (int m = 16; m >= 1; m >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, d, m);
+    const int oo = __shfl_xor_sync(0xffffffffu, ord, m);
+    if (od > d || (od == d && oo < ord)) { d = od; ord = oo; }
+  }
+}
+__device__ int approx_poly_dp_closed_warp(const cb::Pt* src, int count, cb::Pt* dst, double eps, int* stack_buf) {
+  using cb::Pt;
+  if (count == 0) return 0;
+  const int lane = threadIdx.x & 31;
+  int top = 0;
+  auto push = [&](int s_, int e_) { if (lane == 0) { stack_buf[2 * top] = s_; stack_buf[2 * top + 1] = e_; } ++top; };
+  const int init_iters = 3;
+  int slice_s = 0, slice_e = 0, right_s = 0, right_e = 0;
+  Pt start_pt = {-1000000, -1000000}, end_pt = {0, 0}, pt = {0, 0};
+  int pos = 0, new_count = 0;
+  bool le_eps = false;
+  eps *= eps;
+  right_s = 0;
+  for (int i = 0; i < init_iters; i++) {
+    pos = (pos + right_s) % count;
+    start_pt = src[pos];
+    const int base = pos + 1;  // element j (1-based) is src[(base + j - 1) % count]
+    double max_dist = 0;
+    int best = 0x7fffffff;
+    for (int j = 1 + lane; j < count; j += 32) {
+      int pp = base + j - 1; if (pp >= count) pp -= count; if (pp >= count) pp -= count;
+      pt = src[pp];
+      const double dx = pt.x - start_pt.x, dy = pt.y - start_pt.y;
+      const double dist = dx * dx + dy * dy;
+      if (dist > max_dist) { max_dist = dist; best = j; }
+    }
+    warp_argmax(max_dist, best);
+    if (max_dist > 0) right_s = best;   // sequential scan only assigns on dist > max_dist (initially 0)
+    pos = (base + count - 1) % count;   // after the scan the cursor has advanced count times in total
+    le_eps = max_dist <= eps;
+  }
+  if (!le_eps) {
+    right_e = slice_s = pos % count;
+    slice_e = right_s = (right_s + slice_s) % count;
+    push(right_s, right_e);
+    push(slice_s, slice_e);
+  } else {
+    if (lane == 0) dst[new_count] = start_pt;
+    new_count++;
+  }
+  __syncwarp();
+  while (top > 0) {
+    --top;
+    slice_s = stack_buf[2 * top]; slice_e = stack_buf[2 * top + 1];
+    __syncwarp();
+    end_pt = src[slice_e];
+    pos = slice_s;
+    start_pt = src[pos]; if (++pos >= count) pos = 0;
+    if (pos != slice_e) {
+      const int len = (slice_e - pos + count) % count;  // points pos .. slice_e-1 (cyclic)
+      double max_dist = 0;
+      int best = 0x7fffffff;
+      const double dx = end_pt.x - start_pt.x, dy = end_pt.y - start_pt.y;
+      const double L2 = dx * dx + dy * dy;
+      for (int o = lane; o < len; o += 32) {
+        int pp = pos + o; if (pp >= count) pp -= count;
+        pt = src[pp];
+        const double px = pt.x - start_pt.x, py = pt.y - start_pt.y;
+        const double t = px * dx + py * dy;
+        double dist;
+        if (t < 0) dist = px * px + py * py;
+        else if (t > L2) { const double ex = pt.x - end_pt.x, ey = pt.y - end_pt.y; dist = ex * ex + ey * ey; }
+        else { const double cr = py * dx - px * dy; dist = cr * cr / L2; }
+        if (dist > max_dist) { max_dist = dist; best = o; }
+      }
+      warp_argmax(max_dist, best);
+      if (max_dist > 0) { int pp = pos + best; if (pp >= count) pp -= count; right_s = pp; }
+      le_eps = max_dist <= eps;
+    } else {
+      le_eps = true;
+      start_pt = src[slice_s];
+    }
+    if (le_eps) {
+      if (lane == 0) dst[new_count] = start_pt;
+      new_count++;
+    } else {
+      right_e = slice_e;
+      slice_e = right_s;
+      push(right_s, right_e);
+      push(slice_s, slice_e);
+    }
+    __syncwarp();
+  }
+  __syncwarp();
+  // last stage: remove extra points on [almost] straight lines (sequential; lane 0 writes, every lane tracks the state)
+  count = new_count;
+  int result = new_count;
+  if (lane == 0) {
+    pos = count - 1;
+    start_pt = dst[pos]; if (++pos >= count) pos = 0;
+    int wpos = pos;
+    pt = dst[pos]; if (++pos >= count) pos = 0;
+    for (int i = 0; i < count && new_count > 2; i++) {
+      end_pt = dst[pos]; if (++pos >= count) pos = 0;
+      const double dx = end_pt.x - start_pt.x, dy = end_pt.y - start_pt.y;
+      const double dist = fabs((pt.x - start_pt.x) * dy - (pt.y - start_pt.y) * dx);
+      const double sip = (double)(pt.x - start_pt.x) * (end_pt.x - pt.x) + (double)(pt.y - start_pt.y) * (end_pt.y - pt.y);
+      if (dist * dist <= 0.5 * eps * (dx * dx + dy * dy) && dx != 0 && dy != 0 && sip >= 0) {
+        new_count--;
+        dst[wpos] = start_pt = end_pt;
+        if (++wpos >= count) wpos = 0;
+        pt = dst[pos]; if (++pos >= count) pos = 0;
+        i++;
+        continue;
+      }
+      dst[wpos] = start_pt = pt;
+      if (++wpos >= count) wpos = 0;
+      pt = end_pt;
+    }
+    result = new_count;
+  }
+  result = __shfl_sync(0xffffffffu, result, 0);
+  __syncwarp();
+  return result;
+}
+__global__ void __launch_bounds__(256) cb_quad_warp_kernel(HoleInfo* __restrict__ holes, int n_holes, cb::Pt* __restrict__ pool,
+                                                           int* __restrict__ stack_pool) {
+  const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (h >= n_holes) return;
+  HoleInfo& hi = holes[h];
+  if (hi.offset < 0 || hi.n_pts <= kWarpContour) return;
+  const int n = hi.n_pts;
+  cb::Pt* c = pool + hi.offset;
+  cb::Pt* ta = c + n + 2;
+  cb::Pt* tb = ta + n + 2;
+  int* stack = stack_pool + (size_t)hi.offset * 2;
+  // cb::contour_to_quad with the warp-parallel approximation; the bounding-box test already passed in cb_trace_kernel
+  int na = n;
+  const cb::Pt* cur = c;
+  for (int level = 1; level <= cb::kMaxApproxLevel; level++) {
+    int nb = approx_poly_dp_closed_warp(cur, na, tb, (double)(float)level, stack);
+    for (int i = lane; i < nb; i += 32) ta[i] = tb[i];
+    __syncwarp();
+    na = nb; cur = ta;
+    if (na == 4) break;
+    nb = approx_poly_dp_closed_warp(ta, na, tb, (double)(float)level, stack);
+    for (int i = lane; i < nb; i += 32) ta[i] = tb[i];
+    __syncwarp();
+    na = nb;
+    if (na == 4) break;
+  }
+  if (na != 4) return;
+  if (lane == 0) {
+    cb::Pt q[4];
+    if (cb::quad_from_4(ta, q)) {
+      hi.quad_ok = 1;
+      for (int i = 0; i < 4; ++i) hi.quad[i] = q[i];
+    }
   }
 }
 
@@ -388,19 +555,147 @@ struct WarpPar {
   __device__ bool any(bool v) const { return __any_sync(0xffffffffu, v) != 0; }
 };
 
-// one WARP per active image
-__global__ void __launch_bounds__(256) cb_process_kernel(const HoleInfo* __restrict__ holes, ImageState* __restrict__ st,
-                                                         const int* __restrict__ active, int n_img, int pw, int ph, int dilations,
-                                                         cb::Work* __restrict__ works, int* __restrict__ scratch_all,
-                                                         cb::Ptf* __restrict__ corners_out) {
-  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+// coarse phase timers of cb_process_kernel (ns, summed over images and attempts; printed when EZC_CB_TIMING is set)
+__device__ unsigned long long g_cb_ns[6];
+__device__ __forceinline__ unsigned long long cb_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// findQuadNeighbors for one image by a whole thread block.  Same decisions as cb::find_quad_neighbors (cb_logic.h, the
+// definition the CPU harness pins against cv2): the (quad, corner) sweep is sequential because every accepted link
+// changes the state the next search sees; the two O(n) scans inside a step (closest admissible corner; "is a third
+// corner closer") are spread over the block.  The per-slot state the scans read (corner position, link, edge length) is
+// staged in shared memory -- the global Work struct is two dependent loads away per candidate, which made a noisy
+// attempt (1536 quads => 6144 steps x 6144 candidates) cost ~400 ms with one warp.
+constexpr int kProcThreads = 256;
+struct NbShared {
+  float2* pt;     // [4 * nq]  position of corner slot (quad, j)
+  int* nb;        // [4 * nq]  linked quad or -1
+  float* edge;    // [nq]
+  int* count;     // [nq]
+};
+__device__ __forceinline__ void block_min_code(float& d, int& code, float* red_d, int* red_c) {
+  for (int m = 16; m >= 1; m >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, d, m);
+    const int oc = __shfl_xor_sync(0xffffffffu, code, m);
+    if (od < d || (od == d && oc < code)) { d = od; code = oc; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red_d[warp] = d; red_c[warp] = code; }
+  __syncthreads();
+  d = red_d[0]; code = red_c[0];
+#pragma unroll
+  for (int wv = 1; wv < kProcThreads / 32; ++wv) {
+    const float od = red_d[wv];
+    const int oc = red_c[wv];
+    if (od < d || (od == d && oc < code)) { d = od; code = oc; }
+  }
+  __syncthreads();
+}
+__device__ void find_quad_neighbors_block(cb::Work& w, const NbShared& S, float* red_d, int* red_c) {
+  const int nq = w.n_quads;
+  const int tid = threadIdx.x;
+  for (int k = tid; k < nq; k += kProcThreads) {
+    const cb::Quad& q = w.quads[k];
+    S.edge[k] = q.edge_len;
+    S.count[k] = q.count;
+    for (int j = 0; j < 4; ++j) {
+      const cb::Ptf p = w.corners[q.corners[j]].pt;
+      S.pt[4 * k + j] = make_float2(p.x, p.y);
+      S.nb[4 * k + j] = q.nb[j];
+    }
+  }
+  __syncthreads();
+  for (int idx = 0; idx < nq; idx++) {
+    for (int i = 0; i < 4; i++) {
+      if (S.nb[4 * idx + i] >= 0) continue;
+      float min_dist = FLT_MAX;
+      int code = 0x7fffffff;
+      const float2 pt = S.pt[4 * idx + i];
+      const float cur_edge = S.edge[idx];
+      for (int k = tid; k < nq; k += kProcThreads) {
+        if (k == idx) continue;
+        const float ek = S.edge[k];
+        for (int j = 0; j < 4; j++) {
+          if (S.nb[4 * k + j] >= 0) continue;
+          const float2 o = S.pt[4 * k + j];
+          const float dist = cb::normL2Sqrf(pt.x - o.x, pt.y - o.y);
+          if (dist < min_dist && dist <= cur_edge && dist <= ek) {
+            const float ediff = fabsf(cur_edge - ek);
+            if (ediff > 32 * cur_edge || ediff > 32 * ek) continue;
+            code = k * 4 + j; min_dist = dist;
+          }
+        }
+      }
+      block_min_code(min_dist, code, red_d, red_c);
+      if (code == 0x7fffffff || !(min_dist < FLT_MAX)) continue;
+      const int cq = code >> 2, cci = code & 3;
+      if (S.count[idx] >= 4 || S.count[cq] >= 4) continue;
+      const float2 cc = S.pt[4 * cq + cci];
+      int j = 0;
+      for (; j < 4; j++) {
+        if (S.nb[4 * idx + j] == cq) break;
+        const float2 o = S.pt[4 * idx + j];
+        if (cb::normL2Sqrf(cc.x - o.x, cc.y - o.y) < min_dist) break;
+      }
+      if (j < 4) continue;
+      for (j = 0; j < 4; j++) if (S.nb[4 * cq + j] == idx) break;
+      if (j < 4) continue;
+      bool blocked = false;
+      for (int q3 = tid; q3 < nq && !blocked; q3 += kProcThreads) {
+        if (q3 == idx || q3 == cq) continue;
+        for (int k = 0; k < 4; k++) {
+          if (S.nb[4 * q3 + k] < 0) {
+            const float2 o = S.pt[4 * q3 + k];
+            if (cb::normL2Sqrf(cc.x - o.x, cc.y - o.y) < min_dist) { blocked = true; break; }
+          }
+        }
+      }
+      if (__syncthreads_or(blocked ? 1 : 0)) continue;
+      if (tid == 0) {
+        cb::Quad& cur = w.quads[idx];
+        cb::Quad& cqq = w.quads[cq];
+        cb::Corner& ccn = w.corners[cqq.corners[cci]];
+        const float nx = (pt.x + cc.x) * 0.5f, ny = (pt.y + cc.y) * 0.5f;
+        ccn.pt.x = nx; ccn.pt.y = ny;
+        cur.count++;
+        cur.nb[i] = cq;
+        cur.corners[i] = cqq.corners[cci];
+        cqq.count++;
+        cqq.nb[cci] = idx;
+        S.pt[4 * cq + cci] = make_float2(nx, ny);
+        S.pt[4 * idx + i] = make_float2(nx, ny);
+        S.nb[4 * idx + i] = cq;
+        S.nb[4 * cq + cci] = idx;
+        S.count[idx]++;
+        S.count[cq]++;
+      }
+      __syncthreads();
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+}
+
+// one BLOCK per active image
+__global__ void __launch_bounds__(kProcThreads) cb_process_kernel(const HoleInfo* __restrict__ holes, ImageState* __restrict__ st,
+                                                                  const int* __restrict__ active, int n_img, int pw, int ph, int dilations,
+                                                                  cb::Work* __restrict__ works, int* __restrict__ scratch_all,
+                                                                  cb::Ptf* __restrict__ corners_out) {
+  extern __shared__ __align__(16) unsigned char cb_smem[];
+  __shared__ float red_d[kProcThreads / 32];
+  __shared__ int red_c[kProcThreads / 32];
+  const int slot = blockIdx.x;
+  const int tid = threadIdx.x;
   if (slot >= n_img) return;
   const int im = active[slot];
   cb::Work& w = works[im];
   ImageState& S = st[im];
   int* scratch = scratch_all + (size_t)im * cb::kMaxQuads * 4;
-  if (lane == 0) {
+  const unsigned long long t0 = cb_now();
+  if (tid == 0) {
     // generateQuads, second half: the parent contour with the most quads wins (CALIB_CB_FILTER_QUADS).  Counts per parent
     // in an open-addressing table (keys = white-component labels).
     constexpr int TS = 2048;
@@ -430,20 +725,33 @@ __global__ void __launch_bounds__(256) cb_process_kernel(const HoleInfo* __restr
     w.max_quads = total * 3 > 2 ? total * 3 : 2;
     if (w.max_quads > cb::kMaxQuads) w.max_quads = cb::kMaxQuads;
     w.pw = pw; w.ph = ph;
+    atomicAdd(&g_cb_ns[0], cb_now() - t0);
     for (int h = S.hole_begin; h < S.hole_end; ++h) {
       if (!holes[h].quad_ok || holes[h].parent != boardIdx) continue;
       if (w.n_quads >= w.max_quads) break;
       cb::add_quad(w, holes[h].quad, dilations);
     }
     S.n_quads = w.n_quads;
+    __threadfence_block();
   }
-  __syncwarp();
+  __syncthreads();
+  const unsigned long long t1 = cb_now();
+  if (tid == 0) atomicAdd(&g_cb_ns[1], t1 - t0);
   // a complete board needs all its inner squares: fewer quads than that cannot succeed (and leave no trace in
   // prev_sqr_size either), so the quad-graph stage is skipped
-  if (w.n_quads < ((pw - 1) * (ph - 1)) / 2) return;
-  cb::find_quad_neighbors(w, WarpPar());
-  __syncwarp();
-  if (lane == 0) {
+  const int nq = w.n_quads;
+  if (nq < ((pw - 1) * (ph - 1)) / 2) return;
+  {
+    NbShared sh;
+    sh.pt = reinterpret_cast<float2*>(cb_smem);
+    sh.nb = reinterpret_cast<int*>(sh.pt + 4 * cb::kMaxQuads);
+    sh.edge = reinterpret_cast<float*>(sh.nb + 4 * cb::kMaxQuads);
+    sh.count = reinterpret_cast<int*>(sh.edge + cb::kMaxQuads);
+    find_quad_neighbors_block(w, sh, red_d, red_c);
+  }
+  const unsigned long long t2 = cb_now();
+  if (tid == 0) atomicAdd(&g_cb_ns[2], t2 - t1);
+  if (tid == 0) {
     int n_out = 0, prev = S.prev_sqr_size;
     cb::Ptf* out = corners_out + (size_t)im * pw * ph;
     cb::Ptf* tmp = reinterpret_cast<cb::Ptf*>(w.hull);  // partial corner sets are written too; copy on success only
@@ -453,8 +761,10 @@ __global__ void __launch_bounds__(256) cb_process_kernel(const HoleInfo* __restr
       for (int i = 0; i < pw * ph; ++i) out[i] = tmp[i];
       S.found = 1;
     }
+    atomicAdd(&g_cb_ns[3], cb_now() - t2);
   }
 }
+constexpr size_t kProcSmem = (size_t)cb::kMaxQuads * (4 * sizeof(float2) + 4 * sizeof(int) + sizeof(float) + sizeof(int));
 
 // final checks of cv::findChessboardCorners after a successful attempt: board monotony, 8-px border, even/even flip
 __global__ void cb_finalize_kernel(ImageState* __restrict__ st, int n_img, int pw, int ph, int W, int H, cb::Ptf* __restrict__ corners,
@@ -642,10 +952,20 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
     CB_LAUNCH(cb_hole_offset_kernel, nH, P.holes.as<HoleInfo>(), nH, P.need.as<int>());
     CB_LAUNCH(cb_trace_kernel<true>, nH, bin, P.labels.as<int>(), W, H, nH, P.holes.as<HoleInfo>(), P.pool.as<cb::Pt>(), cb::kMaxContourPts);
     CB_LAUNCH(cb_quad_kernel, nH, P.holes.as<HoleInfo>(), nH, P.pool.as<cb::Pt>(), P.stack_pool.as<int>());
+    CB_LAUNCH(cb_quad_warp_kernel, (long long)nH * 32, P.holes.as<HoleInfo>(), nH, P.pool.as<cb::Pt>(), P.stack_pool.as<int>());
     CB_LAUNCH(cb_hole_ranges_kernel, nH, P.holes.as<HoleInfo>(), nH, N, 0, st);
   }
-  CB_LAUNCH(cb_process_kernel, (long long)n_act * 32, P.holes.as<HoleInfo>(), st, list, n_act, pw, ph, dilations, P.works.as<cb::Work>(), P.scratch.as<int>(),
-            P.corners.as<cb::Ptf>());
+  {
+    static bool attr_set = false;
+    if (!attr_set) {
+      EZC_CUDA(cudaFuncSetAttribute(cb_process_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kProcSmem));
+      attr_set = true;
+    }
+    cb_process_kernel<<<n_act, kProcThreads, kProcSmem, ctx->stream>>>(P.holes.as<HoleInfo>(), st, list, n_act, pw, ph, dilations,
+                                                                       P.works.as<cb::Work>(), P.scratch.as<int>(), P.corners.as<cb::Ptf>());
+    EZC_CUDA(cudaGetLastError());
+    ctx->kernel_launches++;
+  }
   return EZC_OK;
 }
 
@@ -818,14 +1138,24 @@ ezc_status ezc_find_chessboard_corners_batch(ezc_context* ctx, const ezc_images*
   ezc::DevBuf d_corners, d_found;
   EZC_CUDA(d_corners.reserve(sizeof(float2) * (size_t)n * npts));
   EZC_CUDA(d_found.reserve((size_t)n));
-  for (int i0 = 0; i0 < n; i0 += sub) {
-    const int nb = std::min(sub, n - i0);
+  // images still crossing PCIe (ezc_images_upload_async): start small so the pipeline fills quickly, then double
+  int cur = imgs->ready.empty() ? sub : std::min(sub, std::max(1, imgs->chunk));
+  for (int i0 = 0; i0 < n;) {
+    const int nb = std::min(cur, n - i0);
     if (ezc_status st = detect_sub_batch(ctx, imgs, i0, nb, pattern_w, pattern_h, final_subpix != 0, d_corners.as<float2>(), d_found.as<uint8_t>()))
       return st;
+    i0 += nb;
+    cur = std::min(sub, cur * 2);
   }
   EZC_CUDA(cudaMemcpyAsync(corners_out, d_corners.p, sizeof(float2) * (size_t)n * npts, cudaMemcpyDeviceToHost, ctx->stream));
   EZC_CUDA(cudaMemcpyAsync(found_out, d_found.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (getenv("EZC_CB_TIMING")) {
+    unsigned long long t[6] = {0};
+    cudaMemcpyFromSymbol(t, g_cb_ns, sizeof(t));
+    fprintf(stderr, "[cb timing, cumulative ms] parent-count %.1f | +add_quad %.1f | neighbours %.1f | groups %.1f\n", t[0] * 1e-6, t[1] * 1e-6,
+            t[2] * 1e-6, t[3] * 1e-6);
+  }
   return EZC_OK;
 }
 
