@@ -440,12 +440,14 @@ CB_HD inline int add_outer_quad(Work& w, int quad_idx) {
         c.pt.x += off.x; c.pt.y += off.y;
       }
       q.corners[j] = quad.corners[i];
-      const int next_i = (i + 1) & 3, prev_i = (i + 3) & 3;
-      const int qp = quad.nb[prev_i];
-      if (qp >= 0 && w.quads[qp].ordered && w.quads[qp].nb[i] >= 0 && w.quads[w.quads[qp].nb[i]].ordered) {
-        const int qn = w.quads[qp].nb[next_i];
-        if (qn >= 0) {
-          q.count = 2;
+      // the second neighbour of the new quad, on either side (k = 1: the side OpenCV has always tried; k = 3: the mirror
+      // case -- without it a missing edge square next to an unordered corner square gets TWO replacement quads)
+      for (int k = 1; k <= 3; k += 2) {
+        const int next_i = (i + k) & 3, prev_i = (i + k + 2) & 3;
+        const int qp = quad.nb[prev_i];
+        if (qp >= 0 && w.quads[qp].ordered && w.quads[qp].nb[i] >= 0 && w.quads[w.quads[qp].nb[i]].ordered) {
+          const int qn = w.quads[qp].nb[i];
+          q.count += 1;
           q.nb[prev_i] = qn;
           w.quads[qn].nb[next_i] = q_index;
           w.quads[qn].count += 1;

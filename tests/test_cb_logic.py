@@ -55,3 +55,21 @@ def test_restated_search_matches_golden(name):
         assert np.abs(fin - G[name + "_final"]).max() <= 0.05, (name, np.abs(fin - G[name + "_final"]).max())
         if name.startswith("render"):
             assert d.max() == 0 and np.abs(fin - G[name + "_final"]).max() <= 0.01
+
+
+@pytest.mark.parametrize("name", ["render0", "warp2"])
+def test_erased_outer_squares_match_cv2(name):
+    """Outer squares painted over: cv2 repairs the grid through addOuterQuad (both second-neighbour sides); the restated
+    logic must take the same decisions -- found flag and corners (pins cb::add_outer_quad, 0/240 mismatches on the
+    full corpus, 66/240 with the one-sided variant)."""
+    import cv2
+    from erased import FLAGS, erased_cases
+    n = 0
+    for cs, im in erased_cases(G[name + "_img"], n_pairs=3, step=2):
+        ok_ref, c_ref = cv2.findChessboardCorners(im, (9, 6), flags=FLAGS)
+        ok, c = P.find_chessboard_corners(im, (9, 6))
+        assert bool(ok) == bool(ok_ref), (name, cs)
+        if ok:
+            assert np.abs(c - c_ref.reshape(-1, 2)).max() <= 0.01, (name, cs)
+        n += 1
+    assert n >= 15

@@ -54,3 +54,27 @@ def test_small_noise_image_is_rejected(ctx):
     found, corners = detect.detect_chessboard(ctx, imgs, 7, 10)
     imgs.close()
     assert not found[0]
+
+
+def test_erased_outer_squares_match_cv2(ctx):
+    """Boards with outer squares painted over, one batch: the detector must repair (or reject) exactly like cv2."""
+    import sys
+    import cv2
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "cb_harness"))
+    from erased import FLAGS, erased_cases
+    from ezcalib_b200 import detect
+    batch, labels = [], []
+    for name in ("render0", "warp0", "warp2"):
+        for cs, im in erased_cases(G[name + "_img"], n_pairs=4, step=1):
+            batch.append(im); labels.append((name, cs))
+    imgs = detect.Images(ctx, np.stack(batch))
+    found, corners = detect.find_chessboard_corners(ctx, imgs, (9, 6), False)
+    imgs.close()
+    n_found = 0
+    for k, im in enumerate(batch):
+        ok_ref, c_ref = cv2.findChessboardCorners(im, (9, 6), flags=FLAGS)
+        assert bool(found[k]) == bool(ok_ref), labels[k]
+        if ok_ref:
+            n_found += 1
+            assert np.abs(corners[k] - c_ref.reshape(-1, 2)).max() <= 0.01, labels[k]
+    assert n_found >= 40 and n_found < len(batch)   # both outcomes are exercised

@@ -35,4 +35,8 @@ for i in range(n):
     if ok:
         ref = cv2.cornerSubPix(host[i], c, (5, 5), (-1, -1), CRIT).reshape(-1, 2)
         diffs.append(float(np.abs(ref - corners[i]).max()))
+if mis:
+    os.makedirs("gpurun_out", exist_ok=True)
+    np.save(f"gpurun_out/cb_mismatch_s{int(sigma)}.npy", host[mis])
+    print("gpu found flags of mismatches:", [bool(found[i]) for i in mis])
 print(f"cv2: {time.time()-t0:.3f}s; flag mismatches {mis}; corner diffs max {max(diffs) if diffs else None}; >0.01: {sum(x > 0.01 for x in diffs)} of {len(diffs)}")
