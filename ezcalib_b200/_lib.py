@@ -78,7 +78,7 @@ def lib():
         L.ezc_corner_subpix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double]
         L.ezc_detect_aprilgrid_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.ezc_detect_chessboard_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
-        L.ezc_find_chessboard_corners_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
+        L.ezc_find_chessboard_corners_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
         L.ezc_apriltag_debug_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p]
         L.ezc_apriltag_debug_count.argtypes = [C.c_void_p, C.c_int32]
         L.ezc_apriltag_debug_get.argtypes = [C.c_void_p] * 8

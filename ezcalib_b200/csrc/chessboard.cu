@@ -239,22 +239,24 @@ __global__ void cb_label_compress_kernel(const uint8_t* __restrict__ bin, int* _
   L[gid] = r;
 }
 __global__ void cb_label_flatten_kernel(const uint8_t* __restrict__ bin, int* __restrict__ L, long long total, long long N,
-                                        const int* __restrict__ active, int* __restrict__ hole_flag) {
+                                        const int* __restrict__ active, int* __restrict__ hole_flag, int white_roots) {
   const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (cg >= total) return;
   const int slot = (int)(cg / N);
   const long long gid = (long long)(active ? active[slot] : slot) * N + (cg - (long long)slot * N);
   const int r = L[L[gid]];   // pixel -> run head -> root (cb_label_compress has flattened the heads)
   L[gid] = r;
-  hole_flag[cg] = (bin[gid] == 0 && r == (int)gid) ? 1 : 0;  // raster-first pixel of a black component (compact index)
+  // raster-first pixel of a black component (hole search) or of a white one (fast check); compact index
+  hole_flag[cg] = (((bin[gid] != 0) == (white_roots != 0)) && r == (int)gid) ? 1 : 0;
 }
 __global__ void cb_hole_list_kernel(const int* __restrict__ flag_scan, const uint8_t* __restrict__ bin, const int* __restrict__ L,
-                                    long long total, long long N, const int* __restrict__ active, int* __restrict__ hole_start) {
+                                    long long total, long long N, const int* __restrict__ active, int* __restrict__ hole_start,
+                                    int white_roots) {
   const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (cg >= total) return;
   const int slot = (int)(cg / N);
   const long long gid = (long long)(active ? active[slot] : slot) * N + (cg - (long long)slot * N);
-  if (bin[gid] == 0 && L[gid] == (int)gid) hole_start[flag_scan[cg]] = (int)gid;
+  if (((bin[gid] != 0) == (white_roots != 0)) && L[gid] == (int)gid) hole_start[flag_scan[cg]] = (int)gid;
 }
 
 // ---------------------------------------------------------------------------------------------- border following
@@ -523,6 +525,212 @@ __global__ void __launch_bounds__(256) cb_quad_warp_kernel(HoleInfo* __restrict_
       for (int i = 0; i < 4; ++i) hi.quad[i] = q[i];
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------- CALIB_CB_FAST_CHECK
+// checkChessboardBinary + checkChessboard (OpenCV calib3d/src/checkchessboard.cpp), the gate the reference switches on
+// (chessboard_detector.hpp:33): blobs of the eroded white / dilated black image whose min-area rectangle has a long side
+// >= 10 px and aspect within [0.3, 3] are "quad hypotheses"; a board is plausible if some run of similar sizes (ratio
+// <= 1.4) holds more than w*h/2 of them with >= 75 % of the expected black and white squares.  Here: 8-connected
+// components of the foreground by the run-based labelling above, the run end points of every component that survive an Akl-Toussaint
+// filter give its convex hull (no border walk), min-area rectangle over the hull edges; the (size, class) lists go to the host, which runs checkQuads.
+__global__ void cb_morph_kernel(const uint8_t* __restrict__ src, long long pitch, long long istride, uint8_t* __restrict__ dst, int W, int H,
+                                int n_img, const int* __restrict__ active, int is_max) {
+  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long N = (long long)W * H;
+  if (cg >= N * n_img) return;
+  const int slot = (int)(cg / N);
+  const int im = active ? active[slot] : slot;
+  const int p = (int)(cg - (long long)slot * N);
+  const int y = p / W, x = p - y * W;
+  const uint8_t* S = src + (long long)im * istride;
+  int m = is_max ? 0 : 255;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= H) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= W) continue;
+      const int v = S[(long long)yy * pitch + xx];
+      m = is_max ? (v > m ? v : m) : (v < m ? v : m);
+    }
+  }
+  dst[(long long)im * N + p] = (uint8_t)m;
+}
+// dst = inv ? (src <= t) : (src > t)   (cv::threshold THRESH_BINARY_INV / THRESH_BINARY), 255 / 0
+__global__ void cb_fg_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long N, int n_img, const int* __restrict__ active,
+                             int thresh, int inv) {
+  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cg >= N * n_img) return;
+  const int slot = (int)(cg / N);
+  const long long gid = (long long)(active ? active[slot] : slot) * N + (cg - (long long)slot * N);
+  const bool above = (int)src[gid] > thresh;
+  dst[gid] = (above != (inv != 0)) ? 255 : 0;
+}
+
+struct FcComp {
+  int start;        // raster-first pixel of the component (global linear index)
+  int n_keep;       // candidate points strictly outside the extreme-point polygon
+  int fill;         // scatter cursor
+  int offset;       // into the point pool, -1 = skipped
+  int ex[8], ey[8]; // extreme points in the 8 principal directions, in angular order (left, top-left, top, ...)
+  unsigned long long key[8];  // atomicMax keys: (direction value + bias) << 32 | pixel
+};
+// The convex hull of a component is the hull of the end points of its horizontal runs, so nothing has to be traced:
+// three pixel-parallel passes (extreme points by atomicMax, survivor count, survivor scatter) replace a sequential
+// border walk whose length for the white background is the whole image frame.
+__global__ void cb_fc_init_kernel(int n_comp, FcComp* __restrict__ comps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_comp) return;
+  FcComp& ci = comps[c];
+  ci.start = 0; ci.n_keep = 0; ci.fill = 0; ci.offset = -1;
+  for (int k = 0; k < 8; ++k) ci.key[k] = 0ull;
+}
+// is pixel (x, y) of the foreground the first or the last pixel of its horizontal run?
+__device__ __forceinline__ bool fc_candidate(const uint8_t* __restrict__ B, int W, int x, int y) {
+  const uint8_t* r = B + (long long)y * W;
+  if (r[x] == 0) return false;
+  return x == 0 || r[x - 1] == 0 || x == W - 1 || r[x + 1] == 0;
+}
+// MODE 0: extreme points; MODE 1: count the candidates strictly outside the polygon of the extreme points; MODE 2: store them
+template <int MODE>
+__global__ void cb_fc_points_kernel(const uint8_t* __restrict__ fg, const int* __restrict__ L, const int* __restrict__ flag_scan, int W, int H,
+                                    int n_img, const int* __restrict__ active, FcComp* __restrict__ comps, cb::Pt* __restrict__ pool) {
+  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long N = (long long)W * H;
+  if (cg >= N * n_img) return;
+  const int slot = (int)(cg / N);
+  const int im = active ? active[slot] : slot;
+  const int p = (int)(cg - (long long)slot * N);
+  const int y = p / W, x = p - y * W;
+  const uint8_t* B = fg + (long long)im * N;
+  if (!fc_candidate(B, W, x, y)) return;
+  const int root = L[(long long)im * N + p];                       // global index of the component's first pixel
+  const int cid = flag_scan[(long long)slot * N + (root - (long long)im * N)];
+  FcComp& ci = comps[cid];
+  if (MODE == 0) {
+    if ((long long)root == (long long)im * N + p) ci.start = root;   // the first pixel of a component starts a run
+    const int kv[8] = {-x, -x - y, -y, x - y, x, x + y, y, y - x};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const unsigned long long key = ((unsigned long long)(unsigned)(kv[k] + (1 << 20)) << 32) | (unsigned)p;
+      if (key > ci.key[k]) atomicMax(&ci.key[k], key);
+    }
+  } else {
+    if (ci.offset == -1) return;
+    bool outside = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int k2 = (k + 1) & 7;
+      const long long ax = ci.ex[k2] - ci.ex[k], ay = ci.ey[k2] - ci.ey[k];
+      if (ax == 0 && ay == 0) continue;
+      const long long cr = ax * (y - ci.ey[k]) - ay * (x - ci.ex[k]);
+      if (cr < 0) { outside = true; break; }
+    }
+    if (!outside) return;
+    if (MODE == 1) atomicAdd(&ci.n_keep, 1);
+    else pool[ci.offset + atomicAdd(&ci.fill, 1)] = cb::Pt{x, y};
+  }
+}
+// decode the extreme points; components whose bounding-box diagonal is below 10 px cannot pass the size test
+__global__ void cb_fc_prefilter_kernel(FcComp* __restrict__ comps, int n_comp, int W) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_comp) return;
+  FcComp& ci = comps[c];
+  for (int k = 0; k < 8; ++k) {
+    const int p = (int)(unsigned)(ci.key[k] & 0xffffffffull);
+    ci.ey[k] = p / W; ci.ex[k] = p - ci.ey[k] * W;
+  }
+  const long long bw = ci.ex[4] - ci.ex[0], bh = ci.ey[6] - ci.ey[2];
+  ci.offset = (bw * bw + bh * bh >= 100) ? 0 : -1;
+}
+__global__ void cb_fc_need_kernel(const FcComp* __restrict__ comps, int n, int* __restrict__ need) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  need[c] = comps[c].offset >= 0 ? 2 * (comps[c].n_keep + 8) + 16 : 0;  // survivors + extreme points, and their hull
+}
+__global__ void cb_fc_offset_kernel(FcComp* __restrict__ comps, int n, const int* __restrict__ need_scan) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  if (comps[c].offset >= 0) comps[c].offset = need_scan[c];
+}
+struct FcHyp { float size; int slot_class; };  // slot_class = image * 2 + class
+// convex hull (monotone chain on heap-sorted points) + min-area rectangle over the hull edges; emits a hypothesis
+__global__ void cb_fc_minrect_kernel(const FcComp* __restrict__ comps, int n_comp, cb::Pt* __restrict__ pool, long long N, int class_id,
+                                     FcHyp* __restrict__ hyps, int* __restrict__ n_hyps, int max_hyps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_comp) return;
+  const FcComp& ci = comps[c];
+  if (ci.offset < 0) return;
+  cb::Pt* a = pool + ci.offset;
+  for (int k = 0; k < 8; ++k) a[ci.n_keep + k] = cb::Pt{ci.ex[k], ci.ey[k]};
+  const int n = ci.n_keep + 8;
+  cb::Pt* h = a + n + 4;
+  auto less = [](const cb::Pt& p, const cb::Pt& q) { return p.x < q.x || (p.x == q.x && p.y < q.y); };
+  // heap sort by (x, y)
+  auto sift = [&](int start, int end) {
+    int root = start;
+    for (;;) {
+      int child = 2 * root + 1;
+      if (child > end) break;
+      if (child + 1 <= end && less(a[child], a[child + 1])) ++child;
+      if (less(a[root], a[child])) { const cb::Pt t = a[root]; a[root] = a[child]; a[child] = t; root = child; }
+      else break;
+    }
+  };
+  for (int st = (n - 2) / 2; st >= 0; --st) sift(st, n - 1);
+  for (int end = n - 1; end > 0; --end) { const cb::Pt t = a[0]; a[0] = a[end]; a[end] = t; sift(0, end - 1); }
+  int k = 0;
+  auto cross = [](const cb::Pt& o, const cb::Pt& p, const cb::Pt& q) { return (long long)(p.x - o.x) * (q.y - o.y) - (long long)(p.y - o.y) * (q.x - o.x); };
+  for (int i = 0; i < n; ++i) {
+    if (i > 0 && a[i].x == a[i - 1].x && a[i].y == a[i - 1].y) continue;
+    while (k >= 2 && cross(h[k - 2], h[k - 1], a[i]) <= 0) k--;
+    h[k++] = a[i];
+  }
+  const int lower = k + 1;
+  for (int i = n - 2; i >= 0; --i) {
+    if (a[i].x == a[i + 1].x && a[i].y == a[i + 1].y) continue;
+    while (k >= lower && cross(h[k - 2], h[k - 1], a[i]) <= 0) k--;
+    h[k++] = a[i];
+  }
+  if (k > 1) k--;  // last point == first
+  // width / height as cv::minAreaRect (4.13) reports them: "width" is the extent along the box direction whose angle lies
+  // in [-90, 0) degrees in image coordinates (x >= 0, y < 0), "height" the other one (measured on cv2)
+  double bw = 0, bh = 0;
+  if (k == 2) {
+    const double dx = h[1].x - h[0].x, dy = h[1].y - h[0].y;
+    const double len = sqrt(dx * dx + dy * dy);
+    const bool along = (dy < 0 && dx >= 0) || (dy > 0 && dx <= 0);
+    bw = along ? len : 0; bh = along ? 0 : len;
+  } else if (k >= 3) {
+    double best = 1e300;
+    for (int e = 0; e < k; ++e) {
+      const cb::Pt p = h[e], q = h[(e + 1) % k];
+      const double ux = q.x - p.x, uy = q.y - p.y;
+      const double len = sqrt(ux * ux + uy * uy);
+      const double cx = ux / len, cy = uy / len;
+      double mn = 0, mx = 0, mh = 0;
+      for (int i = 0; i < k; ++i) {
+        const double vx = h[i].x - p.x, vy = h[i].y - p.y;
+        const double t = vx * cx + vy * cy, d = fabs(vy * cx - vx * cy);
+        mn = t < mn ? t : mn; mx = t > mx ? t : mx; mh = d > mh ? d : mh;
+      }
+      const double w = mx - mn, area = w * mh;
+      if (area < best) {
+        best = area;
+        const bool along = (uy < 0 && ux >= 0) || (uy > 0 && ux <= 0);
+        bw = along ? w : mh; bh = along ? mh : w;
+      }
+    }
+  }
+  const float fw = (float)bw, fh = (float)bh;
+  const float box_size = fw > fh ? fw : fh;
+  if (box_size < 10.0f) return;
+  const float aspect = fw / (fh > 1.f ? fh : 1.f);
+  if (aspect < 0.3f || aspect > 3.0f) return;
+  const int im = (int)(ci.start / N);
+  const int idx = atomicAdd(n_hyps, 1);
+  if (idx < max_hyps) { hyps[idx].size = box_size; hyps[idx].slot_class = im * 2 + class_id; }
 }
 
 // ---------------------------------------------------------------------------------------------- per-image quad logic
@@ -891,6 +1099,8 @@ namespace {
 struct CbPools {
   DevBuf hist, thresh, bin0, bin1, prevbin, eq, lut, labels, flags, scan_tmp, total, hole_start, holes, need, pool, stack_pool;
   DevBuf works, scratch, state, active, corners, found, block, delta, hsum, sub_corners, sub_idx, refresh;
+  DevBuf fc_w0, fc_w1, fc_w2, fc_k0, fc_k1, fc_k2, fc_fg, fc_comps, fc_hyps, fc_count, fc_list;
+  HostPinned fc_h;
   HostPinned h;
 };
 
@@ -929,7 +1139,7 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
   CB_LAUNCH(cb_label_runs_kernel, (long long)H * n_act * 32, bin, P.labels.as<int>(), W, H, n_act, list);
   CB_LAUNCH(cb_label_merge_kernel, total, bin, P.labels.as<int>(), W, H, n_act, list);
   CB_LAUNCH(cb_label_compress_kernel, total, bin, P.labels.as<int>(), W, total, N, list);
-  CB_LAUNCH(cb_label_flatten_kernel, total, bin, P.labels.as<int>(), total, N, list, P.flags.as<int>());
+  CB_LAUNCH(cb_label_flatten_kernel, total, bin, P.labels.as<int>(), total, N, list, P.flags.as<int>(), 0);
   if (ezc_status st = exclusive_scan_i32(ctx, P.flags.as<int>(), P.flags.as<int>(), total, P.scan_tmp, d_tot)) return st;
   EZC_CUDA(cudaMemcpyAsync(P.h.p, d_tot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   EZC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -939,7 +1149,7 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
     EZC_CUDA(P.hole_start.reserve(sizeof(int) * (size_t)nH));
     EZC_CUDA(P.holes.reserve(sizeof(HoleInfo) * (size_t)nH));
     EZC_CUDA(P.need.reserve(sizeof(int) * ((size_t)nH + 1)));
-    CB_LAUNCH(cb_hole_list_kernel, total, P.flags.as<int>(), bin, P.labels.as<int>(), total, N, list, P.hole_start.as<int>());
+    CB_LAUNCH(cb_hole_list_kernel, total, P.flags.as<int>(), bin, P.labels.as<int>(), total, N, list, P.hole_start.as<int>(), 0);
     CB_LAUNCH(cb_hole_init_kernel, nH, P.hole_start.as<int>(), nH, P.holes.as<HoleInfo>(), P.need.as<int>());
     CB_LAUNCH(cb_trace_kernel<false>, nH, bin, P.labels.as<int>(), W, H, nH, P.holes.as<HoleInfo>(), nullptr, cb::kMaxContourPts);
     CB_LAUNCH(cb_hole_need_kernel, nH, P.holes.as<HoleInfo>(), nH, P.need.as<int>());
@@ -981,7 +1191,154 @@ ezc_status sync_state(ezc_context* ctx, CbPools& P, int nb, std::vector<ImageSta
   return upload_list(ctx, P.active, list);
 }
 
-ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, int nb, int pw, int ph, bool final_subpix,
+// checkQuads (checkchessboard.cpp) on the host: a few hundred (size, class) pairs per image.
+static bool fc_check_quads(std::vector<std::pair<float, int>>& quads, int pw, int ph) {
+  const size_t min_quads_count = (size_t)(pw * ph / 2);
+  std::sort(quads.begin(), quads.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first < b.first; });
+  const float size_rel_dev = 0.4f;
+  const int black_count = (int)lrint(std::ceil(pw / 2.0) * std::ceil(ph / 2.0));
+  const int white_count = (int)lrint(std::floor(pw / 2.0) * std::floor(ph / 2.0));
+  for (size_t i = 0; i < quads.size(); i++) {
+    size_t j = i + 1;
+    for (; j < quads.size(); j++)
+      if (quads[j].first / quads[i].first > 1.0f + size_rel_dev) break;
+    if (j + 1 > min_quads_count + i) {
+      int counts[2] = {0, 0};
+      for (size_t k = i; k != j; k++) counts[quads[k].second]++;
+      if (counts[0] < black_count * 0.75 || counts[1] < white_count * 0.75) continue;
+      return true;
+    }
+  }
+  return false;
+}
+
+// fillQuads + checkQuads for the images in `alist` (real indices); images that pass are flagged and leave the list.
+static ezc_status fc_round(ezc_context* ctx, CbPools& P, const uint8_t* white_src, const uint8_t* black_src, int white_thresh, int black_thresh,
+                           int W, int H, int pw, int ph, std::vector<int>& alist, std::vector<char>& pass) {
+  const int n_act = (int)alist.size();
+  if (n_act == 0) return EZC_OK;
+  const long long N = (long long)W * H, total = N * n_act;
+  if (ezc_status st = upload_list(ctx, P.fc_list, alist)) return st;
+  const int* list = P.fc_list.as<int>();
+  const int max_hyps = (int)std::min<long long>(4 << 20, total / 64 + 4096);
+  EZC_CUDA(P.fc_hyps.reserve(sizeof(FcHyp) * (size_t)max_hyps));
+  EZC_CUDA(P.fc_count.reserve(64));
+  EZC_CUDA(cudaMemsetAsync(P.fc_count.p, 0, sizeof(int), ctx->stream));
+  int* d_tot = P.total.as<int>();
+  uint8_t* fg = P.fc_fg.as<uint8_t>();
+  for (int cls = 1; cls >= 0; --cls) {
+    CB_LAUNCH(cb_fg_kernel, total, cls ? white_src : black_src, fg, N, n_act, list, cls ? white_thresh : black_thresh, cls ? 0 : 1);
+    CB_LAUNCH(cb_label_runs_kernel, (long long)H * n_act * 32, fg, P.labels.as<int>(), W, H, n_act, list);
+    CB_LAUNCH(cb_label_merge_kernel, total, fg, P.labels.as<int>(), W, H, n_act, list);
+    CB_LAUNCH(cb_label_compress_kernel, total, fg, P.labels.as<int>(), W, total, N, list);
+    CB_LAUNCH(cb_label_flatten_kernel, total, fg, P.labels.as<int>(), total, N, list, P.flags.as<int>(), 1);
+    if (ezc_status st = exclusive_scan_i32(ctx, P.flags.as<int>(), P.flags.as<int>(), total, P.scan_tmp, d_tot)) return st;
+    EZC_CUDA(cudaMemcpyAsync(P.h.p, d_tot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int nC = *P.h.as<int>();
+    if (nC <= 0) continue;
+    EZC_CUDA(P.fc_comps.reserve(sizeof(FcComp) * (size_t)nC));
+    EZC_CUDA(P.need.reserve(sizeof(int) * ((size_t)nC + 1)));
+    CB_LAUNCH(cb_fc_init_kernel, nC, nC, P.fc_comps.as<FcComp>());
+    CB_LAUNCH(cb_fc_points_kernel<0>, total, fg, P.labels.as<int>(), P.flags.as<int>(), W, H, n_act, list, P.fc_comps.as<FcComp>(), nullptr);
+    CB_LAUNCH(cb_fc_prefilter_kernel, nC, P.fc_comps.as<FcComp>(), nC, W);
+    CB_LAUNCH(cb_fc_points_kernel<1>, total, fg, P.labels.as<int>(), P.flags.as<int>(), W, H, n_act, list, P.fc_comps.as<FcComp>(), nullptr);
+    CB_LAUNCH(cb_fc_need_kernel, nC, P.fc_comps.as<FcComp>(), nC, P.need.as<int>());
+    if (ezc_status st = exclusive_scan_i32(ctx, P.need.as<int>(), P.need.as<int>(), nC, P.scan_tmp, d_tot)) return st;
+    EZC_CUDA(cudaMemcpyAsync(P.h.p, d_tot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int nPts = *P.h.as<int>();
+    if (nPts <= 0) continue;
+    EZC_CUDA(P.pool.reserve(sizeof(cb::Pt) * ((size_t)nPts + 16)));
+    CB_LAUNCH(cb_fc_offset_kernel, nC, P.fc_comps.as<FcComp>(), nC, P.need.as<int>());
+    CB_LAUNCH(cb_fc_points_kernel<2>, total, fg, P.labels.as<int>(), P.flags.as<int>(), W, H, n_act, list, P.fc_comps.as<FcComp>(), P.pool.as<cb::Pt>());
+    CB_LAUNCH(cb_fc_minrect_kernel, nC, P.fc_comps.as<FcComp>(), nC, P.pool.as<cb::Pt>(), N, cls, P.fc_hyps.as<FcHyp>(), P.fc_count.as<int>(), max_hyps);
+  }
+  EZC_CUDA(cudaMemcpyAsync(P.h.p, P.fc_count.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int nHyp = *P.h.as<int>();
+  std::vector<int> next;
+  if (nHyp > max_hyps) {
+    // hypothesis buffer overflow (pathological noise): let everything through to the full search
+    for (int im : alist) pass[im] = 1;
+    alist.clear();
+    return EZC_OK;
+  }
+  EZC_CUDA(P.fc_h.reserve(sizeof(FcHyp) * (size_t)std::max(nHyp, 1)));
+  if (nHyp > 0) {
+    EZC_CUDA(cudaMemcpyAsync(P.fc_h.p, P.fc_hyps.p, sizeof(FcHyp) * (size_t)nHyp, cudaMemcpyDeviceToHost, ctx->stream));
+    EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  const FcHyp* hh = P.fc_h.as<FcHyp>();
+  std::vector<std::vector<std::pair<float, int>>> per(pass.size());
+  for (int i = 0; i < nHyp; ++i) per[hh[i].slot_class >> 1].emplace_back(hh[i].size, hh[i].slot_class & 1);
+  const bool dbg = getenv("EZC_FC_DEBUG") != nullptr;
+  for (int im : alist) {
+    int n0 = 0, n1 = 0;
+    if (dbg) for (auto& q : per[im]) (q.second ? n1 : n0)++;
+    const bool ok = fc_check_quads(per[im], pw, ph);
+    if (dbg) {
+      fprintf(stderr, "[fc] image %d thresholds (%d,%d): %d black + %d white hypotheses -> %s |", im, white_thresh, black_thresh, n0, n1, ok ? "pass" : "fail");
+      for (size_t i = 0; i < per[im].size() && i < 60; ++i) fprintf(stderr, " %.1f%c", per[im][i].first, per[im][i].second ? 'w' : 'b');
+      fprintf(stderr, "\n");
+    }
+    if (ok) pass[im] = 1; else next.push_back(im);
+  }
+  alist.swap(next);
+  return EZC_OK;
+}
+
+// The CALIB_CB_FAST_CHECK gate of cv::findChessboardCorners: images for which neither checkChessboardBinary (on the
+// histogram-binarised image B) nor checkChessboard (on the gray image) sees enough similar blobs leave `list`.
+static ezc_status fast_check_gate(ezc_context* ctx, CbPools& P, const uint8_t* d_img, long long pitch, long long istride, const uint8_t* B,
+                                  int W, int H, int nb, int pw, int ph, std::vector<int>& list) {
+  const long long N = (long long)W * H, total = N * nb;
+  EZC_CUDA(P.fc_w0.reserve(total)); EZC_CUDA(P.fc_w1.reserve(total)); EZC_CUDA(P.fc_w2.reserve(total));
+  EZC_CUDA(P.fc_k0.reserve(total)); EZC_CUDA(P.fc_k1.reserve(total)); EZC_CUDA(P.fc_k2.reserve(total));
+  EZC_CUDA(P.fc_fg.reserve(total));
+  std::vector<char> pass(nb, 0);
+  std::vector<int> alist = list;
+  const uint8_t* white = B;
+  const uint8_t* black = B;
+  uint8_t* wbuf[2] = {P.fc_w0.as<uint8_t>(), P.fc_w1.as<uint8_t>()};   // reused by the gray-level check afterwards
+  uint8_t* kbuf[2] = {P.fc_k0.as<uint8_t>(), P.fc_k1.as<uint8_t>()};
+  // checkChessboardBinary passes if ANY of its four erosion levels passes, so the order of evaluation is free: level 1
+  // (touching squares just separated) is tried first, it is where almost every real board passes; level 0 (squares still
+  // joined at their corners: a handful of huge blobs) is the most expensive and the least likely.  Erosions are cumulative,
+  // so the images of levels 1..3 are built in order and kept; level 0 is the binarised image itself.
+  uint8_t* wl[4] = {nullptr, P.fc_w0.as<uint8_t>(), P.fc_w1.as<uint8_t>(), P.fc_w2.as<uint8_t>()};
+  uint8_t* kl[4] = {nullptr, P.fc_k0.as<uint8_t>(), P.fc_k1.as<uint8_t>(), P.fc_k2.as<uint8_t>()};
+  const int order[4] = {1, 2, 0, 3};
+  int built = 0;
+  for (int oi = 0; oi < 4 && !alist.empty(); ++oi) {
+    const int e = order[oi];
+    for (; built < e; ++built) {   // build level built+1 from level built for the images still undecided
+      const int n_act = (int)alist.size();
+      if (ezc_status st = upload_list(ctx, P.fc_list, alist)) return st;
+      const uint8_t* ws = built == 0 ? B : wl[built];
+      const uint8_t* ks = built == 0 ? B : kl[built];
+      CB_LAUNCH(cb_morph_kernel, N * n_act, ws, (long long)W, N, wl[built + 1], W, H, n_act, P.fc_list.as<int>(), 0);
+      CB_LAUNCH(cb_morph_kernel, N * n_act, ks, (long long)W, N, kl[built + 1], W, H, n_act, P.fc_list.as<int>(), 1);
+    }
+    white = e == 0 ? B : wl[e];
+    black = e == 0 ? B : kl[e];
+    if (ezc_status st = fc_round(ctx, P, white, black, 128, 128, W, H, pw, ph, alist, pass)) return st;
+  }
+  if (!alist.empty()) {
+    const int n_act = (int)alist.size();
+    if (ezc_status st = upload_list(ctx, P.fc_list, alist)) return st;
+    CB_LAUNCH(cb_morph_kernel, N * n_act, d_img, pitch, istride, wbuf[0], W, H, n_act, P.fc_list.as<int>(), 0);
+    CB_LAUNCH(cb_morph_kernel, N * n_act, d_img, pitch, istride, kbuf[0], W, H, n_act, P.fc_list.as<int>(), 1);
+    for (int t = 20; t < 130 && !alist.empty(); t += 20)
+      if (ezc_status st = fc_round(ctx, P, wbuf[0], kbuf[0], t + 70, t, W, H, pw, ph, alist, pass)) return st;
+  }
+  std::vector<int> keep;
+  for (int im : list) if (pass[im]) keep.push_back(im);
+  list.swap(keep);
+  return EZC_OK;
+}
+
+ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, int nb, int pw, int ph, bool final_subpix, bool fast_check,
                             float2* d_corners_out, uint8_t* d_found_out) {
   CbPools& P = cb_pools(ctx);
   const int W = imgs->width, H = imgs->height;
@@ -1013,6 +1370,10 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
   uint8_t* b0 = P.bin0.as<uint8_t>();
   uint8_t* b1 = P.bin1.as<uint8_t>();
   CB_LAUNCH(cb_binarize_kernel, total, d_img, imgs->pitch, imgs->image_stride, W, H, nb, P.thresh.as<int>(), (const int*)nullptr, b0);
+  if (fast_check) {
+    if (ezc_status st = fast_check_gate(ctx, P, d_img, imgs->pitch, imgs->image_stride, b0, W, H, nb, pw, ph, list)) return st;
+    if (ezc_status st = upload_list(ctx, P.active, list)) return st;
+  }
   // ---- phase 1: histogram-binarised image, 8 cumulative dilations (the frame of the previous pass is dilated too)
   for (int dil = 0; dil <= 7 && !list.empty(); ++dil) {
     const int n_act = (int)list.size();
@@ -1121,7 +1482,8 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
 extern "C" {
 
 ezc_status ezc_find_chessboard_corners_batch(ezc_context* ctx, const ezc_images* imgs, int32_t pattern_w, int32_t pattern_h,
-                                             int32_t final_subpix, float* corners_out, uint8_t* found_out, int32_t max_images_in_flight) {
+                                             int32_t final_subpix, int32_t fast_check, float* corners_out, uint8_t* found_out,
+                                             int32_t max_images_in_flight) {
   EZC_CHECK(ctx && imgs && corners_out && found_out, EZC_ERR_INVALID, "ezc_find_chessboard_corners_batch: null argument");
   EZC_CHECK(pattern_w > 2 && pattern_h > 2, EZC_ERR_INVALID, "ezc_find_chessboard_corners_batch: both pattern dimensions must be > 2 (OpenCV rule)");
   EZC_CHECK(pattern_w * pattern_h <= cb::kMaxQuads, EZC_ERR_INVALID, "ezc_find_chessboard_corners_batch: pattern too large");
@@ -1142,7 +1504,7 @@ ezc_status ezc_find_chessboard_corners_batch(ezc_context* ctx, const ezc_images*
   int cur = imgs->ready.empty() ? sub : std::min(sub, std::max(1, imgs->chunk));
   for (int i0 = 0; i0 < n;) {
     const int nb = std::min(cur, n - i0);
-    if (ezc_status st = detect_sub_batch(ctx, imgs, i0, nb, pattern_w, pattern_h, final_subpix != 0, d_corners.as<float2>(), d_found.as<uint8_t>()))
+    if (ezc_status st = detect_sub_batch(ctx, imgs, i0, nb, pattern_w, pattern_h, final_subpix != 0, fast_check != 0, d_corners.as<float2>(), d_found.as<uint8_t>()))
       return st;
     i0 += nb;
     cur = std::min(sub, cur * 2);
@@ -1163,7 +1525,7 @@ ezc_status ezc_find_chessboard_corners_batch(ezc_context* ctx, const ezc_images*
 // arguments), i.e. pattern (nb_cols-1) x (nb_rows-1) inner corners, findChessboardCorners + cornerSubPix (5,5).
 ezc_status ezc_detect_chessboard_batch(ezc_context* ctx, const ezc_images* imgs, int32_t nb_rows, int32_t nb_cols, float* corners_out,
                                        uint8_t* found_out, int32_t max_images_in_flight) {
-  return ezc_find_chessboard_corners_batch(ctx, imgs, nb_cols - 1, nb_rows - 1, 1, corners_out, found_out, max_images_in_flight);
+  return ezc_find_chessboard_corners_batch(ctx, imgs, nb_cols - 1, nb_rows - 1, 1, 1, corners_out, found_out, max_images_in_flight);
 }
 
 }  // extern "C"

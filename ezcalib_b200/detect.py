@@ -132,17 +132,18 @@ def render_targets(ctx: Context, pattern: str, rows: int, cols: int, size: float
     return Images.from_handle(ctx, h, poses.shape[0], height, width)
 
 
-def find_chessboard_corners(ctx: Context, imgs: Images, pattern_size, final_subpix: bool = False, max_images_in_flight: int = 0):
+def find_chessboard_corners(ctx: Context, imgs: Images, pattern_size, final_subpix: bool = False, max_images_in_flight: int = 0,
+                            fast_check: bool = False):
     """cv::findChessboardCorners(img, pattern_size, ADAPTIVE_THRESH+NORMALIZE_IMAGE+FILTER_QUADS+FAST_CHECK) for the batch;
     with final_subpix also the reference's cornerSubPix (5,5).  Returns (found[n] bool, corners[n, pw*ph, 2] float32)."""
     pw, ph = pattern_size
     corners = np.zeros((imgs.n, pw * ph, 2), np.float32)
     found = np.zeros(imgs.n, np.uint8)
-    check(_lib.lib().ezc_find_chessboard_corners_batch(ctx.handle, imgs.handle, int(pw), int(ph), int(bool(final_subpix)), _p(corners), _p(found),
+    check(_lib.lib().ezc_find_chessboard_corners_batch(ctx.handle, imgs.handle, int(pw), int(ph), int(bool(final_subpix)), int(bool(fast_check)), _p(corners), _p(found),
                                                        int(max_images_in_flight)), "ezc_find_chessboard_corners_batch")
     return found.astype(bool), corners
 
 
 def detect_chessboard(ctx: Context, imgs: Images, nb_rows: int, nb_cols: int, max_images_in_flight: int = 0):
     """ChessboardCalibDetector::detectTarget for every image (nb_rows x nb_cols SQUARES, like the reference)."""
-    return find_chessboard_corners(ctx, imgs, (nb_cols - 1, nb_rows - 1), True, max_images_in_flight)
+    return find_chessboard_corners(ctx, imgs, (nb_cols - 1, nb_rows - 1), True, max_images_in_flight, fast_check=True)

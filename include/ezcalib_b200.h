@@ -102,9 +102,10 @@ ezc_status ezc_corner_subpix(ezc_context* ctx, const ezc_images* imgs, float* co
 ezc_status ezc_detect_chessboard_batch(ezc_context* ctx, const ezc_images* imgs, int32_t nb_rows, int32_t nb_cols,
                                        float* corners_out, uint8_t* found_out, int32_t max_images_in_flight);
 /* The same search with an explicit inner-corner pattern; final_subpix = 0 returns what cv::findChessboardCorners itself
- * returns (after its internal (2,2) refinement), for parity tests against cv2. */
+ * returns (after its internal (2,2) refinement), for parity tests against cv2.  fast_check != 0 applies the
+ * CALIB_CB_FAST_CHECK gate (checkChessboardBinary / checkChessboard) before the search, like the reference's flags do. */
 ezc_status ezc_find_chessboard_corners_batch(ezc_context* ctx, const ezc_images* imgs, int32_t pattern_w, int32_t pattern_h,
-                                             int32_t final_subpix, float* corners_out, uint8_t* found_out,
+                                             int32_t final_subpix, int32_t fast_check, float* corners_out, uint8_t* found_out,
                                              int32_t max_images_in_flight);
 
 /* AprilTagCalibDetector::detectTarget (/root/reference/include/target_detectors/aprilgrid_detector.hpp:30-71) for

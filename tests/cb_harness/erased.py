@@ -32,3 +32,24 @@ def erased_cases(img0, n_pairs=4, seed=1, step=1):
             if 0 <= ctr[0] < W and 0 <= ctr[1] < H:
                 cv2.circle(im, (int(ctr[0]), int(ctr[1])), int(sz * 0.72), 235, -1)
         yield cs, im
+
+
+def gate_corpus(G):
+    """Views that stress CALIB_CB_FAST_CHECK: boards shifted partly out of view, shrunk boards (the gate rejects boards
+    the full search would find), blur, noise, and the plain fixtures."""
+    names = [str(n) for n in G["names"]]
+    imgs = [G[nm + "_img"] for nm in names if G[nm + "_img"].shape == (480, 640)]
+    rng = np.random.default_rng(0)
+    for nm in ("render0", "warp1", "warp3"):
+        im = G[nm + "_img"]
+        for dx in (-300, -200, -120, 120, 200, 300):
+            M = np.float32([[1, 0, dx], [0, 1, dx // 3]])
+            imgs.append(cv2.warpAffine(im, M, (640, 480), borderValue=230))
+        for s in (0.3, 0.5):
+            small = cv2.resize(im, None, fx=s, fy=s)
+            canvas = np.full((480, 640), 225, np.uint8)
+            canvas[50:50 + small.shape[0], 80:80 + small.shape[1]] = small
+            imgs.append(canvas)
+        imgs.append(cv2.GaussianBlur(im, (0, 0), 3))
+        imgs.append(np.clip(im.astype(np.int32) + rng.normal(0, 25, im.shape), 0, 255).astype(np.uint8))
+    return imgs
