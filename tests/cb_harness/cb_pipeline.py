@@ -124,12 +124,16 @@ def detect_from_binary(binary: np.ndarray, pw: int, ph: int, dilations: int = 0)
     return bool(found), out, prev.value, nq.value
 
 
-def find_chessboard_corners(img: np.ndarray, pattern_size, refine=True, info=None):
+def find_chessboard_corners(img: np.ndarray, pattern_size, refine=True, info=None, fast_check=False):
     """Restated cv::findChessboardCorners(img, pattern, ADAPTIVE_THRESH+NORMALIZE_IMAGE+FILTER_QUADS[+FAST_CHECK])."""
     pw, ph = pattern_size
     H, W = img.shape
     t = binarize_hist_threshold(img)
     thresh = np.where(img >= t, 255, 0).astype(np.uint8) if t > 0 else img.copy()
+    if fast_check:
+        import fast_check as FC
+        if not FC.fast_check(img, thresh, pattern_size):
+            return False, None
     found, corners = False, None
     prev_sqr_size = 0
     used = img

@@ -73,3 +73,23 @@ def test_erased_outer_squares_match_cv2(name):
             assert np.abs(c - c_ref.reshape(-1, 2)).max() <= 0.01, (name, cs)
         n += 1
     assert n >= 15
+
+
+def test_fast_check_restatement_matches_cv2():
+    """CALIB_CB_FAST_CHECK: the restated checkChessboard equals the exported cv2.checkChessboard, and the restated search
+    with the gate equals cv2.findChessboardCorners with the reference's full flag set (incl. boards only the gate rejects)."""
+    import cv2
+    import fast_check as FC
+    from erased import FLAGS, gate_corpus
+    batch = gate_corpus(G)
+    changed = 0
+    for k, im in enumerate(batch):
+        assert bool(FC.check_chessboard(im, (9, 6))) == bool(cv2.checkChessboard(im, (9, 6))), k
+        if k % 2:
+            continue   # the full searches are the slow part; every other view keeps the CPU suite short
+        ok_gate, _ = cv2.findChessboardCorners(im, (9, 6), flags=FLAGS + cv2.CALIB_CB_FAST_CHECK)
+        ok_full, _ = cv2.findChessboardCorners(im, (9, 6), flags=FLAGS)
+        ok, _ = P.find_chessboard_corners(im, (9, 6), fast_check=True)
+        assert bool(ok) == bool(ok_gate), k
+        changed += int(bool(ok_gate) != bool(ok_full))
+    assert changed >= 1
