@@ -254,6 +254,7 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms2 = float(t.item())
         e2e_ms += ms2
+        detail[model]["e2e_ms_per_iter"] = round(ms2 / K, 4)
         h2d_bytes += P.obs.nbytes + P.poses_init.nbytes + P.target.nbytes + 8 * 12
         d2h_bytes += out[3].nbytes + 8 * 12 + K * 8 * 261
         s2.close()
