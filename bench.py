@@ -280,7 +280,10 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": round(achieved, 3), "peak": round(peak_fp64, 3), "unit": "TFLOP/s",
-                     "frac": round(achieved / peak_fp64, 4) if peak_fp64 else None, "traffic": None,
+                     "frac": round(achieved / peak_fp64, 4) if peak_fp64 else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE radtan5 launch (10,000,080 obs), ncu --set full:
+                     # profiles/ncu_lm_r01_final.txt; algorithmic: 80.0 MB obs + 3.9 MB poses read, 35.6 MB strips written
+                     "traffic": 118.9e6, "traffic_launch": "lm_accumulate_kernel<radtan5,mono> on 10,000,080 observations",
                      "kernel": "lm_accumulate_kernel", "dmma_peak_tflops": round(peak_dmma, 3), "peak_source": "DFMA microbenchmark measured in this run "
                      "(MEASURED_PEAKS.json has no FP64 figure; hbm_gbs there = %s)" % measured_peaks().get("hbm_gbs")},
     }
@@ -378,7 +381,9 @@ def run_detect(ctx, args, rank, world, stream):
                    "h2d_link_gbs": round(h2d_gbs, 2), "h2d_bound_images_per_s": round(h2d_gbs * 1e9 / (DET_W * DET_H) * world, 1)},
            "gpu_launches": int(launches),
            "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
-                        "traffic": None, "kernel": "whole detection pipeline (no single dominant kernel; see profiles/launches_detect_r01.csv)",
+                        "traffic": None, "kernel": "whole detection pipeline (largest shares: at_merge_kernel 24 %, at_pre_kernel 19 %; profiles/launch_shares_r01.txt)",
+                        "top_kernel_traffic": {"kernel": "at_merge_kernel", "dram_bytes_per_image": 137.5e6, "algorithmic_bytes_per_image": alg_bytes,
+                                               "source": "profiles/ncu_detect_r01_final.txt (ncu --set full, 214 views per launch)"},
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if measured_peaks().get("hbm_gbs") else "fallback 6650"}}
     if rank == 0 and not args.no_cpu:
         from oracle import apriltag_oracle as A
