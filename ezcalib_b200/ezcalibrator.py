@@ -136,3 +136,88 @@ def run_multicam_calib(ctx: lm.Context, cameras: list[Camera], target: np.ndarra
     for c, e in zip(cameras[1:], ext):
         c.T_cam0_2_cam = e
     return dict(summary=summ, n_good_pairs=n_good, init=init, extrinsics=ext, obs=obs, pts=pts)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The step BETWEEN the two accelerated halves: initial intrinsics and P3P-RANSAC poses.
+# The reference calls OpenCV for it (cv::solvePnPRansac); so does this mirror, through cv2 -- host code, a few hundred
+# microseconds per view, not on the GPU path yet.
+def setup_initial_calibration(width: int, height: int, prior_fov_deg: float, use_mono_focal: bool):
+    """Camera::setupInitialCalibration (/root/reference/src/camera.cpp:102-120): focal from the prior field of view,
+    principal point at the image centre.  Returns (focal[1|2], pp[2])."""
+    cx, cy = width / 2.0, height / 2.0
+    pi = 2.0 * np.arcsin(1.0)
+    inv_tan = 1.0 / np.tan(prior_fov_deg / 2.0 * (pi / 180.0))
+    f = max(cx * inv_tan, cy * inv_tan)
+    return np.array([f] if use_mono_focal else [f, f], np.float64), np.array([cx, cy], np.float64)
+
+
+def fit_to_so3(R: np.ndarray) -> np.ndarray:
+    """Sophus::SO3d::fitToSO3 (closest rotation in the Frobenius sense: U diag(1,1,det(UV^T)) V^T)."""
+    U, _, Vt = np.linalg.svd(R)
+    D = np.diag([1.0, 1.0, np.linalg.det(U @ Vt)])
+    return U @ D @ Vt
+
+
+def compute_p3p_ransac(corners_px: np.ndarray, target: np.ndarray, focal: np.ndarray, pp: np.ndarray, width: int, height: int,
+                       n_target_pts: int | None = None):
+    """EZCalibrator::computeP3PRansac (/root/reference/src/ezcalibrator.cpp:560-628).  Returns (ok, pose7, n_inliers).
+    Pixels are normalised with the PRIOR intrinsics (no distortion), points outside the image dropped, >= 32 points and
+    >= 32 inliers required when the target has >= 32 points, cv::solvePnPRansac(identity K, 1000 iterations,
+    threshold 4 / mean focal, confidence 0.999, AP3P), Rodrigues -> float32 -> fitToSO3."""
+    import cv2
+    n_target_pts = len(target) if n_target_pts is None else n_target_pts
+    fx = float(focal[0])
+    fy = float(focal[-1])
+    u, v = corners_px[:, 0].astype(np.float32), corners_px[:, 1].astype(np.float32)
+    inside = (u > -0.5) & (v > -0.5) & (u < np.float32(width) - np.float32(0.5)) & (v < np.float32(height) - np.float32(0.5))
+    x = ((u.astype(np.float64) - pp[0]) / fx).astype(np.float32)[inside]
+    y = ((v.astype(np.float64) - pp[1]) / fy).astype(np.float32)[inside]
+    un = np.stack([x, y], axis=1)
+    w3 = np.asarray(target, np.float64)[inside].astype(np.float32)
+    if len(un) < 32 and n_target_pts >= 32:
+        return False, None, 0
+    mean_focal = fx if len(focal) == 1 else 0.5 * (fx + fy)
+    ok, rvec, tvec, inl = cv2.solvePnPRansac(w3.reshape(-1, 1, 3), un.reshape(-1, 1, 2), np.eye(3, dtype=np.float32), None,
+                                             useExtrinsicGuess=False, iterationsCount=1000, reprojectionError=float(4.0 / mean_focal),
+                                             confidence=0.999, flags=cv2.SOLVEPNP_AP3P)
+    n_inl = 0 if inl is None else len(inl)
+    if not ok or (n_inl < 32 and n_target_pts >= 32):
+        return False, None, n_inl
+    R, _ = cv2.Rodrigues(rvec)
+    R = fit_to_so3(R.astype(np.float32).astype(np.float64))
+    t = tvec.reshape(3).astype(np.float32).astype(np.float64)
+    return True, np.concatenate([synth.quat_from_matrix(R), t]), n_inl
+
+
+def run_calibration(ctx: lm.Context, images: np.ndarray, target_kind: str, nb_rows: int, nb_cols: int, size: float, space: float,
+                    model: str, use_mono_focal: bool, prior_fov_deg: float, names=None):
+    """EZCalibrator::runCalibration for one camera (/root/reference/src/ezcalibrator.cpp:14-103) over a set of gray images
+    [n, H, W]: batched GPU detection, the reference's image loop replayed on its results, P3P-RANSAC initial poses, the
+    three-stage GPU solve.  Returns (camera, target, processed image indices)."""
+    from . import detect
+    n, H, W = images.shape
+    imgs = detect.Images(ctx, images, async_upload=True)
+    if target_kind == "chessboard":
+        target = synth.chessboard_target(nb_rows, nb_cols, size)
+        found, corners = detect.detect_chessboard(ctx, imgs, nb_rows, nb_cols)
+    elif target_kind == "aprilgrid":
+        target = synth.aprilgrid_target(nb_rows, nb_cols, size, space)
+        found, corners, _ = detect.detect_aprilgrid(ctx, imgs, nb_rows, nb_cols)
+    else:
+        raise ValueError(f"unknown target {target_kind!r}")
+    imgs.close()
+    focal, pp = setup_initial_calibration(W, H, prior_fov_deg, use_mono_focal)
+    dist = np.zeros(len(synth.GT_DIST[model]))   # all coefficients start at 0 (member defaults of the dist_model classes)
+    cam = Camera(model, use_mono_focal, W, H, focal, pp, dist)
+    processed = replay_skip_rule([bool(f) for f in found])
+    for i in processed:
+        if not found[i]:
+            continue
+        ok, pose, _ = compute_p3p_ransac(corners[i], target, focal, pp, W, H)
+        if ok:
+            cam.frames.append(CalibFrame(names[i] if names is not None else str(i), corners[i].astype(np.float32), pose))
+    if not cam.frames:
+        raise RuntimeError("no frame with a detected target and a P3P pose")
+    compute_calibration(ctx, cam, target)
+    return cam, target, processed
