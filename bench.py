@@ -237,27 +237,33 @@ def run_gpu(args):
         detail[model]["accumulate_ms"] = round(acc_ms, 4)
         solver.close()
         del obs_dev
-        # -------- e2e: host buffers through the public C ABI, copies inside the timed region
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0.record(stream)
-        s2 = lm.LmSolver(ctx, mid, True, obs_pin.numpy(), P.target, P.width, P.height, n_blocks_global=n_views * world)
-        s2.set_params(P.focal_init, P.pp_init, P.dist_init, poses_pin.numpy())
-        summ2, _ = s2.solve(max_num_iterations=K, **fixed)
-        out = s2.get_params()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms2 = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms2], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms2 = float(t.item())
+        # -------- e2e: host buffers through the public C ABI, copies inside the timed region.  One solve takes ~12 ms of
+        # wall time, so a single host hiccup (another tenant, the clock sampler) can be 10x the signal: the median of
+        # three identical solves is reported.
+        e2e_runs = []
+        for _rep in range(3):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0.record(stream)
+            s2 = lm.LmSolver(ctx, mid, True, obs_pin.numpy(), P.target, P.width, P.height, n_blocks_global=n_views * world)
+            s2.set_params(P.focal_init, P.pp_init, P.dist_init, poses_pin.numpy())
+            summ2, _ = s2.solve(max_num_iterations=K, **fixed)
+            out = s2.get_params()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms2], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms2 = float(t.item())
+            e2e_runs.append(ms2)
+            s2.close()
+        ms2 = float(np.median(e2e_runs))
         e2e_ms += ms2
         detail[model]["e2e_ms_per_iter"] = round(ms2 / K, 4)
         h2d_bytes += P.obs.nbytes + P.poses_init.nbytes + P.target.nbytes + 8 * 12
         d2h_bytes += out[3].nbytes + 8 * 12 + K * 8 * 261
-        s2.close()
     clocks = sampler.stop()
     launches = ctx.kernel_launches() - (launches0 or 0)
 
