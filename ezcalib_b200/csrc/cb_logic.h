@@ -56,6 +56,7 @@ struct Work {
   Ptf hull_in[kMaxQuads];
   Ptf hull[kMaxQuads];
   int pw, ph;           // pattern_size.width / height (inner corners)
+  int scan_pos;         // findConnectedQuads resumes its seed search here (quads before it are labelled or isolated for good)
 };
 
 CB_HD inline float normL2Sqrf(float dx, float dy) { return dx * dx + dy * dy; }
@@ -240,8 +241,8 @@ CB_HD inline bool contour_to_quad(const Pt* contour, int n, Pt* tmp_a, Pt* tmp_b
 }
 
 // add a quad (generateQuads, second loop)
-CB_HD inline void add_quad(Work& w, const Pt q[4], int dilations) {
-  const int qi = w.n_quads++;
+// quad `qi` of the work set from an approximated contour (generateQuads' per-quad part); independent per quad
+CB_HD inline void add_quad_at(Work& w, int qi, const Pt q[4], int dilations) {
   Quad& Q = w.quads[qi];
   Q.count = 0; Q.group_idx = -1; Q.row = 0; Q.col = 0; Q.ordered = 0;
   for (int i = 0; i < 4; ++i) {
@@ -266,6 +267,7 @@ CB_HD inline void add_quad(Work& w, const Pt q[4], int dilations) {
   const int comp = 2 * dilations;
   Q.edge_len += 2 * sqrtf(Q.edge_len) * comp + comp * comp;
 }
+CB_HD inline void add_quad(Work& w, const Pt q[4], int dilations) { add_quad_at(w, w.n_quads++, q, dilations); }
 
 // ------------------------------------------------------------------------------------------ findQuadNeighbors
 // `Par` lets a warp share the two O(n_quads) scans of every (quad, corner) step without changing the sequential
@@ -352,9 +354,13 @@ CB_HD inline void find_quad_neighbors(Work& w, const Par& par) {
 CB_HD inline void find_connected_quads(Work& w, int group_idx) {
   w.n_group = 0;
   int top = 0;
-  for (int i = 0; i < w.n_quads; i++) {
+  // OpenCV rescans from 0 for every group; a quad passed over once (already labelled, or without neighbours) is passed
+  // over forever -- labels are never removed and only quads of the group being processed gain neighbours -- so the scan
+  // resumes where the previous seed was found (O(n) instead of O(n * groups) on noise with hundreds of groups).
+  for (int i = w.scan_pos; i < w.n_quads; i++) {
     Quad* q = &w.quads[i];
     if (q->count <= 0 || q->group_idx >= 0) continue;
+    w.scan_pos = i + 1;
     w.stack[top++] = i;
     w.group[w.n_group++] = i;
     q->group_idx = group_idx;
@@ -780,6 +786,7 @@ CB_HD inline bool check_board_monotony(const Ptf* c, int pw, int ph) {
 CB_HD inline bool process_groups(Work& w, Ptf* out_pts, int* n_out_pts, int* prev_sqr_size, int* scratch) {
   *n_out_pts = 0;
   if (w.n_quads <= 0) return false;
+  w.scan_pos = 0;
   for (int group_idx = 0;; group_idx++) {
     find_connected_quads(w, group_idx);
     if (w.n_group == 0) break;

@@ -99,12 +99,13 @@ __global__ void cb_select_threshold_kernel(const int* __restrict__ hist_all, int
 
 __global__ void cb_binarize_kernel(const uint8_t* __restrict__ img, long long pitch, long long istride, int W, int H, int n_img,
                                    const int* __restrict__ thresh, const int* __restrict__ active, uint8_t* __restrict__ out) {
-  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
   const long long N = (long long)W * H;
-  if (cg >= N * n_img) return;
-  const int slot = (int)(cg / N);
+  if (pix_ >= N) return;
+  const int slot = blockIdx.y;
+  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
   const int im = active ? active[slot] : slot;   // `active` = compact list of image indices still searching
-  const int p = (int)(cg - (long long)slot * N);
+  const int p = (int)pix_;
   const long long gid = (long long)im * N + p;
   const int y = p / W, x = p - y * W;
   const uint8_t v = img[(long long)im * istride + (long long)y * pitch + x];
@@ -115,12 +116,13 @@ __global__ void cb_binarize_kernel(const uint8_t* __restrict__ img, long long pi
 // cv::dilate(src, dst, Mat(), Point(-1,-1), 1): 3x3 max, pixels outside the image are ignored
 __global__ void cb_dilate_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int W, int H, int n_img,
                                  const int* __restrict__ active) {
-  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
   const long long N = (long long)W * H;
-  if (cg >= N * n_img) return;
-  const int slot = (int)(cg / N);
+  if (pix_ >= N) return;
+  const int slot = blockIdx.y;
+  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
   const int im = active ? active[slot] : slot;   // `active` = compact list of image indices still searching
-  const int p = (int)(cg - (long long)slot * N);
+  const int p = (int)pix_;
   const long long gid = (long long)im * N + p;
   const int y = p / W, x = p - y * W;
   const uint8_t* S = src + (long long)im * N;
@@ -140,12 +142,13 @@ __global__ void cb_dilate_kernel(const uint8_t* __restrict__ src, uint8_t* __res
 
 // rectangle(img, (0,0), (W-1,H-1), 255, 3, LINE_8): a 3-pixel white frame (checked against cv2)
 __global__ void cb_frame_kernel(uint8_t* __restrict__ img, int W, int H, int n_img, const int* __restrict__ active) {
-  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
   const long long N = (long long)W * H;
-  if (cg >= N * n_img) return;
-  const int slot = (int)(cg / N);
+  if (pix_ >= N) return;
+  const int slot = blockIdx.y;
+  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
   const int im = active ? active[slot] : slot;   // `active` = compact list of image indices still searching
-  const int p = (int)(cg - (long long)slot * N);
+  const int p = (int)pix_;
   const long long gid = (long long)im * N + p;
   const int y = p / W, x = p - y * W;
   if (x < 3 || y < 3 || x >= W - 3 || y >= H - 3) img[gid] = 255;
@@ -204,12 +207,13 @@ __global__ void cb_label_runs_kernel(const uint8_t* __restrict__ bin, int* __res
 }
 __global__ void cb_label_merge_kernel(const uint8_t* __restrict__ bin, int* __restrict__ L, int W, int H, int n_img,
                                       const int* __restrict__ active) {
-  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
   const long long N = (long long)W * H;
-  if (cg >= N * n_img) return;
-  const int slot = (int)(cg / N);
+  if (pix_ >= N) return;
+  const int slot = blockIdx.y;
+  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
   const int im = active ? active[slot] : slot;   // `active` = compact list of image indices still searching
-  const int p = (int)(cg - (long long)slot * N);
+  const int p = (int)pix_;
   const long long gid = (long long)im * N + p;
   const int y = p / W, x = p - y * W;
   if (y == 0) return;
@@ -228,10 +232,11 @@ __global__ void cb_label_merge_kernel(const uint8_t* __restrict__ bin, int* __re
 // run heads -> roots (pointer jumping; concurrent writes only ever shorten a path to a valid ancestor)
 __global__ void cb_label_compress_kernel(const uint8_t* __restrict__ bin, int* __restrict__ L, int W, long long total, long long N,
                                          const int* __restrict__ active) {
-  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (cg >= total) return;
-  const int slot = (int)(cg / N);
-  const int p = (int)(cg - (long long)slot * N);
+  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
+  if (pix_ >= N) return;
+  const int slot = blockIdx.y;
+  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
+  const int p = (int)pix_;
   const long long gid = (long long)(active ? active[slot] : slot) * N + p;
   const int x = p % W;
   if (x != 0 && (bin[gid - 1] != 0) == (bin[gid] != 0)) return;  // not a run head
@@ -240,10 +245,11 @@ __global__ void cb_label_compress_kernel(const uint8_t* __restrict__ bin, int* _
 }
 __global__ void cb_label_flatten_kernel(const uint8_t* __restrict__ bin, int* __restrict__ L, long long total, long long N,
                                         const int* __restrict__ active, int* __restrict__ hole_flag, int white_roots) {
-  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (cg >= total) return;
-  const int slot = (int)(cg / N);
-  const long long gid = (long long)(active ? active[slot] : slot) * N + (cg - (long long)slot * N);
+  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
+  if (pix_ >= N) return;
+  const int slot = blockIdx.y;
+  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
+  const long long gid = (long long)(active ? active[slot] : slot) * N + pix_;
   const int r = L[L[gid]];   // pixel -> run head -> root (cb_label_compress has flattened the heads)
   L[gid] = r;
   // raster-first pixel of a black component (hole search) or of a white one (fast check); compact index
@@ -252,10 +258,11 @@ __global__ void cb_label_flatten_kernel(const uint8_t* __restrict__ bin, int* __
 __global__ void cb_hole_list_kernel(const int* __restrict__ flag_scan, const uint8_t* __restrict__ bin, const int* __restrict__ L,
                                     long long total, long long N, const int* __restrict__ active, int* __restrict__ hole_start,
                                     int white_roots) {
-  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (cg >= total) return;
-  const int slot = (int)(cg / N);
-  const long long gid = (long long)(active ? active[slot] : slot) * N + (cg - (long long)slot * N);
+  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
+  if (pix_ >= N) return;
+  const int slot = blockIdx.y;
+  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
+  const long long gid = (long long)(active ? active[slot] : slot) * N + pix_;
   if (((bin[gid] != 0) == (white_roots != 0)) && L[gid] == (int)gid) hole_start[flag_scan[cg]] = (int)gid;
 }
 
@@ -536,12 +543,13 @@ __global__ void __launch_bounds__(256) cb_quad_warp_kernel(HoleInfo* __restrict_
 // filter give its convex hull (no border walk), min-area rectangle over the hull edges; the (size, class) lists go to the host, which runs checkQuads.
 __global__ void cb_morph_kernel(const uint8_t* __restrict__ src, long long pitch, long long istride, uint8_t* __restrict__ dst, int W, int H,
                                 int n_img, const int* __restrict__ active, int is_max) {
-  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
   const long long N = (long long)W * H;
-  if (cg >= N * n_img) return;
-  const int slot = (int)(cg / N);
+  if (pix_ >= N) return;
+  const int slot = blockIdx.y;
+  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
   const int im = active ? active[slot] : slot;
-  const int p = (int)(cg - (long long)slot * N);
+  const int p = (int)pix_;
   const int y = p / W, x = p - y * W;
   const uint8_t* S = src + (long long)im * istride;
   int m = is_max ? 0 : 255;
@@ -560,18 +568,19 @@ __global__ void cb_morph_kernel(const uint8_t* __restrict__ src, long long pitch
 // dst = inv ? (src <= t) : (src > t)   (cv::threshold THRESH_BINARY_INV / THRESH_BINARY), 255 / 0
 __global__ void cb_fg_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long N, int n_img, const int* __restrict__ active,
                              int thresh, int inv) {
-  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (cg >= N * n_img) return;
-  const int slot = (int)(cg / N);
-  const long long gid = (long long)(active ? active[slot] : slot) * N + (cg - (long long)slot * N);
+  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
+  if (pix_ >= N) return;
+  const int slot = blockIdx.y;
+  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
+  const long long gid = (long long)(active ? active[slot] : slot) * N + pix_;
   const bool above = (int)src[gid] > thresh;
   dst[gid] = (above != (inv != 0)) ? 255 : 0;
 }
 
 struct FcComp {
   int start;        // raster-first pixel of the component (global linear index)
-  int n_keep;       // candidate points strictly outside the extreme-point polygon
-  int fill;         // scatter cursor
+  int n_cand;       // run end points of the component (upper bound of what is stored)
+  int fill;         // points stored = candidates strictly outside the extreme-point polygon
   int offset;       // into the point pool, -1 = skipped
   int ex[8], ey[8]; // extreme points in the 8 principal directions, in angular order (left, top-left, top, ...)
   unsigned long long key[8];  // atomicMax keys: (direction value + bias) << 32 | pixel
@@ -583,8 +592,26 @@ __global__ void cb_fc_init_kernel(int n_comp, FcComp* __restrict__ comps) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_comp) return;
   FcComp& ci = comps[c];
-  ci.start = 0; ci.n_keep = 0; ci.fill = 0; ci.offset = -1;
+  ci.start = 0; ci.n_cand = 0; ci.fill = 0; ci.offset = -1;
   for (int k = 0; k < 8; ++k) ci.key[k] = 0ull;
+}
+// Run heads of the foreground are pointed at their roots (what cb_label_compress does for both colours) and every root
+// draws a component id from a counter -- the gate does not care about the order of the components, so neither a full
+// flatten pass nor a prefix sum over the pixels is needed.  cidmap is indexed like the compact hole flags.
+__global__ void cb_fc_roots_kernel(const uint8_t* __restrict__ fg, int* __restrict__ L, int W, long long total, long long N,
+                                   const int* __restrict__ active, int* __restrict__ cidmap, int* __restrict__ counter) {
+  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
+  if (pix_ >= N) return;
+  const int slot = blockIdx.y;
+  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
+  const int p = (int)pix_;
+  const long long gid = (long long)(active ? active[slot] : slot) * N + p;
+  if (fg[gid] == 0) return;
+  const int x = p % W;
+  if (x != 0 && fg[gid - 1] != 0) return;   // not a run head
+  const int r = cbl_find(L, (int)gid);
+  L[gid] = r;
+  if (r == (int)gid) cidmap[cg] = atomicAdd(counter, 1);
 }
 // is pixel (x, y) of the foreground the first or the last pixel of its horizontal run?
 __device__ __forceinline__ bool fc_candidate(const uint8_t* __restrict__ B, int W, int x, int y) {
@@ -592,24 +619,26 @@ __device__ __forceinline__ bool fc_candidate(const uint8_t* __restrict__ B, int 
   if (r[x] == 0) return false;
   return x == 0 || r[x - 1] == 0 || x == W - 1 || r[x + 1] == 0;
 }
-// MODE 0: extreme points; MODE 1: count the candidates strictly outside the polygon of the extreme points; MODE 2: store them
+// MODE 0: extreme points + candidate count; MODE 1: store the candidates strictly outside the polygon of the extreme points
 template <int MODE>
-__global__ void cb_fc_points_kernel(const uint8_t* __restrict__ fg, const int* __restrict__ L, const int* __restrict__ flag_scan, int W, int H,
+__global__ void cb_fc_points_kernel(const uint8_t* __restrict__ fg, const int* __restrict__ L, const int* __restrict__ cidmap, int W, int H,
                                     int n_img, const int* __restrict__ active, FcComp* __restrict__ comps, cb::Pt* __restrict__ pool) {
-  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
   const long long N = (long long)W * H;
-  if (cg >= N * n_img) return;
-  const int slot = (int)(cg / N);
+  if (pix_ >= N) return;
+  const int slot = blockIdx.y;
+  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
   const int im = active ? active[slot] : slot;
-  const int p = (int)(cg - (long long)slot * N);
+  const int p = (int)pix_;
   const int y = p / W, x = p - y * W;
   const uint8_t* B = fg + (long long)im * N;
   if (!fc_candidate(B, W, x, y)) return;
-  const int root = L[(long long)im * N + p];                       // global index of the component's first pixel
-  const int cid = flag_scan[(long long)slot * N + (root - (long long)im * N)];
+  const int root = L[L[(long long)im * N + p]];                     // pixel -> run head -> root (global index)
+  const int cid = cidmap[(long long)slot * N + (root - (long long)im * N)];
   FcComp& ci = comps[cid];
   if (MODE == 0) {
     if ((long long)root == (long long)im * N + p) ci.start = root;   // the first pixel of a component starts a run
+    atomicAdd(&ci.n_cand, 1);
     const int kv[8] = {-x, -x - y, -y, x - y, x, x + y, y, y - x};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -627,9 +656,7 @@ __global__ void cb_fc_points_kernel(const uint8_t* __restrict__ fg, const int* _
       const long long cr = ax * (y - ci.ey[k]) - ay * (x - ci.ex[k]);
       if (cr < 0) { outside = true; break; }
     }
-    if (!outside) return;
-    if (MODE == 1) atomicAdd(&ci.n_keep, 1);
-    else pool[ci.offset + atomicAdd(&ci.fill, 1)] = cb::Pt{x, y};
+    if (outside) pool[ci.offset + atomicAdd(&ci.fill, 1)] = cb::Pt{x, y};
   }
 }
 // decode the extreme points; components whose bounding-box diagonal is below 10 px cannot pass the size test
@@ -647,7 +674,7 @@ __global__ void cb_fc_prefilter_kernel(FcComp* __restrict__ comps, int n_comp, i
 __global__ void cb_fc_need_kernel(const FcComp* __restrict__ comps, int n, int* __restrict__ need) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
-  need[c] = comps[c].offset >= 0 ? 2 * (comps[c].n_keep + 8) + 16 : 0;  // survivors + extreme points, and their hull
+  need[c] = comps[c].offset >= 0 ? 2 * (comps[c].n_cand + 8) + 16 : 0;  // stored points (<= candidates) + extreme points, and their hull
 }
 __global__ void cb_fc_offset_kernel(FcComp* __restrict__ comps, int n, const int* __restrict__ need_scan) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -663,8 +690,8 @@ __global__ void cb_fc_minrect_kernel(const FcComp* __restrict__ comps, int n_com
   const FcComp& ci = comps[c];
   if (ci.offset < 0) return;
   cb::Pt* a = pool + ci.offset;
-  for (int k = 0; k < 8; ++k) a[ci.n_keep + k] = cb::Pt{ci.ex[k], ci.ey[k]};
-  const int n = ci.n_keep + 8;
+  for (int k = 0; k < 8; ++k) a[ci.fill + k] = cb::Pt{ci.ex[k], ci.ey[k]};
+  const int n = ci.fill + 8;
   cb::Pt* h = a + n + 4;
   auto less = [](const cb::Pt& p, const cb::Pt& q) { return p.x < q.x || (p.x == q.x && p.y < q.y); };
   // heap sort by (x, y)
@@ -739,7 +766,45 @@ struct ImageState {
   int prev_sqr_size;
   int n_quads;
   int hole_begin, hole_end;
+  int total_quads;               // contours of this attempt that became quads
+  unsigned long long best;       // (quads of the winning parent << 32) | (0x7fffffff - index of its last quad's hole)
 };
+
+// generateQuads, second half (CALIB_CB_FILTER_QUADS): the parent contour with the most quads wins.  OpenCV decides it in
+// one sequential pass -- boardIdx moves to a parent when its running count strictly exceeds the current one's -- which
+// ends at the parent that reaches the maximal count FIRST, i.e. among the parents with the maximal final count the one
+// whose LAST quad comes earliest.  Exact per-parent counts (indexed by the parent's label = pixel index) and last-hole
+// indices by atomics, the winner by one 64-bit atomicMax per image; the touched entries are cleared afterwards.
+__global__ void cb_state_reset_kernel(ImageState* __restrict__ st, const int* __restrict__ active, int n_act) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_act) return;
+  ImageState& S = st[active[i]];
+  S.total_quads = 0; S.best = 0ull; S.n_quads = 0;
+}
+__global__ void cb_parent_count_kernel(const HoleInfo* __restrict__ holes, int n_holes, int* __restrict__ pcnt, int* __restrict__ plast) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_holes || !holes[h].quad_ok) return;
+  const int p = holes[h].parent;
+  atomicAdd(&pcnt[p], 1);
+  atomicMax(&plast[p], h + 1);
+}
+__global__ void cb_parent_select_kernel(const HoleInfo* __restrict__ holes, int n_holes, long long N, const int* __restrict__ pcnt,
+                                        const int* __restrict__ plast, ImageState* __restrict__ st) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_holes || !holes[h].quad_ok) return;
+  const int p = holes[h].parent;
+  ImageState& S = st[(int)(holes[h].start / N)];
+  atomicAdd(&S.total_quads, 1);
+  if (plast[p] == h + 1)   // one candidate per parent is enough
+    atomicMax(&S.best, ((unsigned long long)(unsigned)pcnt[p] << 32) | (unsigned)(0x7fffffff - h));
+}
+__global__ void cb_parent_clear_kernel(const HoleInfo* __restrict__ holes, int n_holes, int* __restrict__ pcnt, int* __restrict__ plast) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_holes || !holes[h].quad_ok) return;
+  const int p = holes[h].parent;
+  pcnt[p] = 0; plast[p] = 0;
+}
+
 
 __global__ void cb_hole_ranges_kernel(const HoleInfo* __restrict__ holes, int n_holes, long long N, int n_img, ImageState* __restrict__ st) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
@@ -903,45 +968,38 @@ __global__ void __launch_bounds__(kProcThreads) cb_process_kernel(const HoleInfo
   ImageState& S = st[im];
   int* scratch = scratch_all + (size_t)im * cb::kMaxQuads * 4;
   const unsigned long long t0 = cb_now();
-  if (tid == 0) {
-    // generateQuads, second half: the parent contour with the most quads wins (CALIB_CB_FILTER_QUADS).  Counts per parent
-    // in an open-addressing table (keys = white-component labels).
-    constexpr int TS = 2048;
-    int* keys = scratch;
-    int* cnts = scratch + TS;
-    for (int i = 0; i < TS; ++i) { keys[i] = -1; cnts[i] = 0; }
-    int boardIdx = -1, boardCount = 0, total = 0, distinct = 0;
-    for (int h = S.hole_begin; h < S.hole_end; ++h) {
-      if (!holes[h].quad_ok) continue;
-      ++total;
-      const int p = holes[h].parent;
-      unsigned hsh = ((unsigned)p * 2654435761u) >> 21;  // 11 bits
-      int cnt = 0;
-      for (int probe = 0; probe < TS; ++probe) {
-        const int sl = (hsh + probe) & (TS - 1);
-        if (keys[sl] == p) { cnt = ++cnts[sl]; break; }
-        if (keys[sl] == -1) {
-          if (distinct < TS - 1) { keys[sl] = p; ++distinct; cnt = ++cnts[sl]; }
-          else cnt = 1;  // table full (thousands of distinct parents: noise); such a parent never wins
-          break;
-        }
-      }
-      if (boardIdx == p) boardCount = cnt;
-      else if (boardIdx < 0 || boardCount < cnt) { boardIdx = p; boardCount = cnt; }
-    }
-    w.n_quads = 0;
-    w.max_quads = total * 3 > 2 ? total * 3 : 2;
-    if (w.max_quads > cb::kMaxQuads) w.max_quads = cb::kMaxQuads;
-    w.pw = pw; w.ph = ph;
-    atomicAdd(&g_cb_ns[0], cb_now() - t0);
-    for (int h = S.hole_begin; h < S.hole_end; ++h) {
-      if (!holes[h].quad_ok || holes[h].parent != boardIdx) continue;
-      if (w.n_quads >= w.max_quads) break;
-      cb::add_quad(w, holes[h].quad, dilations);
-    }
-    S.n_quads = w.n_quads;
-    __threadfence_block();
+  // the winning parent was selected by cb_parent_select_kernel; its quads are appended in hole order (the order
+  // generateQuads visits the contours) by the whole block: flags, block-wide exclusive scan, independent quad set-up
+  __shared__ int scan_w[kProcThreads / 32];
+  __shared__ int s_base;
+  const int total = S.total_quads;
+  int max_quads = total * 3 > 2 ? total * 3 : 2;
+  if (max_quads > cb::kMaxQuads) max_quads = cb::kMaxQuads;
+  const int boardIdx = S.best ? holes[0x7fffffff - (int)(unsigned)(S.best & 0xffffffffull)].parent : -1;
+  if (tid == 0) { s_base = 0; w.max_quads = max_quads; w.pw = pw; w.ph = ph; }
+  __syncthreads();
+  for (int h0 = S.hole_begin; h0 < S.hole_end; h0 += kProcThreads) {
+    const int h = h0 + tid;
+    const bool take = h < S.hole_end && holes[h].quad_ok && holes[h].parent == boardIdx;
+    const unsigned bal = __ballot_sync(0xffffffffu, take);
+    const int warp = tid >> 5, lane = tid & 31;
+    if (lane == 0) scan_w[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_base, all = 0;
+    for (int wv = 0; wv < kProcThreads / 32; ++wv) { if (wv < warp) before += scan_w[wv]; all += scan_w[wv]; }
+    const int idx = before + __popc(bal & ((1u << lane) - 1u));
+    if (take && idx < max_quads) cb::add_quad_at(w, idx, holes[h].quad, dilations);
+    __syncthreads();
+    if (tid == 0) s_base += all;
+    __syncthreads();
+    if (s_base >= max_quads) break;
   }
+  if (tid == 0) {
+    w.n_quads = s_base < max_quads ? s_base : max_quads;
+    S.n_quads = w.n_quads;
+    atomicAdd(&g_cb_ns[0], cb_now() - t0);
+  }
+  __threadfence_block();
   __syncthreads();
   const unsigned long long t1 = cb_now();
   if (tid == 0) atomicAdd(&g_cb_ns[1], t1 - t0);
@@ -1031,13 +1089,14 @@ __global__ void cb_apply_lut_kernel(const uint8_t* __restrict__ img, long long p
 // cv::adaptiveThreshold(MEAN_C, BINARY): separable box sums with replicated border, per-image block size
 __global__ void cb_box_h_kernel(const uint8_t* __restrict__ src, int W, int H, int n_img, const int* __restrict__ list,
                                 const int* __restrict__ block, int* __restrict__ out) {
-  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
   const long long N = (long long)W * H;
-  if (cg >= N * n_img) return;
-  const int slot = (int)(cg / N);
+  if (pix_ >= N) return;
+  const int slot = blockIdx.y;
+  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
   const int im = list[slot];
   const int b = block[im];
-  const int p = (int)(cg - (long long)slot * N);
+  const int p = (int)pix_;
   const long long gid = (long long)im * N + p;
   const int y = p / W, x = p - y * W;
   const uint8_t* S = src + (long long)im * N + (long long)y * W;
@@ -1049,13 +1108,14 @@ __global__ void cb_box_h_kernel(const uint8_t* __restrict__ src, int W, int H, i
 __global__ void cb_box_v_thresh_kernel(const uint8_t* __restrict__ src, const int* __restrict__ hs, int W, int H, int n_img,
                                        const int* __restrict__ list, const int* __restrict__ block, const int* __restrict__ delta,
                                        uint8_t* __restrict__ out) {
-  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
   const long long N = (long long)W * H;
-  if (cg >= N * n_img) return;
-  const int slot = (int)(cg / N);
+  if (pix_ >= N) return;
+  const int slot = blockIdx.y;
+  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
   const int im = list[slot];
   const int b = block[im];
-  const int p = (int)(cg - (long long)slot * N);
+  const int p = (int)pix_;
   const long long gid = (long long)im * N + p;
   const int y = p / W, x = p - y * W;
   const int* S = hs + (long long)im * N;
@@ -1068,10 +1128,11 @@ __global__ void cb_box_v_thresh_kernel(const uint8_t* __restrict__ src, const in
   out[gid] = ((int)src[gid] - mean > -delta[im]) ? 255 : 0;
 }
 __global__ void cb_copy_active_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long N, int n_img, const int* __restrict__ list) {
-  const long long cg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (cg >= N * n_img) return;
-  const int slot = (int)(cg / N);
-  const long long gid = (long long)list[slot] * N + (cg - (long long)slot * N);
+  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
+  if (pix_ >= N) return;
+  const int slot = blockIdx.y;
+  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
+  const long long gid = (long long)list[slot] * N + pix_;
   dst[gid] = src[gid];
 }
 __global__ void cb_gather_corners_kernel(const cb::Ptf* __restrict__ corners, const uint8_t* __restrict__ found, int n_img, int npts,
@@ -1099,6 +1160,7 @@ namespace {
 struct CbPools {
   DevBuf hist, thresh, bin0, bin1, prevbin, eq, lut, labels, flags, scan_tmp, total, hole_start, holes, need, pool, stack_pool;
   DevBuf works, scratch, state, active, corners, found, block, delta, hsum, sub_corners, sub_idx, refresh;
+  DevBuf pcnt, plast;   // per-pixel-label quad counters (kept zero between attempts)
   DevBuf fc_w0, fc_w1, fc_w2, fc_k0, fc_k1, fc_k2, fc_fg, fc_comps, fc_hyps, fc_count, fc_list;
   HostPinned fc_h;
   HostPinned h;
@@ -1122,6 +1184,16 @@ CbPools& cb_pools(ezc_context* ctx) {
     }                                                                                 \
   } while (0)
 
+// per-pixel kernels: grid.x covers one image, grid.y the images (no 64-bit division to split a flat index)
+#define CB_LAUNCH_PIX(kernel, n_pix, n_images, ...)                                                         \
+  do {                                                                                                      \
+    if ((n_pix) > 0 && (n_images) > 0) {                                                                    \
+      kernel<<<dim3((unsigned)(((n_pix) + 255) / 256), (unsigned)(n_images)), 256, 0, ctx->stream>>>(__VA_ARGS__); \
+      EZC_CUDA(cudaGetLastError());                                                                         \
+      ctx->kernel_launches++;                                                                               \
+    }                                                                                                       \
+  } while (0)
+
 // Upload a compact list of image indices; returns its device pointer.
 ezc_status upload_list(ezc_context* ctx, DevBuf& buf, const std::vector<int>& list) {
   EZC_CUDA(buf.reserve(sizeof(int) * std::max<size_t>(list.size(), 1)));
@@ -1137,9 +1209,9 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
   const int* list = P.active.as<int>();
   int* d_tot = P.total.as<int>();
   CB_LAUNCH(cb_label_runs_kernel, (long long)H * n_act * 32, bin, P.labels.as<int>(), W, H, n_act, list);
-  CB_LAUNCH(cb_label_merge_kernel, total, bin, P.labels.as<int>(), W, H, n_act, list);
-  CB_LAUNCH(cb_label_compress_kernel, total, bin, P.labels.as<int>(), W, total, N, list);
-  CB_LAUNCH(cb_label_flatten_kernel, total, bin, P.labels.as<int>(), total, N, list, P.flags.as<int>(), 0);
+  CB_LAUNCH_PIX(cb_label_merge_kernel, N, n_act, bin, P.labels.as<int>(), W, H, n_act, list);
+  CB_LAUNCH_PIX(cb_label_compress_kernel, N, n_act, bin, P.labels.as<int>(), W, total, N, list);
+  CB_LAUNCH_PIX(cb_label_flatten_kernel, N, n_act, bin, P.labels.as<int>(), total, N, list, P.flags.as<int>(), 0);
   if (ezc_status st = exclusive_scan_i32(ctx, P.flags.as<int>(), P.flags.as<int>(), total, P.scan_tmp, d_tot)) return st;
   EZC_CUDA(cudaMemcpyAsync(P.h.p, d_tot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   EZC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1149,7 +1221,7 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
     EZC_CUDA(P.hole_start.reserve(sizeof(int) * (size_t)nH));
     EZC_CUDA(P.holes.reserve(sizeof(HoleInfo) * (size_t)nH));
     EZC_CUDA(P.need.reserve(sizeof(int) * ((size_t)nH + 1)));
-    CB_LAUNCH(cb_hole_list_kernel, total, P.flags.as<int>(), bin, P.labels.as<int>(), total, N, list, P.hole_start.as<int>(), 0);
+    CB_LAUNCH_PIX(cb_hole_list_kernel, N, n_act, P.flags.as<int>(), bin, P.labels.as<int>(), total, N, list, P.hole_start.as<int>(), 0);
     CB_LAUNCH(cb_hole_init_kernel, nH, P.hole_start.as<int>(), nH, P.holes.as<HoleInfo>(), P.need.as<int>());
     CB_LAUNCH(cb_trace_kernel<false>, nH, bin, P.labels.as<int>(), W, H, nH, P.holes.as<HoleInfo>(), nullptr, cb::kMaxContourPts);
     CB_LAUNCH(cb_hole_need_kernel, nH, P.holes.as<HoleInfo>(), nH, P.need.as<int>());
@@ -1164,6 +1236,12 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
     CB_LAUNCH(cb_quad_kernel, nH, P.holes.as<HoleInfo>(), nH, P.pool.as<cb::Pt>(), P.stack_pool.as<int>());
     CB_LAUNCH(cb_quad_warp_kernel, (long long)nH * 32, P.holes.as<HoleInfo>(), nH, P.pool.as<cb::Pt>(), P.stack_pool.as<int>());
     CB_LAUNCH(cb_hole_ranges_kernel, nH, P.holes.as<HoleInfo>(), nH, N, 0, st);
+  }
+  CB_LAUNCH(cb_state_reset_kernel, n_act, st, list, n_act);
+  if (nH > 0) {
+    CB_LAUNCH(cb_parent_count_kernel, nH, P.holes.as<HoleInfo>(), nH, P.pcnt.as<int>(), P.plast.as<int>());
+    CB_LAUNCH(cb_parent_select_kernel, nH, P.holes.as<HoleInfo>(), nH, N, P.pcnt.as<int>(), P.plast.as<int>(), st);
+    CB_LAUNCH(cb_parent_clear_kernel, nH, P.holes.as<HoleInfo>(), nH, P.pcnt.as<int>(), P.plast.as<int>());
   }
   {
     static bool attr_set = false;
@@ -1227,12 +1305,11 @@ static ezc_status fc_round(ezc_context* ctx, CbPools& P, const uint8_t* white_sr
   int* d_tot = P.total.as<int>();
   uint8_t* fg = P.fc_fg.as<uint8_t>();
   for (int cls = 1; cls >= 0; --cls) {
-    CB_LAUNCH(cb_fg_kernel, total, cls ? white_src : black_src, fg, N, n_act, list, cls ? white_thresh : black_thresh, cls ? 0 : 1);
+    CB_LAUNCH_PIX(cb_fg_kernel, N, n_act, cls ? white_src : black_src, fg, N, n_act, list, cls ? white_thresh : black_thresh, cls ? 0 : 1);
     CB_LAUNCH(cb_label_runs_kernel, (long long)H * n_act * 32, fg, P.labels.as<int>(), W, H, n_act, list);
-    CB_LAUNCH(cb_label_merge_kernel, total, fg, P.labels.as<int>(), W, H, n_act, list);
-    CB_LAUNCH(cb_label_compress_kernel, total, fg, P.labels.as<int>(), W, total, N, list);
-    CB_LAUNCH(cb_label_flatten_kernel, total, fg, P.labels.as<int>(), total, N, list, P.flags.as<int>(), 1);
-    if (ezc_status st = exclusive_scan_i32(ctx, P.flags.as<int>(), P.flags.as<int>(), total, P.scan_tmp, d_tot)) return st;
+    CB_LAUNCH_PIX(cb_label_merge_kernel, N, n_act, fg, P.labels.as<int>(), W, H, n_act, list);
+    EZC_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(int), ctx->stream));
+    CB_LAUNCH_PIX(cb_fc_roots_kernel, N, n_act, fg, P.labels.as<int>(), W, total, N, list, P.flags.as<int>(), d_tot);
     EZC_CUDA(cudaMemcpyAsync(P.h.p, d_tot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     EZC_CUDA(cudaStreamSynchronize(ctx->stream));
     const int nC = *P.h.as<int>();
@@ -1240,9 +1317,8 @@ static ezc_status fc_round(ezc_context* ctx, CbPools& P, const uint8_t* white_sr
     EZC_CUDA(P.fc_comps.reserve(sizeof(FcComp) * (size_t)nC));
     EZC_CUDA(P.need.reserve(sizeof(int) * ((size_t)nC + 1)));
     CB_LAUNCH(cb_fc_init_kernel, nC, nC, P.fc_comps.as<FcComp>());
-    CB_LAUNCH(cb_fc_points_kernel<0>, total, fg, P.labels.as<int>(), P.flags.as<int>(), W, H, n_act, list, P.fc_comps.as<FcComp>(), nullptr);
+    CB_LAUNCH_PIX(cb_fc_points_kernel<0>, N, n_act, fg, P.labels.as<int>(), P.flags.as<int>(), W, H, n_act, list, P.fc_comps.as<FcComp>(), nullptr);
     CB_LAUNCH(cb_fc_prefilter_kernel, nC, P.fc_comps.as<FcComp>(), nC, W);
-    CB_LAUNCH(cb_fc_points_kernel<1>, total, fg, P.labels.as<int>(), P.flags.as<int>(), W, H, n_act, list, P.fc_comps.as<FcComp>(), nullptr);
     CB_LAUNCH(cb_fc_need_kernel, nC, P.fc_comps.as<FcComp>(), nC, P.need.as<int>());
     if (ezc_status st = exclusive_scan_i32(ctx, P.need.as<int>(), P.need.as<int>(), nC, P.scan_tmp, d_tot)) return st;
     EZC_CUDA(cudaMemcpyAsync(P.h.p, d_tot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1251,7 +1327,7 @@ static ezc_status fc_round(ezc_context* ctx, CbPools& P, const uint8_t* white_sr
     if (nPts <= 0) continue;
     EZC_CUDA(P.pool.reserve(sizeof(cb::Pt) * ((size_t)nPts + 16)));
     CB_LAUNCH(cb_fc_offset_kernel, nC, P.fc_comps.as<FcComp>(), nC, P.need.as<int>());
-    CB_LAUNCH(cb_fc_points_kernel<2>, total, fg, P.labels.as<int>(), P.flags.as<int>(), W, H, n_act, list, P.fc_comps.as<FcComp>(), P.pool.as<cb::Pt>());
+    CB_LAUNCH_PIX(cb_fc_points_kernel<1>, N, n_act, fg, P.labels.as<int>(), P.flags.as<int>(), W, H, n_act, list, P.fc_comps.as<FcComp>(), P.pool.as<cb::Pt>());
     CB_LAUNCH(cb_fc_minrect_kernel, nC, P.fc_comps.as<FcComp>(), nC, P.pool.as<cb::Pt>(), N, cls, P.fc_hyps.as<FcHyp>(), P.fc_count.as<int>(), max_hyps);
   }
   EZC_CUDA(cudaMemcpyAsync(P.h.p, P.fc_count.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1317,8 +1393,8 @@ static ezc_status fast_check_gate(ezc_context* ctx, CbPools& P, const uint8_t* d
       if (ezc_status st = upload_list(ctx, P.fc_list, alist)) return st;
       const uint8_t* ws = built == 0 ? B : wl[built];
       const uint8_t* ks = built == 0 ? B : kl[built];
-      CB_LAUNCH(cb_morph_kernel, N * n_act, ws, (long long)W, N, wl[built + 1], W, H, n_act, P.fc_list.as<int>(), 0);
-      CB_LAUNCH(cb_morph_kernel, N * n_act, ks, (long long)W, N, kl[built + 1], W, H, n_act, P.fc_list.as<int>(), 1);
+      CB_LAUNCH_PIX(cb_morph_kernel, N, n_act, ws, (long long)W, N, wl[built + 1], W, H, n_act, P.fc_list.as<int>(), 0);
+      CB_LAUNCH_PIX(cb_morph_kernel, N, n_act, ks, (long long)W, N, kl[built + 1], W, H, n_act, P.fc_list.as<int>(), 1);
     }
     white = e == 0 ? B : wl[e];
     black = e == 0 ? B : kl[e];
@@ -1327,8 +1403,8 @@ static ezc_status fast_check_gate(ezc_context* ctx, CbPools& P, const uint8_t* d
   if (!alist.empty()) {
     const int n_act = (int)alist.size();
     if (ezc_status st = upload_list(ctx, P.fc_list, alist)) return st;
-    CB_LAUNCH(cb_morph_kernel, N * n_act, d_img, pitch, istride, wbuf[0], W, H, n_act, P.fc_list.as<int>(), 0);
-    CB_LAUNCH(cb_morph_kernel, N * n_act, d_img, pitch, istride, kbuf[0], W, H, n_act, P.fc_list.as<int>(), 1);
+    CB_LAUNCH_PIX(cb_morph_kernel, N, n_act, d_img, pitch, istride, wbuf[0], W, H, n_act, P.fc_list.as<int>(), 0);
+    CB_LAUNCH_PIX(cb_morph_kernel, N, n_act, d_img, pitch, istride, kbuf[0], W, H, n_act, P.fc_list.as<int>(), 1);
     for (int t = 20; t < 130 && !alist.empty(); t += 20)
       if (ezc_status st = fc_round(ctx, P, wbuf[0], kbuf[0], t + 70, t, W, H, pw, ph, alist, pass)) return st;
   }
@@ -1352,6 +1428,8 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
   EZC_CUDA(P.total.reserve(64)); EZC_CUDA(P.h.reserve(4096));
   EZC_CUDA(P.works.reserve(sizeof(cb::Work) * (size_t)nb)); EZC_CUDA(P.scratch.reserve(sizeof(int) * cb::kMaxQuads * 4 * (size_t)nb));
   EZC_CUDA(P.state.reserve(sizeof(ImageState) * nb));
+  EZC_CUDA(P.pcnt.reserve(sizeof(int) * total)); EZC_CUDA(P.plast.reserve(sizeof(int) * total));
+  EZC_CUDA(cudaMemsetAsync(P.pcnt.p, 0, sizeof(int) * total, ctx->stream)); EZC_CUDA(cudaMemsetAsync(P.plast.p, 0, sizeof(int) * total, ctx->stream));
   EZC_CUDA(P.corners.reserve(sizeof(cb::Ptf) * (size_t)npts * nb)); EZC_CUDA(P.found.reserve(nb));
   EZC_CUDA(P.holes.reserve(sizeof(HoleInfo) * 16));
   std::vector<ImageState> h_state(nb, ImageState{0, 0, 0, 0, 0});
@@ -1369,7 +1447,7 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
   CB_LAUNCH(cb_select_threshold_kernel, nb, P.hist.as<int>(), nb, W, H, P.thresh.as<int>());
   uint8_t* b0 = P.bin0.as<uint8_t>();
   uint8_t* b1 = P.bin1.as<uint8_t>();
-  CB_LAUNCH(cb_binarize_kernel, total, d_img, imgs->pitch, imgs->image_stride, W, H, nb, P.thresh.as<int>(), (const int*)nullptr, b0);
+  CB_LAUNCH_PIX(cb_binarize_kernel, N, nb, d_img, imgs->pitch, imgs->image_stride, W, H, nb, P.thresh.as<int>(), (const int*)nullptr, b0);
   if (fast_check) {
     if (ezc_status st = fast_check_gate(ctx, P, d_img, imgs->pitch, imgs->image_stride, b0, W, H, nb, pw, ph, list)) return st;
     if (ezc_status st = upload_list(ctx, P.active, list)) return st;
@@ -1377,9 +1455,9 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
   // ---- phase 1: histogram-binarised image, 8 cumulative dilations (the frame of the previous pass is dilated too)
   for (int dil = 0; dil <= 7 && !list.empty(); ++dil) {
     const int n_act = (int)list.size();
-    CB_LAUNCH(cb_dilate_kernel, N * n_act, b0, b1, W, H, n_act, P.active.as<int>());
+    CB_LAUNCH_PIX(cb_dilate_kernel, N, n_act, b0, b1, W, H, n_act, P.active.as<int>());
     std::swap(b0, b1);
-    CB_LAUNCH(cb_frame_kernel, N * n_act, b0, W, H, n_act, P.active.as<int>());
+    CB_LAUNCH_PIX(cb_frame_kernel, N, n_act, b0, W, H, n_act, P.active.as<int>());
     if (ezc_status st = run_attempt(ctx, P, b0, W, H, n_act, pw, ph, dil)) return st;
     if (ezc_status st = sync_state(ctx, P, nb, h_state, list)) return st;
   }
@@ -1417,25 +1495,25 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
           // new block size: adaptive threshold of the equalised image, then `dil` dilations -> prev_thresh_img
           if (ezc_status st = upload_list(ctx, P.refresh, fresh)) return st;
           const int nf = (int)fresh.size();
-          CB_LAUNCH(cb_box_h_kernel, N * nf, P.eq.as<uint8_t>(), W, H, nf, P.refresh.as<int>(), P.block.as<int>(), P.hsum.as<int>());
-          CB_LAUNCH(cb_box_v_thresh_kernel, N * nf, P.eq.as<uint8_t>(), P.hsum.as<int>(), W, H, nf, P.refresh.as<int>(), P.block.as<int>(),
+          CB_LAUNCH_PIX(cb_box_h_kernel, N, nf, P.eq.as<uint8_t>(), W, H, nf, P.refresh.as<int>(), P.block.as<int>(), P.hsum.as<int>());
+          CB_LAUNCH_PIX(cb_box_v_thresh_kernel, N, nf, P.eq.as<uint8_t>(), P.hsum.as<int>(), W, H, nf, P.refresh.as<int>(), P.block.as<int>(),
                     P.delta.as<int>(), tmp);
           for (int d = 0; d < dil; ++d) {
-            CB_LAUNCH(cb_dilate_kernel, N * nf, tmp, th, W, H, nf, P.refresh.as<int>());
-            CB_LAUNCH(cb_copy_active_kernel, N * nf, th, tmp, N, nf, P.refresh.as<int>());
+            CB_LAUNCH_PIX(cb_dilate_kernel, N, nf, tmp, th, W, H, nf, P.refresh.as<int>());
+            CB_LAUNCH_PIX(cb_copy_active_kernel, N, nf, th, tmp, N, nf, P.refresh.as<int>());
           }
-          CB_LAUNCH(cb_copy_active_kernel, N * nf, tmp, prevb, N, nf, P.refresh.as<int>());
+          CB_LAUNCH_PIX(cb_copy_active_kernel, N, nf, tmp, prevb, N, nf, P.refresh.as<int>());
         }
         if (!old.empty() && dil > 0) {
           // same block size as before: one more dilation of prev_thresh_img
           if (ezc_status st = upload_list(ctx, P.refresh, old)) return st;
           const int no = (int)old.size();
-          CB_LAUNCH(cb_dilate_kernel, N * no, prevb, tmp, W, H, no, P.refresh.as<int>());
-          CB_LAUNCH(cb_copy_active_kernel, N * no, tmp, prevb, N, no, P.refresh.as<int>());
+          CB_LAUNCH_PIX(cb_dilate_kernel, N, no, prevb, tmp, W, H, no, P.refresh.as<int>());
+          CB_LAUNCH_PIX(cb_copy_active_kernel, N, no, tmp, prevb, N, no, P.refresh.as<int>());
         }
         const int n_act = (int)list.size();
-        CB_LAUNCH(cb_copy_active_kernel, N * n_act, prevb, th, N, n_act, P.active.as<int>());
-        CB_LAUNCH(cb_frame_kernel, N * n_act, th, W, H, n_act, P.active.as<int>());
+        CB_LAUNCH_PIX(cb_copy_active_kernel, N, n_act, prevb, th, N, n_act, P.active.as<int>());
+        CB_LAUNCH_PIX(cb_frame_kernel, N, n_act, th, W, H, n_act, P.active.as<int>());
         // no edge-length compensation in the fallback (empirically what cv2 4.13 does: exact on all phase-2 fixtures)
         if (ezc_status st = run_attempt(ctx, P, th, W, H, n_act, pw, ph, 0)) return st;
         if (ezc_status st = sync_state(ctx, P, nb, h_state, list)) return st;
