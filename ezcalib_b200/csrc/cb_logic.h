@@ -311,7 +311,12 @@ CB_HD inline void find_quad_neighbors(Work& w, const Par& par) {
       if (code != 0x7fffffff && min_dist < FLT_MAX) {
         const int closest_quad = code >> 2, closest_corner_idx = code & 3;
         Quad& cq = w.quads[closest_quad];
-        if (cur.count >= 4 || cq.count >= 4) continue;
+#ifdef CB_DEBUG2
+#define CBD(msg) fprintf(stderr, "   q%d c%d (%.1f,%.1f) -> q%d c%d dist %.1f: %s\n", idx, i, pt.x, pt.y, closest_quad, closest_corner_idx, min_dist, msg)
+#else
+#define CBD(msg)
+#endif
+        if (cur.count >= 4 || cq.count >= 4) { CBD("count>=4"); continue; }
         Corner& cc = w.corners[cq.corners[closest_corner_idx]];
         int j = 0;
         for (; j < 4; j++) {
@@ -319,9 +324,9 @@ CB_HD inline void find_quad_neighbors(Work& w, const Par& par) {
           const Ptf o = w.corners[cur.corners[j]].pt;
           if (normL2Sqrf(cc.pt.x - o.x, cc.pt.y - o.y) < min_dist) break;
         }
-        if (j < 4) continue;
+        if (j < 4) { CBD("own corner closer / already neighbour"); continue; }
         for (j = 0; j < 4; j++) if (cq.nb[j] == idx) break;
-        if (j < 4) continue;
+        if (j < 4) { CBD("already linked back"); continue; }
         // is some free corner of a third quad closer to closest_corner than this one?
         bool blocked = false;
         for (int q3 = par.lane(); q3 < nq && !blocked; q3 += par.lanes()) {
@@ -334,7 +339,8 @@ CB_HD inline void find_quad_neighbors(Work& w, const Par& par) {
             }
           }
         }
-        if (par.any(blocked)) continue;
+        if (par.any(blocked)) { CBD("third corner closer"); continue; }
+        CBD("LINK");
         if (par.lane() == 0) {
           cc.pt.x = (pt.x + cc.pt.x) * 0.5f;
           cc.pt.y = (pt.y + cc.pt.y) * 0.5f;
