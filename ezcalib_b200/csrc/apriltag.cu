@@ -8,14 +8,16 @@
 // core.  Here a whole batch of images resident in HBM goes through data-parallel stages, and every stage is
 // arranged so that its result is IDENTICAL to the reference's sequential semantics (float32 operation order
 // included; this translation unit is compiled with -fmad=false and uses bit-exact libm restatements):
-//   1  u8 -> float, 3-tap Gaussian blur (with the reference's border quirk), gradient magnitude / atan2
-//   2  compaction of the pixels above the gradient threshold (raster order == compact order)
+//   1  ONE tiled kernel: u8 -> float, 3-tap Gaussian blur (with the reference's border quirk) in shared memory, gradient
+//      magnitude, activity bit mask (1 bit / pixel) and -- only for the ~5 % active pixels -- the bit-exact atan2
+//   2  compaction of the active pixels from the scanned per-word popcounts (raster order == compact order)
 //   3  edge emission in generation order (count, scan, scatter)
 //   4  connected components of the edge graph (lock-free union-find); edges of different components never
 //      interact in Edge::mergeEdges, so the reference's single sequential sweep over the cost-sorted edge
 //      list factorises into one independent sequential sweep PER COMPONENT
 //   5  stable radix sort of the edges by (component, cost) -- generation order inside equal keys
-//   6  one thread per component: the exact union-find / span-merge sweep of Edge.cc:69-117
+//   6  one WARP per component: the exact union-find / span-merge sweep of Edge.cc:69-117 (roots of the next 32 edges
+//      resolved in parallel, only candidate merges replayed in order)
 //   7  stable radix sort of the clustered pixels by representative (== std::map order, raster inside)
 //   8  one thread per cluster: weighted line fit, segment orientation vote (float32 sums in raster order)
 //   9  10-px spatial hash, child lists, depth-4 quad search, tag decoding, de-duplication, cornerSubPix
@@ -278,29 +280,6 @@ __global__ void at_compact_words_kernel(const uint32_t* __restrict__ amask, cons
   }
 }
 
-// ---- stage 2: compaction -----------------------------------------------------------------------
-// cidx[] holds the exclusive scan of the flags == compact id of every active pixel (raster order preserved).
-__global__ void at_compact_kernel(const int* __restrict__ cidx, const float* __restrict__ theta, const float* __restrict__ mag,
-                                  long long total, int W, int H, int n_active, int* __restrict__ apix,
-                                  float* __restrict__ a_theta, float* __restrict__ a_mag, int* __restrict__ parent,
-                                  int* __restrict__ setsize, float* __restrict__ tmin, float* __restrict__ tmax,
-                                  float* __restrict__ mmin, float* __restrict__ mmax) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  const long long N = (long long)W * H;
-  const int p = (int)(gid % N);
-  const int y = p / W, x = p - y * W;
-  const float mg = mag[gid];
-  if (!(x + 1 < W && y + 1 < H && mg >= kMinMag)) return;
-  const int c = cidx[gid];
-  const float th = theta[gid];
-  apix[c] = (int)gid;  // global dense index (image * N + pixel); sub-batches are sized to keep it < 2^31
-  a_theta[c] = th; a_mag[c] = mg;
-  parent[c] = c; setsize[c] = 1;
-  tmin[c] = th; tmax[c] = th; mmin[c] = mg; mmax[c] = mg;
-  (void)n_active;
-}
-
 // ---- stage 3: edges (Edge.cc:14-67) ------------------------------------------------------------------
 __device__ __forceinline__ int edge_cost(float theta0, float theta1, float mag1) {
   if (mag1 < kMinMag) return -1;
@@ -310,35 +289,7 @@ __device__ __forceinline__ int edge_cost(float theta0, float theta1, float mag1)
   return (int)(normErr * 100);
 }
 
-template <bool EMIT>
-__global__ void at_edges_kernel(const int* __restrict__ apix, const float* __restrict__ theta, const float* __restrict__ mag,
-                                const int* __restrict__ cidx, int n_active, int W, int H, int* __restrict__ ecount,
-                                const int* __restrict__ eoff, int* __restrict__ eA, int* __restrict__ eB,
-                                uint8_t* __restrict__ ecost) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_active) return;
-  const long long g = apix[c];
-  const long long N = (long long)W * H;
-  const int p = (int)(g % N);
-  const int y = p / W, x = p - y * W;
-  const float th0 = theta[g];
-  int n = 0;
-  int o = EMIT ? eoff[c] : 0;
-  auto consider = [&](long long gn) {
-    const int cost = edge_cost(th0, theta[gn], mag[gn]);
-    if (cost >= 0) {
-      if (EMIT) { eA[o] = c; eB[o] = cidx[gn]; ecost[o] = (uint8_t)cost; ++o; }
-      ++n;
-    }
-  };
-  consider(g + 1);          // horizontal
-  consider(g + W);          // vertical
-  consider(g + W + 1);      // downward diagonal
-  if (x != 0) consider(g + W - 1);  // upward diagonal
-  if (!EMIT) ecount[c] = n;
-}
-
-// Fused-path variant: the neighbour's activity bit replaces the mag test (active <=> mag >= minMag), its compact id comes
+// The neighbour's activity bit replaces the mag test (active <=> mag >= minMag), its compact id comes
 // from the scanned word counts and its theta from the compact array -- no full-size theta / mag / index images are read.
 template <bool EMIT>
 __global__ void at_edges_words_kernel(const int* __restrict__ apix, const float* __restrict__ a_theta, const uint32_t* __restrict__ amask,

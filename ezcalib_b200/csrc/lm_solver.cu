@@ -45,7 +45,6 @@ constexpr int R1_HCC = 0;                     // [12][12] upper triangle used
 constexpr int R1_COST = 144;                  // cost at x
 constexpr int R1_SCHUR = 145;                 // start of the lm_schur section
 constexpr int R1_SIZE = 256;                   // 145 + S(<=78) b(k) gc(k) xnorm2 nres nused fail gmax
-constexpr int R2_SIZE = 5;                    // g.delta, delta H delta, |step|^2, |cand|^2, cand cost
 
 __host__ __device__ inline int tile_index(int ti, int tj, int NT) { return ti * NT - ti * (ti - 1) / 2 + (tj - ti); }
 
