@@ -253,12 +253,19 @@ __device__ __forceinline__ int compact_id(const uint32_t* __restrict__ amask, co
   return aoff[wi] + __popc(amask[wi] & ((1u << bit) - 1u));
 }
 
+// One 32-byte record per union-find node (UnionFindSimple's parent/size + Edge.cc's theta/mag spans): the merge sweep
+// touches all six values of both roots of every candidate edge, i.e. two sectors instead of twelve scattered ones.
+struct __align__(32) UfNode {
+  int parent, size;
+  float tmin, tmax, mmin, mmax;
+  int pad0, pad1;
+};
+
 // stage 2 for the fused path: one thread per mask word, emits its active pixels in raster order
 __global__ void at_compact_words_kernel(const uint32_t* __restrict__ amask, const int* __restrict__ aoff, long long n_words, int wpr,
                                         int W, int H, const float* __restrict__ theta, const float* __restrict__ mag,
                                         int* __restrict__ apix, float* __restrict__ a_theta, float* __restrict__ a_mag,
-                                        int* __restrict__ parent, int* __restrict__ setsize, float* __restrict__ tmin,
-                                        float* __restrict__ tmax, float* __restrict__ mmin, float* __restrict__ mmax) {
+                                        UfNode* __restrict__ nodes) {
   const long long wi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (wi >= n_words) return;
   uint32_t m = amask[wi];
@@ -274,8 +281,7 @@ __global__ void at_compact_words_kernel(const uint32_t* __restrict__ amask, cons
     const float th = theta[g], mg = mag[g];
     apix[c] = (int)g;
     a_theta[c] = th; a_mag[c] = mg;
-    parent[c] = c; setsize[c] = 1;
-    tmin[c] = th; tmax[c] = th; mmin[c] = mg; mmax[c] = mg;
+    nodes[c] = UfNode{c, 1, th, th, mg, mg, 0, 0};
     ++c;
   }
 }
@@ -402,15 +408,14 @@ __device__ __forceinline__ int uf_find(int* parent, int x) {
 // so it is dropped; (B) the remaining candidates are replayed one by one, in order, by the whole warp
 // (uniform control flow, lane 0 writes), re-resolving their roots first because an earlier candidate of the
 // same batch may have merged them.
-__device__ __forceinline__ int uf_find_ro(const int* parent, int x) {
-  int p = parent[x];
-  while (p != x) { x = p; p = parent[x]; }
+__device__ __forceinline__ int uf_find_ro(const UfNode* nodes, int x) {
+  int p = nodes[x].parent;
+  while (p != x) { x = p; p = nodes[x].parent; }
   return x;
 }
 
 __global__ void __launch_bounds__(256) at_merge_kernel(const uint32_t* __restrict__ order, const int* __restrict__ starts, int n_comp,
-                                                         const int* __restrict__ eA, const int* __restrict__ eB, int* parent,
-                                                         int* setsize, float* tmin, float* tmax, float* mmin, float* mmax) {
+                                                         const int* __restrict__ eA, const int* __restrict__ eB, UfNode* nodes) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= n_comp) return;
@@ -421,24 +426,29 @@ __global__ void __launch_bounds__(256) at_merge_kernel(const uint32_t* __restric
     if (i < end) {
       const uint32_t e = order[i];
       const int a = eA[e], b = eB[e];
-      ra = uf_find_ro(parent, a);
-      rb = uf_find_ro(parent, b);
+      ra = uf_find_ro(nodes, a);
+      rb = uf_find_ro(nodes, b);
       // path shortening (UnionFindSimple compresses too; it never changes a representative)
-      if (parent[a] != ra) parent[a] = ra;
-      if (parent[b] != rb) parent[b] = rb;
+      if (nodes[a].parent != ra) nodes[a].parent = ra;
+      if (nodes[b].parent != rb) nodes[b].parent = rb;
     }
     unsigned cand = __ballot_sync(0xffffffffu, i < end && ra != rb);
     __syncwarp();
     while (cand) {
       const int l = __ffs(cand) - 1;
       cand &= cand - 1;
-      const int ida = uf_find_ro(parent, __shfl_sync(0xffffffffu, ra, l));
-      const int idb = uf_find_ro(parent, __shfl_sync(0xffffffffu, rb, l));
+      const int ida = uf_find_ro(nodes, __shfl_sync(0xffffffffu, ra, l));
+      const int idb = uf_find_ro(nodes, __shfl_sync(0xffffffffu, rb, l));
       if (ida != idb) {
-        const int sza = setsize[ida], szb = setsize[idb];
-        const float tmina = tmin[ida], tmaxa = tmax[ida];
-        const float tminb = tmin[idb], tmaxb = tmax[idb];
-        const float mmina = mmin[ida], mmaxa = mmax[ida], mminb = mmin[idb], mmaxb = mmax[idb];
+        // the whole record of each root in two 16-byte loads
+        const int4 a0 = *reinterpret_cast<const int4*>(&nodes[ida]);
+        const float2 a1 = *reinterpret_cast<const float2*>(&nodes[ida].mmin);
+        const int4 b0 = *reinterpret_cast<const int4*>(&nodes[idb]);
+        const float2 b1 = *reinterpret_cast<const float2*>(&nodes[idb].mmin);
+        const int sza = a0.y, szb = b0.y;
+        const float tmina = __int_as_float(a0.z), tmaxa = __int_as_float(a0.w);
+        const float tminb = __int_as_float(b0.z), tmaxb = __int_as_float(b0.w);
+        const float mmina = a1.x, mmaxa = a1.y, mminb = b1.x, mmaxb = b1.y;
         const float costa = (tmaxa - tmina);
         const float costb = (tmaxb - tminb);
         const float bshift = mod2pi_ref((tmina + tmaxa) / 2, (tminb + tmaxb) / 2) - (tminb + tmaxb) / 2;
@@ -451,11 +461,9 @@ __global__ void __launch_bounds__(256) at_merge_kernel(const uint32_t* __restric
         if (costab <= (fminr(costa, costb) + kThetaThresh / (sza + szb)) &&
             (mmaxab - mminab) <= fminr(mmaxa - mmina, mmaxb - mminb) + kMagThresh / (sza + szb)) {
           if (lane == 0) {
-            int idab;  // UnionFindSimple::connectNodes (UnionFindSimple.cc:25-44)
-            if (sza > szb) { parent[idb] = ida; setsize[ida] = sza + szb; idab = ida; }
-            else { parent[ida] = idb; setsize[idb] = szb + sza; idab = idb; }
-            tmin[idab] = tminab; tmax[idab] = tmaxab;
-            mmin[idab] = mminab; mmax[idab] = mmaxab;
+            // UnionFindSimple::connectNodes (UnionFindSimple.cc:25-44)
+            if (sza > szb) { nodes[idb].parent = ida; nodes[ida] = UfNode{ida, sza + szb, tminab, tmaxab, mminab, mmaxab, 0, 0}; }
+            else { nodes[ida].parent = idb; nodes[idb] = UfNode{idb, szb + sza, tminab, tmaxab, mminab, mmaxab, 0, 0}; }
           }
         }
       }
@@ -464,21 +472,26 @@ __global__ void __launch_bounds__(256) at_merge_kernel(const uint32_t* __restric
   }
 }
 
-// ---- stage 7: clusters ---------------------------------------------------------------------------
-__global__ void at_rep_kernel(const int* __restrict__ parent, const int* __restrict__ setsize, int n_active, int* __restrict__ rep,
-                              int* __restrict__ keep) {
+// parent / size arrays of the forest (debug export)
+__global__ void at_split_nodes_kernel(const UfNode* __restrict__ nodes, int n, int* __restrict__ parent, int* __restrict__ setsize) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  parent[i] = nodes[i].parent; setsize[i] = nodes[i].size;
+}
+
+__global__ void at_rep_kernel(const UfNode* __restrict__ nodes, int n_active, int* __restrict__ rep, int* __restrict__ keep) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_active) return;
   int r = i;
-  while (parent[r] != r) r = parent[r];
+  while (nodes[r].parent != r) r = nodes[r].parent;
   rep[i] = r;
-  keep[i] = setsize[r] >= kMinSegmentSize ? 1 : 0;  // TagDetector.cc:248
+  keep[i] = nodes[r].size >= kMinSegmentSize ? 1 : 0;  // TagDetector.cc:248
 }
-__global__ void at_keep_compact_kernel(const int* __restrict__ keep_scan, const int* __restrict__ rep, const int* __restrict__ setsize,
+__global__ void at_keep_compact_kernel(const int* __restrict__ keep_scan, const int* __restrict__ rep, const UfNode* __restrict__ nodes,
                                        int n_active, uint32_t* __restrict__ list) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_active) return;
-  if (setsize[rep[i]] >= kMinSegmentSize) list[keep_scan[i]] = (uint32_t)i;
+  if (nodes[rep[i]].size >= kMinSegmentSize) list[keep_scan[i]] = (uint32_t)i;
 }
 
 // ---- stage 8: line fit per cluster (GLine2D.cc:54-87, GLineSegment2D.cc:9-24, TagDetector.cc:265-325) ---------
@@ -1069,7 +1082,7 @@ namespace {
 
 struct Pools {
   DevBuf fr, seg, theta, mag, cidx, scan_tmp, total, amask, acount, dbg_theta, dbg_mag;
-  DevBuf apix, a_theta, a_mag, parent, setsize, tmin, tmax, mmin, mmax, ecount, label;
+  DevBuf apix, a_theta, a_mag, nodes, parent, setsize, ecount, label;
   DevBuf eA, eB, ecost, order0, order1, flags, starts;
   DevBuf rep, keep, plist0, plist1, cstart, segs_raw, seg_valid, segs, img_count, seg_start;
   DevBuf cell_of, cell_count, cell_start, cell_fill, cell_items, ccount, children;
@@ -1149,14 +1162,11 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
   if (ezc_status st = read_int(ctx, d_tot, &nA, P)) return st;
   const size_t cap = (size_t)std::max(nA, 1);
   EZC_CUDA(P.apix.reserve(sizeof(int) * cap)); EZC_CUDA(P.a_theta.reserve(sizeof(float) * cap)); EZC_CUDA(P.a_mag.reserve(sizeof(float) * cap));
-  EZC_CUDA(P.parent.reserve(sizeof(int) * cap)); EZC_CUDA(P.setsize.reserve(sizeof(int) * cap));
-  EZC_CUDA(P.tmin.reserve(sizeof(float) * cap)); EZC_CUDA(P.tmax.reserve(sizeof(float) * cap));
-  EZC_CUDA(P.mmin.reserve(sizeof(float) * cap)); EZC_CUDA(P.mmax.reserve(sizeof(float) * cap));
+  EZC_CUDA(P.nodes.reserve(sizeof(UfNode) * cap));
   EZC_CUDA(P.ecount.reserve(sizeof(int) * (cap + 1))); EZC_CUDA(P.label.reserve(sizeof(int) * cap));
   EZC_CUDA(P.rep.reserve(sizeof(int) * cap)); EZC_CUDA(P.keep.reserve(sizeof(int) * (cap + 1)));
   AT_LAUNCH(at_compact_words_kernel, n_words, P.amask.as<uint32_t>(), P.acount.as<int>(), n_words, wpr, W, H, P.theta.as<float>(),
-            P.mag.as<float>(), P.apix.as<int>(), P.a_theta.as<float>(), P.a_mag.as<float>(), P.parent.as<int>(), P.setsize.as<int>(),
-            P.tmin.as<float>(), P.tmax.as<float>(), P.mmin.as<float>(), P.mmax.as<float>());
+            P.mag.as<float>(), P.apix.as<int>(), P.a_theta.as<float>(), P.a_mag.as<float>(), P.nodes.as<UfNode>());
   // ---- 3: edges
   AT_LAUNCH(at_edges_words_kernel<false>, nA, P.apix.as<int>(), P.a_theta.as<float>(), P.amask.as<uint32_t>(), P.acount.as<int>(), wpr,
             nA, W, H, P.ecount.as<int>(), nullptr, nullptr, nullptr, nullptr);
@@ -1192,8 +1202,7 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
     EZC_CUDA(P.starts.reserve(sizeof(int) * ((size_t)nComp + 2)));
     AT_LAUNCH(at_starts_kernel, nE, P.flags.as<int>(), d_tot, nE, P.starts.as<int>());
     // ---- 6: merge sweep
-    AT_LAUNCH(at_merge_kernel, (long long)nComp * 32, o0, P.starts.as<int>(), nComp, P.eA.as<int>(), P.eB.as<int>(), P.parent.as<int>(),
-              P.setsize.as<int>(), P.tmin.as<float>(), P.tmax.as<float>(), P.mmin.as<float>(), P.mmax.as<float>());
+    AT_LAUNCH(at_merge_kernel, (long long)nComp * 32, o0, P.starts.as<int>(), nComp, P.eA.as<int>(), P.eB.as<int>(), P.nodes.as<UfNode>());
   }
   if (dbg && nb == 1) {
     dbg->theta.resize(N); dbg->mag.resize(N);
@@ -1203,6 +1212,8 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
     std::vector<uint8_t> ec(nE);
     std::vector<uint32_t> ord(nE);
     if (nA) {
+      EZC_CUDA(P.parent.reserve(sizeof(int) * (size_t)nA)); EZC_CUDA(P.setsize.reserve(sizeof(int) * (size_t)nA));
+      AT_LAUNCH(at_split_nodes_kernel, nA, P.nodes.as<UfNode>(), nA, P.parent.as<int>(), P.setsize.as<int>());
       EZC_CUDA(cudaMemcpyAsync(apix.data(), P.apix.p, sizeof(int) * nA, cudaMemcpyDeviceToHost, ctx->stream));
       EZC_CUDA(cudaMemcpyAsync(par.data(), P.parent.p, sizeof(int) * nA, cudaMemcpyDeviceToHost, ctx->stream));
       EZC_CUDA(cudaMemcpyAsync(ssz.data(), P.setsize.p, sizeof(int) * nA, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1220,7 +1231,7 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
     for (int i = 0; i < nA; ++i) { int r = i; while (par[r] != r) r = par[r]; dbg->rep[apix[i]] = apix[r]; dbg->size[apix[i]] = ssz[r]; }
   }
   // ---- 7: clusters = pixels grouped by representative (ascending), raster order inside
-  AT_LAUNCH(at_rep_kernel, nA, P.parent.as<int>(), P.setsize.as<int>(), nA, P.rep.as<int>(), P.keep.as<int>());
+  AT_LAUNCH(at_rep_kernel, nA, P.nodes.as<UfNode>(), nA, P.rep.as<int>(), P.keep.as<int>());
   if (ezc_status st = exclusive_scan_i32(ctx, P.keep.as<int>(), P.keep.as<int>(), nA, P.scan_tmp, d_tot)) return st;
   int nK = 0;
   if (ezc_status st = read_int(ctx, d_tot, &nK, P)) return st;
@@ -1228,7 +1239,7 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
   EZC_CUDA(P.plist0.reserve(sizeof(uint32_t) * kcap)); EZC_CUDA(P.plist1.reserve(sizeof(uint32_t) * kcap));
   uint32_t* l0 = P.plist0.as<uint32_t>();
   uint32_t* l1 = P.plist1.as<uint32_t>();
-  AT_LAUNCH(at_keep_compact_kernel, nA, P.keep.as<int>(), P.rep.as<int>(), P.setsize.as<int>(), nA, l0);
+  AT_LAUNCH(at_keep_compact_kernel, nA, P.keep.as<int>(), P.rep.as<int>(), P.nodes.as<UfNode>(), nA, l0);
   for (int shift = 0; shift < bits_for(std::max(nA, 2)); shift += 8) {
     if (ezc_status st = radix_pass(ctx, l0, l1, nK, DigitArray{P.rep.as<int>(), shift}, P.sort)) return st;
     std::swap(l0, l1);
