@@ -358,19 +358,17 @@ __global__ void at_ccl_flatten_kernel(int* L, int n) {
 }
 
 // ---- stage 5: sort functors --------------------------------------------------------------------------
-// Sort key of an edge: (component label << 7) | cost   (cost <= 100 fits 7 bits); 11-bit digits from the LSB:
-// [cost | label bits 0..3], label bits 4..14, label bits 15..25 -> three passes for up to 2^26 active pixels.
-constexpr int kSortBits = 11;
-struct DigitEdgeKey {
-  const int* label; const int* eA; const uint8_t* cost; int shift;   // shift into the 33-bit key
-  __device__ int operator()(uint32_t e) const {
-    const unsigned long long key = ((unsigned long long)(unsigned)label[eA[e]] << 7) | cost[e];
-    return (int)((key >> shift) & ((1u << kSortBits) - 1u));
-  }
+struct DigitCost {
+  const uint8_t* cost;
+  __device__ int operator()(uint32_t e) const { return cost[e]; }
+};
+struct DigitLabelOfEdge {
+  const int* label; const int* eA; int shift;
+  __device__ int operator()(uint32_t e) const { return (label[eA[e]] >> shift) & 255; }
 };
 struct DigitArray {
   const int* key; int shift;
-  __device__ int operator()(uint32_t v) const { return (key[v] >> shift) & ((1 << kSortBits) - 1); }
+  __device__ int operator()(uint32_t v) const { return (key[v] >> shift) & 255; }
 };
 __global__ void at_iota_kernel(uint32_t* v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1189,9 +1187,10 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
   uint32_t* o0 = P.order0.as<uint32_t>();
   uint32_t* o1 = P.order1.as<uint32_t>();
   AT_LAUNCH(at_iota_kernel, nE, o0, nE);
-  for (int shift = 0; shift < 7 + bits_for(std::max(nA, 2)); shift += kSortBits) {
-    if (ezc_status st = radix_pass<kSortBits>(ctx, o0, o1, nE, DigitEdgeKey{P.label.as<int>(), P.eA.as<int>(), P.ecost.as<uint8_t>(), shift}, P.sort))
-      return st;
+  if (ezc_status st = radix_pass(ctx, o0, o1, nE, DigitCost{P.ecost.as<uint8_t>()}, P.sort)) return st;
+  std::swap(o0, o1);
+  for (int shift = 0; shift < bits_for(std::max(nA, 2)); shift += 8) {
+    if (ezc_status st = radix_pass(ctx, o0, o1, nE, DigitLabelOfEdge{P.label.as<int>(), P.eA.as<int>(), shift}, P.sort)) return st;
     std::swap(o0, o1);
   }
   // component boundaries -> starts
@@ -1241,8 +1240,8 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
   uint32_t* l0 = P.plist0.as<uint32_t>();
   uint32_t* l1 = P.plist1.as<uint32_t>();
   AT_LAUNCH(at_keep_compact_kernel, nA, P.keep.as<int>(), P.rep.as<int>(), P.nodes.as<UfNode>(), nA, l0);
-  for (int shift = 0; shift < bits_for(std::max(nA, 2)); shift += kSortBits) {
-    if (ezc_status st = radix_pass<kSortBits>(ctx, l0, l1, nK, DigitArray{P.rep.as<int>(), shift}, P.sort)) return st;
+  for (int shift = 0; shift < bits_for(std::max(nA, 2)); shift += 8) {
+    if (ezc_status st = radix_pass(ctx, l0, l1, nK, DigitArray{P.rep.as<int>(), shift}, P.sort)) return st;
     std::swap(l0, l1);
   }
   int nC = 0;

@@ -99,49 +99,41 @@ inline ezc_status exclusive_scan_i32(ezc_context* ctx, const int* in, int* out, 
 }
 
 // ------------------------------------------------------------------------------------------ radix sort
-// BITS-wide digits (8 or 11): 11-bit digits sort a 33-bit key in three passes instead of five.  The histogram table
-// has bins x n_warps entries and is prefix-summed every pass, so the wide-digit variant gives every warp a longer chunk
-// (same table size) and runs 4 warps per block (2048 bins x 4 warps x 4 B = 32 KB of shared memory).
-template <int BITS> struct RadixCfg {
-  static constexpr int kBins = 1 << BITS;
-  static constexpr int kWarps = BITS > 8 ? 4 : 8;
-  static constexpr int kChunk = BITS > 8 ? 8192 : 1024;  // items per warp per pass
-};
+constexpr int kSortWarps = 8;
+constexpr int kSortChunk = 1024;  // items per warp per pass
 
-template <int BITS, class DigitFn>
-__global__ void __launch_bounds__(RadixCfg<BITS>::kWarps * 32) radix_hist_kernel(const uint32_t* __restrict__ vals, int n, int n_warps,
-                                                                                   DigitFn digit, int* __restrict__ counts) {
-  using Cfg = RadixCfg<BITS>;
-  __shared__ int h[Cfg::kWarps][Cfg::kBins];
+template <class DigitFn>
+__global__ void __launch_bounds__(kSortWarps * 32) radix_hist_kernel(const uint32_t* __restrict__ vals, int n, int n_warps,
+                                                                       DigitFn digit, int* __restrict__ counts) {
+  __shared__ int h[kSortWarps][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * Cfg::kWarps + warp;
-  for (int b = lane; b < Cfg::kBins; b += 32) h[warp][b] = 0;
+  const int gw = blockIdx.x * kSortWarps + warp;
+  for (int b = lane; b < 256; b += 32) h[warp][b] = 0;
   __syncwarp();
   if (gw < n_warps) {
-    const int beg = gw * Cfg::kChunk, end = min(n, beg + Cfg::kChunk);
+    const int beg = gw * kSortChunk, end = min(n, beg + kSortChunk);
     for (int i = beg + lane; i < end; i += 32) atomicAdd(&h[warp][digit(vals[i])], 1);
     __syncwarp();
-    for (int b = lane; b < Cfg::kBins; b += 32) counts[(size_t)b * n_warps + gw] = h[warp][b];
+    for (int b = lane; b < 256; b += 32) counts[(size_t)b * n_warps + gw] = h[warp][b];
   }
 }
 
-template <int BITS, class DigitFn>
-__global__ void __launch_bounds__(RadixCfg<BITS>::kWarps * 32) radix_scatter_kernel(const uint32_t* __restrict__ vals, uint32_t* __restrict__ out,
-                                                                                      int n, int n_warps, DigitFn digit,
-                                                                                      const int* __restrict__ offsets) {
-  using Cfg = RadixCfg<BITS>;
-  __shared__ int off[Cfg::kWarps][Cfg::kBins];
+template <class DigitFn>
+__global__ void __launch_bounds__(kSortWarps * 32) radix_scatter_kernel(const uint32_t* __restrict__ vals, uint32_t* __restrict__ out,
+                                                                          int n, int n_warps, DigitFn digit,
+                                                                          const int* __restrict__ offsets) {
+  __shared__ int off[kSortWarps][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * Cfg::kWarps + warp;
+  const int gw = blockIdx.x * kSortWarps + warp;
   if (gw >= n_warps) return;
-  for (int b = lane; b < Cfg::kBins; b += 32) off[warp][b] = offsets[(size_t)b * n_warps + gw];
+  for (int b = lane; b < 256; b += 32) off[warp][b] = offsets[(size_t)b * n_warps + gw];
   __syncwarp();
-  const int beg = gw * Cfg::kChunk, end = min(n, beg + Cfg::kChunk);
+  const int beg = gw * kSortChunk, end = min(n, beg + kSortChunk);
   for (int i0 = beg; i0 < end; i0 += 32) {
     const int i = i0 + lane;
     const bool act = i < end;
     uint32_t v = 0;
-    int d = Cfg::kBins + lane;  // inactive lanes get unique pseudo-digits
+    int d = 256 + lane;  // inactive lanes get unique pseudo-digits
     if (act) { v = vals[i]; d = digit(v); }
     const unsigned m = __match_any_sync(0xffffffffu, d);
     const int rank = __popc(m & ((1u << lane) - 1u));
@@ -160,19 +152,18 @@ struct SortTemp {
   DevBuf counts, scan_tmp;
 };
 
-// One stable pass: reorders vals[n] into out[n] by the BITS-bit digit digit(v).
-template <int BITS, class DigitFn>
+// One stable pass: reorders vals[n] into out[n] by the 8-bit digit digit(v).
+template <class DigitFn>
 inline ezc_status radix_pass(ezc_context* ctx, const uint32_t* vals, uint32_t* out, int n, DigitFn digit, SortTemp& t) {
-  using Cfg = RadixCfg<BITS>;
   if (n <= 0) return EZC_OK;
-  const int n_warps = (n + Cfg::kChunk - 1) / Cfg::kChunk;
-  const int grid = (n_warps + Cfg::kWarps - 1) / Cfg::kWarps;
-  EZC_CUDA(t.counts.reserve(sizeof(int) * Cfg::kBins * (size_t)n_warps));
-  radix_hist_kernel<BITS><<<grid, Cfg::kWarps * 32, 0, ctx->stream>>>(vals, n, n_warps, digit, t.counts.as<int>());
+  const int n_warps = (n + kSortChunk - 1) / kSortChunk;
+  const int grid = (n_warps + kSortWarps - 1) / kSortWarps;
+  EZC_CUDA(t.counts.reserve(sizeof(int) * 256 * (size_t)n_warps));
+  radix_hist_kernel<<<grid, kSortWarps * 32, 0, ctx->stream>>>(vals, n, n_warps, digit, t.counts.as<int>());
   EZC_CUDA(cudaGetLastError());
   ctx->kernel_launches++;
-  if (ezc_status st = exclusive_scan_i32(ctx, t.counts.as<int>(), t.counts.as<int>(), (long long)Cfg::kBins * n_warps, t.scan_tmp, nullptr)) return st;
-  radix_scatter_kernel<BITS><<<grid, Cfg::kWarps * 32, 0, ctx->stream>>>(vals, out, n, n_warps, digit, t.counts.as<int>());
+  if (ezc_status st = exclusive_scan_i32(ctx, t.counts.as<int>(), t.counts.as<int>(), 256LL * n_warps, t.scan_tmp, nullptr)) return st;
+  radix_scatter_kernel<<<grid, kSortWarps * 32, 0, ctx->stream>>>(vals, out, n, n_warps, digit, t.counts.as<int>());
   EZC_CUDA(cudaGetLastError());
   ctx->kernel_launches++;
   return EZC_OK;
