@@ -1202,7 +1202,14 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
     EZC_CUDA(P.starts.reserve(sizeof(int) * ((size_t)nComp + 2)));
     AT_LAUNCH(at_starts_kernel, nE, P.flags.as<int>(), d_tot, nE, P.starts.as<int>());
     // ---- 6: merge sweep
-    AT_LAUNCH(at_merge_kernel, (long long)nComp * 32, o0, P.starts.as<int>(), nComp, P.eA.as<int>(), P.eB.as<int>(), P.nodes.as<UfNode>());
+    {
+      // 64-thread blocks: a block lives as long as its longest component, small blocks free their SM slots sooner
+      const long long nthr = (long long)nComp * 32;
+      at_merge_kernel<<<(unsigned)((nthr + 63) / 64), 64, 0, ctx->stream>>>(o0, P.starts.as<int>(), nComp, P.eA.as<int>(), P.eB.as<int>(),
+                                                                          P.nodes.as<UfNode>());
+      EZC_CUDA(cudaGetLastError());
+      ctx->kernel_launches++;
+    }
   }
   if (dbg && nb == 1) {
     dbg->theta.resize(N); dbg->mag.resize(N);
