@@ -1570,8 +1570,11 @@ ezc_status ezc_find_chessboard_corners_batch(ezc_context* ctx, const ezc_images*
   const int n = imgs->n;
   if (n == 0) return EZC_OK;
   const long long N = (long long)imgs->width * imgs->height;
-  int sub = (int)std::max<long long>(1, std::min<long long>((1LL << 30) / N, 2LL * 1024 * 1024 * 1024 / (N * 16)));
-  sub = std::min(sub, 256);
+  // images in flight: ~31 B/px of per-pixel scratch (binary images, labels, flags, parent counters, gate images), bounded to
+  // ~16 GiB of the 180 GB.  Large sub-batches matter: a view that passes the gate and fails the search runs its 56
+  // attempts in ~0.4 s while the rest of its sub-batch is long done, so the fewer sub-batches the fewer serial tails.
+  int sub = (int)std::max<long long>(1, std::min<long long>((1LL << 30) / N, 8LL * 1024 * 1024 * 1024 / (N * 16)));
+  sub = std::min(sub, 512);
   if (max_images_in_flight > 0) sub = std::min(sub, max_images_in_flight);
   sub = std::min(sub, n);
   const int npts = pattern_w * pattern_h;
