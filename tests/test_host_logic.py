@@ -1,5 +1,6 @@
 """CPU: host-side logic that mirrors the reference's orchestration (no GPU needed)."""
 import numpy as np
+import pytest
 
 from ezcalib_b200 import ezcalibrator as E
 from ezcalib_b200 import synth
@@ -51,3 +52,37 @@ def test_target_coordinates_follow_the_reference():
 def test_prior_intrinsics_rule():
     f, cx, cy = synth.prior_intrinsics(1280, 1024, 70.0)
     assert cx == 640 and cy == 512 and abs(f - 640 / np.tan(np.radians(35.0))) < 1e-9
+
+
+def test_initial_calibration_and_p3p_glue():
+    """Camera::setupInitialCalibration (camera.cpp:102-120) and EZCalibrator::computeP3PRansac (ezcalibrator.cpp:560-628)
+    as the host mirror restates them: prior focal from the field of view, poses from cv2.solvePnPRansac on pixels
+    normalised with the PRIOR intrinsics; the pose must reproject the target close to the observations."""
+    cv2 = pytest.importorskip("cv2")
+    from ezcalib_b200 import ezcalibrator as E, synth
+    W, H = 1280, 1024
+    f0, pp0 = E.setup_initial_calibration(W, H, 70.0, True)
+    assert f0.shape == (1,) and abs(f0[0] - max(W / 2, H / 2) / np.tan(np.deg2rad(35.0))) < 1e-9
+    assert np.array_equal(pp0, [W / 2, H / 2])
+    f2, _ = E.setup_initial_calibration(W, H, 70.0, False)
+    assert f2.shape == (2,) and f2[0] == f2[1] == f0[0]
+    R = E.fit_to_so3(np.eye(3) + 1e-3 * np.arange(9).reshape(3, 3))
+    assert abs(np.linalg.det(R) - 1) < 1e-12 and np.allclose(R @ R.T, np.eye(3), atol=1e-12)
+    model = "radtan5"
+    d = synth.GT_DIST[model]
+    tgt = synth.chessboard_target(7, 10, 0.05)
+    rng = np.random.Generator(np.random.Philox(key=3))
+    poses = synth.sample_poses(rng, 4, tgt, model, 900.0, 645.0, 505.0, d, W, H, margin=90, tilt_sigma=0.3)
+    for pose in poses:
+        px = synth.project(model, 900.0, 900.0, 645.0, 505.0, d, pose, tgt).astype(np.float32)
+        ok, p7, n_inl = E.compute_p3p_ransac(px, tgt, f0, pp0, W, H)
+        assert ok and n_inl >= 32 and abs(np.linalg.norm(p7[:4]) - 1) < 1e-9
+        # pinhole reprojection with the prior intrinsics (the returned pose is EPnP on the inliers, the lens distortion is
+        # not modelled at this stage): a sane initial pose, not a fit
+        rep = synth.project("rad1", f0[0], f0[0], pp0[0], pp0[1], [0.0], p7, tgt)
+        err = np.linalg.norm(rep - px, axis=1)
+        assert np.median(err) < 15.0
+    # too few points in the image: the frame is skipped like the reference does (>= 32 required for a >= 32-point target)
+    px = np.full((54, 2), -1.0, np.float32)
+    px[:10] = 100.0 + np.arange(20).reshape(10, 2)
+    assert E.compute_p3p_ransac(px, tgt, f0, pp0, W, H)[0] is False
