@@ -1581,14 +1581,12 @@ ezc_status ezc_find_chessboard_corners_batch(ezc_context* ctx, const ezc_images*
   ezc::DevBuf d_corners, d_found;
   EZC_CUDA(d_corners.reserve(sizeof(float2) * (size_t)n * npts));
   EZC_CUDA(d_found.reserve((size_t)n));
-  // images still crossing PCIe (ezc_images_upload_async): start small so the pipeline fills quickly, then double
-  int cur = imgs->ready.empty() ? sub : std::min(sub, std::max(1, imgs->chunk));
-  for (int i0 = 0; i0 < n;) {
-    const int nb = std::min(cur, n - i0);
+  // No sub-batch ramp under ezc_images_upload_async here (unlike the AprilGrid path): a chessboard sub-batch costs ~10x its
+  // upload time and every extra sub-batch risks another serial tail, so waiting ~15 ms for the first 256 images is cheaper.
+  for (int i0 = 0; i0 < n; i0 += sub) {
+    const int nb = std::min(sub, n - i0);
     if (ezc_status st = detect_sub_batch(ctx, imgs, i0, nb, pattern_w, pattern_h, final_subpix != 0, fast_check != 0, d_corners.as<float2>(), d_found.as<uint8_t>()))
       return st;
-    i0 += nb;
-    cur = std::min(sub, cur * 2);
   }
   EZC_CUDA(cudaMemcpyAsync(corners_out, d_corners.p, sizeof(float2) * (size_t)n * npts, cudaMemcpyDeviceToHost, ctx->stream));
   EZC_CUDA(cudaMemcpyAsync(found_out, d_found.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
