@@ -354,14 +354,20 @@ def run_detect(ctx, args, rank, world, stream):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e0.record(stream)
-    im2 = detect.Images(ctx, pin.numpy(), async_upload=True)   # copies on a second stream overlap detection of earlier sub-batches
-    s2, c2, n2 = detect.detect_aprilgrid(ctx, im2, DET_ROWS, DET_COLS)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms2 = e0.elapsed_time(e1)
-    im2.close()
-    assert np.array_equal(c2, corners) and np.array_equal(n2, ndet)
+    runs = []
+    for _rep in range(3):   # median of three identical host-buffer runs (one run is ~0.1 s of wall time: host hiccups show)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        im2 = detect.Images(ctx, pin.numpy(), async_upload=True)   # copies on a second stream overlap detection of earlier sub-batches
+        s2, c2, n2 = detect.detect_aprilgrid(ctx, im2, DET_ROWS, DET_COLS)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        runs.append(e0.elapsed_time(e1))
+        im2.close()
+        assert np.array_equal(c2, corners) and np.array_equal(n2, ndet)
+    ms2 = float(np.median(runs))
     # what the PCIe link of this box delivers for the same pinned buffer (context for e2e: it is transfer bound)
     dst = torch.empty(pin.numel(), dtype=torch.uint8, device="cuda")
     dst.copy_(pin.view(-1), non_blocking=True)
@@ -451,14 +457,18 @@ def run_detect_chessboard(ctx, args, rank, world, stream, cfg="cfg1"):
     host_all = imgs.download(0, n)
     pin = torch.from_numpy(host_all).pin_memory()
     torch.cuda.synchronize()
-    e0.record(stream)
-    im2 = detect.Images(ctx, pin.numpy(), async_upload=True)
-    f2, c2 = detect.detect_chessboard(ctx, im2, 7, 10)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms2 = e0.elapsed_time(e1)
-    im2.close()
-    assert np.array_equal(f2, found) and np.array_equal(c2, corners)
+    runs = []
+    for _rep in range(3):   # median of three identical host-buffer runs
+        torch.cuda.synchronize()
+        e0.record(stream)
+        im2 = detect.Images(ctx, pin.numpy(), async_upload=True)
+        f2, c2 = detect.detect_chessboard(ctx, im2, 7, 10)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        runs.append(e0.elapsed_time(e1))
+        im2.close()
+        assert np.array_equal(f2, found) and np.array_equal(c2, corners)
+    ms2 = float(np.median(runs))
     alg_bytes = W * H + 8 * 54
     peak = measured_peaks().get("hbm_gbs", 6650.0)
     out = {"metric": "images/s detect+subpix (chessboard)", "value": round(value, 2), "unit": "images/s",
