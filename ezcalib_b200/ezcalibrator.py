@@ -221,3 +221,98 @@ def run_calibration(ctx: lm.Context, images: np.ndarray, target_kind: str, nb_ro
         raise RuntimeError("no frame with a detected target and a P3P pose")
     compute_calibration(ctx, cam, target)
     return cam, target, processed
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Result file: byte-compatible with writeCamerasCalib of the reference.
+def _fixed9(v: float) -> str:
+    """std::fixed << std::setprecision(9)"""
+    return f"{float(v):.9f}"
+
+
+def cameras_calib_yaml(cameras: list, input_paths=None, stds=None) -> str:
+    """The text writeCamerasCalib (/root/reference/apps/ezcalib.cpp:69-187) writes for these cameras: `%YAML:1.0`, one
+    `camN:` block per camera with image_size, `intrisics_parameters` [sic] fx fy cx cy and the +/- comment line,
+    distortion_coefs with its +/- line, and for N > 0 the 3x4 row-major `T_cam0_2_cam`; nine fixed decimals.
+    stds: per camera (focal_std[1|2], pp_std[2], dist_std[nd]) from the covariance (ezc_lm_covariance); zeros if None."""
+    out = ["%YAML:1.0\n", "---\n\n", "#Camera Calibration Parameters\n\n"]
+    for i, cam in enumerate(cameras):
+        fx = float(cam.focal[0])
+        fy = float(cam.focal[0] if cam.use_mono_focal else cam.focal[1])
+        nd = len(cam.dist)
+        if stds is not None and stds[i] is not None:
+            fstd, pstd, dstd = stds[i]
+            fstd = [float(fstd[0]), float(fstd[0] if cam.use_mono_focal or len(fstd) < 2 else fstd[1])]
+        else:
+            fstd, pstd, dstd = [0.0, 0.0], [0.0, 0.0], [0.0] * nd
+        out.append(f"\n#Camera #{i}\n")
+        out.append(f"cam{i}:\n")
+        out.append(f"  input_images_folder: {input_paths[i] if input_paths else ''}\n")
+        out.append(f"  use_mono_focal: {int(bool(cam.use_mono_focal))}\n")
+        out.append(f"  dist_model: {cam.model}\n")
+        out.append(f"  image_size: [{int(cam.width)}, {int(cam.height)}]\n")
+        out.append("  intrisics_parameters: [" + ", ".join(_fixed9(v) for v in (fx, fy, cam.pp[0], cam.pp[1])) + "]\n")
+        out.append("                         # +/- [" + ", ".join(_fixed9(v) for v in (fstd[0], fstd[1], pstd[0], pstd[1])) + "]\n")
+        out.append("  distortion_coefs: [" + ", ".join(_fixed9(v) for v in cam.dist) + "]\n")
+        out.append("                         # +/- [" + ", ".join(_fixed9(v) for v in dstd) + "]\n")
+        if i > 0:
+            T = synth.pose_to_matrix34(cam.T_cam0_2_cam)
+            out.append(f"  #Transformation from cam0 frame to cam #{i} frame.\n")
+            out.append("  T_cam0_2_cam: [")
+            for r in range(3):
+                if r > 0:
+                    out.append("                ")
+                for c in range(4):
+                    out.append(_fixed9(T[r, c]) + ("]\n" if (r == 2 and c == 3) else ", "))
+                out.append("\n")
+    return "".join(out)
+
+
+def write_cameras_calib(cameras: list, path: str = "cam_calib.yaml", input_paths=None, stds=None) -> str:
+    """writeCamerasCalib: same path rules (a missing or foreign extension becomes .yaml, an existing file is replaced)."""
+    import os
+    root, ext = os.path.splitext(path)
+    if ext != ".yaml":
+        path = root + ".yaml"
+    if os.path.exists(path):
+        os.remove(path)
+    with open(path, "w") as f:
+        f.write(cameras_calib_yaml(cameras, input_paths, stds))
+    return path
+
+
+def read_calib_config(path: str) -> dict:
+    """The configuration file of the reference (calib_*_config.yaml; apps/ezcalib.cpp:10-68 setupCameras and
+    src/ezcalibrator.cpp:846-898 setupCalibrationProblem): one entry per camera for input_images_folder / use_mono_focal /
+    dist_model / prior_fov (all four lists must have the same length), the target description, the debug flag.
+    Errors raise ValueError where the reference prints and calls exit(-1)."""
+    import yaml
+    with open(path) as f:
+        text = f.read()
+    lines = text.splitlines()
+    if lines and lines[0].startswith("%YAML"):
+        lines = lines[1:]          # OpenCV's "%YAML 1.0" / "%YAML:1.0" directive is not something PyYAML accepts
+    cfg = yaml.safe_load("\n".join(lines)) or {}
+    folders = cfg.get("input_images_folder")
+    if not isinstance(folders, list):
+        raise ValueError("input_images_folder must be a sequence (one folder per camera)")
+    n = len(folders)
+    for key in ("use_mono_focal", "dist_model", "prior_fov"):
+        v = cfg.get(key)
+        if not isinstance(v, list) or len(v) != n:
+            raise ValueError(f"Config file must have as many {key} entries as provided input image folders")
+    for m in cfg["dist_model"]:
+        if m not in synth.MODEL_ID:
+            raise ValueError(f"The provided distortion model: {m} is not implemented")
+    target = cfg.get("target_type")
+    out = {"cameras": [dict(input_images_folder=str(folders[i]), use_mono_focal=bool(int(cfg["use_mono_focal"][i])),
+                            dist_model=str(cfg["dist_model"][i]), prior_fov=float(cfg["prior_fov"][i])) for i in range(n)],
+           "target_type": target, "target_nb_rows": int(cfg["target_nb_rows"]), "target_nb_cols": int(cfg["target_nb_cols"]),
+           "debug": int(cfg.get("debug", 0))}
+    if target == "aprilgrid":
+        out["tag_size"], out["tag_space"] = float(cfg["tag_size"]), float(cfg["tag_space"])
+    elif target == "chessboard":
+        out["square_size"] = float(cfg["square_size"])
+    else:
+        raise ValueError(f"Not implemented target type: {target} (implemented: chessboard / aprilgrid)")
+    return out

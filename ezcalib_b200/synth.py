@@ -437,3 +437,10 @@ def se3_log(pose: np.ndarray) -> np.ndarray:
         half = 0.5 * theta
         Vinv = np.eye(3) - 0.5 * Om + (1.0 - theta * math.cos(half) / (2.0 * math.sin(half))) / (theta * theta) * (Om @ Om)
     return np.concatenate([Vinv @ t, om])
+
+
+def pose_to_matrix34(pose: np.ndarray) -> np.ndarray:
+    """Sophus::SE3d::matrix3x4() of a pose stored as qx qy qz qw tx ty tz."""
+    pose = np.asarray(pose, np.float64)
+    R = np.stack([quat_rotate(pose[:4], e) for e in np.eye(3)], axis=1)
+    return np.concatenate([R, pose[4:7, None]], axis=1)

@@ -86,3 +86,50 @@ def test_initial_calibration_and_p3p_glue():
     px = np.full((54, 2), -1.0, np.float32)
     px[:10] = 100.0 + np.arange(20).reshape(10, 2)
     assert E.compute_p3p_ransac(px, tgt, f0, pp0, W, H)[0] is False
+
+
+def test_result_yaml_matches_the_reference_writer(tmp_path):
+    """writeCamerasCalib (apps/ezcalib.cpp:69-187): the exact text for a two-camera result, incl. the [sic] key
+    `intrisics_parameters`, the +/- comment lines, nine fixed decimals, the blank line after every matrix row."""
+    cam0 = E.Camera("radtan5", True, 1280, 1024, np.array([900.123456789]), np.array([645.5, 505.25]),
+                    np.array([-0.2, 0.05, 0.0, 0.001, -0.002]))
+    cam1 = E.Camera("kannalabrandt", False, 1920, 1080, np.array([600.0, 601.5]), np.array([960.0, 540.0]), np.array([0.1, 0.01, 0.0, 0.0]),
+                    T_cam0_2_cam=np.array([0.0, 0.0, 0.0, 1.0, -0.12, 0.001, 0.0005]))
+    stds = [([0.5], [0.25, 0.125], [1e-3] * 5), ([0.5, 0.75], [0.25, 0.125], [1e-3] * 4)]
+    txt = E.cameras_calib_yaml([cam0, cam1], ["/data/cam0/", "/data/cam1/"], stds)
+    expect = (
+        "%YAML:1.0\n---\n\n#Camera Calibration Parameters\n\n"
+        "\n#Camera #0\ncam0:\n  input_images_folder: /data/cam0/\n  use_mono_focal: 1\n  dist_model: radtan5\n  image_size: [1280, 1024]\n"
+        "  intrisics_parameters: [900.123456789, 900.123456789, 645.500000000, 505.250000000]\n"
+        "                         # +/- [0.500000000, 0.500000000, 0.250000000, 0.125000000]\n"
+        "  distortion_coefs: [-0.200000000, 0.050000000, 0.000000000, 0.001000000, -0.002000000]\n"
+        "                         # +/- [0.001000000, 0.001000000, 0.001000000, 0.001000000, 0.001000000]\n"
+        "\n#Camera #1\ncam1:\n  input_images_folder: /data/cam1/\n  use_mono_focal: 0\n  dist_model: kannalabrandt\n  image_size: [1920, 1080]\n"
+        "  intrisics_parameters: [600.000000000, 601.500000000, 960.000000000, 540.000000000]\n"
+        "                         # +/- [0.500000000, 0.750000000, 0.250000000, 0.125000000]\n"
+        "  distortion_coefs: [0.100000000, 0.010000000, 0.000000000, 0.000000000]\n"
+        "                         # +/- [0.001000000, 0.001000000, 0.001000000, 0.001000000]\n"
+        "  #Transformation from cam0 frame to cam #1 frame.\n"
+        "  T_cam0_2_cam: [1.000000000, 0.000000000, 0.000000000, -0.120000000, \n"
+        "                0.000000000, 1.000000000, 0.000000000, 0.001000000, \n"
+        "                0.000000000, 0.000000000, 1.000000000, 0.000500000]\n\n")
+    assert txt == expect
+    p = E.write_cameras_calib([cam0, cam1], str(tmp_path / "out.txt"), ["/data/cam0/", "/data/cam1/"], stds)
+    assert p.endswith("out.yaml") and open(p).read() == expect
+
+
+def test_config_reader_follows_the_reference_format(tmp_path):
+    """setupCameras / setupCalibrationProblem: the reference's own file layout (its '%YAML 1.0' header included)."""
+    cfg = tmp_path / "calib.yaml"
+    cfg.write_text("%YAML 1.0\n---\n\ninput_images_folder:\n  - /data/left/\n  - /data/right/\n\nuse_mono_focal: # (if 0: fx != fy)\n  - 1\n  - 0\n\n"
+                   "dist_model: # (rad1, ...)\n  - radtan5\n  - kannalabrandt\n\nprior_fov:\n  - 70.0\n  - 120.0\n\n\n"
+                   "target_type: \"chessboard\" # (chessboard / aprilgrid)\n\ntarget_nb_rows: 7\ntarget_nb_cols: 12\n\nsquare_size: 0.05\n\ndebug: 0")
+    c = E.read_calib_config(str(cfg))
+    assert [k["dist_model"] for k in c["cameras"]] == ["radtan5", "kannalabrandt"]
+    assert [k["use_mono_focal"] for k in c["cameras"]] == [True, False]
+    assert c["cameras"][1]["prior_fov"] == 120.0 and c["target_type"] == "chessboard"
+    assert (c["target_nb_rows"], c["target_nb_cols"], c["square_size"], c["debug"]) == (7, 12, 0.05, 0)
+    bad = tmp_path / "bad.yaml"
+    bad.write_text(cfg.read_text().replace("  - 70.0\n  - 120.0\n", "  - 70.0\n"))
+    with pytest.raises(ValueError, match="prior_fov"):
+        E.read_calib_config(str(bad))
