@@ -836,40 +836,60 @@ __device__ __forceinline__ unsigned long long cb_now() {
   return t;
 }
 
-// findQuadNeighbors for one image by a whole thread block.  Same decisions as cb::find_quad_neighbors (cb_logic.h, the
-// definition the CPU harness pins against cv2): the (quad, corner) sweep is sequential because every accepted link
-// changes the state the next search sees; the two O(n) scans inside a step (closest admissible corner; "is a third
-// corner closer") are spread over the block.  The per-slot state the scans read (corner position, link, edge length) is
-// staged in shared memory -- the global Work struct is two dependent loads away per candidate, which made a noisy
-// attempt (1536 quads => 6144 steps x 6144 candidates) cost ~400 ms with one warp.
+// findQuadNeighbors for one image.  Same decisions as cb::find_quad_neighbors (cb_logic.h, the definition the CPU
+// harness pins against cv2): the (quad, corner) sweep is sequential because every accepted link changes the state the
+// next search sees.  The per-slot state the two scans of a step read (corner position, link, edge length) is staged in
+// shared memory -- the global Work struct is two dependent loads away per candidate, which made a noisy attempt (1536
+// quads => 6144 steps x 6144 candidates) cost ~400 ms -- and the scans only visit the grid cells their search disc
+// touches (find_quad_neighbors_grid below): ~6 ms for such an attempt.
 constexpr int kProcThreads = 256;
+// 16-bit counters in shared memory (atomicAdd on the containing 32-bit word)
+__device__ __forceinline__ void atomicAdd_u16(unsigned short* p) {
+  unsigned int* w = reinterpret_cast<unsigned int*>(reinterpret_cast<size_t>(p) & ~size_t(3));
+  atomicAdd(w, (reinterpret_cast<size_t>(p) & 2) ? 0x10000u : 1u);
+}
+__device__ __forceinline__ unsigned short fetch_inc_u16(unsigned short* p) {
+  unsigned int* w = reinterpret_cast<unsigned int*>(reinterpret_cast<size_t>(p) & ~size_t(3));
+  const bool hi = (reinterpret_cast<size_t>(p) & 2) != 0;
+  const unsigned int old = atomicAdd(w, hi ? 0x10000u : 1u);
+  return (unsigned short)(hi ? (old >> 16) : (old & 0xffffu));
+}
 struct NbShared {
   float2* pt;     // [4 * nq]  position of corner slot (quad, j)
   int* nb;        // [4 * nq]  linked quad or -1
   float* edge;    // [nq]
   int* count;     // [nq]
 };
-__device__ __forceinline__ void block_min_code(float& d, int& code, float* red_d, int* red_c) {
-  for (int m = 16; m >= 1; m >>= 1) {
-    const float od = __shfl_xor_sync(0xffffffffu, d, m);
-    const int oc = __shfl_xor_sync(0xffffffffu, code, m);
-    if (od < d || (od == d && oc < code)) { d = od; code = oc; }
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { red_d[warp] = d; red_c[warp] = code; }
-  __syncthreads();
-  d = red_d[0]; code = red_c[0];
-#pragma unroll
-  for (int wv = 1; wv < kProcThreads / 32; ++wv) {
-    const float od = red_d[wv];
-    const int oc = red_c[wv];
-    if (od < d || (od == d && oc < code)) { d = od; code = oc; }
-  }
-  __syncthreads();
+// Uniform grid over the corner slots (counting sort by cell): the two scans of a step only have to look at the cells a
+// disc of radius sqrt(edge_len) (resp. sqrt(min_dist)) touches, so ONE warp does a step with shuffles only -- no block
+// barriers.  Free slots never move (a link averages the two corners it consumes, and consumed slots are skipped), so the
+// grid is built once per attempt.  Same decisions as the exhaustive scan: minimum over (distance, slot code).
+constexpr int kGridCells = 4608;
+struct NbGrid {
+  unsigned short* start;   // [kGridCells + 1]
+  unsigned short* cursor;  // [kGridCells]
+  unsigned short* items;   // [4 * kMaxQuads] slot codes sorted by cell
+  int cell, gw, gh;
+};
+__device__ __forceinline__ int grid_cell_of(const NbGrid& G, float x, float y) {
+  int cx = (int)floorf(x / (float)G.cell), cy = (int)floorf(y / (float)G.cell);
+  cx = min(max(cx, 0), G.gw - 1); cy = min(max(cy, 0), G.gh - 1);
+  return cy * G.gw + cx;
 }
-__device__ void find_quad_neighbors_block(cb::Work& w, const NbShared& S, float* red_d, int* red_c) {
+template <class F>
+__device__ __forceinline__ void grid_query(const NbGrid& G, float x, float y, float r, int lane, F&& f) {
+  const float c = (float)G.cell;
+  const int cx0 = min(max((int)floorf((x - r) / c), 0), G.gw - 1), cx1 = min(max((int)floorf((x + r) / c), 0), G.gw - 1);
+  const int cy0 = min(max((int)floorf((y - r) / c), 0), G.gh - 1), cy1 = min(max((int)floorf((y + r) / c), 0), G.gh - 1);
+  for (int cy = cy0; cy <= cy1; ++cy) {
+    const int beg = G.start[cy * G.gw + cx0], end = G.start[cy * G.gw + cx1 + 1];
+    for (int it = beg + lane; it < end; it += 32) f((int)G.items[it]);
+  }
+}
+__device__ void find_quad_neighbors_grid(cb::Work& w, const NbShared& S, const NbGrid& G) {
   const int nq = w.n_quads;
   const int tid = threadIdx.x;
+  // ---- stage the per-slot state and build the grid (whole block)
   for (int k = tid; k < nq; k += kProcThreads) {
     const cb::Quad& q = w.quads[k];
     S.edge[k] = q.edge_len;
@@ -880,72 +900,94 @@ __device__ void find_quad_neighbors_block(cb::Work& w, const NbShared& S, float*
       S.nb[4 * k + j] = q.nb[j];
     }
   }
+  for (int c = tid; c < kGridCells; c += kProcThreads) G.cursor[c] = 0;
   __syncthreads();
-  for (int idx = 0; idx < nq; idx++) {
-    for (int i = 0; i < 4; i++) {
-      if (S.nb[4 * idx + i] >= 0) continue;
-      float min_dist = FLT_MAX;
-      int code = 0x7fffffff;
-      const float2 pt = S.pt[4 * idx + i];
-      const float cur_edge = S.edge[idx];
-      for (int k = tid; k < nq; k += kProcThreads) {
-        if (k == idx) continue;
-        const float ek = S.edge[k];
-        for (int j = 0; j < 4; j++) {
-          if (S.nb[4 * k + j] >= 0) continue;
-          const float2 o = S.pt[4 * k + j];
+  for (int sl = tid; sl < 4 * nq; sl += kProcThreads) atomicAdd_u16(&G.cursor[grid_cell_of(G, S.pt[sl].x, S.pt[sl].y)]);
+  __syncthreads();
+  if (tid < 32) {   // exclusive scan of the cell counts by one warp (144 cells per lane)
+    constexpr int per = kGridCells / 32;
+    int sum = 0;
+    for (int c = tid * per; c < (tid + 1) * per; ++c) sum += G.cursor[c];
+    int inc = sum;
+    for (int m = 1; m < 32; m <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, m); if (tid >= m) inc += o; }
+    int run = inc - sum;
+    for (int c = tid * per; c < (tid + 1) * per; ++c) { const int n = G.cursor[c]; G.start[c] = (unsigned short)run; G.cursor[c] = (unsigned short)run; run += n; }
+    if (tid == 31) G.start[kGridCells] = (unsigned short)run;
+  }
+  __syncthreads();
+  for (int sl = tid; sl < 4 * nq; sl += kProcThreads) {
+    const int c = grid_cell_of(G, S.pt[sl].x, S.pt[sl].y);
+    G.items[fetch_inc_u16(&G.cursor[c])] = (unsigned short)sl;
+  }
+  __syncthreads();
+  // ---- the sequential sweep, one warp
+  if (tid < 32) {
+    const int lane = tid;
+    for (int idx = 0; idx < nq; idx++) {
+      for (int i = 0; i < 4; i++) {
+        if (S.nb[4 * idx + i] >= 0) continue;
+        float min_dist = FLT_MAX;
+        int code = 0x7fffffff;
+        const float2 pt = S.pt[4 * idx + i];
+        const float cur_edge = S.edge[idx];
+        grid_query(G, pt.x, pt.y, sqrtf(cur_edge) + 1.f, lane, [&](int sl) {
+          const int k = sl >> 2;
+          if (k == idx || S.nb[sl] >= 0) return;
+          const float ek = S.edge[k];
+          const float2 o = S.pt[sl];
           const float dist = cb::normL2Sqrf(pt.x - o.x, pt.y - o.y);
-          if (dist < min_dist && dist <= cur_edge && dist <= ek) {
+          if ((dist < min_dist || (dist == min_dist && sl < code)) && dist <= cur_edge && dist <= ek) {
             const float ediff = fabsf(cur_edge - ek);
-            if (ediff > 32 * cur_edge || ediff > 32 * ek) continue;
-            code = k * 4 + j; min_dist = dist;
+            if (ediff > 32 * cur_edge || ediff > 32 * ek) return;
+            code = sl; min_dist = dist;
           }
+        });
+        for (int m = 16; m >= 1; m >>= 1) {
+          const float od = __shfl_xor_sync(0xffffffffu, min_dist, m);
+          const int oc = __shfl_xor_sync(0xffffffffu, code, m);
+          if (od < min_dist || (od == min_dist && oc < code)) { min_dist = od; code = oc; }
         }
-      }
-      block_min_code(min_dist, code, red_d, red_c);
-      if (code == 0x7fffffff || !(min_dist < FLT_MAX)) continue;
-      const int cq = code >> 2, cci = code & 3;
-      if (S.count[idx] >= 4 || S.count[cq] >= 4) continue;
-      const float2 cc = S.pt[4 * cq + cci];
-      int j = 0;
-      for (; j < 4; j++) {
-        if (S.nb[4 * idx + j] == cq) break;
-        const float2 o = S.pt[4 * idx + j];
-        if (cb::normL2Sqrf(cc.x - o.x, cc.y - o.y) < min_dist) break;
-      }
-      if (j < 4) continue;
-      for (j = 0; j < 4; j++) if (S.nb[4 * cq + j] == idx) break;
-      if (j < 4) continue;
-      bool blocked = false;
-      for (int q3 = tid; q3 < nq && !blocked; q3 += kProcThreads) {
-        if (q3 == idx || q3 == cq) continue;
-        for (int k = 0; k < 4; k++) {
-          if (S.nb[4 * q3 + k] < 0) {
-            const float2 o = S.pt[4 * q3 + k];
-            if (cb::normL2Sqrf(cc.x - o.x, cc.y - o.y) < min_dist) { blocked = true; break; }
-          }
+        if (code == 0x7fffffff || !(min_dist < FLT_MAX)) continue;
+        const int cq = code >> 2, cci = code & 3;
+        if (S.count[idx] >= 4 || S.count[cq] >= 4) continue;
+        const float2 cc = S.pt[4 * cq + cci];
+        int j = 0;
+        for (; j < 4; j++) {
+          if (S.nb[4 * idx + j] == cq) break;
+          const float2 o = S.pt[4 * idx + j];
+          if (cb::normL2Sqrf(cc.x - o.x, cc.y - o.y) < min_dist) break;
         }
+        if (j < 4) continue;
+        for (j = 0; j < 4; j++) if (S.nb[4 * cq + j] == idx) break;
+        if (j < 4) continue;
+        bool blocked = false;
+        grid_query(G, cc.x, cc.y, sqrtf(min_dist) + 1.f, lane, [&](int sl) {
+          const int q3 = sl >> 2;
+          if (q3 == idx || q3 == cq || S.nb[sl] >= 0) return;
+          const float2 o = S.pt[sl];
+          if (cb::normL2Sqrf(cc.x - o.x, cc.y - o.y) < min_dist) blocked = true;
+        });
+        if (__any_sync(0xffffffffu, blocked)) continue;
+        if (lane == 0) {
+          cb::Quad& cur = w.quads[idx];
+          cb::Quad& cqq = w.quads[cq];
+          cb::Corner& ccn = w.corners[cqq.corners[cci]];
+          const float nx = (pt.x + cc.x) * 0.5f, ny = (pt.y + cc.y) * 0.5f;
+          ccn.pt.x = nx; ccn.pt.y = ny;
+          cur.count++;
+          cur.nb[i] = cq;
+          cur.corners[i] = cqq.corners[cci];
+          cqq.count++;
+          cqq.nb[cci] = idx;
+          S.pt[4 * cq + cci] = make_float2(nx, ny);
+          S.pt[4 * idx + i] = make_float2(nx, ny);
+          S.nb[4 * idx + i] = cq;
+          S.nb[4 * cq + cci] = idx;
+          S.count[idx]++;
+          S.count[cq]++;
+        }
+        __syncwarp();
       }
-      if (__syncthreads_or(blocked ? 1 : 0)) continue;
-      if (tid == 0) {
-        cb::Quad& cur = w.quads[idx];
-        cb::Quad& cqq = w.quads[cq];
-        cb::Corner& ccn = w.corners[cqq.corners[cci]];
-        const float nx = (pt.x + cc.x) * 0.5f, ny = (pt.y + cc.y) * 0.5f;
-        ccn.pt.x = nx; ccn.pt.y = ny;
-        cur.count++;
-        cur.nb[i] = cq;
-        cur.corners[i] = cqq.corners[cci];
-        cqq.count++;
-        cqq.nb[cci] = idx;
-        S.pt[4 * cq + cci] = make_float2(nx, ny);
-        S.pt[4 * idx + i] = make_float2(nx, ny);
-        S.nb[4 * idx + i] = cq;
-        S.nb[4 * cq + cci] = idx;
-        S.count[idx]++;
-        S.count[cq]++;
-      }
-      __syncthreads();
     }
   }
   __threadfence_block();
@@ -956,10 +998,8 @@ __device__ void find_quad_neighbors_block(cb::Work& w, const NbShared& S, float*
 __global__ void __launch_bounds__(kProcThreads) cb_process_kernel(const HoleInfo* __restrict__ holes, ImageState* __restrict__ st,
                                                                   const int* __restrict__ active, int n_img, int pw, int ph, int dilations,
                                                                   cb::Work* __restrict__ works, int* __restrict__ scratch_all,
-                                                                  cb::Ptf* __restrict__ corners_out) {
+                                                                  cb::Ptf* __restrict__ corners_out, int W, int H) {
   extern __shared__ __align__(16) unsigned char cb_smem[];
-  __shared__ float red_d[kProcThreads / 32];
-  __shared__ int red_c[kProcThreads / 32];
   const int slot = blockIdx.x;
   const int tid = threadIdx.x;
   if (slot >= n_img) return;
@@ -1013,7 +1053,14 @@ __global__ void __launch_bounds__(kProcThreads) cb_process_kernel(const HoleInfo
     sh.nb = reinterpret_cast<int*>(sh.pt + 4 * cb::kMaxQuads);
     sh.edge = reinterpret_cast<float*>(sh.nb + 4 * cb::kMaxQuads);
     sh.count = reinterpret_cast<int*>(sh.edge + cb::kMaxQuads);
-    find_quad_neighbors_block(w, sh, red_d, red_c);
+    NbGrid G;
+    G.start = reinterpret_cast<unsigned short*>(sh.count + cb::kMaxQuads);
+    G.cursor = G.start + kGridCells + 2;
+    G.items = G.cursor + kGridCells;
+    G.cell = max(16, (int)ceilf(sqrtf((float)W * (float)H / 4096.f)));
+    G.gw = (W + G.cell - 1) / G.cell; G.gh = (H + G.cell - 1) / G.cell;
+    while (G.gw * G.gh > kGridCells) { ++G.cell; G.gw = (W + G.cell - 1) / G.cell; G.gh = (H + G.cell - 1) / G.cell; }
+    find_quad_neighbors_grid(w, sh, G);
   }
   const unsigned long long t2 = cb_now();
   if (tid == 0) atomicAdd(&g_cb_ns[2], t2 - t1);
@@ -1030,7 +1077,8 @@ __global__ void __launch_bounds__(kProcThreads) cb_process_kernel(const HoleInfo
     atomicAdd(&g_cb_ns[3], cb_now() - t2);
   }
 }
-constexpr size_t kProcSmem = (size_t)cb::kMaxQuads * (4 * sizeof(float2) + 4 * sizeof(int) + sizeof(float) + sizeof(int));
+constexpr size_t kProcSmem = (size_t)cb::kMaxQuads * (4 * sizeof(float2) + 4 * sizeof(int) + sizeof(float) + sizeof(int)) +
+                             sizeof(unsigned short) * (2 * kGridCells + 4 + 4 * cb::kMaxQuads);
 
 // final checks of cv::findChessboardCorners after a successful attempt: board monotony, 8-px border, even/even flip
 __global__ void cb_finalize_kernel(ImageState* __restrict__ st, int n_img, int pw, int ph, int W, int H, cb::Ptf* __restrict__ corners,
@@ -1250,7 +1298,7 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
       attr_set = true;
     }
     cb_process_kernel<<<n_act, kProcThreads, kProcSmem, ctx->stream>>>(P.holes.as<HoleInfo>(), st, list, n_act, pw, ph, dilations,
-                                                                       P.works.as<cb::Work>(), P.scratch.as<int>(), P.corners.as<cb::Ptf>());
+                                                                       P.works.as<cb::Work>(), P.scratch.as<int>(), P.corners.as<cb::Ptf>(), W, H);
     EZC_CUDA(cudaGetLastError());
     ctx->kernel_launches++;
   }
