@@ -305,12 +305,15 @@ __global__ void cb_trace_kernel(const uint8_t* __restrict__ bin, const int* __re
     int i3x = x0, i3y = y0, prev_s = s ^ 4;
     int x = x0, y = y0;
     for (;;) {
-      int i4x, i4y;
-      for (;;) {
-        ++s;
-        i4x = i3x + DX[s & 7]; i4y = i3y + DY[s & 7];
-        if (val(i4x, i4y)) break;
-      }
+      // the 8 neighbours of the current pixel with independent loads (the probe loop of icvFetchContour would issue them
+      // one dependent load after the other), then the first foreground neighbour in rotation order from the mask
+      unsigned m8 = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m8 |= (val(i3x + DX[k], i3y + DY[k]) ? 1u : 0u) << k;
+      const int s1 = (s + 1) & 7;
+      const unsigned rot = ((m8 | (m8 << 8)) >> s1) & 0xffu;
+      s = s1 + (__ffs(rot) - 1);   // rot != 0: the pixel we came from is foreground
+      const int i4x = i3x + DX[s & 7], i4y = i3y + DY[s & 7];
       s &= 7;
       if (s != prev_s) {
         if (STORE) { if (n < hi.n_pts) out[n] = cb::Pt{x, y}; }
@@ -387,7 +390,8 @@ __device__ int approx_poly_dp_closed_warp(const cb::Pt* src, int count, cb::Pt* 
   if (count == 0) return 0;
   const int lane = threadIdx.x & 31;
   int top = 0;
-  auto push = [&](int s_, int e_) { if (lane == 0) { stack_buf[2 * top] = s_; stack_buf[2 * top + 1] = e_; } ++top; };
+  // every lane performs the (identical) stack and output writes itself, so it reads back its own stores: no warp sync
+  auto push = [&](int s_, int e_) { stack_buf[2 * top] = s_; stack_buf[2 * top + 1] = e_; ++top; };
   const int init_iters = 3;
   int slice_s = 0, slice_e = 0, right_s = 0, right_e = 0;
   Pt start_pt = {-1000000, -1000000}, end_pt = {0, 0}, pt = {0, 0};
@@ -419,14 +423,12 @@ __device__ int approx_poly_dp_closed_warp(const cb::Pt* src, int count, cb::Pt* 
     push(right_s, right_e);
     push(slice_s, slice_e);
   } else {
-    if (lane == 0) dst[new_count] = start_pt;
+    dst[new_count] = start_pt;
     new_count++;
   }
-  __syncwarp();
   while (top > 0) {
     --top;
     slice_s = stack_buf[2 * top]; slice_e = stack_buf[2 * top + 1];
-    __syncwarp();
     end_pt = src[slice_e];
     pos = slice_s;
     start_pt = src[pos]; if (++pos >= count) pos = 0;
@@ -436,7 +438,9 @@ __device__ int approx_poly_dp_closed_warp(const cb::Pt* src, int count, cb::Pt* 
       int best = 0x7fffffff;
       const double dx = end_pt.x - start_pt.x, dy = end_pt.y - start_pt.y;
       const double L2 = dx * dx + dy * dy;
-      for (int o = lane; o < len; o += 32) {
+      // short ranges (the bulk on ragged contours) are scanned by every lane redundantly: no shuffles at all
+      const bool small = len <= 4;
+      for (int o = small ? 0 : lane; o < len; o += small ? 1 : 32) {
         int pp = pos + o; if (pp >= count) pp -= count;
         pt = src[pp];
         const double px = pt.x - start_pt.x, py = pt.y - start_pt.y;
@@ -447,7 +451,7 @@ __device__ int approx_poly_dp_closed_warp(const cb::Pt* src, int count, cb::Pt* 
         else { const double cr = py * dx - px * dy; dist = cr * cr / L2; }
         if (dist > max_dist) { max_dist = dist; best = o; }
       }
-      warp_argmax(max_dist, best);
+      if (!small) warp_argmax(max_dist, best);
       if (max_dist > 0) { int pp = pos + best; if (pp >= count) pp -= count; right_s = pp; }
       le_eps = max_dist <= eps;
     } else {
@@ -455,7 +459,7 @@ __device__ int approx_poly_dp_closed_warp(const cb::Pt* src, int count, cb::Pt* 
       start_pt = src[slice_s];
     }
     if (le_eps) {
-      if (lane == 0) dst[new_count] = start_pt;
+      dst[new_count] = start_pt;
       new_count++;
     } else {
       right_e = slice_e;
@@ -463,7 +467,6 @@ __device__ int approx_poly_dp_closed_warp(const cb::Pt* src, int count, cb::Pt* 
       push(right_s, right_e);
       push(slice_s, slice_e);
     }
-    __syncwarp();
   }
   __syncwarp();
   // last stage: remove extra points on [almost] straight lines (sequential; lane 0 writes, every lane tracks the state)
