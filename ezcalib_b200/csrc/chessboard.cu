@@ -385,13 +385,14 @@ __device__ __forceinline__ void warp_argmax(double& d, int& ord) {
     if (od > d || (od == d && oo < ord)) { d = od; ord = oo; }
   }
 }
-__device__ int approx_poly_dp_closed_warp(const cb::Pt* src, int count, cb::Pt* dst, double eps, int* stack_buf) {
+template <class StackT>
+__device__ int approx_poly_dp_closed_warp(const cb::Pt* src, int count, cb::Pt* dst, double eps, StackT* stack_buf) {
   using cb::Pt;
   if (count == 0) return 0;
   const int lane = threadIdx.x & 31;
   int top = 0;
   // every lane performs the (identical) stack and output writes itself, so it reads back its own stores: no warp sync
-  auto push = [&](int s_, int e_) { stack_buf[2 * top] = s_; stack_buf[2 * top + 1] = e_; ++top; };
+  auto push = [&](int s_, int e_) { stack_buf[2 * top] = (StackT)s_; stack_buf[2 * top + 1] = (StackT)e_; ++top; };
   const int init_iters = 3;
   int slice_s = 0, slice_e = 0, right_s = 0, right_e = 0;
   Pt start_pt = {-1000000, -1000000}, end_pt = {0, 0}, pt = {0, 0};
@@ -500,26 +501,33 @@ __device__ int approx_poly_dp_closed_warp(const cb::Pt* src, int count, cb::Pt* 
   __syncwarp();
   return result;
 }
-__global__ void __launch_bounds__(256) cb_quad_warp_kernel(HoleInfo* __restrict__ holes, int n_holes, cb::Pt* __restrict__ pool,
-                                                           int* __restrict__ stack_pool) {
-  const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+// One warp (= one block) per long contour; the two approximation buffers and the subdivision stack live in shared memory:
+// Douglas-Peucker on a ragged contour is a chain of thousands of tiny dependent steps, each a couple of loads.
+// Two capacity classes (shared memory per block decides how many contours an SM works on at once): CAP = 512 holds the
+// bulk, CAP = kMaxContourPts the few giants; LO is the exclusive lower bound of the class.
+template <int CAP> constexpr size_t quad_warp_smem() { return 2 * sizeof(cb::Pt) * (CAP + 4) + sizeof(unsigned short) * (4 * CAP + 16); }
+template <int CAP, int LO>
+__global__ void __launch_bounds__(32) cb_quad_warp_kernel(HoleInfo* __restrict__ holes, int n_holes, cb::Pt* __restrict__ pool) {
+  extern __shared__ __align__(16) unsigned char qw_smem[];
+  const int h = blockIdx.x;
+  const int lane = threadIdx.x;
   if (h >= n_holes) return;
   HoleInfo& hi = holes[h];
-  if (hi.offset < 0 || hi.n_pts <= kWarpContour) return;
+  if (hi.offset < 0 || hi.n_pts <= LO || hi.n_pts > CAP) return;
   const int n = hi.n_pts;
-  cb::Pt* c = pool + hi.offset;
-  cb::Pt* ta = c + n + 2;
-  cb::Pt* tb = ta + n + 2;
-  int* stack = stack_pool + (size_t)hi.offset * 2;
+  const cb::Pt* c = pool + hi.offset;
+  cb::Pt* ta = reinterpret_cast<cb::Pt*>(qw_smem);
+  cb::Pt* tb = ta + CAP + 4;
+  unsigned short* stack = reinterpret_cast<unsigned short*>(tb + CAP + 4);
   // cb::contour_to_quad with the warp-parallel approximation; the bounding-box test already passed in cb_trace_kernel
   int na = n;
-  const cb::Pt* cur = c;
+  for (int i = lane; i < n; i += 32) ta[i] = c[i];
+  __syncwarp();
   for (int level = 1; level <= cb::kMaxApproxLevel; level++) {
-    int nb = approx_poly_dp_closed_warp(cur, na, tb, (double)(float)level, stack);
+    int nb = approx_poly_dp_closed_warp(ta, na, tb, (double)(float)level, stack);
     for (int i = lane; i < nb; i += 32) ta[i] = tb[i];
     __syncwarp();
-    na = nb; cur = ta;
+    na = nb;
     if (na == 4) break;
     nb = approx_poly_dp_closed_warp(ta, na, tb, (double)(float)level, stack);
     for (int i = lane; i < nb; i += 32) ta[i] = tb[i];
@@ -1285,7 +1293,20 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
     CB_LAUNCH(cb_hole_offset_kernel, nH, P.holes.as<HoleInfo>(), nH, P.need.as<int>());
     CB_LAUNCH(cb_trace_kernel<true>, nH, bin, P.labels.as<int>(), W, H, nH, P.holes.as<HoleInfo>(), P.pool.as<cb::Pt>(), cb::kMaxContourPts);
     CB_LAUNCH(cb_quad_kernel, nH, P.holes.as<HoleInfo>(), nH, P.pool.as<cb::Pt>(), P.stack_pool.as<int>());
-    CB_LAUNCH(cb_quad_warp_kernel, (long long)nH * 32, P.holes.as<HoleInfo>(), nH, P.pool.as<cb::Pt>(), P.stack_pool.as<int>());
+    {
+      static bool qw_attr = false;
+      if (!qw_attr) {
+        EZC_CUDA(cudaFuncSetAttribute(cb_quad_warp_kernel<cb::kMaxContourPts, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)quad_warp_smem<cb::kMaxContourPts>()));
+        qw_attr = true;
+      }
+      cb_quad_warp_kernel<512, kWarpContour><<<nH, 32, quad_warp_smem<512>(), ctx->stream>>>(P.holes.as<HoleInfo>(), nH, P.pool.as<cb::Pt>());
+      EZC_CUDA(cudaGetLastError());
+      cb_quad_warp_kernel<cb::kMaxContourPts, 512><<<nH, 32, quad_warp_smem<cb::kMaxContourPts>(), ctx->stream>>>(P.holes.as<HoleInfo>(), nH,
+                                                                                                              P.pool.as<cb::Pt>());
+      EZC_CUDA(cudaGetLastError());
+      ctx->kernel_launches += 2;
+    }
     CB_LAUNCH(cb_hole_ranges_kernel, nH, P.holes.as<HoleInfo>(), nH, N, 0, st);
   }
   CB_LAUNCH(cb_state_reset_kernel, n_act, st, list, n_act);
