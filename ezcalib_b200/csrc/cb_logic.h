@@ -281,9 +281,29 @@ struct SerialPar {
   CB_HD bool any(bool v) const { return v; }
 };
 
+// Linking rule of findQuadNeighbors as cv2 >= 4.9 behaves (measured on cv2 4.13): a corner of another quad
+// is a candidate if its squared distance is within kNbSqrScale x the squared shortest edge of both quads AND it is a
+// DIAGONAL neighbour: the candidate corner and the candidate quad's opposite corner both lie in the same quadrant of this
+// quad (w.r.t. the lines through the mid points of its opposite edges) as the corner being matched.  The same test
+// restricts which third corners can veto a link.
+constexpr float kNbSqrScale = 2.f;
+CB_HD inline Ptf mid_pt(const Ptf& a, const Ptf& b) { return Ptf{(a.x + b.x) / 2, (a.y + b.y) / 2}; }
+CB_HD inline bool same_side_of_line(const Ptf& l1, const Ptf& l2, const Ptf& p1, const Ptf& p2) {
+  const float dx = l2.x - l1.x, dy = l2.y - l1.y;
+  const float a = dx * (p1.y - l1.y) - dy * (p1.x - l1.x);
+  const float b = dx * (p2.y - l1.y) - dy * (p2.x - l1.x);
+  return a * b > 0;
+}
+CB_HD inline bool diagonal_neighbour(const Work& w, const Quad& q, int i, const Ptf& other, const Ptf& other_diag) {
+  const Ptf c0 = w.corners[q.corners[i]].pt, c1 = w.corners[q.corners[(i + 1) & 3]].pt, c2 = w.corners[q.corners[(i + 2) & 3]].pt,
+            c3 = w.corners[q.corners[(i + 3) & 3]].pt;
+  const Ptf m1 = mid_pt(c0, c1), m2 = mid_pt(c2, c3), m3 = mid_pt(c1, c2), m4 = mid_pt(c3, c0);
+  return same_side_of_line(m1, m2, c0, other) && same_side_of_line(m3, m4, c0, other) && same_side_of_line(m1, m2, c0, other_diag) &&
+         same_side_of_line(m3, m4, c0, other_diag);
+}
+
 template <class Par>
 CB_HD inline void find_quad_neighbors(Work& w, const Par& par) {
-  const float thresh_scale = 1.f;
   const int nq = w.n_quads;
   for (int idx = 0; idx < nq; idx++) {
     Quad& cur = w.quads[idx];
@@ -300,9 +320,10 @@ CB_HD inline void find_quad_neighbors(Work& w, const Par& par) {
           if (qk.nb[j] >= 0) continue;
           const Ptf o = w.corners[qk.corners[j]].pt;
           const float dist = normL2Sqrf(pt.x - o.x, pt.y - o.y);
-          if (dist < min_dist && dist <= cur_edge * thresh_scale && dist <= qk.edge_len * thresh_scale) {
-            const float ediff = fabsf(cur_edge - qk.edge_len);
-            if (ediff > 32 * cur_edge || ediff > 32 * qk.edge_len) continue;
+          if (dist < min_dist && dist <= cur_edge * kNbSqrScale && dist <= qk.edge_len * kNbSqrScale) {
+            // edges that differ by more than 1:4 in length (16 in squared length) are incompatible
+            if (qk.edge_len > 16 * cur_edge || cur_edge > 16 * qk.edge_len) continue;
+            if (!diagonal_neighbour(w, cur, i, o, w.corners[qk.corners[(j + 2) & 3]].pt)) continue;
             code = k * 4 + j; min_dist = dist;
           }
         }
@@ -335,7 +356,8 @@ CB_HD inline void find_quad_neighbors(Work& w, const Par& par) {
           for (int k = 0; k < 4; k++) {
             if (q.nb[k] < 0) {
               const Ptf o = w.corners[q.corners[k]].pt;
-              if (normL2Sqrf(cc.pt.x - o.x, cc.pt.y - o.y) < min_dist) { blocked = true; break; }
+              if (normL2Sqrf(cc.pt.x - o.x, cc.pt.y - o.y) < min_dist &&
+                  diagonal_neighbour(w, cq, closest_corner_idx, o, w.corners[q.corners[(k + 2) & 3]].pt)) { blocked = true; break; }
             }
           }
         }

@@ -897,6 +897,14 @@ __device__ __forceinline__ void grid_query(const NbGrid& G, float x, float y, fl
     for (int it = beg + lane; it < end; it += 32) f((int)G.items[it]);
   }
 }
+// cb::diagonal_neighbour on the staged slot positions
+__device__ __forceinline__ bool diagonal_neighbour_s(const NbShared& S, int q, int i, float2 other, float2 other_diag) {
+  const float2 a0 = S.pt[4 * q + i], a1 = S.pt[4 * q + ((i + 1) & 3)], a2 = S.pt[4 * q + ((i + 2) & 3)], a3 = S.pt[4 * q + ((i + 3) & 3)];
+  const cb::Ptf c0{a0.x, a0.y}, c1{a1.x, a1.y}, c2{a2.x, a2.y}, c3{a3.x, a3.y}, o{other.x, other.y}, od{other_diag.x, other_diag.y};
+  const cb::Ptf m1 = cb::mid_pt(c0, c1), m2 = cb::mid_pt(c2, c3), m3 = cb::mid_pt(c1, c2), m4 = cb::mid_pt(c3, c0);
+  return cb::same_side_of_line(m1, m2, c0, o) && cb::same_side_of_line(m3, m4, c0, o) && cb::same_side_of_line(m1, m2, c0, od) &&
+         cb::same_side_of_line(m3, m4, c0, od);
+}
 __device__ void find_quad_neighbors_grid(cb::Work& w, const NbShared& S, const NbGrid& G) {
   const int nq = w.n_quads;
   const int tid = threadIdx.x;
@@ -941,15 +949,15 @@ __device__ void find_quad_neighbors_grid(cb::Work& w, const NbShared& S, const N
         int code = 0x7fffffff;
         const float2 pt = S.pt[4 * idx + i];
         const float cur_edge = S.edge[idx];
-        grid_query(G, pt.x, pt.y, sqrtf(cur_edge) + 1.f, lane, [&](int sl) {
+        grid_query(G, pt.x, pt.y, sqrtf(cur_edge * cb::kNbSqrScale) + 1.f, lane, [&](int sl) {
           const int k = sl >> 2;
           if (k == idx || S.nb[sl] >= 0) return;
           const float ek = S.edge[k];
           const float2 o = S.pt[sl];
           const float dist = cb::normL2Sqrf(pt.x - o.x, pt.y - o.y);
-          if ((dist < min_dist || (dist == min_dist && sl < code)) && dist <= cur_edge && dist <= ek) {
-            const float ediff = fabsf(cur_edge - ek);
-            if (ediff > 32 * cur_edge || ediff > 32 * ek) return;
+          if ((dist < min_dist || (dist == min_dist && sl < code)) && dist <= cur_edge * cb::kNbSqrScale && dist <= ek * cb::kNbSqrScale) {
+            if (ek > 16 * cur_edge || cur_edge > 16 * ek) return;
+            if (!diagonal_neighbour_s(S, idx, i, o, S.pt[4 * k + (((sl & 3) + 2) & 3)])) return;
             code = sl; min_dist = dist;
           }
         });
@@ -976,7 +984,8 @@ __device__ void find_quad_neighbors_grid(cb::Work& w, const NbShared& S, const N
           const int q3 = sl >> 2;
           if (q3 == idx || q3 == cq || S.nb[sl] >= 0) return;
           const float2 o = S.pt[sl];
-          if (cb::normL2Sqrf(cc.x - o.x, cc.y - o.y) < min_dist) blocked = true;
+          if (cb::normL2Sqrf(cc.x - o.x, cc.y - o.y) < min_dist && diagonal_neighbour_s(S, cq, cci, o, S.pt[4 * q3 + (((sl & 3) + 2) & 3)]))
+            blocked = true;
         });
         if (__any_sync(0xffffffffu, blocked)) continue;
         if (lane == 0) {
