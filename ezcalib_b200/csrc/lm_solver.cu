@@ -44,7 +44,8 @@ constexpr int kLYZ = 100;          // per-view Schur record: L(21) pad z(6) @22,
 constexpr int R1_HCC = 0;                     // [12][12] upper triangle used
 constexpr int R1_COST = 144;                  // cost at x
 constexpr int R1_SCHUR = 145;                 // start of the lm_schur section
-constexpr int R1_SIZE = 256;                   // 145 + S(<=78) b(k) gc(k) xnorm2 nres nused fail gmax
+constexpr int R1_SIZE = 320;                   // 145 + S(<=78) b(k) gc(k) xnorm2 nres nused fail + one gmax slot per rank (<= 64)
+constexpr int kMaxSlotRanks = 64;
 
 __host__ __device__ inline int tile_index(int ti, int tj, int NT) { return ti * NT - ti * (ti - 1) / 2 + (tj - ti); }
 
@@ -479,7 +480,8 @@ __global__ void __launch_bounds__(128) lm_schur_kernel(const SchurArgs a) {
 // Fixed-order reduction of the per-warp Schur partials into the packed layout
 //   [S upper triangle (k(k+1)/2) | Y^T z (k) | g_c (k) | |x|^2, n_res, n_used, fail | gmax(max)].
 // grid = nv blocks of 256 threads.
-__global__ void lm_schur_reduce_kernel(const double* __restrict__ part, int n_warps, int k, int KG, double* __restrict__ out) {
+__global__ void lm_schur_reduce_kernel(const double* __restrict__ part, int n_warps, int k, int KG, double* __restrict__ out, int rank,
+                                       int n_slots) {
   __shared__ double sh[256];
   const int nS = k * (k + 1) / 2;
   const int q = blockIdx.x;
@@ -514,7 +516,14 @@ __global__ void lm_schur_reduce_kernel(const double* __restrict__ part, int n_wa
     if ((int)threadIdx.x < m) sh[threadIdx.x] = is_max ? fmax(sh[threadIdx.x], sh[threadIdx.x + m]) : sh[threadIdx.x] + sh[threadIdx.x + m];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[q] = sh[0];
+  if (threadIdx.x == 0) {
+    if (is_max) {
+      // the maximum travels through the SUM all-reduce of the packed buffer: one slot per rank, zero in the others
+      for (int r = 0; r < n_slots; ++r) out[q + r] = (r == rank) ? sh[0] : 0.0;
+    } else {
+      out[q] = sh[0];
+    }
+  }
 }
 
 struct BacksubArgs {
@@ -918,7 +927,9 @@ ezc_status run_schur(ezc_lm_solver* s, double radius, bool first, bool reuse, bo
   else lm_schur_kernel<12><<<grid, 128, 0, ctx->stream>>>(a);
   if (ezc_status st = launch_check(ctx, "lm_schur")) return st;
   // per-warp partials -> red1[R1_SCHUR ..] in fixed order (last value, the gradient max-norm, is max-reduced)
-  lm_schur_reduce_kernel<<<nv, 256, 0, ctx->stream>>>(s->part2.as<double>(), grid * 4, k, k <= 7 ? 1 : 2, s->red1[s->sb].as<double>() + R1_SCHUR);
+  const bool slots = ctx->world <= kMaxSlotRanks;
+  lm_schur_reduce_kernel<<<nv, 256, 0, ctx->stream>>>(s->part2.as<double>(), grid * 4, k, k <= 7 ? 1 : 2, s->red1[s->sb].as<double>() + R1_SCHUR,
+                                                      slots ? ctx->rank : 0, slots ? std::max(ctx->world, 1) : 1);
   return launch_check(ctx, "lm_schur_reduce");
 }
 
@@ -1062,9 +1073,16 @@ ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summ
     if (ezc_status st = run_schur(s, radius, first, reuse_diagonal, false, opt->min_lm_diagonal, opt->max_lm_diagonal)) return st;
     ++n_lin;
     const int n1 = R1_SCHUR + nS + 2 * k + 4;
-    allreduce(s, s->red1[s->sb].as<double>() + R1_SCHUR, n1 - R1_SCHUR, 0);
-    allreduce(s, s->red1[s->sb].as<double>() + n1, 1, 1);
-    EZC_CUDA(cudaMemcpyAsync(h, s->red1[s->sb].p, sizeof(double) * (n1 + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    // ONE collective per synchronisation point: the gradient max-norm rides in per-rank slots of the summed buffer
+    const bool slots = ctx->world <= kMaxSlotRanks;
+    const int n_slots = slots ? std::max(ctx->world, 1) : 1;
+    if (slots) {
+      allreduce(s, s->red1[s->sb].as<double>() + R1_SCHUR, n1 - R1_SCHUR + n_slots, 0);
+    } else {
+      allreduce(s, s->red1[s->sb].as<double>() + R1_SCHUR, n1 - R1_SCHUR, 0);
+      allreduce(s, s->red1[s->sb].as<double>() + n1, 1, 1);
+    }
+    EZC_CUDA(cudaMemcpyAsync(h, s->red1[s->sb].p, sizeof(double) * (n1 + n_slots), cudaMemcpyDeviceToHost, ctx->stream));
     EZC_CUDA(cudaStreamSynchronize(ctx->stream));
     const double* hs = h + R1_SCHUR;
     const double* Ssum = hs;
@@ -1073,7 +1091,8 @@ ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summ
     const double xn2_p = hs[nS + 2 * k + 0];
     const double nres = hs[nS + 2 * k + 1];
     const double fail = hs[nS + 2 * k + 3];
-    const double gmax_p = hs[nS + 2 * k + 4];
+    double gmax_p = 0.0;
+    for (int r = 0; r < n_slots; ++r) gmax_p = std::max(gmax_p, hs[nS + 2 * k + 4 + r]);
     if (fresh_jacobian) {
       x_cost = h[R1_COST];
       for (int a = 0; a < k; ++a) for (int b = a; b < k; ++b) Hcc[a * k + b] = Hcc[b * k + a] = h[R1_HCC + a * kMaxK + b];
@@ -1143,7 +1162,9 @@ ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summ
       const int grid = std::max(1, (nb + 127) / 128);
       lm_backsub_kernel<<<grid, 128, 0, ctx->stream>>>(ba);
       if (ezc_status st = launch_check(ctx, "lm_backsub")) return st;
-      lm_reduce_rows_kernel<<<4, 256, 0, ctx->stream>>>(s->part3.as<double>(), grid, 4, 4, s->red2.as<double>());
+      // model-cost sums land right behind the candidate's H_cc / cost block (the Schur section of the alternate buffer is
+      // free until that buffer becomes current): one all-reduce and one copy cover both
+      lm_reduce_rows_kernel<<<4, 256, 0, ctx->stream>>>(s->part3.as<double>(), grid, 4, 4, s->red1[1 - s->sb].as<double>() + R1_SCHUR);
       if (ezc_status st = launch_check(ctx, "lm_reduce_rows")) return st;
       // candidate shared parameters
       s->cam_cand = s->cam;
@@ -1154,13 +1175,11 @@ ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summ
       const int alt = 1 - s->sb;
       if (ezc_status st = run_accumulate(s, 1 - s->cur, s->cam_cand, alt)) return st;
       ++n_jac;
-      allreduce(s, s->red2.as<double>(), 4, 0);
-      allreduce(s, s->red1[alt].as<double>(), R1_SCHUR, 0);
-      EZC_CUDA(cudaMemcpyAsync(h, s->red2.p, sizeof(double) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-      EZC_CUDA(cudaMemcpyAsync(h + 4, s->red1[alt].as<double>() + R1_COST, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      allreduce(s, s->red1[alt].as<double>(), R1_SCHUR + 4, 0);
+      EZC_CUDA(cudaMemcpyAsync(h, s->red1[alt].as<double>() + R1_COST, sizeof(double) * 5, cudaMemcpyDeviceToHost, ctx->stream));
       EZC_CUDA(cudaStreamSynchronize(ctx->stream));
-      double gd = h[0], dHd = h[1];
-      step2 = h[2]; cn2 = h[3]; cand_cost = h[4];
+      double gd = h[1], dHd = h[2];
+      step2 = h[3]; cn2 = h[4]; cand_cost = h[0];
       for (int a = 0; a < k; ++a) {
         gd += gc[a] * dc[a];
         double row = 0.0;
