@@ -167,20 +167,25 @@ __global__ void __launch_bounds__(256) at_pre_kernel(const uint8_t* __restrict__
   const uint8_t* I = img + (long long)im * istride;
   lut[tid] = c_u8f[tid];
   __syncthreads();
+  // thread (lx, ly) = (tid & 63, tid >> 6) walks rows ly, ly+4, ... and columns tx (+64 for the halo columns): no
+  // division per element, column-dependent quantities are computed once
+  const int lx = tid & 63, ly = tid >> 6;
+  const float f0 = c_filt[0], f1 = c_filt[1], f2 = c_filt[2];
   // A. pixels (clamped coordinates: out-of-image entries are never consumed)
-  for (int i = tid; i < kUH * kUW; i += 256) {
-    const int r = i / kUW, c = i - r * kUW;
-    const int y = min(max(y0 - 2 + r, 0), H - 1), x = min(max(x0 - 2 + c, 0), W - 1);
-    u[r][c] = lut[I[(long long)y * pitch + x]];
+  {
+    const int xa = min(max(x0 - 2 + lx, 0), W - 1), xb = min(max(x0 - 2 + 64 + lx, 0), W - 1);
+    for (int r = ly; r < kUH; r += 4) {
+      const uint8_t* row = I + (long long)min(max(y0 - 2 + r, 0), H - 1) * pitch;
+      u[r][lx] = lut[row[xa]];
+      if (lx < kUW - 64) u[r][64 + lx] = lut[row[xb]];
+    }
   }
   __syncthreads();
   // B. horizontal pass (Gaussian.cc:40-68 with its absolute-offset comparison, see at_blur_h_kernel)
-  const float f0 = c_filt[0], f1 = c_filt[1], f2 = c_filt[2];
-  for (int i = tid; i < kHH * kHW; i += 256) {
-    const int r = i / kHW, c = i - r * kHW;
-    const int y = y0 - 2 + r, x = x0 - 1 + c;
-    float v = 0.f;
-    if (x >= 0 && x < W && y >= 0 && y < H) {
+  {
+    auto hval = [&](int r, int c) -> float {
+      const int y = y0 - 2 + r, x = x0 - 1 + c;
+      if (x < 0 || x >= W || y < 0 || y >= H) return 0.f;
       double acc = 0;
       if (x >= 2 && x <= W - 2) {
         acc += (double)(u[r][c + 2] * f0); acc += (double)(u[r][c + 1] * f1); acc += (double)(u[r][c] * f2);
@@ -197,25 +202,30 @@ __global__ void __launch_bounds__(256) at_pre_kernel(const uint8_t* __restrict__
           acc += (double)(a * f0); acc += (double)(a * f1); acc += (double)(a * f2);
         }
       }
-      v = (float)acc;
+      return (float)acc;
+    };
+    for (int r = ly; r < kHH; r += 4) {
+      hb[r][lx] = hval(r, lx);
+      if (lx < kHW - 64) hb[r][64 + lx] = hval(r, 64 + lx);
     }
-    hb[r][c] = v;
   }
   __syncthreads();
   // C. vertical pass (replicated border)
-  for (int i = tid; i < kSH * kSW; i += 256) {
-    const int r = i / kSW, c = i - r * kSW;
-    const int y = y0 - 1 + r, x = x0 - 1 + c;
-    float v = 0.f;
-    if (x >= 0 && x < W && y >= 0 && y < H) {
+  {
+    auto sval = [&](int r, int c) -> float {
+      const int y = y0 - 1 + r, x = x0 - 1 + c;
+      if (x < 0 || x >= W || y < 0 || y >= H) return 0.f;
       const int rp = min(y + 1, H - 1) - (y0 - 2), rm = max(y - 1, 0) - (y0 - 2), rc = y - (y0 - 2);
       double acc = 0;
       acc += (double)(hb[rp][c] * f0);
       acc += (double)(hb[rc][c] * f1);
       acc += (double)(hb[rm][c] * f2);
-      v = (float)acc;
+      return (float)acc;
+    };
+    for (int r = ly; r < kSH; r += 4) {
+      sb[r][lx] = sval(r, lx);
+      if (lx < kSW - 64) sb[r][64 + lx] = sval(r, 64 + lx);
     }
-    sb[r][c] = v;
   }
   __syncthreads();
   // D. gradient, activity mask, lazy theta: warp w owns rows 4w..4w+3, two 32-pixel words per row
