@@ -2,17 +2,24 @@
 """bench.py -- headline benchmark of the B200-native EZCalib hot path.
 
 Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
-line.  A "step" is one Levenberg-Marquardt iteration (linear solve of the Schur-reduced system,
-candidate evaluation, accept/reject and -- when accepted -- the Jacobian / normal-equation build at
-the new point) over the cfg5 workload of BASELINE.json: 10,000,080 observations per GPU
-(69,445 views x 144 AprilGrid corners), for each of the 7 distortion models (mono focal).
+line.  A "step" is one Levenberg-Marquardt iteration (Schur pieces for the current radius, linear solve of the reduced
+system, back-substitution, speculative evaluation of cost + Jacobian + normal equations at the candidate,
+accept/reject) over the cfg5 workload of BASELINE.json: 10,000,080 observations per GPU (69,445 views x 144 AprilGrid
+corners), for each of the 7 distortion models (mono focal).  Exactly K iterations are timed per model for any K (a
+long solve that converges is continued from the initial parameters, see solve_exactly).
 
   value   = 10M-observation LM iterations per second, whole job, inputs resident in HBM
             (observations processed per second / 10,000,080; aggregate over the 7 models)
   e2e     = the same through the host-buffer C ABI (ezc_lm_create + set_params + solve + get_params):
             pinned host buffers, H2D of observations/poses and D2H of the results inside the timed region
+            (median of three identical solves: one solve is ~12 ms of wall time)
   roofline= the dominant kernel (lm_accumulate) against the FP64 DFMA peak measured in the same run
   cpu_baseline = the CPU oracle ("restated Ceres", oracle/lm_oracle.cpp) on a bounded sample
+  detect / detect_chessboard / detect_chessboard_stereo = images/s detect+subpix for BASELINE.json's cfg3 (AprilGrid
+            2448x2048), cfg1 (chessboard 1280x1024, rad-tan 5) and cfg2 (stereo chessboard 1920x1080, Kannala-Brandt)
+            geometries, each with its own e2e (pinned host images, asynchronous upload), HBM roofline and the reference
+            (the reference's own AprilTag code / cv2 with the reference's flags) timed on the host cores with a parity
+            check on the sample
 
 `--impl reference` times the reference's CPU path: Ceres itself is not available in this image
 (SURVEY.md 8c), so this is the oracle port with all host threads on a bounded sample.
