@@ -552,16 +552,31 @@ __global__ void __launch_bounds__(128) lm_backsub_kernel(const BacksubArgs a) {
     if (cnt > 0.0) {
       double L[6][6], tt[6], y[6], d[6];
       {
+        // 16-byte loads: L (21 values + pad) and z (6) are 14 double2 from the 800-byte aligned record
+        const double2* r2 = reinterpret_cast<const double2*>(rec);
+        double lin[28];
+#pragma unroll
+        for (int j = 0; j < 14; ++j) { const double2 v = r2[j]; lin[2 * j] = v.x; lin[2 * j + 1] = v.y; }
         int q = 0;
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
-          for (int j = 0; j <= i; ++j) L[i][j] = rec[q++];
+          for (int j = 0; j <= i; ++j) L[i][j] = lin[q++];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) tt[i] = lin[22 + i];
       }
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        double sacc = rec[22 + i];
-        for (int c = 0; c < k; ++c) sacc -= rec[28 + i * kMaxK + c] * a.uc[c];
+        const double2* y2 = reinterpret_cast<const double2*>(rec + 28 + i * kMaxK);
+        double sacc = tt[i];
+#pragma unroll
+        for (int j = 0; j < kMaxK / 2; ++j) {
+          if (2 * j < k) {
+            const double2 v = y2[j];
+            sacc -= v.x * a.uc[2 * j];
+            if (2 * j + 1 < k) sacc -= v.y * a.uc[2 * j + 1];
+          }
+        }
         tt[i] = sacc;
       }
 #pragma unroll
