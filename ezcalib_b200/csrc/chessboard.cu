@@ -8,14 +8,15 @@
 // behaviour observed in this image (cv2 4.13.0), see cb_logic.h and tests/test_cb_logic.py.
 //
 // Structure: the image-level passes run as data-parallel kernels over the whole batch -- histogram binarisation,
-// 3x3 dilation, white frame, union-find labelling (black 4-connected = the "holes" cv::findContours(RETR_CCOMP) reports,
-// white 8-connected = their parents), one thread per hole for Suzuki border following (CHAIN_APPROX_SIMPLE) and for
-// approxPolyDP/quad filtering -- and the small, irregular quad-graph logic (neighbour linking, grouping, ordering,
-// corner extraction; a few dozen quads) runs with one thread per image from cb_logic.h.  The attempt loop of
-// cv::findChessboardCorners (8 dilations of the histogram-binarised image, then 6 adaptive thresholds x 8 dilations on
-// the equalised image) is driven by the host for all images of the batch in lock-step; images that are done drop out.
-// Known deviation: CALIB_CB_FAST_CHECK is an early-exit heuristic of OpenCV and is not evaluated (an image it would
-// reject goes through the full search and is then rejected by it).
+// 3x3 dilation, white frame, run-based union-find labelling (black 4-connected = the "holes"
+// cv::findContours(RETR_CCOMP) reports, white 8-connected = their parents), Suzuki border following
+// (CHAIN_APPROX_SIMPLE) per hole, approxPolyDP/quad filtering per hole (one thread for short borders, one warp with the
+// contour in shared memory for long ones) -- and the quad-graph logic (neighbour linking on a shared-memory grid,
+// grouping, ordering, corner extraction) runs with one block per image on the rules of cb_logic.h.  The attempt loop
+// of cv::findChessboardCorners (the histogram-binarised image undilated and then with 1..7 dilations, then 6 adaptive
+// thresholds x 8 dilation levels on the equalised image) is driven by the host for all images of the batch in
+// lock-step; images that are done drop out.  CALIB_CB_FAST_CHECK (checkChessboardBinary + checkChessboard) is
+// evaluated first when the caller asks for it (fast_check_gate below).
 #include <algorithm>
 #include <vector>
 
@@ -1533,11 +1534,14 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
     if (ezc_status st = fast_check_gate(ctx, P, d_img, imgs->pitch, imgs->image_stride, b0, W, H, nb, pw, ph, list)) return st;
     if (ezc_status st = upload_list(ctx, P.active, list)) return st;
   }
-  // ---- phase 1: histogram-binarised image, 8 cumulative dilations (the frame of the previous pass is dilated too)
+  // ---- phase 1: histogram-binarised image; attempt 0 runs on it undilated, attempts 1..7 add one dilation each (the
+  // frame of the previous pass is dilated too). cv2 4.13's first failing level on pre-dilated ideal boards pins this.
   for (int dil = 0; dil <= 7 && !list.empty(); ++dil) {
     const int n_act = (int)list.size();
-    CB_LAUNCH_PIX(cb_dilate_kernel, N, n_act, b0, b1, W, H, n_act, P.active.as<int>());
-    std::swap(b0, b1);
+    if (dil > 0) {
+      CB_LAUNCH_PIX(cb_dilate_kernel, N, n_act, b0, b1, W, H, n_act, P.active.as<int>());
+      std::swap(b0, b1);
+    }
     CB_LAUNCH_PIX(cb_frame_kernel, N, n_act, b0, W, H, n_act, P.active.as<int>());
     if (ezc_status st = run_attempt(ctx, P, b0, W, H, n_act, pw, ph, dil)) return st;
     if (ezc_status st = sync_state(ctx, P, nb, h_state, list)) return st;

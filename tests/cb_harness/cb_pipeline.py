@@ -138,7 +138,10 @@ def find_chessboard_corners(img: np.ndarray, pattern_size, refine=True, info=Non
     prev_sqr_size = 0
     used = img
     for dilations in range(0, 8):
-        thresh = cv2.dilate(thresh, None, iterations=1)
+        # cv2 4.13: the first attempt runs on the undilated binary image (pinned on
+        # pre-dilated ideal boards: cv2's first failing level matches only this way)
+        if dilations > 0:
+            thresh = cv2.dilate(thresh, None, iterations=1)
         cv2.rectangle(thresh, (0, 0), (W - 1, H - 1), 255, 3, cv2.LINE_8)
         ok, c, prev, nq = detect_from_binary(thresh, pw, ph, dilations)
         if prev:
