@@ -23,6 +23,7 @@
 #include "cb_logic.h"
 #include <cstdlib>
 
+#include "cb_rows.cuh"
 #include "images.cuh"
 #include "scan_sort.cuh"
 
@@ -98,63 +99,6 @@ __global__ void cb_select_threshold_kernel(const int* __restrict__ hist_all, int
   thresh[im] = t;
 }
 
-__global__ void cb_binarize_kernel(const uint8_t* __restrict__ img, long long pitch, long long istride, int W, int H, int n_img,
-                                   const int* __restrict__ thresh, const int* __restrict__ active, uint8_t* __restrict__ out) {
-  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
-  const long long N = (long long)W * H;
-  if (pix_ >= N) return;
-  const int slot = blockIdx.y;
-  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
-  const int im = active ? active[slot] : slot;   // `active` = compact list of image indices still searching
-  const int p = (int)pix_;
-  const long long gid = (long long)im * N + p;
-  const int y = p / W, x = p - y * W;
-  const uint8_t v = img[(long long)im * istride + (long long)y * pitch + x];
-  const int t = thresh[im];
-  out[gid] = t > 0 ? (v >= t ? 255 : 0) : v;
-}
-
-// cv::dilate(src, dst, Mat(), Point(-1,-1), 1): 3x3 max, pixels outside the image are ignored
-__global__ void cb_dilate_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int W, int H, int n_img,
-                                 const int* __restrict__ active) {
-  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
-  const long long N = (long long)W * H;
-  if (pix_ >= N) return;
-  const int slot = blockIdx.y;
-  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
-  const int im = active ? active[slot] : slot;   // `active` = compact list of image indices still searching
-  const int p = (int)pix_;
-  const long long gid = (long long)im * N + p;
-  const int y = p / W, x = p - y * W;
-  const uint8_t* S = src + (long long)im * N;
-  uint8_t m = 0;
-  for (int dy = -1; dy <= 1; ++dy) {
-    const int yy = y + dy;
-    if (yy < 0 || yy >= H) continue;
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int xx = x + dx;
-      if (xx < 0 || xx >= W) continue;
-      const uint8_t v = S[(long long)yy * W + xx];
-      m = v > m ? v : m;
-    }
-  }
-  dst[gid] = m;
-}
-
-// rectangle(img, (0,0), (W-1,H-1), 255, 3, LINE_8): a 3-pixel white frame (checked against cv2)
-__global__ void cb_frame_kernel(uint8_t* __restrict__ img, int W, int H, int n_img, const int* __restrict__ active) {
-  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
-  const long long N = (long long)W * H;
-  if (pix_ >= N) return;
-  const int slot = blockIdx.y;
-  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
-  const int im = active ? active[slot] : slot;   // `active` = compact list of image indices still searching
-  const int p = (int)pix_;
-  const long long gid = (long long)im * N + p;
-  const int y = p / W, x = p - y * W;
-  if (x < 3 || y < 3 || x >= W - 3 || y >= H - 3) img[gid] = 255;
-}
-
 // ---------------------------------------------------------------------------------------------- labelling
 // One union-find over all pixels: black pixels connect 4-way (holes of cv::findContours), white pixels 8-way.
 // label = smallest linear index of the component = its raster-first pixel (where the border following starts).
@@ -206,65 +150,98 @@ __global__ void cb_label_runs_kernel(const uint8_t* __restrict__ bin, int* __res
     prev_last = __shfl_sync(0xffffffffu, v, 31);
   }
 }
-__global__ void cb_label_merge_kernel(const uint8_t* __restrict__ bin, int* __restrict__ L, int W, int H, int n_img,
-                                      const int* __restrict__ active) {
-  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
-  const long long N = (long long)W * H;
-  if (pix_ >= N) return;
-  const int slot = blockIdx.y;
-  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
-  const int im = active ? active[slot] : slot;   // `active` = compact list of image indices still searching
-  const int p = (int)pix_;
-  const long long gid = (long long)im * N + p;
-  const int y = p / W, x = p - y * W;
-  if (y == 0) return;
-  const bool v = bin[gid] != 0;
-  const bool up = bin[gid - W] != 0;
-  if (up == v) {
-    const bool start_here = (x == 0) || ((bin[gid - 1] != 0) != v);
-    const bool start_up = (x == 0) || ((bin[gid - W - 1] != 0) != up);
-    if (start_here || start_up) cbl_union(L, (int)gid, (int)(gid - W));
-  } else if (v) {
-    // white pixel under a black one: the diagonal neighbours of the upper row are separate runs
-    if (x + 1 < W && bin[gid - W + 1] != 0) cbl_union(L, (int)gid, (int)(gid - W + 1));
-    if (x > 0 && bin[gid - W - 1] != 0) cbl_union(L, (int)gid, (int)(gid - W - 1));
+// ---- the same steps on 16-pixel row chunks (cb_rows.cuh): run logic on 16-bit masks, labels touched only at run heads.
+// After the merge step a pixel is the root of its component iff L[p] == p, a run head points at its root once
+// cb_label_heads has run, and every other pixel points at its run head -- so "root of pixel p" is L[L[p]] and no pass
+// ever rewrites the 4-byte labels of all pixels.  Holes (black roots) are listed in raster order through per-block
+// counts: heads counts them, a scan over the blocks (not the pixels) gives each block its offset, list writes them.
+__device__ __forceinline__ void row_masks(const uint8_t* __restrict__ row, int x0, int W, bool vec, uint32_t& v, uint32_t& left, uint32_t& right) {
+  v = nz16(ld16(row, x0, W, vec, 0u));
+  left = x0 > 0 ? (row[x0 - 1] != 0 ? 1u : 0u) : 0u;
+  right = x0 + 16 < W ? (row[x0 + 16] != 0 ? 1u : 0u) : 0u;
+}
+__global__ void cb_label_merge16_kernel(const uint8_t* __restrict__ bin, int* __restrict__ L, int W, int H, const int* __restrict__ active, bool vec) {
+  const ChunkPos c = chunk_pos(W, H);
+  if (!c.ok || c.y == 0) return;
+  const int im = active ? active[blockIdx.y] : (int)blockIdx.y;
+  const long long base = ((long long)im * H + c.y) * W;
+  uint32_t v, vl, vr, u, ul, ur;
+  row_masks(bin + base, c.x0, W, vec, v, vl, vr);
+  row_masks(bin + base - W, c.x0, W, vec, u, ul, ur);
+  const uint32_t valid = valid16(c.x0, W);
+  const uint32_t first = c.x0 == 0 ? 1u : 0u;
+  const uint32_t vprev = ((v << 1) | vl) & 0xffffu, uprev = ((u << 1) | ul) & 0xffffu, unext = (u >> 1) | (ur << 15);
+  const uint32_t start_here = (v ^ vprev) | first, start_up = (u ^ uprev) | first;
+  uint32_t same = ~(v ^ u) & (start_here | start_up) & valid;   // a new vertical adjacency between runs of one colour starts here
+  const uint32_t wb = v & ~u & valid;                            // white under black: the upper diagonals are separate runs
+  uint32_t dr = wb & unext, dl = wb & uprev & ~first;
+  const int g0 = (int)(base + c.x0);
+  while (same) { const int k = __ffs(same) - 1; same &= same - 1; cbl_union(L, g0 + k, g0 + k - W); }
+  while (dr) { const int k = __ffs(dr) - 1; dr &= dr - 1; cbl_union(L, g0 + k, g0 + k - W + 1); }
+  while (dl) { const int k = __ffs(dl) - 1; dl &= dl - 1; cbl_union(L, g0 + k, g0 + k - W - 1); }
+}
+// run heads -> roots (pointer jumping; concurrent writes only ever shorten a path to a valid ancestor); counts the roots
+// of the wanted colour per block
+__global__ void cb_label_heads_kernel(const uint8_t* __restrict__ bin, int* __restrict__ L, int W, int H, const int* __restrict__ active, bool vec,
+                                      int white_roots, int* __restrict__ block_count) {
+  const ChunkPos c = chunk_pos(W, H);
+  int cnt = 0;
+  if (c.ok) {
+    const int im = active ? active[blockIdx.y] : (int)blockIdx.y;
+    const long long base = ((long long)im * H + c.y) * W;
+    uint32_t v, vl, vr;
+    row_masks(bin + base, c.x0, W, vec, v, vl, vr);
+    uint32_t heads = ((v ^ (((v << 1) | vl) & 0xffffu)) | (c.x0 == 0 ? 1u : 0u)) & valid16(c.x0, W);
+    const uint32_t want = white_roots ? v : ~v;
+    const int g0 = (int)(base + c.x0);
+    while (heads) {
+      const int k = __ffs(heads) - 1; heads &= heads - 1;
+      const int r = cbl_find(L, g0 + k);
+      L[g0 + k] = r;
+      cnt += (r == g0 + k && ((want >> k) & 1u)) ? 1 : 0;
+    }
+  }
+  __shared__ int wsum[8];
+  for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += wsum[w];
+    block_count[(long long)blockIdx.y * gridDim.x + blockIdx.x] = t;
   }
 }
-// run heads -> roots (pointer jumping; concurrent writes only ever shorten a path to a valid ancestor)
-__global__ void cb_label_compress_kernel(const uint8_t* __restrict__ bin, int* __restrict__ L, int W, long long total, long long N,
-                                         const int* __restrict__ active) {
-  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
-  if (pix_ >= N) return;
-  const int slot = blockIdx.y;
-  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
-  const int p = (int)pix_;
-  const long long gid = (long long)(active ? active[slot] : slot) * N + p;
-  const int x = p % W;
-  if (x != 0 && (bin[gid - 1] != 0) == (bin[gid] != 0)) return;  // not a run head
-  const int r = cbl_find(L, (int)gid);
-  L[gid] = r;
-}
-__global__ void cb_label_flatten_kernel(const uint8_t* __restrict__ bin, int* __restrict__ L, long long total, long long N,
-                                        const int* __restrict__ active, int* __restrict__ hole_flag, int white_roots) {
-  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
-  if (pix_ >= N) return;
-  const int slot = blockIdx.y;
-  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
-  const long long gid = (long long)(active ? active[slot] : slot) * N + pix_;
-  const int r = L[L[gid]];   // pixel -> run head -> root (cb_label_compress has flattened the heads)
-  L[gid] = r;
-  // raster-first pixel of a black component (hole search) or of a white one (fast check); compact index
-  hole_flag[cg] = (((bin[gid] != 0) == (white_roots != 0)) && r == (int)gid) ? 1 : 0;
-}
-__global__ void cb_hole_list_kernel(const int* __restrict__ flag_scan, const uint8_t* __restrict__ bin, const int* __restrict__ L,
-                                    long long total, long long N, const int* __restrict__ active, int* __restrict__ hole_start,
-                                    int white_roots) {
-  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
-  if (pix_ >= N) return;
-  const int slot = blockIdx.y;
-  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
-  const long long gid = (long long)(active ? active[slot] : slot) * N + pix_;
-  if (((bin[gid] != 0) == (white_roots != 0)) && L[gid] == (int)gid) hole_start[flag_scan[cg]] = (int)gid;
+// block_off = exclusive scan of block_count; roots of the wanted colour in raster order -> hole_start
+__global__ void cb_root_list_kernel(const uint8_t* __restrict__ bin, const int* __restrict__ L, int W, int H, const int* __restrict__ active, bool vec,
+                                    int white_roots, const int* __restrict__ block_count, const int* __restrict__ block_off,
+                                    int* __restrict__ hole_start) {
+  const long long bi = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+  if (block_count[bi] == 0) return;
+  const ChunkPos c = chunk_pos(W, H);
+  uint32_t roots = 0;
+  int g0 = 0;
+  if (c.ok) {
+    const int im = active ? active[blockIdx.y] : (int)blockIdx.y;
+    const long long base = ((long long)im * H + c.y) * W;
+    uint32_t v, vl, vr;
+    row_masks(bin + base, c.x0, W, vec, v, vl, vr);
+    uint32_t heads = ((v ^ (((v << 1) | vl) & 0xffffu)) | (c.x0 == 0 ? 1u : 0u)) & valid16(c.x0, W) & (white_roots ? v : ~v);
+    g0 = (int)(base + c.x0);
+    while (heads) {
+      const int k = __ffs(heads) - 1; heads &= heads - 1;
+      if (L[g0 + k] == g0 + k) roots |= 1u << k;
+    }
+  }
+  // exclusive scan of the per-thread root counts over the block (threads are in raster order)
+  const int mine = __popc(roots);
+  int incl = mine;
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+  __shared__ int wtot[8];
+  if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  int pos = block_off[bi] + incl - mine;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) pos += wtot[w];
+  while (roots) { const int k = __ffs(roots) - 1; roots &= roots - 1; hole_start[pos++] = g0 + k; }
 }
 
 // ---------------------------------------------------------------------------------------------- border following
@@ -332,7 +309,7 @@ __global__ void cb_trace_kernel(const uint8_t* __restrict__ bin, const int* __re
   if (!STORE) {
     hi.n_pts = n;
     hi.minx = minx; hi.maxx = maxx; hi.miny = miny; hi.maxy = maxy;
-    hi.parent = L[(long long)im * N + (long long)y0 * W + x0];
+    hi.parent = L[L[(long long)im * N + (long long)y0 * W + x0]];   // pixel -> run head -> root
     hi.quad_ok = 0;
     // only contours that can become a quad get storage: bounding rect area >= 25 and a sane vertex count
     const bool want = n >= 4 && (maxx - minx + 1) * (maxy - miny + 1) >= 25;
@@ -553,42 +530,6 @@ __global__ void __launch_bounds__(32) cb_quad_warp_kernel(HoleInfo* __restrict__
 // <= 1.4) holds more than w*h/2 of them with >= 75 % of the expected black and white squares.  Here: 8-connected
 // components of the foreground by the run-based labelling above, the run end points of every component that survive an Akl-Toussaint
 // filter give its convex hull (no border walk), min-area rectangle over the hull edges; the (size, class) lists go to the host, which runs checkQuads.
-__global__ void cb_morph_kernel(const uint8_t* __restrict__ src, long long pitch, long long istride, uint8_t* __restrict__ dst, int W, int H,
-                                int n_img, const int* __restrict__ active, int is_max) {
-  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
-  const long long N = (long long)W * H;
-  if (pix_ >= N) return;
-  const int slot = blockIdx.y;
-  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
-  const int im = active ? active[slot] : slot;
-  const int p = (int)pix_;
-  const int y = p / W, x = p - y * W;
-  const uint8_t* S = src + (long long)im * istride;
-  int m = is_max ? 0 : 255;
-  for (int dy = -1; dy <= 1; ++dy) {
-    const int yy = y + dy;
-    if (yy < 0 || yy >= H) continue;
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int xx = x + dx;
-      if (xx < 0 || xx >= W) continue;
-      const int v = S[(long long)yy * pitch + xx];
-      m = is_max ? (v > m ? v : m) : (v < m ? v : m);
-    }
-  }
-  dst[(long long)im * N + p] = (uint8_t)m;
-}
-// dst = inv ? (src <= t) : (src > t)   (cv::threshold THRESH_BINARY_INV / THRESH_BINARY), 255 / 0
-__global__ void cb_fg_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long N, int n_img, const int* __restrict__ active,
-                             int thresh, int inv) {
-  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
-  if (pix_ >= N) return;
-  const int slot = blockIdx.y;
-  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
-  const long long gid = (long long)(active ? active[slot] : slot) * N + pix_;
-  const bool above = (int)src[gid] > thresh;
-  dst[gid] = (above != (inv != 0)) ? 255 : 0;
-}
-
 struct FcComp {
   int start;        // raster-first pixel of the component (global linear index)
   int n_cand;       // run end points of the component (upper bound of what is stored)
@@ -607,69 +548,78 @@ __global__ void cb_fc_init_kernel(int n_comp, FcComp* __restrict__ comps) {
   ci.start = 0; ci.n_cand = 0; ci.fill = 0; ci.offset = -1;
   for (int k = 0; k < 8; ++k) ci.key[k] = 0ull;
 }
-// Run heads of the foreground are pointed at their roots (what cb_label_compress does for both colours) and every root
-// draws a component id from a counter -- the gate does not care about the order of the components, so neither a full
-// flatten pass nor a prefix sum over the pixels is needed.  cidmap is indexed like the compact hole flags.
-__global__ void cb_fc_roots_kernel(const uint8_t* __restrict__ fg, int* __restrict__ L, int W, long long total, long long N,
-                                   const int* __restrict__ active, int* __restrict__ cidmap, int* __restrict__ counter) {
-  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
-  if (pix_ >= N) return;
-  const int slot = blockIdx.y;
-  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
-  const int p = (int)pix_;
-  const long long gid = (long long)(active ? active[slot] : slot) * N + p;
-  if (fg[gid] == 0) return;
-  const int x = p % W;
-  if (x != 0 && fg[gid - 1] != 0) return;   // not a run head
-  const int r = cbl_find(L, (int)gid);
-  L[gid] = r;
-  if (r == (int)gid) cidmap[cg] = atomicAdd(counter, 1);
+// Run heads of the foreground are pointed at their roots and every root draws a component id from a counter -- the gate
+// does not care about the order of the components, so no prefix sum is needed.  cidmap is indexed by the compact pixel
+// index (slot * N + pixel) and only written / read at roots.
+__global__ void cb_fc_roots16_kernel(const uint8_t* __restrict__ fg, int* __restrict__ L, int W, int H, const int* __restrict__ active, bool vec,
+                                     int* __restrict__ cidmap, int* __restrict__ counter) {
+  const ChunkPos c = chunk_pos(W, H);
+  if (!c.ok) return;
+  const int im = active ? active[blockIdx.y] : (int)blockIdx.y;
+  const long long N = (long long)W * H, base = (long long)im * N + (long long)c.y * W;
+  uint32_t v, vl, vr;
+  row_masks(fg + base, c.x0, W, vec, v, vl, vr);
+  uint32_t heads = v & ~((v << 1) | vl);   // first pixel of a foreground run (x == 0: vl = 0)
+  const int g0 = (int)(base + c.x0);
+  while (heads) {
+    const int k = __ffs(heads) - 1; heads &= heads - 1;
+    const int r = cbl_find(L, g0 + k);
+    L[g0 + k] = r;
+    if (r == g0 + k) cidmap[(long long)blockIdx.y * N + (r - (long long)im * N)] = atomicAdd(counter, 1);
+  }
 }
-// is pixel (x, y) of the foreground the first or the last pixel of its horizontal run?
-__device__ __forceinline__ bool fc_candidate(const uint8_t* __restrict__ B, int W, int x, int y) {
-  const uint8_t* r = B + (long long)y * W;
-  if (r[x] == 0) return false;
-  return x == 0 || r[x - 1] == 0 || x == W - 1 || r[x + 1] == 0;
-}
+// The run end points of the foreground (first or last pixel of a horizontal run) are the hull candidates.
 // MODE 0: extreme points + candidate count; MODE 1: store the candidates strictly outside the polygon of the extreme points
 template <int MODE>
-__global__ void cb_fc_points_kernel(const uint8_t* __restrict__ fg, const int* __restrict__ L, const int* __restrict__ cidmap, int W, int H,
-                                    int n_img, const int* __restrict__ active, FcComp* __restrict__ comps, cb::Pt* __restrict__ pool) {
-  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
-  const long long N = (long long)W * H;
-  if (pix_ >= N) return;
-  const int slot = blockIdx.y;
-  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
-  const int im = active ? active[slot] : slot;
-  const int p = (int)pix_;
-  const int y = p / W, x = p - y * W;
-  const uint8_t* B = fg + (long long)im * N;
-  if (!fc_candidate(B, W, x, y)) return;
-  const int root = L[L[(long long)im * N + p]];                     // pixel -> run head -> root (global index)
-  const int cid = cidmap[(long long)slot * N + (root - (long long)im * N)];
-  FcComp& ci = comps[cid];
-  if (MODE == 0) {
-    if ((long long)root == (long long)im * N + p) ci.start = root;   // the first pixel of a component starts a run
-    atomicAdd(&ci.n_cand, 1);
-    const int kv[8] = {-x, -x - y, -y, x - y, x, x + y, y, y - x};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const unsigned long long key = ((unsigned long long)(unsigned)(kv[k] + (1 << 20)) << 32) | (unsigned)p;
-      if (key > ci.key[k]) atomicMax(&ci.key[k], key);
+__global__ void cb_fc_points16_kernel(const uint8_t* __restrict__ fg, const int* __restrict__ L, const int* __restrict__ cidmap, int W, int H,
+                                      const int* __restrict__ active, bool vec, FcComp* __restrict__ comps, cb::Pt* __restrict__ pool) {
+  const ChunkPos c = chunk_pos(W, H);
+  if (!c.ok) return;
+  const int im = active ? active[blockIdx.y] : (int)blockIdx.y;
+  const long long N = (long long)W * H, ibase = (long long)im * N, base = ibase + (long long)c.y * W;
+  uint32_t v, vl, vr;
+  row_masks(fg + base, c.x0, W, vec, v, vl, vr);
+  const uint32_t vprev = ((v << 1) | vl) & 0xffffu, vnext = (v >> 1) | (vr << 15);
+  uint32_t cand = v & (~vprev | ~vnext) & 0xffffu;   // x == 0 / x == W-1: the missing neighbour reads as background
+  const int g0 = (int)(base + c.x0);
+  const int y = c.y;
+  int last_head = -1, cid = -1, pending = 0;
+  while (cand) {
+    const int k = __ffs(cand) - 1; cand &= cand - 1;
+    const int x = c.x0 + k, g = g0 + k;
+    const int head = L[g];                 // pixel -> run head (a run head that is a root points at itself)
+    if (head != last_head) {
+      const int root = L[head];
+      const int ncid = cidmap[(long long)blockIdx.y * N + (root - ibase)];
+      if (MODE == 0 && pending && ncid != cid) { atomicAdd(&comps[cid].n_cand, pending); pending = 0; }
+      cid = ncid; last_head = head;
+      if (MODE == 0 && root == g) comps[cid].start = root;   // the first pixel of a component starts a run
     }
-  } else {
-    if (ci.offset == -1) return;
-    bool outside = false;
+    FcComp& ci = comps[cid];
+    if (MODE == 0) {
+      ++pending;
+      const int p = (int)(g - ibase);
+      const int kv[8] = {-x, -x - y, -y, x - y, x, x + y, y, y - x};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int k2 = (k + 1) & 7;
-      const long long ax = ci.ex[k2] - ci.ex[k], ay = ci.ey[k2] - ci.ey[k];
-      if (ax == 0 && ay == 0) continue;
-      const long long cr = ax * (y - ci.ey[k]) - ay * (x - ci.ex[k]);
-      if (cr < 0) { outside = true; break; }
+      for (int q = 0; q < 8; ++q) {
+        const unsigned long long key = ((unsigned long long)(unsigned)(kv[q] + (1 << 20)) << 32) | (unsigned)p;
+        if (key > ci.key[q]) atomicMax(&ci.key[q], key);
+      }
+    } else {
+      if (ci.offset == -1) continue;
+      bool outside = false;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int q2 = (q + 1) & 7;
+        const long long ax = ci.ex[q2] - ci.ex[q], ay = ci.ey[q2] - ci.ey[q];
+        if (ax == 0 && ay == 0) continue;
+        const long long cr = ax * (y - ci.ey[q]) - ay * (x - ci.ex[q]);
+        if (cr < 0) { outside = true; break; }
+      }
+      if (outside) pool[ci.offset + atomicAdd(&ci.fill, 1)] = cb::Pt{x, y};
     }
-    if (outside) pool[ci.offset + atomicAdd(&ci.fill, 1)] = cb::Pt{x, y};
   }
+  if (MODE == 0 && pending) atomicAdd(&comps[cid].n_cand, pending);
 }
 // decode the extreme points; components whose bounding-box diagonal is below 10 px cannot pass the size test
 __global__ void cb_fc_prefilter_kernel(FcComp* __restrict__ comps, int n_comp, int W) {
@@ -1230,6 +1180,7 @@ struct CbPools {
   DevBuf hist, thresh, bin0, bin1, prevbin, eq, lut, labels, flags, scan_tmp, total, hole_start, holes, need, pool, stack_pool;
   DevBuf works, scratch, state, active, corners, found, block, delta, hsum, sub_corners, sub_idx, refresh;
   DevBuf pcnt, plast;   // per-pixel-label quad counters (kept zero between attempts)
+  DevBuf blk_cnt, blk_off;   // roots per block of the chunk grid and their exclusive scan
   DevBuf fc_w0, fc_w1, fc_w2, fc_k0, fc_k1, fc_k2, fc_fg, fc_comps, fc_hyps, fc_count, fc_list;
   HostPinned fc_h;
   HostPinned h;
@@ -1263,6 +1214,25 @@ CbPools& cb_pools(ezc_context* ctx) {
     }                                                                                                       \
   } while (0)
 
+// 16-pixel row chunks (cb_rows.cuh): grid.x covers the chunks of one image, grid.y the images
+#define CB_LAUNCH_CH(kernel, W_, H_, n_images, ...)                                                         \
+  do {                                                                                                      \
+    if ((n_images) > 0) {                                                                                   \
+      kernel<<<dim3(chunk_blocks((W_), (H_)), (unsigned)(n_images)), 256, 0, ctx->stream>>>(__VA_ARGS__);    \
+      EZC_CUDA(cudaGetLastError());                                                                         \
+      ctx->kernel_launches++;                                                                               \
+    }                                                                                                       \
+  } while (0)
+
+#define CB_LAUNCH_FRAME(img_, n_images, active_)                                                                                       \
+  do {                                                                                                                                  \
+    if ((n_images) > 0) {                                                                                                               \
+      cb_frame_border_kernel<<<dim3((unsigned)((6 * (W + H) + 255) / 256), (unsigned)(n_images)), 256, 0, ctx->stream>>>((img_), W, H, (active_)); \
+      EZC_CUDA(cudaGetLastError());                                                                                                     \
+      ctx->kernel_launches++;                                                                                                           \
+    }                                                                                                                                   \
+  } while (0)
+
 // Upload a compact list of image indices; returns its device pointer.
 ezc_status upload_list(ezc_context* ctx, DevBuf& buf, const std::vector<int>& list) {
   EZC_CUDA(buf.reserve(sizeof(int) * std::max<size_t>(list.size(), 1)));
@@ -1277,11 +1247,13 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
   const long long N = (long long)W * H, total = N * n_act;
   const int* list = P.active.as<int>();
   int* d_tot = P.total.as<int>();
+  const bool vec = (W % 16) == 0;
+  const long long n_blk = (long long)chunk_blocks(W, H) * n_act;
+  EZC_CUDA(P.blk_cnt.reserve(sizeof(int) * (size_t)n_blk)); EZC_CUDA(P.blk_off.reserve(sizeof(int) * (size_t)n_blk));
   CB_LAUNCH(cb_label_runs_kernel, (long long)H * n_act * 32, bin, P.labels.as<int>(), W, H, n_act, list);
-  CB_LAUNCH_PIX(cb_label_merge_kernel, N, n_act, bin, P.labels.as<int>(), W, H, n_act, list);
-  CB_LAUNCH_PIX(cb_label_compress_kernel, N, n_act, bin, P.labels.as<int>(), W, total, N, list);
-  CB_LAUNCH_PIX(cb_label_flatten_kernel, N, n_act, bin, P.labels.as<int>(), total, N, list, P.flags.as<int>(), 0);
-  if (ezc_status st = exclusive_scan_i32(ctx, P.flags.as<int>(), P.flags.as<int>(), total, P.scan_tmp, d_tot)) return st;
+  CB_LAUNCH_CH(cb_label_merge16_kernel, W, H, n_act, bin, P.labels.as<int>(), W, H, list, vec);
+  CB_LAUNCH_CH(cb_label_heads_kernel, W, H, n_act, bin, P.labels.as<int>(), W, H, list, vec, 0, P.blk_cnt.as<int>());
+  if (ezc_status st = exclusive_scan_i32(ctx, P.blk_cnt.as<int>(), P.blk_off.as<int>(), n_blk, P.scan_tmp, d_tot)) return st;
   EZC_CUDA(cudaMemcpyAsync(P.h.p, d_tot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   EZC_CUDA(cudaStreamSynchronize(ctx->stream));
   const int nH = *P.h.as<int>();
@@ -1290,7 +1262,7 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
     EZC_CUDA(P.hole_start.reserve(sizeof(int) * (size_t)nH));
     EZC_CUDA(P.holes.reserve(sizeof(HoleInfo) * (size_t)nH));
     EZC_CUDA(P.need.reserve(sizeof(int) * ((size_t)nH + 1)));
-    CB_LAUNCH_PIX(cb_hole_list_kernel, N, n_act, P.flags.as<int>(), bin, P.labels.as<int>(), total, N, list, P.hole_start.as<int>(), 0);
+    CB_LAUNCH_CH(cb_root_list_kernel, W, H, n_act, bin, P.labels.as<int>(), W, H, list, vec, 0, P.blk_cnt.as<int>(), P.blk_off.as<int>(), P.hole_start.as<int>());
     CB_LAUNCH(cb_hole_init_kernel, nH, P.hole_start.as<int>(), nH, P.holes.as<HoleInfo>(), P.need.as<int>());
     CB_LAUNCH(cb_trace_kernel<false>, nH, bin, P.labels.as<int>(), W, H, nH, P.holes.as<HoleInfo>(), nullptr, cb::kMaxContourPts);
     CB_LAUNCH(cb_hole_need_kernel, nH, P.holes.as<HoleInfo>(), nH, P.need.as<int>());
@@ -1380,6 +1352,7 @@ static ezc_status fc_round(ezc_context* ctx, CbPools& P, const uint8_t* white_sr
   const long long N = (long long)W * H, total = N * n_act;
   if (ezc_status st = upload_list(ctx, P.fc_list, alist)) return st;
   const int* list = P.fc_list.as<int>();
+  const bool vec = (W % 16) == 0;
   const int max_hyps = (int)std::min<long long>(4 << 20, total / 64 + 4096);
   EZC_CUDA(P.fc_hyps.reserve(sizeof(FcHyp) * (size_t)max_hyps));
   EZC_CUDA(P.fc_count.reserve(64));
@@ -1387,11 +1360,11 @@ static ezc_status fc_round(ezc_context* ctx, CbPools& P, const uint8_t* white_sr
   int* d_tot = P.total.as<int>();
   uint8_t* fg = P.fc_fg.as<uint8_t>();
   for (int cls = 1; cls >= 0; --cls) {
-    CB_LAUNCH_PIX(cb_fg_kernel, N, n_act, cls ? white_src : black_src, fg, N, n_act, list, cls ? white_thresh : black_thresh, cls ? 0 : 1);
+    CB_LAUNCH_CH(cb_fg16_kernel, W, H, n_act, cls ? white_src : black_src, fg, W, H, list, cls ? white_thresh : black_thresh, cls ? 0 : 1, vec);
     CB_LAUNCH(cb_label_runs_kernel, (long long)H * n_act * 32, fg, P.labels.as<int>(), W, H, n_act, list);
-    CB_LAUNCH_PIX(cb_label_merge_kernel, N, n_act, fg, P.labels.as<int>(), W, H, n_act, list);
+    CB_LAUNCH_CH(cb_label_merge16_kernel, W, H, n_act, fg, P.labels.as<int>(), W, H, list, vec);
     EZC_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(int), ctx->stream));
-    CB_LAUNCH_PIX(cb_fc_roots_kernel, N, n_act, fg, P.labels.as<int>(), W, total, N, list, P.flags.as<int>(), d_tot);
+    CB_LAUNCH_CH(cb_fc_roots16_kernel, W, H, n_act, fg, P.labels.as<int>(), W, H, list, vec, P.flags.as<int>(), d_tot);
     EZC_CUDA(cudaMemcpyAsync(P.h.p, d_tot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     EZC_CUDA(cudaStreamSynchronize(ctx->stream));
     const int nC = *P.h.as<int>();
@@ -1399,7 +1372,7 @@ static ezc_status fc_round(ezc_context* ctx, CbPools& P, const uint8_t* white_sr
     EZC_CUDA(P.fc_comps.reserve(sizeof(FcComp) * (size_t)nC));
     EZC_CUDA(P.need.reserve(sizeof(int) * ((size_t)nC + 1)));
     CB_LAUNCH(cb_fc_init_kernel, nC, nC, P.fc_comps.as<FcComp>());
-    CB_LAUNCH_PIX(cb_fc_points_kernel<0>, N, n_act, fg, P.labels.as<int>(), P.flags.as<int>(), W, H, n_act, list, P.fc_comps.as<FcComp>(), nullptr);
+    CB_LAUNCH_CH(cb_fc_points16_kernel<0>, W, H, n_act, fg, P.labels.as<int>(), P.flags.as<int>(), W, H, list, vec, P.fc_comps.as<FcComp>(), nullptr);
     CB_LAUNCH(cb_fc_prefilter_kernel, nC, P.fc_comps.as<FcComp>(), nC, W);
     CB_LAUNCH(cb_fc_need_kernel, nC, P.fc_comps.as<FcComp>(), nC, P.need.as<int>());
     if (ezc_status st = exclusive_scan_i32(ctx, P.need.as<int>(), P.need.as<int>(), nC, P.scan_tmp, d_tot)) return st;
@@ -1409,7 +1382,7 @@ static ezc_status fc_round(ezc_context* ctx, CbPools& P, const uint8_t* white_sr
     if (nPts <= 0) continue;
     EZC_CUDA(P.pool.reserve(sizeof(cb::Pt) * ((size_t)nPts + 16)));
     CB_LAUNCH(cb_fc_offset_kernel, nC, P.fc_comps.as<FcComp>(), nC, P.need.as<int>());
-    CB_LAUNCH_PIX(cb_fc_points_kernel<1>, N, n_act, fg, P.labels.as<int>(), P.flags.as<int>(), W, H, n_act, list, P.fc_comps.as<FcComp>(), P.pool.as<cb::Pt>());
+    CB_LAUNCH_CH(cb_fc_points16_kernel<1>, W, H, n_act, fg, P.labels.as<int>(), P.flags.as<int>(), W, H, list, vec, P.fc_comps.as<FcComp>(), P.pool.as<cb::Pt>());
     CB_LAUNCH(cb_fc_minrect_kernel, nC, P.fc_comps.as<FcComp>(), nC, P.pool.as<cb::Pt>(), N, cls, P.fc_hyps.as<FcHyp>(), P.fc_count.as<int>(), max_hyps);
   }
   EZC_CUDA(cudaMemcpyAsync(P.h.p, P.fc_count.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1451,6 +1424,8 @@ static ezc_status fc_round(ezc_context* ctx, CbPools& P, const uint8_t* white_sr
 static ezc_status fast_check_gate(ezc_context* ctx, CbPools& P, const uint8_t* d_img, long long pitch, long long istride, const uint8_t* B,
                                   int W, int H, int nb, int pw, int ph, std::vector<int>& list) {
   const long long N = (long long)W * H, total = N * nb;
+  const bool vec = (W % 16) == 0;
+  const bool vec_src = vec && pitch % 16 == 0 && istride % 16 == 0 && ((uintptr_t)d_img & 15) == 0;
   EZC_CUDA(P.fc_w0.reserve(total)); EZC_CUDA(P.fc_w1.reserve(total)); EZC_CUDA(P.fc_w2.reserve(total));
   EZC_CUDA(P.fc_k0.reserve(total)); EZC_CUDA(P.fc_k1.reserve(total)); EZC_CUDA(P.fc_k2.reserve(total));
   EZC_CUDA(P.fc_fg.reserve(total));
@@ -1475,8 +1450,8 @@ static ezc_status fast_check_gate(ezc_context* ctx, CbPools& P, const uint8_t* d
       if (ezc_status st = upload_list(ctx, P.fc_list, alist)) return st;
       const uint8_t* ws = built == 0 ? B : wl[built];
       const uint8_t* ks = built == 0 ? B : kl[built];
-      CB_LAUNCH_PIX(cb_morph_kernel, N, n_act, ws, (long long)W, N, wl[built + 1], W, H, n_act, P.fc_list.as<int>(), 0);
-      CB_LAUNCH_PIX(cb_morph_kernel, N, n_act, ks, (long long)W, N, kl[built + 1], W, H, n_act, P.fc_list.as<int>(), 1);
+      CB_LAUNCH_CH(cb_morph16_kernel<false>, W, H, n_act, ws, (long long)W, N, vec, wl[built + 1], W, H, P.fc_list.as<int>(), vec);
+      CB_LAUNCH_CH(cb_morph16_kernel<true>, W, H, n_act, ks, (long long)W, N, vec, kl[built + 1], W, H, P.fc_list.as<int>(), vec);
     }
     white = e == 0 ? B : wl[e];
     black = e == 0 ? B : kl[e];
@@ -1485,8 +1460,8 @@ static ezc_status fast_check_gate(ezc_context* ctx, CbPools& P, const uint8_t* d
   if (!alist.empty()) {
     const int n_act = (int)alist.size();
     if (ezc_status st = upload_list(ctx, P.fc_list, alist)) return st;
-    CB_LAUNCH_PIX(cb_morph_kernel, N, n_act, d_img, pitch, istride, wbuf[0], W, H, n_act, P.fc_list.as<int>(), 0);
-    CB_LAUNCH_PIX(cb_morph_kernel, N, n_act, d_img, pitch, istride, kbuf[0], W, H, n_act, P.fc_list.as<int>(), 1);
+    CB_LAUNCH_CH(cb_morph16_kernel<false>, W, H, n_act, d_img, pitch, istride, vec_src, wbuf[0], W, H, P.fc_list.as<int>(), vec);
+    CB_LAUNCH_CH(cb_morph16_kernel<true>, W, H, n_act, d_img, pitch, istride, vec_src, kbuf[0], W, H, P.fc_list.as<int>(), vec);
     for (int t = 20; t < 130 && !alist.empty(); t += 20)
       if (ezc_status st = fc_round(ctx, P, wbuf[0], kbuf[0], t + 70, t, W, H, pw, ph, alist, pass)) return st;
   }
@@ -1529,7 +1504,10 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
   CB_LAUNCH(cb_select_threshold_kernel, nb, P.hist.as<int>(), nb, W, H, P.thresh.as<int>());
   uint8_t* b0 = P.bin0.as<uint8_t>();
   uint8_t* b1 = P.bin1.as<uint8_t>();
-  CB_LAUNCH_PIX(cb_binarize_kernel, N, nb, d_img, imgs->pitch, imgs->image_stride, W, H, nb, P.thresh.as<int>(), (const int*)nullptr, b0);
+  const bool vec = (W % 16) == 0;   // packed working images: rows and images start 16-byte aligned
+  const bool vec_src = imgs->pitch % 16 == 0 && imgs->image_stride % 16 == 0 && ((uintptr_t)d_img & 15) == 0 && vec;
+  CB_LAUNCH_CH(cb_binarize16_kernel, W, H, nb, d_img, (long long)imgs->pitch, (long long)imgs->image_stride, vec_src, W, H, P.thresh.as<int>(),
+               (const int*)nullptr, b0, vec);
   if (fast_check) {
     if (ezc_status st = fast_check_gate(ctx, P, d_img, imgs->pitch, imgs->image_stride, b0, W, H, nb, pw, ph, list)) return st;
     if (ezc_status st = upload_list(ctx, P.active, list)) return st;
@@ -1538,11 +1516,12 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
   // frame of the previous pass is dilated too). cv2 4.13's first failing level on pre-dilated ideal boards pins this.
   for (int dil = 0; dil <= 7 && !list.empty(); ++dil) {
     const int n_act = (int)list.size();
+    if (getenv("EZC_CB_TIMING")) fprintf(stderr, "[cb] phase 1 attempt %d: %d of %d views\n", dil, n_act, nb);
     if (dil > 0) {
-      CB_LAUNCH_PIX(cb_dilate_kernel, N, n_act, b0, b1, W, H, n_act, P.active.as<int>());
+      CB_LAUNCH_CH(cb_morph16_kernel<true>, W, H, n_act, b0, (long long)W, N, vec, b1, W, H, P.active.as<int>(), vec);
       std::swap(b0, b1);
     }
-    CB_LAUNCH_PIX(cb_frame_kernel, N, n_act, b0, W, H, n_act, P.active.as<int>());
+    CB_LAUNCH_FRAME(b0, n_act, P.active.as<int>());
     if (ezc_status st = run_attempt(ctx, P, b0, W, H, n_act, pw, ph, dil)) return st;
     if (ezc_status st = sync_state(ctx, P, nb, h_state, list)) return st;
   }
@@ -1584,7 +1563,7 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
           CB_LAUNCH_PIX(cb_box_v_thresh_kernel, N, nf, P.eq.as<uint8_t>(), P.hsum.as<int>(), W, H, nf, P.refresh.as<int>(), P.block.as<int>(),
                     P.delta.as<int>(), tmp);
           for (int d = 0; d < dil; ++d) {
-            CB_LAUNCH_PIX(cb_dilate_kernel, N, nf, tmp, th, W, H, nf, P.refresh.as<int>());
+            CB_LAUNCH_CH(cb_morph16_kernel<true>, W, H, nf, tmp, (long long)W, N, vec, th, W, H, P.refresh.as<int>(), vec);
             CB_LAUNCH_PIX(cb_copy_active_kernel, N, nf, th, tmp, N, nf, P.refresh.as<int>());
           }
           CB_LAUNCH_PIX(cb_copy_active_kernel, N, nf, tmp, prevb, N, nf, P.refresh.as<int>());
@@ -1593,12 +1572,12 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
           // same block size as before: one more dilation of prev_thresh_img
           if (ezc_status st = upload_list(ctx, P.refresh, old)) return st;
           const int no = (int)old.size();
-          CB_LAUNCH_PIX(cb_dilate_kernel, N, no, prevb, tmp, W, H, no, P.refresh.as<int>());
+          CB_LAUNCH_CH(cb_morph16_kernel<true>, W, H, no, prevb, (long long)W, N, vec, tmp, W, H, P.refresh.as<int>(), vec);
           CB_LAUNCH_PIX(cb_copy_active_kernel, N, no, tmp, prevb, N, no, P.refresh.as<int>());
         }
         const int n_act = (int)list.size();
         CB_LAUNCH_PIX(cb_copy_active_kernel, N, n_act, prevb, th, N, n_act, P.active.as<int>());
-        CB_LAUNCH_PIX(cb_frame_kernel, N, n_act, th, W, H, n_act, P.active.as<int>());
+        CB_LAUNCH_FRAME(th, n_act, P.active.as<int>());
         // no edge-length compensation in the fallback (empirically what cv2 4.13 does: exact on all phase-2 fixtures)
         if (ezc_status st = run_attempt(ctx, P, th, W, H, n_act, pw, ph, 0)) return st;
         if (ezc_status st = sync_state(ctx, P, nb, h_state, list)) return st;

@@ -53,3 +53,26 @@ def gate_corpus(G):
         imgs.append(cv2.GaussianBlur(im, (0, 0), 3))
         imgs.append(np.clip(im.astype(np.int32) + rng.normal(0, 25, im.shape), 0, 255).astype(np.uint8))
     return imgs
+
+
+def ideal_board(S, shear=0.0, W=1400, H=900, ry=1.0):
+    """10x7 ideal (unblurred) squares of S px, optionally sheared / squashed: with `predilated` below this pins which
+    dilation level each attempt of the histogram phase works on ("First attempt")."""
+    img = np.full((H, W), 255, np.uint8)
+    x0, y0 = 150, 120
+    for r in range(7):
+        for c in range(10):
+            if (r + c) % 2 == 0:
+                pts = [(x0 + cx * S + shear * cy * S, y0 + cy * S * ry) for (cx, cy) in ((c, r), (c + 1, r), (c + 1, r + 1), (c, r + 1))]
+                cv2.fillConvexPoly(img, np.round(np.array(pts)).astype(np.int32), 0)
+    return img
+
+
+def predilated(img, levels):
+    """Yields (m, image dilated m times) for m in `levels`."""
+    cur, m = img.copy(), 0
+    for target in sorted(levels):
+        while m < target:
+            cur = cv2.dilate(cur, None, iterations=1)
+            m += 1
+        yield m, cur.copy()

@@ -75,6 +75,22 @@ def test_erased_outer_squares_match_cv2(name):
     assert n >= 15
 
 
+@pytest.mark.parametrize("S,shear,ry", [(30, 0.0, 1.0), (43, 0.0026, 1.0), (50, 0.0, 0.7)])
+def test_predilated_ideal_boards_fail_at_cv2s_level(S, shear, ry):
+    """Ideal boards dilated m times before the call: cv2 stops finding them at a level that depends on which image its
+    first attempt works on (the undilated one) and on the linking rule's distance bound; the restatement must stop at
+    the same m (45/45 boards on the full scan)."""
+    import cv2
+    from erased import FLAGS, ideal_board, predilated
+    seen = set()
+    for m, im in predilated(ideal_board(S, shear, ry=ry), range(int(S * ry) // 5, int(S * ry) // 3 + 2)):
+        ok_ref, _ = cv2.findChessboardCorners(im, (9, 6), flags=FLAGS)
+        ok, _ = P.find_chessboard_corners(im, (9, 6))
+        assert bool(ok) == bool(ok_ref), (S, shear, ry, m)
+        seen.add(bool(ok_ref))
+    assert seen == {True, False}   # the range brackets cv2's boundary
+
+
 def test_fast_check_restatement_matches_cv2():
     """CALIB_CB_FAST_CHECK: the restated checkChessboard equals the exported cv2.checkChessboard, and the restated search
     with the gate equals cv2.findChessboardCorners with the reference's full flag set (incl. boards only the gate rejects)."""

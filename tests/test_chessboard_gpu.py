@@ -80,6 +80,53 @@ def test_erased_outer_squares_match_cv2(ctx):
     assert n_found >= 40 and n_found < len(batch)   # both outcomes are exercised
 
 
+def test_predilated_ideal_boards_fail_at_cv2s_level(ctx):
+    """Ideal boards dilated m times before the call, levels around cv2's boundary: found flags must equal cv2's (pins the
+    undilated first attempt of the histogram phase and the linking rule's distance bound)."""
+    import sys
+    import cv2
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "cb_harness"))
+    from erased import FLAGS, ideal_board, predilated
+    from ezcalib_b200 import detect
+    batch, labels = [], []
+    for (S, shear, ry) in ((30, 0.0, 1.0), (43, 0.0026, 1.0), (50, 0.0, 0.7), (60, 0.0, 1.0)):
+        for m, im in predilated(ideal_board(S, shear, ry=ry), range(int(S * ry) // 5, int(S * ry) // 3 + 2)):
+            batch.append(im); labels.append((S, shear, ry, m))
+    imgs = detect.Images(ctx, np.stack(batch))
+    found, corners = detect.find_chessboard_corners(ctx, imgs, (9, 6), False)
+    imgs.close()
+    seen = set()
+    for k, im in enumerate(batch):
+        ok_ref, c_ref = cv2.findChessboardCorners(im, (9, 6), flags=FLAGS)
+        assert bool(found[k]) == bool(ok_ref), labels[k]
+        seen.add(bool(ok_ref))
+        if ok_ref:
+            assert np.abs(corners[k] - c_ref.reshape(-1, 2)).max() <= 0.01, labels[k]
+    assert seen == {True, False}
+
+
+def test_unaligned_width_matches_cv2(ctx):
+    """Image widths that are not multiples of 16 take the byte-load path of the 16-pixel row chunks: same answers."""
+    import cv2
+    from ezcalib_b200 import detect
+    cv2.ipp.setUseIPP(False)
+    FLAGS = cv2.CALIB_CB_ADAPTIVE_THRESH + cv2.CALIB_CB_NORMALIZE_IMAGE + cv2.CALIB_CB_FILTER_QUADS + cv2.CALIB_CB_FAST_CHECK
+    n_found = 0
+    for name, cut in (("render0", 3), ("warp2", 9), ("render1", 13)):
+        img = np.ascontiguousarray(G[name + "_img"][:-1, :-cut])
+        assert img.shape[1] % 16 != 0
+        imgs = detect.Images(ctx, img[None])
+        found, corners = detect.find_chessboard_corners(ctx, imgs, (9, 6), True, fast_check=True)
+        imgs.close()
+        ok_ref, c_ref = cv2.findChessboardCorners(img, (9, 6), flags=FLAGS)
+        assert bool(found[0]) == bool(ok_ref), name
+        if ok_ref:
+            c_ref = cv2.cornerSubPix(img, c_ref, (5, 5), (-1, -1), (cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_COUNT, 100, 0.05))
+            assert np.abs(corners[0] - c_ref.reshape(-1, 2)).max() <= 0.01, name
+            n_found += 1
+    assert n_found >= 2
+
+
 def test_fast_check_gate_matches_cv2(ctx):
     """CALIB_CB_FAST_CHECK on: found flags must equal cv2's with the reference's full flag set -- including the shrunk
     boards that the gate rejects although the search alone finds them -- and the gate must not change found corners."""
