@@ -30,19 +30,38 @@
 namespace ezc {
 
 // ---------------------------------------------------------------------------------------------- histogram binarisation
-__global__ void cb_hist_kernel(const uint8_t* __restrict__ img, long long pitch, long long istride, int W, int H, int* __restrict__ hist) {
-  __shared__ int sh[256];
+// 16-pixel chunks, one shared-memory histogram per warp (a chessboard image is bimodal: a single histogram serialises on
+// two bins), equal neighbouring pixels counted once
+__global__ void cb_hist_kernel(const uint8_t* __restrict__ img, long long pitch, long long istride, bool vec, int W, int H, int* __restrict__ hist) {
+  __shared__ int sh[8][256];
   const int im = blockIdx.y;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+  for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&sh[0][0])[i] = 0;
   __syncthreads();
-  const long long N = (long long)W * H;
+  int* mine = sh[threadIdx.x >> 5];
   const uint8_t* I = img + (long long)im * istride;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (long long)gridDim.x * blockDim.x) {
-    const int y = (int)(p / W), x = (int)(p - (long long)y * W);
-    atomicAdd(&sh[I[(long long)y * pitch + x]], 1);
+  const int cpr = (W + 15) >> 4, n_chunks = cpr * H;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_chunks; idx += gridDim.x * blockDim.x) {
+    const int y = idx / cpr, x0 = (idx - y * cpr) << 4;
+    const Chunk16 c = ld16(I + (long long)y * pitch, x0, W, vec, 0u);
+    const int n = W - x0 < 16 ? W - x0 : 16;
+    int prev = -1, cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (k < n) {
+        const int v = (c.w[k >> 2] >> (8 * (k & 3))) & 0xff;
+        if (v == prev) ++cnt;
+        else { if (cnt) atomicAdd(&mine[prev], cnt); prev = v; cnt = 1; }
+      }
+    }
+    if (cnt) atomicAdd(&mine[prev], cnt);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) if (sh[i]) atomicAdd(&hist[im * 256 + i], sh[i]);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w][i];
+    if (t) atomicAdd(&hist[im * 256 + i], t);
+  }
 }
 
 // icvBinarizationHistogramBased (calibinit.cpp): threshold from the smoothed histogram's maxima; one thread per image
@@ -644,13 +663,9 @@ __global__ void cb_fc_offset_kernel(FcComp* __restrict__ comps, int n, const int
   if (comps[c].offset >= 0) comps[c].offset = need_scan[c];
 }
 struct FcHyp { float size; int slot_class; };  // slot_class = image * 2 + class
-// convex hull (monotone chain on heap-sorted points) + min-area rectangle over the hull edges; emits a hypothesis
-__global__ void cb_fc_minrect_kernel(const FcComp* __restrict__ comps, int n_comp, cb::Pt* __restrict__ pool, long long N, int class_id,
-                                     FcHyp* __restrict__ hyps, int* __restrict__ n_hyps, int max_hyps) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_comp) return;
-  const FcComp& ci = comps[c];
-  if (ci.offset < 0) return;
+// convex hull (monotone chain on sorted points) + min-area rectangle over the hull edges; emits a hypothesis.
+// Serial version on global memory: only for components whose candidate list does not fit the block version below.
+__device__ void fc_minrect_serial(const FcComp& ci, cb::Pt* __restrict__ pool, double& bw_out, double& bh_out) {
   cb::Pt* a = pool + ci.offset;
   for (int k = 0; k < 8; ++k) a[ci.fill + k] = cb::Pt{ci.ex[k], ci.ey[k]};
   const int n = ci.fill + 8;
@@ -710,6 +725,115 @@ __global__ void cb_fc_minrect_kernel(const FcComp* __restrict__ comps, int n_com
         const bool along = (uy < 0 && ux >= 0) || (uy > 0 && ux <= 0);
         bw = along ? w : mh; bh = along ? mh : w;
       }
+    }
+  }
+  bw_out = bw; bh_out = bh;
+}
+// width / height of the min-area rectangle over hull h[0..k) (packed x << 16 | y) for edge e, as the serial version computes them
+__device__ __forceinline__ double fc_edge_rect(const uint32_t* __restrict__ h, int k, int e, double& bw, double& bh) {
+  const double px = (double)(h[e] >> 16), py = (double)(h[e] & 0xffffu);
+  const uint32_t qk = h[e + 1 == k ? 0 : e + 1];
+  const double ux = (double)(qk >> 16) - px, uy = (double)(qk & 0xffffu) - py;
+  const double len = sqrt(ux * ux + uy * uy);
+  const double cx = ux / len, cy = uy / len;
+  double mn = 0, mx = 0, mh = 0;
+  for (int i = 0; i < k; ++i) {
+    const double vx = (double)(h[i] >> 16) - px, vy = (double)(h[i] & 0xffffu) - py;
+    const double t = vx * cx + vy * cy, d = fabs(vy * cx - vx * cy);
+    mn = t < mn ? t : mn; mx = t > mx ? t : mx; mh = d > mh ? d : mh;
+  }
+  const double w = mx - mn;
+  const bool along = (uy < 0 && ux >= 0) || (uy > 0 && ux <= 0);
+  bw = along ? w : mh; bh = along ? mh : w;
+  return w * mh;
+}
+// One block per component: the candidates are sorted (bitonic, keys x << 16 | y) and the hull is built in shared memory,
+// the rectangles of the hull edges are evaluated in parallel; the first edge with the smallest area wins, as in the
+// sequential scan.  (A single thread on global memory needed up to 1.2 ms for one large blob.)
+constexpr int kFcSortCap = 4096;
+constexpr int kFcThreads = 64;
+__global__ void __launch_bounds__(kFcThreads) cb_fc_minrect_kernel(const FcComp* __restrict__ comps, int n_comp, cb::Pt* __restrict__ pool, long long N,
+                                                                   int class_id, int small_coords, FcHyp* __restrict__ hyps, int* __restrict__ n_hyps,
+                                                                   int max_hyps) {
+  const int c = blockIdx.x;
+  const FcComp& ci = comps[c];
+  if (ci.offset < 0) return;
+  __shared__ uint32_t key[kFcSortCap];
+  __shared__ uint32_t hull[kFcSortCap + 1];
+  __shared__ int s_k;
+  __shared__ double s_area[kFcThreads], s_bw[kFcThreads], s_bh[kFcThreads];
+  __shared__ int s_e[kFcThreads];
+  const int tid = threadIdx.x;
+  const int n = ci.fill + 8;
+  double bw = 0, bh = 0;
+  if (n > kFcSortCap || !small_coords) {
+    if (tid != 0) return;
+    fc_minrect_serial(ci, pool, bw, bh);
+  } else {
+    const cb::Pt* a = pool + ci.offset;
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int i = tid; i < m; i += kFcThreads) {
+      uint32_t kk = 0xffffffffu;
+      if (i < ci.fill) kk = ((uint32_t)a[i].x << 16) | (uint32_t)a[i].y;
+      else if (i < n) kk = ((uint32_t)ci.ex[i - ci.fill] << 16) | (uint32_t)ci.ey[i - ci.fill];
+      key[i] = kk;
+    }
+    __syncthreads();
+    for (int size = 2; size <= m; size <<= 1)
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = tid; t < (m >> 1); t += kFcThreads) {
+          const int lo = ((t / stride) * stride << 1) + (t % stride), hi = lo + stride;
+          const bool up = (lo & size) == 0;
+          const uint32_t x = key[lo], y = key[hi];
+          if ((x > y) == up) { key[lo] = y; key[hi] = x; }
+        }
+        __syncthreads();
+      }
+    if (tid == 0) {
+      auto cross = [](uint32_t o, uint32_t p, uint32_t q) {
+        return (long long)((int)(p >> 16) - (int)(o >> 16)) * ((int)(q & 0xffffu) - (int)(o & 0xffffu)) -
+               (long long)((int)(p & 0xffffu) - (int)(o & 0xffffu)) * ((int)(q >> 16) - (int)(o >> 16));
+      };
+      int k = 0;
+      for (int i = 0; i < n; ++i) {
+        if (i > 0 && key[i] == key[i - 1]) continue;
+        while (k >= 2 && cross(hull[k - 2], hull[k - 1], key[i]) <= 0) k--;
+        hull[k++] = key[i];
+      }
+      const int lower = k + 1;
+      for (int i = n - 2; i >= 0; --i) {
+        if (key[i] == key[i + 1]) continue;
+        while (k >= lower && cross(hull[k - 2], hull[k - 1], key[i]) <= 0) k--;
+        hull[k++] = key[i];
+      }
+      if (k > 1) k--;  // last point == first
+      s_k = k;
+    }
+    __syncthreads();
+    const int k = s_k;
+    double best = 1e300, bbw = 0, bbh = 0;
+    int best_e = 0x7fffffff;
+    if (k >= 3)
+      for (int e = tid; e < k; e += kFcThreads) {
+        double w_, h_;
+        const double area = fc_edge_rect(hull, k, e, w_, h_);
+        if (area < best) { best = area; bbw = w_; bbh = h_; best_e = e; }
+      }
+    s_area[tid] = best; s_bw[tid] = bbw; s_bh[tid] = bbh; s_e[tid] = best_e;
+    __syncthreads();
+    if (tid != 0) return;
+    if (k == 2) {
+      const double dx = (double)(hull[1] >> 16) - (double)(hull[0] >> 16), dy = (double)(hull[1] & 0xffffu) - (double)(hull[0] & 0xffffu);
+      const double len = sqrt(dx * dx + dy * dy);
+      const bool along = (dy < 0 && dx >= 0) || (dy > 0 && dx <= 0);
+      bw = along ? len : 0; bh = along ? 0 : len;
+    } else if (k >= 3) {
+      // the sequential scan keeps the FIRST edge with the strictly smallest area (it starts from best = 1e300)
+      double ba = 1e300;
+      int be = 0x7fffffff;
+      for (int t = 0; t < kFcThreads; ++t)
+        if (s_e[t] != 0x7fffffff && (s_area[t] < ba || (s_area[t] == ba && s_e[t] < be))) { ba = s_area[t]; be = s_e[t]; bw = s_bw[t]; bh = s_bh[t]; }
     }
   }
   const float fw = (float)bw, fh = (float)bh;
@@ -1383,7 +1507,10 @@ static ezc_status fc_round(ezc_context* ctx, CbPools& P, const uint8_t* white_sr
     EZC_CUDA(P.pool.reserve(sizeof(cb::Pt) * ((size_t)nPts + 16)));
     CB_LAUNCH(cb_fc_offset_kernel, nC, P.fc_comps.as<FcComp>(), nC, P.need.as<int>());
     CB_LAUNCH_CH(cb_fc_points16_kernel<1>, W, H, n_act, fg, P.labels.as<int>(), P.flags.as<int>(), W, H, list, vec, P.fc_comps.as<FcComp>(), P.pool.as<cb::Pt>());
-    CB_LAUNCH(cb_fc_minrect_kernel, nC, P.fc_comps.as<FcComp>(), nC, P.pool.as<cb::Pt>(), N, cls, P.fc_hyps.as<FcHyp>(), P.fc_count.as<int>(), max_hyps);
+    cb_fc_minrect_kernel<<<nC, kFcThreads, 0, ctx->stream>>>(P.fc_comps.as<FcComp>(), nC, P.pool.as<cb::Pt>(), N, cls, (W < 65536 && H < 65536) ? 1 : 0,
+                                                             P.fc_hyps.as<FcHyp>(), P.fc_count.as<int>(), max_hyps);
+    EZC_CUDA(cudaGetLastError());
+    ctx->kernel_launches++;
   }
   EZC_CUDA(cudaMemcpyAsync(P.h.p, P.fc_count.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   EZC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1494,18 +1621,18 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
   for (int i = 0; i < nb; ++i) list[i] = i;
   EZC_CUDA(cudaMemcpyAsync(P.state.p, h_state.data(), sizeof(ImageState) * nb, cudaMemcpyHostToDevice, ctx->stream));
   if (ezc_status st = upload_list(ctx, P.active, list)) return st;
+  const bool vec = (W % 16) == 0;   // packed working images: rows and images start 16-byte aligned
+  const bool vec_src = imgs->pitch % 16 == 0 && imgs->image_stride % 16 == 0 && ((uintptr_t)d_img & 15) == 0 && vec;
   EZC_CUDA(cudaMemsetAsync(P.hist.p, 0, sizeof(int) * 256 * nb, ctx->stream));
   {
     dim3 grid(std::max(1, std::min(64, (int)((N + 255) / 256))), nb);
-    cb_hist_kernel<<<grid, 256, 0, ctx->stream>>>(d_img, imgs->pitch, imgs->image_stride, W, H, P.hist.as<int>());
+    cb_hist_kernel<<<grid, 256, 0, ctx->stream>>>(d_img, imgs->pitch, imgs->image_stride, vec_src, W, H, P.hist.as<int>());
     EZC_CUDA(cudaGetLastError());
     ctx->kernel_launches++;
   }
   CB_LAUNCH(cb_select_threshold_kernel, nb, P.hist.as<int>(), nb, W, H, P.thresh.as<int>());
   uint8_t* b0 = P.bin0.as<uint8_t>();
   uint8_t* b1 = P.bin1.as<uint8_t>();
-  const bool vec = (W % 16) == 0;   // packed working images: rows and images start 16-byte aligned
-  const bool vec_src = imgs->pitch % 16 == 0 && imgs->image_stride % 16 == 0 && ((uintptr_t)d_img & 15) == 0 && vec;
   CB_LAUNCH_CH(cb_binarize16_kernel, W, H, nb, d_img, (long long)imgs->pitch, (long long)imgs->image_stride, vec_src, W, H, P.thresh.as<int>(),
                (const int*)nullptr, b0, vec);
   if (fast_check) {
