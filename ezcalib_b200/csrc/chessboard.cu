@@ -347,13 +347,20 @@ __global__ void cb_hole_need_kernel(const HoleInfo* __restrict__ holes, int n_ho
   if (h >= n_holes) return;
   need[h] = (holes[h].offset >= 0 && holes[h].n_pts > 0) ? 3 * holes[h].n_pts + 8 : 0;  // contour + 2 approx buffers
 }
-__global__ void cb_hole_offset_kernel(HoleInfo* __restrict__ holes, int n_holes, const int* __restrict__ need_scan) {
+constexpr int kWarpContour = 96;    // up to here: one thread per hole (cb_quad_kernel)
+constexpr int kWarpContourMid = 512;  // up to here: a warp with 512-vertex buffers, beyond: kMaxContourPts-vertex buffers
+// pool offsets; holes with long contours go to the work lists of the warp kernels (counts[0] / counts[1])
+__global__ void cb_hole_offset_kernel(HoleInfo* __restrict__ holes, int n_holes, const int* __restrict__ need_scan, int* __restrict__ list_mid,
+                                      int* __restrict__ list_big, int* __restrict__ counts) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= n_holes) return;
-  if (holes[h].offset >= 0) holes[h].offset = need_scan[h];
+  if (holes[h].offset < 0) return;
+  holes[h].offset = need_scan[h];
+  const int n = holes[h].n_pts;
+  if (n > kWarpContourMid) list_big[atomicAdd(&counts[1], 1)] = h;
+  else if (n > kWarpContour) list_mid[atomicAdd(&counts[0], 1)] = h;
 }
 // approxPolyDP levels 1..7 + convexity + FILTER_QUADS tests: one thread per hole (contours up to kWarpContour vertices)
-constexpr int kWarpContour = 96;
 __global__ void cb_quad_kernel(HoleInfo* __restrict__ holes, int n_holes, cb::Pt* __restrict__ pool, int* __restrict__ stack_pool) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= n_holes) return;
@@ -503,14 +510,9 @@ __device__ int approx_poly_dp_closed_warp(const cb::Pt* src, int count, cb::Pt* 
 // Two capacity classes (shared memory per block decides how many contours an SM works on at once): CAP = 512 holds the
 // bulk, CAP = kMaxContourPts the few giants; LO is the exclusive lower bound of the class.
 template <int CAP> constexpr size_t quad_warp_smem() { return 2 * sizeof(cb::Pt) * (CAP + 4) + sizeof(unsigned short) * (4 * CAP + 16); }
-template <int CAP, int LO>
-__global__ void __launch_bounds__(32) cb_quad_warp_kernel(HoleInfo* __restrict__ holes, int n_holes, cb::Pt* __restrict__ pool) {
-  extern __shared__ __align__(16) unsigned char qw_smem[];
-  const int h = blockIdx.x;
+template <int CAP>
+__device__ void quad_warp_one(HoleInfo& hi, const cb::Pt* __restrict__ pool, unsigned char* qw_smem) {
   const int lane = threadIdx.x;
-  if (h >= n_holes) return;
-  HoleInfo& hi = holes[h];
-  if (hi.offset < 0 || hi.n_pts <= LO || hi.n_pts > CAP) return;
   const int n = hi.n_pts;
   const cb::Pt* c = pool + hi.offset;
   cb::Pt* ta = reinterpret_cast<cb::Pt*>(qw_smem);
@@ -539,6 +541,18 @@ __global__ void __launch_bounds__(32) cb_quad_warp_kernel(HoleInfo* __restrict__
       hi.quad_ok = 1;
       for (int i = 0; i < 4; ++i) hi.quad[i] = q[i];
     }
+  }
+}
+// The holes with more than kWarpContour vertices are few among possibly 10^5 holes of a noisy threshold image: they are
+// collected in two work lists (cb_hole_offset_kernel) and a fixed grid of warps walks each list.
+template <int CAP>
+__global__ void __launch_bounds__(32) cb_quad_warp_kernel(HoleInfo* __restrict__ holes, const int* __restrict__ list, const int* __restrict__ count,
+                                                          const cb::Pt* __restrict__ pool) {
+  extern __shared__ __align__(16) unsigned char qw_smem[];
+  const int n = *count;
+  for (int it = blockIdx.x; it < n; it += gridDim.x) {
+    quad_warp_one<CAP>(holes[list[it]], pool, qw_smem);
+    __syncwarp();
   }
 }
 
@@ -1219,15 +1233,19 @@ __global__ void cb_equalize_lut_kernel(const int* __restrict__ hist_all, int n_i
     lut[i] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
   }
 }
-__global__ void cb_apply_lut_kernel(const uint8_t* __restrict__ img, long long pitch, long long istride, int W, int H, int n_img,
-                                    const uint8_t* __restrict__ lut, uint8_t* __restrict__ out) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long N = (long long)W * H;
-  if (gid >= N * n_img) return;
-  const int im = (int)(gid / N);
-  const int p = (int)(gid - (long long)im * N);
-  const int y = p / W, x = p - y * W;
-  out[gid] = lut[im * 256 + img[(long long)im * istride + (long long)y * pitch + x]];
+__global__ void cb_apply_lut_kernel(const uint8_t* __restrict__ img, long long pitch, long long istride, bool vec_src, int W, int H,
+                                    const int* __restrict__ active, const uint8_t* __restrict__ lut, uint8_t* __restrict__ out, bool vec_dst) {
+  const ChunkPos c = chunk_pos(W, H);
+  if (!c.ok) return;
+  const int im = active ? active[blockIdx.y] : (int)blockIdx.y;
+  Chunk16 v = ld16(img + (long long)im * istride + (long long)c.y * pitch, c.x0, W, vec_src, 0u);
+  const uint8_t* T = lut + im * 256;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t w = v.w[k];
+    v.w[k] = (uint32_t)T[w & 0xff] | ((uint32_t)T[(w >> 8) & 0xff] << 8) | ((uint32_t)T[(w >> 16) & 0xff] << 16) | ((uint32_t)T[w >> 24] << 24);
+  }
+  st16(out + ((long long)im * H + c.y) * W, c.x0, W, vec_dst, v);
 }
 // cv::adaptiveThreshold(MEAN_C, BINARY): separable box sums with replicated border, per-image block size
 __global__ void cb_box_h_kernel(const uint8_t* __restrict__ src, int W, int H, int n_img, const int* __restrict__ list,
@@ -1305,6 +1323,7 @@ struct CbPools {
   DevBuf works, scratch, state, active, corners, found, block, delta, hsum, sub_corners, sub_idx, refresh;
   DevBuf pcnt, plast;   // per-pixel-label quad counters (kept zero between attempts)
   DevBuf blk_cnt, blk_off;   // roots per block of the chunk grid and their exclusive scan
+  DevBuf qlist, qcount;      // work lists of the holes with long contours
   DevBuf fc_w0, fc_w1, fc_w2, fc_k0, fc_k1, fc_k2, fc_fg, fc_comps, fc_hyps, fc_count, fc_list;
   HostPinned fc_h;
   HostPinned h;
@@ -1396,20 +1415,26 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
     const int nPts = *P.h.as<int>();
     EZC_CUDA(P.pool.reserve(sizeof(cb::Pt) * ((size_t)nPts + 16)));
     EZC_CUDA(P.stack_pool.reserve(sizeof(int) * 2 * ((size_t)nPts + 16)));
-    CB_LAUNCH(cb_hole_offset_kernel, nH, P.holes.as<HoleInfo>(), nH, P.need.as<int>());
+    EZC_CUDA(P.qlist.reserve(sizeof(int) * 2 * (size_t)nH)); EZC_CUDA(P.qcount.reserve(64));
+    EZC_CUDA(cudaMemsetAsync(P.qcount.p, 0, 2 * sizeof(int), ctx->stream));
+    int* list_mid = P.qlist.as<int>();
+    int* list_big = list_mid + nH;
+    CB_LAUNCH(cb_hole_offset_kernel, nH, P.holes.as<HoleInfo>(), nH, P.need.as<int>(), list_mid, list_big, P.qcount.as<int>());
     CB_LAUNCH(cb_trace_kernel<true>, nH, bin, P.labels.as<int>(), W, H, nH, P.holes.as<HoleInfo>(), P.pool.as<cb::Pt>(), cb::kMaxContourPts);
     CB_LAUNCH(cb_quad_kernel, nH, P.holes.as<HoleInfo>(), nH, P.pool.as<cb::Pt>(), P.stack_pool.as<int>());
     {
       static bool qw_attr = false;
       if (!qw_attr) {
-        EZC_CUDA(cudaFuncSetAttribute(cb_quad_warp_kernel<cb::kMaxContourPts, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        EZC_CUDA(cudaFuncSetAttribute(cb_quad_warp_kernel<cb::kMaxContourPts>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)quad_warp_smem<cb::kMaxContourPts>()));
         qw_attr = true;
       }
-      cb_quad_warp_kernel<512, kWarpContour><<<nH, 32, quad_warp_smem<512>(), ctx->stream>>>(P.holes.as<HoleInfo>(), nH, P.pool.as<cb::Pt>());
+      const int g_mid = std::min(nH, ctx->sm_count * 16), g_big = std::min(nH, ctx->sm_count * 3);
+      cb_quad_warp_kernel<kWarpContourMid><<<g_mid, 32, quad_warp_smem<kWarpContourMid>(), ctx->stream>>>(P.holes.as<HoleInfo>(), list_mid,
+                                                                                                          P.qcount.as<int>(), P.pool.as<cb::Pt>());
       EZC_CUDA(cudaGetLastError());
-      cb_quad_warp_kernel<cb::kMaxContourPts, 512><<<nH, 32, quad_warp_smem<cb::kMaxContourPts>(), ctx->stream>>>(P.holes.as<HoleInfo>(), nH,
-                                                                                                              P.pool.as<cb::Pt>());
+      cb_quad_warp_kernel<cb::kMaxContourPts><<<g_big, 32, quad_warp_smem<cb::kMaxContourPts>(), ctx->stream>>>(
+          P.holes.as<HoleInfo>(), list_big, P.qcount.as<int>() + 1, P.pool.as<cb::Pt>());
       EZC_CUDA(cudaGetLastError());
       ctx->kernel_launches += 2;
     }
@@ -1660,7 +1685,8 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
     EZC_CUDA(P.eq.reserve(total)); EZC_CUDA(P.lut.reserve(256 * nb)); EZC_CUDA(P.prevbin.reserve(total));
     EZC_CUDA(P.block.reserve(sizeof(int) * nb)); EZC_CUDA(P.delta.reserve(sizeof(int) * nb)); EZC_CUDA(P.hsum.reserve(sizeof(int) * total));
     CB_LAUNCH(cb_equalize_lut_kernel, nb, P.hist.as<int>(), nb, (int)N, P.lut.as<uint8_t>());
-    CB_LAUNCH(cb_apply_lut_kernel, total, d_img, imgs->pitch, imgs->image_stride, W, H, nb, P.lut.as<uint8_t>(), P.eq.as<uint8_t>());
+    CB_LAUNCH_CH(cb_apply_lut_kernel, W, H, (int)list.size(), d_img, (long long)imgs->pitch, (long long)imgs->image_stride, vec_src, W, H, P.active.as<int>(),
+                 P.lut.as<uint8_t>(), P.eq.as<uint8_t>(), vec);   // only the images that enter the fallback
     std::vector<int> h_block(nb, 0), h_delta(nb, 0), prev_block(nb, -1);
     for (int i = 0; i < nb; ++i) h_state[i].prev_sqr_size = 0;  // prev_sqr_size restarts at 0 with the fallback
     EZC_CUDA(cudaMemcpyAsync(P.state.p, h_state.data(), sizeof(ImageState) * nb, cudaMemcpyHostToDevice, ctx->stream));
@@ -1731,7 +1757,8 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
     EZC_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < nb; ++i) if (!h_phase2[i]) std::copy(&ident[(size_t)i * 256], &ident[(size_t)i * 256] + 256, &h_lut[(size_t)i * 256]);
     EZC_CUDA(cudaMemcpyAsync(P.lut.p, h_lut.data(), 256 * (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
-    CB_LAUNCH(cb_apply_lut_kernel, total, d_img, imgs->pitch, imgs->image_stride, W, H, nb, P.lut.as<uint8_t>(), P.eq.as<uint8_t>());
+    CB_LAUNCH_CH(cb_apply_lut_kernel, W, H, nb, d_img, (long long)imgs->pitch, (long long)imgs->image_stride, vec_src, W, H, (const int*)nullptr,
+                 P.lut.as<uint8_t>(), P.eq.as<uint8_t>(), vec);
     view.d = P.eq.as<uint8_t>(); view.pitch = W; view.image_stride = N;
   }
   if (ezc_status st = subpix_device(ctx, &view, P.sub_corners.as<float2>(), P.sub_idx.as<int>(), nb * npts, 2, 2, 15, 0.1)) return st;
