@@ -276,6 +276,9 @@ struct HoleInfo {
   cb::Pt quad[4];
 };
 
+// chain-code direction s -> (dx, dy) = ({1,1,0,-1,-1,-1,0,1}, {0,-1,-1,-1,0,1,1,1}) from 2-bit packed tables
+__device__ __forceinline__ int dir_dx(int s) { return (int)((0x901Au >> (2 * s)) & 3u) - 1; }
+__device__ __forceinline__ int dir_dy(int s) { return (int)((0xA901u >> (2 * s)) & 3u) - 1; }
 template <bool STORE>
 __global__ void cb_trace_kernel(const uint8_t* __restrict__ bin, const int* __restrict__ L, int W, int H, int n_holes,
                                 HoleInfo* __restrict__ holes, cb::Pt* __restrict__ pool, int max_pts) {
@@ -293,12 +296,12 @@ __global__ void cb_trace_kernel(const uint8_t* __restrict__ bin, const int* __re
   int n = 0, minx = x0, maxx = x0, miny = y0, maxy = y0;
   cb::Pt* out = STORE ? pool + hi.offset : nullptr;
   int s = 0, s_end = 0;
-  do { s = (s - 1) & 7; } while (!val(x0 + DX[s], y0 + DY[s]) && s != s_end);
-  if (s == s_end && !val(x0 + DX[s], y0 + DY[s])) {
+  do { s = (s - 1) & 7; } while (!val(x0 + dir_dx(s), y0 + dir_dy(s)) && s != s_end);
+  if (s == s_end && !val(x0 + dir_dx(s), y0 + dir_dy(s))) {
     if (STORE) out[0] = cb::Pt{x0, y0};
     n = 1;
   } else {
-    const int i1x = x0 + DX[s], i1y = y0 + DY[s];
+    const int i1x = x0 + dir_dx(s), i1y = y0 + dir_dy(s);
     int i3x = x0, i3y = y0, prev_s = s ^ 4;
     int x = x0, y = y0;
     for (;;) {
@@ -310,15 +313,16 @@ __global__ void cb_trace_kernel(const uint8_t* __restrict__ bin, const int* __re
       const int s1 = (s + 1) & 7;
       const unsigned rot = ((m8 | (m8 << 8)) >> s1) & 0xffu;
       s = s1 + (__ffs(rot) - 1);   // rot != 0: the pixel we came from is foreground
-      const int i4x = i3x + DX[s & 7], i4y = i3y + DY[s & 7];
       s &= 7;
+      const int sdx = dir_dx(s), sdy = dir_dy(s);   // arithmetic table: an indexed local array costs a local-memory load per step
+      const int i4x = i3x + sdx, i4y = i3y + sdy;
       if (s != prev_s) {
         if (STORE) { if (n < hi.n_pts) out[n] = cb::Pt{x, y}; }
         ++n;
         minx = x < minx ? x : minx; maxx = x > maxx ? x : maxx; miny = y < miny ? y : miny; maxy = y > maxy ? y : maxy;
         prev_s = s;
       }
-      x += DX[s]; y += DY[s];
+      x += sdx; y += sdy;
       if (i4x == x0 && i4y == y0 && i3x == i1x && i3y == i1y) break;
       i3x = i4x; i3y = i4y;
       s = (s + 4) & 7;
@@ -1387,7 +1391,7 @@ ezc_status upload_list(ezc_context* ctx, DevBuf& buf, const std::vector<int>& li
 // framed) -> processQuads.  Per-pixel buffers are indexed by the REAL image index; only the hole flags are compact.
 ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, int H, int n_act, int pw, int ph, int dilations) {
   if (n_act <= 0) return EZC_OK;
-  const long long N = (long long)W * H, total = N * n_act;
+  const long long N = (long long)W * H;
   const int* list = P.active.as<int>();
   int* d_tot = P.total.as<int>();
   const bool vec = (W % 16) == 0;
