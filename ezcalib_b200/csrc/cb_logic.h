@@ -222,22 +222,23 @@ CB_HD inline bool contour_to_quad(const Pt* contour, int n, Pt* tmp_a, Pt* tmp_b
   }
   const int min_area = 25;
   if ((maxx - minx + 1) * (maxy - miny + 1) < min_area) return false;
-  // OpenCV 4.13 behaviour (checked against cv2 vertex by vertex): every level works on the OUTPUT of the previous
-  // level (and each level is applied twice), not on the original contour.
-  int na = n;
-  const Pt* cur = contour;
+  // OpenCV 4.13 behaviour, pinned on refined corners that are bit-identical to cv2's only this way (tests/test_cb_logic.py):
+  // every level approximates twice -- the contour, then its own output -- and a 4-gon from either call ends the search;
+  // the NEXT level starts from the output of this level's FIRST call (not from the original contour, and not from the
+  // second call's output).  Two buffers suffice: the second call may overwrite the first call's input.
+  const Pt* src = contour;
+  int nsrc = n;
+  Pt* A = tmp_a;
+  Pt* B = tmp_b;
   for (int level = 1; level <= kMaxApproxLevel; level++) {
-    int nb = approx_poly_dp_closed(cur, na, tmp_b, (double)(float)level, stack_buf);
-    for (int i = 0; i < nb; ++i) tmp_a[i] = tmp_b[i];
-    na = nb; cur = tmp_a;
-    if (na == 4) break;
-    nb = approx_poly_dp_closed(tmp_a, na, tmp_b, (double)(float)level, stack_buf);
-    for (int i = 0; i < nb; ++i) tmp_a[i] = tmp_b[i];
-    na = nb;
-    if (na == 4) break;
+    const int nf = approx_poly_dp_closed(src, nsrc, A, (double)(float)level, stack_buf);
+    if (nf == 4) return quad_from_4(A, q);
+    const int ns = approx_poly_dp_closed(A, nf, B, (double)(float)level, stack_buf);
+    if (ns == 4) return quad_from_4(B, q);
+    src = A; nsrc = nf;
+    Pt* t = A; A = B; B = t;
   }
-  if (na != 4) return false;
-  return quad_from_4(tmp_a, q);
+  return false;
 }
 
 // add a quad (generateQuads, second loop)

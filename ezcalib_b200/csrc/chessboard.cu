@@ -523,25 +523,27 @@ __device__ void quad_warp_one(HoleInfo& hi, const cb::Pt* __restrict__ pool, uns
   cb::Pt* tb = ta + CAP + 4;
   unsigned short* stack = reinterpret_cast<unsigned short*>(tb + CAP + 4);
   // cb::contour_to_quad with the warp-parallel approximation; the bounding-box test already passed in cb_trace_kernel
-  int na = n;
   for (int i = lane; i < n; i += 32) ta[i] = c[i];
   __syncwarp();
-  for (int level = 1; level <= cb::kMaxApproxLevel; level++) {
-    int nb = approx_poly_dp_closed_warp(ta, na, tb, (double)(float)level, stack);
-    for (int i = lane; i < nb; i += 32) ta[i] = tb[i];
+  // same schedule as cb::contour_to_quad: first call on the previous level's first output, second call on its own output
+  cb::Pt* X = ta;   // input of this level's first call
+  cb::Pt* Y = tb;
+  int nx = n;
+  const cb::Pt* fin = nullptr;
+  for (int level = 1; level <= cb::kMaxApproxLevel && !fin; level++) {
+    const int nf = approx_poly_dp_closed_warp(X, nx, Y, (double)(float)level, stack);
     __syncwarp();
-    na = nb;
-    if (na == 4) break;
-    nb = approx_poly_dp_closed_warp(ta, na, tb, (double)(float)level, stack);
-    for (int i = lane; i < nb; i += 32) ta[i] = tb[i];
+    if (nf == 4) { fin = Y; break; }
+    const int ns = approx_poly_dp_closed_warp(Y, nf, X, (double)(float)level, stack);
     __syncwarp();
-    na = nb;
-    if (na == 4) break;
+    if (ns == 4) { fin = X; break; }
+    cb::Pt* t = X; X = Y; Y = t;
+    nx = nf;
   }
-  if (na != 4) return;
+  if (!fin) return;
   if (lane == 0) {
     cb::Pt q[4];
-    if (cb::quad_from_4(ta, q)) {
+    if (cb::quad_from_4(fin, q)) {
       hi.quad_ok = 1;
       for (int i = 0; i < 4; ++i) hi.quad[i] = q[i];
     }

@@ -91,6 +91,21 @@ def test_predilated_ideal_boards_fail_at_cv2s_level(S, shear, ry):
     assert seen == {True, False}   # the range brackets cv2's boundary
 
 
+def test_approx_schedule_pinned_on_shifted_views():
+    """Two shifted views where one quad's approxPolyDP levels matter: the refined corners equal cv2's bit for bit only if
+    each level's first call starts from the previous level's FIRST output (cumulative second outputs: one corner off by
+    0.04 px; always from the original contour: other fixtures break)."""
+    import cv2
+    from erased import FLAGS, gate_corpus
+    cv2.ipp.setUseIPP(False)
+    imgs = gate_corpus(G)
+    for k in (0, 12, 13, 16, 18):
+        ok_ref, c_ref = cv2.findChessboardCorners(imgs[k], (9, 6), flags=FLAGS)
+        ok, c = P.find_chessboard_corners(imgs[k], (9, 6))
+        assert ok and ok_ref
+        assert np.array_equal(c, c_ref.reshape(-1, 2)), k
+
+
 def test_fast_check_restatement_matches_cv2():
     """CALIB_CB_FAST_CHECK: the restated checkChessboard equals the exported cv2.checkChessboard, and the restated search
     with the gate equals cv2.findChessboardCorners with the reference's full flag set (incl. boards only the gate rejects)."""

@@ -154,6 +154,6 @@ def test_fast_check_gate_matches_cv2(ctx):
             n_close += int(np.abs(c_gate[k] - c_ref.reshape(-1, 2)).max() <= 0.01)
             assert np.array_equal(c_gate[k], c_full[k])   # the gate never changes a found board
     assert changed >= 1           # the corpus contains boards only the gate rejects
-    # raw corners: identical attempt and quads on all but the hardest views (shrunk board found in the fallback phase,
-    # one shifted view differing by 0.04 px at one corner) -- DESIGN.md section 4b
-    assert n_close >= n_found - 3, (n_close, n_found)
+    # raw corners: identical attempt and quads on all but one view (a 0.3-scale board found in the fallback phase, whose
+    # squares are 8 px: cv2 finds it from a threshold image this restatement does not reproduce) -- DESIGN.md section 4b
+    assert n_close >= n_found - 1, (n_close, n_found)
