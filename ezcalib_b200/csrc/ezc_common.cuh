@@ -112,16 +112,53 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Pinned host buffers are expensive to create (cudaMallocHost / cudaFreeHost take milliseconds -- more than the 80 MB
+// observation upload of a solver): released buffers are kept, like the device blocks above.
+struct HostCache {
+  std::mutex m;
+  std::multimap<size_t, void*> blocks;
+  size_t bytes = 0;
+  size_t limit = size_t(256) << 20;
+  void* take(size_t want, size_t& got) {
+    std::lock_guard<std::mutex> g(m);
+    auto it = blocks.lower_bound(want);
+    if (it == blocks.end() || it->first > 2 * want + 4096) return nullptr;
+    void* p = it->second;
+    got = it->first;
+    bytes -= it->first;
+    blocks.erase(it);
+    return p;
+  }
+  bool give(void* p, size_t sz) {
+    std::lock_guard<std::mutex> g(m);
+    if (bytes + sz > limit) return false;
+    blocks.emplace(sz, p);
+    bytes += sz;
+    return true;
+  }
+};
+inline HostCache& host_cache() {
+  static HostCache* c = new HostCache;  // intentionally leaked
+  return *c;
+}
 struct HostPinned {
   void* p = nullptr;
   size_t cap = 0;
-  ~HostPinned() { if (p) cudaFreeHost(p); }
+  HostPinned() = default;
+  HostPinned(const HostPinned&) = delete;
+  HostPinned& operator=(const HostPinned&) = delete;
+  ~HostPinned() { release(); }
+  void release() {
+    if (p && !host_cache().give(p, cap)) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+  }
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr; cap = 0;
+    release();
+    size_t got = 0;
+    if (void* q = host_cache().take(bytes, got)) { p = q; cap = got; return cudaSuccess; }
     cudaError_t e = cudaMallocHost(&p, bytes);
-    if (e == cudaSuccess) cap = bytes;
+    if (e == cudaSuccess) cap = bytes; else p = nullptr;
     return e;
   }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }

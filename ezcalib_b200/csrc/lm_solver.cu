@@ -25,6 +25,7 @@
 //                   iteration's normal equations already exist (speculative evaluation).
 // Accept / reject, radius update and termination follow Ceres' TrustRegionMinimizer on the host.
 #include <algorithm>
+#include <chrono>
 #include <cfloat>
 #include <cmath>
 #include <limits>
@@ -864,8 +865,11 @@ ezc_status create_common(ezc_context* ctx, const ezc_lm_problem* p, bool device_
   s->nd = num_dist(p->model);
   s->kfull = s->nf + 2 + s->nd;
   s->per_block_cam = p->cams_per_block != 0;
+  const bool timing = getenv("EZC_LM_TIMING") != nullptr;
+  const auto tc0 = std::chrono::steady_clock::now();
   ezc_status st = alloc_state(s);
   if (st != EZC_OK) { delete s; return st; }
+  if (timing) { cudaStreamSynchronize(ctx->stream); fprintf(stderr, "[lm create] alloc_state %.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count()); }
   const size_t n_obs = (size_t)p->n_blocks * p->obs_per_block;
   if (device_ptrs) {
     s->d_obs = reinterpret_cast<const float2*>(p->obs);
@@ -880,6 +884,7 @@ ezc_status create_common(ezc_context* ctx, const ezc_lm_problem* p, bool device_
     s->d_obs = s->obs_buf.as<float2>();
     s->d_pts = s->pts_buf.as<double>();
   }
+  if (timing) fprintf(stderr, "[lm create] total %.3f ms (%zu observation bytes)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count(), n_obs * sizeof(float2));
   *out = s;
   return EZC_OK;
 }
