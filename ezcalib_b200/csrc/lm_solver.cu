@@ -771,6 +771,7 @@ struct ezc_lm_solver {
   DevBuf part, cost_part, scale_p, diag_p, lyz, step_p;
   DevBuf part2, part3, red2, gmaxbuf, rmse, dbg;
   HostPinned h_red;
+  HostPinned h_stage;   // pose download staging for pageable destinations
   // state of the current variable pattern
   int k = 0, NT = 2, DA = 8;
   int cols[kMaxK];
@@ -1026,8 +1027,16 @@ ezc_status ezc_lm_set_params(ezc_lm_solver* s, const double* focal, const double
     for (int i = 0; i < s->nd; ++i) s->cam.dist[i] = dist[i];
   }
   s->cur = 0;
+  const bool timing = getenv("EZC_LM_TIMING") != nullptr;
+  const auto ts0 = std::chrono::steady_clock::now();
   if (nb) EZC_CUDA(cudaMemcpyAsync(s->poses[0].p, poses, sizeof(double) * 7 * nb, cudaMemcpyHostToDevice, s->ctx->stream));
   EZC_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  if (timing) {
+    cudaPointerAttributes at{};
+    cudaPointerGetAttributes(&at, poses);
+    fprintf(stderr, "[lm set_params] pose upload %.3f ms (%zu bytes, host memory type %d)\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count(), sizeof(double) * 7 * (size_t)nb, (int)at.type);
+  }
   s->have_params = true;
   return EZC_OK;
 }
@@ -1048,8 +1057,20 @@ ezc_status ezc_lm_get_params(ezc_lm_solver* s, double* focal, double* pp, double
     if (dist) for (int i = 0; i < s->nd; ++i) dist[i] = s->cam.dist[i];
   }
   if (poses && nb) {
-    EZC_CUDA(cudaMemcpyAsync(poses, s->poses[s->cur].p, sizeof(double) * 7 * nb, cudaMemcpyDeviceToHost, s->ctx->stream));
+    // a pageable destination makes the driver stage the copy at a fraction of the link rate: stage it ourselves through
+    // a (cached) pinned buffer and finish with a host memcpy
+    const size_t bytes = sizeof(double) * 7 * (size_t)nb;
+    cudaPointerAttributes at{};
+    const bool pinned = cudaPointerGetAttributes(&at, poses) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    void* dst = poses;
+    if (!pinned) {
+      EZC_CUDA(s->h_stage.reserve(bytes));
+      dst = s->h_stage.p;
+    }
+    EZC_CUDA(cudaMemcpyAsync(dst, s->poses[s->cur].p, bytes, cudaMemcpyDeviceToHost, s->ctx->stream));
     EZC_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    if (!pinned) std::memcpy(poses, dst, bytes);
   }
   return EZC_OK;
 }

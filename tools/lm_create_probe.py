@@ -15,7 +15,7 @@ for rep in range(4):
     torch.cuda.synchronize(); t0=time.perf_counter()
     s2 = lm.LmSolver(ctx, mid, True, obs_pin.numpy(), P.target, P.width, P.height)
     torch.cuda.synchronize(); t1=time.perf_counter()
-    s2.set_params(P.focal_init, P.pp_init, P.dist_init, poses_pin.numpy())
+    ta=time.perf_counter(); s2.set_params(P.focal_init, P.pp_init, P.dist_init, poses_pin.numpy()); tb=time.perf_counter(); print('set_params wall %.3f ms'%(1e3*(tb-ta)), poses_pin.dtype, poses_pin.is_pinned())
     summ2,_ = s2.solve(max_num_iterations=10, **fixed)
-    out = s2.get_params(); s2.close()
+    tc=time.perf_counter(); out = s2.get_params(); td=time.perf_counter(); print('get_params wall %.3f ms'%(1e3*(td-tc))); s2.close()
     torch.cuda.synchronize(); print('rep',rep,'create %.3f ms total %.3f ms'%(1e3*(t1-t0),1e3*(time.perf_counter()-t0)), flush=True)
