@@ -1794,10 +1794,14 @@ ezc_status ezc_find_chessboard_corners_batch(ezc_context* ctx, const ezc_images*
   const int n = imgs->n;
   if (n == 0) return EZC_OK;
   const long long N = (long long)imgs->width * imgs->height;
-  // images in flight: ~31 B/px of per-pixel scratch (binary images, labels, flags, parent counters, gate images), bounded to
-  // ~16 GiB of the 180 GB.  Large sub-batches matter: a view that passes the gate and fails the search runs its 56
-  // attempts in ~0.4 s while the rest of its sub-batch is long done, so the fewer sub-batches the fewer serial tails.
-  int sub = (int)std::max<long long>(1, std::min<long long>((1LL << 30) / N, 8LL * 1024 * 1024 * 1024 / (N * 16)));
+  // images in flight: ~32 B/px of per-pixel scratch (binary images, labels, component ids, parent counters, gate images),
+  // bounded to 48 GiB and to half of what the device has free (180 GB HBM).  Large sub-batches matter: a view that passes
+  // the gate and fails the search runs its 56 attempts in ~0.16 s while the rest of its sub-batch is long done, so the
+  // fewer sub-batches the fewer serial tails.  (2^30 pixels per sub-batch keeps linear pixel indices in 32 bits.)
+  size_t free_b = 0, total_b = 0;
+  EZC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const long long budget = std::min<long long>(48LL << 30, (long long)((free_b + ezc::dev_cache().bytes) / 2));
+  int sub = (int)std::max<long long>(1, std::min<long long>((1LL << 30) / N, budget / (N * 32)));
   sub = std::min(sub, 512);
   if (max_images_in_flight > 0) sub = std::min(sub, max_images_in_flight);
   sub = std::min(sub, n);
@@ -1806,7 +1810,7 @@ ezc_status ezc_find_chessboard_corners_batch(ezc_context* ctx, const ezc_images*
   EZC_CUDA(d_corners.reserve(sizeof(float2) * (size_t)n * npts));
   EZC_CUDA(d_found.reserve((size_t)n));
   // No sub-batch ramp under ezc_images_upload_async here (unlike the AprilGrid path): a chessboard sub-batch costs ~10x its
-  // upload time and every extra sub-batch risks another serial tail, so waiting ~15 ms for the first 256 images is cheaper.
+  // upload time and every extra sub-batch risks another serial tail, so waiting for the upload of the first sub-batch is cheaper.
   for (int i0 = 0; i0 < n; i0 += sub) {
     const int nb = std::min(sub, n - i0);
     if (ezc_status st = detect_sub_batch(ctx, imgs, i0, nb, pattern_w, pattern_h, final_subpix != 0, fast_check != 0, d_corners.as<float2>(), d_found.as<uint8_t>()))
