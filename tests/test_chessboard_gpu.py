@@ -127,6 +127,39 @@ def test_unaligned_width_matches_cv2(ctx):
     assert n_found >= 2
 
 
+def test_occluding_discs_match_cv2(ctx):
+    """A gray disc painted over the first corner (darker than, equal to and brighter than the binarisation threshold), at
+    the fixture size and upscaled 2x: found flags and corners must equal cv2's with the reference's flags."""
+    import cv2
+    from ezcalib_b200 import detect
+    cv2.ipp.setUseIPP(False)
+    FLAGS = cv2.CALIB_CB_ADAPTIVE_THRESH + cv2.CALIB_CB_NORMALIZE_IMAGE + cv2.CALIB_CB_FILTER_QUADS + cv2.CALIB_CB_FAST_CHECK
+    outcomes = set()
+    for scale in (1, 2):
+        batch, labels = [], []
+        for name in ("render0", "warp2"):
+            base = G[name + "_img"]
+            ok, c = cv2.findChessboardCorners(base, (9, 6))
+            assert ok
+            x, y = c.reshape(-1, 2)[0]
+            for val in (100, 128, 160, 200):
+                img = base.copy()
+                cv2.circle(img, (int(x), int(y)), 40, val, -1)
+                if scale != 1:
+                    img = cv2.resize(img, None, fx=scale, fy=scale, interpolation=cv2.INTER_LINEAR)
+                batch.append(img); labels.append((name, val, scale))
+        imgs = detect.Images(ctx, np.stack(batch))
+        found, corners = detect.find_chessboard_corners(ctx, imgs, (9, 6), False, fast_check=True)
+        imgs.close()
+        for k, img in enumerate(batch):
+            ok_ref, c_ref = cv2.findChessboardCorners(img, (9, 6), flags=FLAGS)
+            assert bool(found[k]) == bool(ok_ref), labels[k]
+            outcomes.add(bool(ok_ref))
+            if ok_ref:
+                assert np.abs(corners[k] - c_ref.reshape(-1, 2)).max() <= 0.01, labels[k]
+    assert False in outcomes   # the occluded board is rejected somewhere: the full 56-attempt search runs
+
+
 def test_fast_check_gate_matches_cv2(ctx):
     """CALIB_CB_FAST_CHECK on: found flags must equal cv2's with the reference's full flag set -- including the shrunk
     boards that the gate rejects although the search alone finds them -- and the gate must not change found corners."""
