@@ -57,7 +57,6 @@ struct Work {
   Ptf hull[kMaxQuads];
   int pw, ph;           // pattern_size.width / height (inner corners)
   int scan_pos;         // findConnectedQuads resumes its seed search here (quads before it are labelled or isolated for good)
-  int dilations;        // dilation count the attempt compensates edge lengths for (0: undilated attempt and the whole fallback phase)
 };
 
 CB_HD inline float normL2Sqrf(float dx, float dy) { return dx * dx + dy * dy; }
@@ -326,11 +325,11 @@ CB_HD inline void find_quad_neighbors(Work& w, const Par& par) {
             // edges that differ by more than 1:4 in length (16 in squared length) are incompatible
             if (qk.edge_len > 16 * cur_edge || cur_edge > 16 * qk.edge_len) continue;
             if (!diagonal_neighbour(w, cur, i, o, w.corners[qk.corners[(j + 2) & 3]].pt)) continue;
-            // ... and, in attempts without dilation compensation, also from the candidate quad's side.  Pinned on three views
-            // (DESIGN.md 4b): a 0.3-scale board in the fallback phase needs the symmetric test (two squares of one row 9 px
-            // apart pass the one-sided test and scramble the corner order), a noisy view at 7 dilations needs the one-sided
-            // one (cv2 links a blob to its side neighbour there and does not find the board).
-            if (w.dilations == 0 && !diagonal_neighbour(w, qk, j, pt, w.corners[cur.corners[(i + 2) & 3]].pt)) continue;
+            // ... and also from the candidate quad's side when that quad is at least as large as this one.  Pinned on
+            // discriminating views: a 0.3-scale board needs the candidate-side test (two squares of one row
+            // 9 px apart pass the one-sided test and scramble the corner order); noisy views at 5-7 dilations need it
+            // NOT to apply when a large blob looks at its small side neighbour (cv2 links them and finds no board).
+            if (qk.edge_len >= cur_edge && !diagonal_neighbour(w, qk, j, pt, w.corners[cur.corners[(i + 2) & 3]].pt)) continue;
             code = k * 4 + j; min_dist = dist;
           }
         }

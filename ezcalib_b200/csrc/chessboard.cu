@@ -1053,7 +1053,7 @@ __device__ void find_quad_neighbors_grid(cb::Work& w, const NbShared& S, const N
           if ((dist < min_dist || (dist == min_dist && sl < code)) && dist <= cur_edge * cb::kNbSqrScale && dist <= ek * cb::kNbSqrScale) {
             if (ek > 16 * cur_edge || cur_edge > 16 * ek) return;
             if (!diagonal_neighbour_s(S, idx, i, o, S.pt[4 * k + (((sl & 3) + 2) & 3)])) return;
-            if (w.dilations == 0 && !diagonal_neighbour_s(S, k, sl & 3, pt, S.pt[4 * idx + ((i + 2) & 3)])) return;   // see cb_logic.h
+            if (ek >= cur_edge && !diagonal_neighbour_s(S, k, sl & 3, pt, S.pt[4 * idx + ((i + 2) & 3)])) return;   // see cb_logic.h
             code = sl; min_dist = dist;
           }
         });
@@ -1132,7 +1132,7 @@ __global__ void __launch_bounds__(kProcThreads) cb_process_kernel(const HoleInfo
   int max_quads = total * 3 > 2 ? total * 3 : 2;
   if (max_quads > cb::kMaxQuads) max_quads = cb::kMaxQuads;
   const int boardIdx = S.best ? holes[0x7fffffff - (int)(unsigned)(S.best & 0xffffffffull)].parent : -1;
-  if (tid == 0) { s_base = 0; w.max_quads = max_quads; w.pw = pw; w.ph = ph; w.dilations = dilations; }
+  if (tid == 0) { s_base = 0; w.max_quads = max_quads; w.pw = pw; w.ph = ph; }
   __syncthreads();
   for (int h0 = S.hole_begin; h0 < S.hole_end; h0 += kProcThreads) {
     const int h = h0 + tid;

@@ -45,7 +45,6 @@ int cbh_detect_from_contours(const int32_t* pts, const int32_t* lengths, const i
   }
   const int total = (int)quads_parent.size();
   w.n_quads = 0;
-  w.dilations = dilations;
   w.max_quads = total * 3 > 2 ? total * 3 : 2;
   if (w.max_quads > cb::kMaxQuads) w.max_quads = cb::kMaxQuads;
   w.pw = pw; w.ph = ph;

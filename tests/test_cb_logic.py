@@ -108,9 +108,9 @@ def test_approx_schedule_pinned_on_shifted_views():
 
 def test_diagonal_test_sides_pinned():
     """Which quad applies the diagonal-neighbour test: a 0.3-scale board found in the fallback phase
-    equals cv2 bit for bit only with the test applied from both quads' sides; a noisy view at 7 dilations (rendered by
-    tools/chessboard_noise_probe.py, sigma 10) is NOT found by cv2 -- it links a blob one-sidedly there -- and must not
-    be found here either."""
+    equals cv2 bit for bit only with the test also applied from the candidate quad's side; two noisy views (rendered by
+    tools/chessboard_noise_probe.py, sigma 10 and 6) are NOT found by cv2 at 7 dilations / in the fallback at 6 -- a large
+    blob is linked to its small side neighbour from the blob's side only -- and must not be found here either."""
     import cv2
     from erased import FLAGS, gate_corpus
     cv2.ipp.setUseIPP(False)
@@ -120,10 +120,11 @@ def test_diagonal_test_sides_pinned():
     ok, c = P.find_chessboard_corners(small, (9, 6), info=info)
     assert ok and ok_ref and info["phase"] == 2
     assert np.array_equal(c, c_ref.reshape(-1, 2))
-    noisy = np.load(os.path.join(os.path.dirname(__file__), "golden", "chessboard_noisy_d7.npz"))["img"]
-    ok_ref, _ = cv2.findChessboardCorners(noisy, (9, 6), flags=FLAGS)
-    ok, _ = P.find_chessboard_corners(noisy, (9, 6))
-    assert not ok_ref and not ok
+    for name in ("chessboard_noisy_d7.npz", "chessboard_noisy_fallback_d6.npz"):
+        noisy = np.load(os.path.join(os.path.dirname(__file__), "golden", name))["img"]
+        ok_ref, _ = cv2.findChessboardCorners(noisy, (9, 6), flags=FLAGS)
+        ok, _ = P.find_chessboard_corners(noisy, (9, 6))
+        assert not ok_ref and not ok, name
 
 
 def test_fast_check_restatement_matches_cv2():

@@ -165,13 +165,14 @@ def test_noisy_view_at_seven_dilations_is_rejected_like_cv2(ctx):
     in attempts with dilation compensation) and the grid comes out scrambled.  Same decision here."""
     import cv2
     from ezcalib_b200 import detect
-    noisy = np.load(os.path.join(os.path.dirname(__file__), "golden", "chessboard_noisy_d7.npz"))["img"]
     FLAGS = cv2.CALIB_CB_ADAPTIVE_THRESH + cv2.CALIB_CB_NORMALIZE_IMAGE + cv2.CALIB_CB_FILTER_QUADS + cv2.CALIB_CB_FAST_CHECK
-    ok_ref, _ = cv2.findChessboardCorners(noisy, (9, 6), flags=FLAGS)
-    imgs = detect.Images(ctx, noisy[None])
-    found, _ = detect.find_chessboard_corners(ctx, imgs, (9, 6), True, fast_check=True)
-    imgs.close()
-    assert not ok_ref and not found[0]
+    for name in ("chessboard_noisy_d7.npz", "chessboard_noisy_fallback_d6.npz"):
+        noisy = np.load(os.path.join(os.path.dirname(__file__), "golden", name))["img"]
+        ok_ref, _ = cv2.findChessboardCorners(noisy, (9, 6), flags=FLAGS)
+        imgs = detect.Images(ctx, noisy[None])
+        found, _ = detect.find_chessboard_corners(ctx, imgs, (9, 6), True, fast_check=True)
+        imgs.close()
+        assert not ok_ref and not found[0], name
 
 
 def test_fast_check_gate_matches_cv2(ctx):
