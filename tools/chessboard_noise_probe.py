@@ -28,6 +28,7 @@ t = time.time(); found, corners = detect.detect_chessboard(ctx, imgs, 7, 10); dt
 print(f"gpu: {n} views in {dt:.3f}s, found {int(found.sum())}")
 FLAGS = cv2.CALIB_CB_ADAPTIVE_THRESH + cv2.CALIB_CB_NORMALIZE_IMAGE + cv2.CALIB_CB_FILTER_QUADS + cv2.CALIB_CB_FAST_CHECK
 CRIT = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 100, 0.05)
+cv2.ipp.setUseIPP(False)   # OpenCV's generic code path, which the kernels restate (IPP's sampler moves weak corners)
 t0 = time.time(); diffs = []; mis = []
 for i in range(n):
     ok, c = cv2.findChessboardCorners(host[i], (9, 6), flags=FLAGS)
