@@ -530,6 +530,16 @@ def run_detect_chessboard(ctx, args, rank, world, stream, cfg="cfg1"):
             flags_equal = flags_equal and bool(ok) == bool(found[i])
             if ok and found[i]:
                 worst = max(worst, float(np.abs(c - corners[i]).max()))
+        # parity against OpenCV's generic code path (what the kernels restate; IPP's sampler moves weak corners): untimed
+        ipp_was = cv2.ipp.useIPP()
+        cv2.ipp.setUseIPP(False)
+        worst_generic = 0.0
+        for i in idx_found[:12]:
+            ok, c = cv2.findChessboardCorners(host_all[i], (9, 6), flags=flags)
+            if ok:
+                c = cv2.cornerSubPix(host_all[i], c, (5, 5), (-1, -1), crit).reshape(-1, 2)
+                worst_generic = max(worst_generic, float(np.abs(c - corners[i]).max()))
+        cv2.ipp.setUseIPP(ipp_was)
         n_found, n_fail = int(found.sum()), int(n - found.sum())
         est = (t_found / max(len(idx_found), 1)) * n_found + (t_fail / max(len(idx_fail), 1)) * n_fail
         out["cpu_baseline"] = {"value": round(n / est, 3), "unit": "images/s", "cores": host_cores(), "kind": "reference",
@@ -537,7 +547,8 @@ def run_detect_chessboard(ctx, args, rank, world, stream, cfg="cfg1"):
                                          "(cv2 %s, %d threads), weighted to the batch mix (%d found / %d not found); mean %.1f ms per found view, %.1f ms per "
                                          "not-found view" % (len(idx_found), len(idx_fail), cv2.__version__, cv2.getNumThreads(), n_found, n_fail,
                                                              1e3 * t_found / max(len(idx_found), 1), 1e3 * t_fail / max(len(idx_fail), 1)),
-                               "found_flags_equal": bool(flags_equal), "max_corner_diff_px": round(worst, 6)}
+                               "found_flags_equal": bool(flags_equal), "max_corner_diff_px": round(worst, 6),
+                               "max_corner_diff_px_without_ipp": round(worst_generic, 6)}
     imgs.close()
     return out
 
