@@ -9,6 +9,7 @@ import pytest
 
 from ezcalib_b200 import synth
 from oracle import lm_oracle as O
+from oracle import lm_ref as R
 
 pytestmark = pytest.mark.gpu
 
@@ -39,6 +40,10 @@ def test_residual_jacobian_matches_jets(ctx, model, mono):
         assert np.allclose(r1, r0, rtol=1e-12, atol=1e-10)
         scale = np.abs(J0).max()
         assert np.max(np.abs(J1 - J0)) <= 1e-11 * scale, (model, mono, np.max(np.abs(J1 - J0)), scale)
+        # and against the reference's own functor headers compiled unmodified (oracle/_ref/liblm_ref.so)
+        r2, J2, _ = R.residual_jacobian(mid, mono, focal, pp, dist, pose, wpt, u, v)
+        assert np.allclose(r1, r2, rtol=1e-12, atol=1e-10)
+        assert np.max(np.abs(J1 - J2)) <= 1e-11 * scale, (model, mono, np.max(np.abs(J1 - J2)), scale)
 
 
 def _oracle_normal_equations(P, mid, focal, pp, dist, poses, cols):
