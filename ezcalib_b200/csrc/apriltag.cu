@@ -1431,6 +1431,7 @@ ezc_status ezc_apriltag_debug_run(ezc_context* ctx, const ezc_images* imgs, int3
   const int nb_tags = nb_rows * nb_cols;
   Pools P;
   ezc::DevBuf d_corners, d_ndet, d_succ;
+  ezc::SyncOnExit sync_on_exit(ctx->stream);
   EZC_CUDA(d_corners.reserve(sizeof(float2) * (size_t)imgs->n * 4 * nb_tags));
   EZC_CUDA(d_ndet.reserve(sizeof(int) * (size_t)imgs->n));
   EZC_CUDA(d_succ.reserve((size_t)imgs->n));

@@ -1801,13 +1801,14 @@ ezc_status ezc_find_chessboard_corners_batch(ezc_context* ctx, const ezc_images*
   // fewer sub-batches the fewer serial tails.  (2^30 pixels per sub-batch keeps linear pixel indices in 32 bits.)
   size_t free_b = 0, total_b = 0;
   EZC_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  const long long budget = std::min<long long>(48LL << 30, (long long)((free_b + ezc::dev_cache().bytes) / 2));
+  const long long budget = std::min<long long>(48LL << 30, (long long)((free_b + ezc::dev_cache_bytes(ctx->device)) / 2));
   int sub = (int)std::max<long long>(1, std::min<long long>((1LL << 30) / N, budget / (N * 32)));
   sub = std::min(sub, 512);
   if (max_images_in_flight > 0) sub = std::min(sub, max_images_in_flight);
   sub = std::min(sub, n);
   const int npts = pattern_w * pattern_h;
   ezc::DevBuf d_corners, d_found;
+  ezc::SyncOnExit sync_on_exit(ctx->stream);
   EZC_CUDA(d_corners.reserve(sizeof(float2) * (size_t)n * npts));
   EZC_CUDA(d_found.reserve((size_t)n));
   // No sub-batch ramp under ezc_images_upload_async here (unlike the AprilGrid path): a chessboard sub-batch costs ~10x its

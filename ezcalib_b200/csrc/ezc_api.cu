@@ -37,7 +37,26 @@ ezc_status ezc_create(int32_t device, ezc_context** out) {
   c->sm_count = prop.multiProcessorCount;
   EZC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
+  {
+    std::lock_guard<std::mutex> g(ezc::dev_cache(device).m);
+    ++ezc::live_contexts(device);
+  }
   *out = c;
+  return EZC_OK;
+}
+
+ezc_status ezc_trim_cache(int32_t device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return EZC_OK; }
+  for (int d = 0; d < n && d < 64; ++d) {
+    if (device >= 0 && d != device) continue;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(d);
+    cudaDeviceSynchronize();
+    ezc::dev_cache(d).flush();
+    cudaSetDevice(prev);
+  }
   return EZC_OK;
 }
 
@@ -49,6 +68,12 @@ void ezc_destroy(ezc_context* ctx) {
   if (ctx->cb_pools && ctx->cb_pools_free) ctx->cb_pools_free(ctx->cb_pools);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  bool last = false;
+  {
+    std::lock_guard<std::mutex> g(ezc::dev_cache(ctx->device).m);
+    last = --ezc::live_contexts(ctx->device) <= 0;
+  }
+  if (last) ezc::dev_cache(ctx->device).flush();  // other allocators in the process (torch, NCCL) get the memory back
   delete ctx;
 }
 

@@ -70,26 +70,54 @@ struct DevCache {
     bytes = 0;
   }
 };
-inline DevCache& dev_cache() {
-  static DevCache* c = new DevCache;  // intentionally leaked
-  return *c;
+// One cache per device: a block cudaMalloc'ed on GPU a must never be handed to a context on GPU b.
+inline DevCache& dev_cache(int device) {
+  static DevCache* caches[64] = {};  // intentionally leaked
+  static std::mutex m;
+  std::lock_guard<std::mutex> g(m);
+  if (device < 0 || device >= 64) device = 0;
+  if (!caches[device]) caches[device] = new DevCache;
+  return *caches[device];
+}
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; }
+  return d;
+}
+inline DevCache& dev_cache() { return dev_cache(current_device()); }
+inline size_t dev_cache_bytes(int device) {
+  DevCache& c = dev_cache(device);
+  std::lock_guard<std::mutex> g(c.m);
+  return c.bytes;
+}
+// number of live contexts per device; the last ezc_destroy on a device flushes its cache
+inline int& live_contexts(int device) {
+  static int n[64] = {};
+  return n[(device < 0 || device >= 64) ? 0 : device];
 }
 
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  int dev = -1;  // device the block lives on
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p && !dev_cache().give(p, cap)) cudaFree(p);
+    if (p && !dev_cache(dev).give(p, cap)) cudaFree(p);
     p = nullptr; cap = 0;
+  }
+  // Error paths destroy DevBufs while kernels may still be queued on `stream`: wait before the block can be recycled.
+  void release_after(cudaStream_t stream) {
+    if (p) cudaStreamSynchronize(stream);
+    release();
   }
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
     release();
-    DevCache& c = dev_cache();
+    dev = current_device();
+    DevCache& c = dev_cache(dev);
     {
       std::lock_guard<std::mutex> g(c.m);
       auto it = c.blocks.lower_bound(bytes);
@@ -110,6 +138,14 @@ struct DevBuf {
     return e;
   }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Declared AFTER the local DevBufs of an entry point: runs before their destructors on every return path (error returns
+// included), so a block is never recycled while kernels that use it are still queued on the stream.
+struct SyncOnExit {
+  cudaStream_t s;
+  explicit SyncOnExit(cudaStream_t stream) : s(stream) {}
+  ~SyncOnExit() { cudaStreamSynchronize(s); }
 };
 
 // Pinned host buffers are expensive to create (cudaMallocHost / cudaFreeHost take milliseconds -- more than the 80 MB

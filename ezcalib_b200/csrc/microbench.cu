@@ -46,6 +46,7 @@ extern "C" ezc_status ezc_measure_fp64_peak(ezc_context* ctx, double* tflops_out
   EZC_CHECK(ctx && tflops_out, EZC_ERR_INVALID, "ezc_measure_fp64_peak: null argument");
   EZC_CUDA(cudaSetDevice(ctx->device));
   ezc::DevBuf buf;
+  ezc::SyncOnExit sync_on_exit(ctx->stream);
   EZC_CUDA(buf.reserve(64));
   const int iters = 4096, grid = ctx->sm_count * 8, block = 256;
   cudaEvent_t e0, e1;
@@ -73,6 +74,7 @@ extern "C" ezc_status ezc_measure_dmma_peak(ezc_context* ctx, double* tflops_out
   EZC_CHECK(ctx && tflops_out, EZC_ERR_INVALID, "ezc_measure_dmma_peak: null argument");
   EZC_CUDA(cudaSetDevice(ctx->device));
   ezc::DevBuf buf;
+  ezc::SyncOnExit sync_on_exit(ctx->stream);
   EZC_CUDA(buf.reserve(64));
   const int iters = 4096, grid = ctx->sm_count * 8, block = 256;
   cudaEvent_t e0, e1;

@@ -277,6 +277,7 @@ ezc_status ezc_corner_subpix(ezc_context* ctx, const ezc_images* imgs, float* co
     EZC_CHECK(corners[2 * i] >= 0 && corners[2 * i] < imgs->width && corners[2 * i + 1] >= 0 && corners[2 * i + 1] < imgs->height,
               EZC_ERR_INVALID, "ezc_corner_subpix: corner %d (%g,%g) outside the image", i, corners[2 * i], corners[2 * i + 1]);
   ezc::DevBuf dc, di;
+  ezc::SyncOnExit sync_on_exit(ctx->stream);
   EZC_CUDA(dc.reserve(sizeof(float2) * n));
   EZC_CUDA(di.reserve(sizeof(int32_t) * n));
   EZC_CUDA(cudaMemcpyAsync(dc.p, corners, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));

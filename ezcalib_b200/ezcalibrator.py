@@ -140,8 +140,6 @@ def run_multicam_calib(ctx: lm.Context, cameras: list[Camera], target: np.ndarra
 
 # ------------------------------------------------------------------------------------------------------------------
 # The step BETWEEN the two accelerated halves: initial intrinsics and P3P-RANSAC poses.
-# The reference calls OpenCV for it (cv::solvePnPRansac); so does this mirror, through cv2 -- host code, a few hundred
-# microseconds per view, not on the GPU path yet.
 def setup_initial_calibration(width: int, height: int, prior_fov_deg: float, use_mono_focal: bool):
     """Camera::setupInitialCalibration (/root/reference/src/camera.cpp:102-120): focal from the prior field of view,
     principal point at the image centre.  Returns (focal[1|2], pp[2])."""
@@ -152,42 +150,43 @@ def setup_initial_calibration(width: int, height: int, prior_fov_deg: float, use
     return np.array([f] if use_mono_focal else [f, f], np.float64), np.array([cx, cy], np.float64)
 
 
-def fit_to_so3(R: np.ndarray) -> np.ndarray:
-    """Sophus::SO3d::fitToSO3 (closest rotation in the Frobenius sense: U diag(1,1,det(UV^T)) V^T)."""
-    U, _, Vt = np.linalg.svd(R)
-    D = np.diag([1.0, 1.0, np.linalg.det(U @ Vt)])
-    return U @ D @ Vt
-
-
-def compute_p3p_ransac(corners_px: np.ndarray, target: np.ndarray, focal: np.ndarray, pp: np.ndarray, width: int, height: int,
-                       n_target_pts: int | None = None):
-    """EZCalibrator::computeP3PRansac (/root/reference/src/ezcalibrator.cpp:560-628).  Returns (ok, pose7, n_inliers).
+def compute_p3p_ransac_batch(ctx: lm.Context, corners_px: np.ndarray, target: np.ndarray, focal: np.ndarray, pp: np.ndarray, width: int,
+                             height: int, n_target_pts: int | None = None, want_debug: bool = False):
+    """EZCalibrator::computeP3PRansac (/root/reference/src/ezcalibrator.cpp:560-628) for a batch of views on the GPU
+    (ezc_p3p_ransac_batch, one warp per view; csrc/p3p.cu).  corners_px [n_views, n_pts, 2] float32 pixels, (-1,-1) = missing.
     Pixels are normalised with the PRIOR intrinsics (no distortion), points outside the image dropped, >= 32 points and
-    >= 32 inliers required when the target has >= 32 points, cv::solvePnPRansac(identity K, 1000 iterations,
-    threshold 4 / mean focal, confidence 0.999, AP3P), Rodrigues -> float32 -> fitToSO3."""
-    import cv2
-    n_target_pts = len(target) if n_target_pts is None else n_target_pts
-    fx = float(focal[0])
-    fy = float(focal[-1])
-    u, v = corners_px[:, 0].astype(np.float32), corners_px[:, 1].astype(np.float32)
-    inside = (u > -0.5) & (v > -0.5) & (u < np.float32(width) - np.float32(0.5)) & (v < np.float32(height) - np.float32(0.5))
-    x = ((u.astype(np.float64) - pp[0]) / fx).astype(np.float32)[inside]
-    y = ((v.astype(np.float64) - pp[1]) / fy).astype(np.float32)[inside]
-    un = np.stack([x, y], axis=1)
-    w3 = np.asarray(target, np.float64)[inside].astype(np.float32)
-    if len(un) < 32 and n_target_pts >= 32:
-        return False, None, 0
+    >= 32 inliers required when the target has >= 32 points; cv::solvePnPRansac(identity K, 1000 iterations, threshold
+    4 / mean focal, confidence 0.999, AP3P) restated (RANSAC with cv::RNG's sequence + EPnP on the inliers),
+    Rodrigues -> float32 -> fitToSO3.  Returns (ok[n_views] bool, poses7[n_views, 7], n_inliers[n_views]) and, with
+    want_debug, also (inlier mask [n_views, n_pts], rvec_tvec [n_views, 6], RANSAC iterations [n_views])."""
+    import ctypes as C
+
+    from . import _lib
+    corners = np.ascontiguousarray(corners_px, np.float32)
+    assert corners.ndim == 3 and corners.shape[2] == 2
+    n_views, n_pts = corners.shape[:2]
+    tg = np.ascontiguousarray(target, np.float64)
+    assert tg.shape == (n_pts, 3)
+    n_target_pts = n_pts if n_target_pts is None else int(n_target_pts)
+    focal = np.ascontiguousarray(focal, np.float64)
+    ppa = np.ascontiguousarray(pp, np.float64)
+    fx, fy = float(focal[0]), float(focal[-1])
     mean_focal = fx if len(focal) == 1 else 0.5 * (fx + fy)
-    ok, rvec, tvec, inl = cv2.solvePnPRansac(w3.reshape(-1, 1, 3), un.reshape(-1, 1, 2), np.eye(3, dtype=np.float32), None,
-                                             useExtrinsicGuess=False, iterationsCount=1000, reprojectionError=float(4.0 / mean_focal),
-                                             confidence=0.999, flags=cv2.SOLVEPNP_AP3P)
-    n_inl = 0 if inl is None else len(inl)
-    if not ok or (n_inl < 32 and n_target_pts >= 32):
-        return False, None, n_inl
-    R, _ = cv2.Rodrigues(rvec)
-    R = fit_to_so3(R.astype(np.float32).astype(np.float64))
-    t = tvec.reshape(3).astype(np.float32).astype(np.float64)
-    return True, np.concatenate([synth.quat_from_matrix(R), t]), n_inl
+    ok = np.zeros(n_views, np.uint8)
+    poses = np.zeros((n_views, 7))
+    ninl = np.zeros(n_views, np.int32)
+    mask = np.zeros((n_views, n_pts), np.uint8) if want_debug else None
+    rt = np.zeros((n_views, 6)) if want_debug else None
+    nit = np.zeros(n_views, np.int32) if want_debug else None
+
+    def p(a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
+    _lib.check(_lib.lib().ezc_p3p_ransac_batch(ctx.handle, p(corners), p(tg), n_views, n_pts, n_target_pts, p(focal), len(focal), p(ppa),
+                                               int(width), int(height), 1000, 4.0 / mean_focal, 0.999, 32, p(ok), p(poses), p(ninl), p(mask),
+                                               p(rt), p(nit)), "ezc_p3p_ransac_batch")
+    if want_debug:
+        return ok.astype(bool), poses, ninl, mask.astype(bool), rt, nit
+    return ok.astype(bool), poses, ninl
 
 
 def run_calibration(ctx: lm.Context, images: np.ndarray, target_kind: str, nb_rows: int, nb_cols: int, size: float, space: float,
@@ -211,12 +210,12 @@ def run_calibration(ctx: lm.Context, images: np.ndarray, target_kind: str, nb_ro
     dist = np.zeros(len(synth.GT_DIST[model]))   # all coefficients start at 0 (member defaults of the dist_model classes)
     cam = Camera(model, use_mono_focal, W, H, focal, pp, dist)
     processed = replay_skip_rule([bool(f) for f in found])
-    for i in processed:
-        if not found[i]:
-            continue
-        ok, pose, _ = compute_p3p_ransac(corners[i], target, focal, pp, W, H)
-        if ok:
-            cam.frames.append(CalibFrame(names[i] if names is not None else str(i), corners[i].astype(np.float32), pose))
+    cand = [i for i in processed if found[i]]
+    if cand:
+        ok, poses, _ = compute_p3p_ransac_batch(ctx, np.asarray(corners)[cand], target, focal, pp, W, H)
+        for k, i in enumerate(cand):
+            if ok[k]:   # quirk Q4: a frame is stored only if P3P succeeds
+                cam.frames.append(CalibFrame(names[i] if names is not None else str(i), corners[i].astype(np.float32), poses[k]))
     if not cam.frames:
         raise RuntimeError("no frame with a detected target and a P3P pose")
     compute_calibration(ctx, cam, target)

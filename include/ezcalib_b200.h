@@ -44,6 +44,9 @@ ezc_status ezc_set_stream(ezc_context* ctx, void* cuda_stream);
 ezc_status ezc_set_allreduce(ezc_context* ctx, ezc_allreduce_fn fn, void* user, int32_t rank, int32_t world);
 /* Number of kernels of this library launched on the context so far (bench.py "gpu_launches"). */
 uint64_t ezc_kernel_launches(const ezc_context* ctx);
+/* Give the cached device blocks of `device` (-1: every device) back to the driver.  The cache is per device and is
+ * also flushed when the last context of a device is destroyed. */
+ezc_status ezc_trim_cache(int32_t device);
 ezc_status ezc_synchronize(ezc_context* ctx);
 /* Roofline denominator for the FP64-bound LM kernels: DFMA-saturating microbenchmark (TFLOP/s). */
 ezc_status ezc_measure_fp64_peak(ezc_context* ctx, double* tflops_out);
@@ -130,6 +133,25 @@ int32_t ezc_apriltag_debug_count(const ezc_apriltag_debug* d, int32_t what);
 ezc_status ezc_apriltag_debug_get(const ezc_apriltag_debug* d, float* theta, float* mag, int32_t* edges /*[n][3]*/,
                                   int32_t* rep, int32_t* size, float* segments /*[n][6]*/, float* quads /*[n][9]*/);
 void ezc_apriltag_debug_free(ezc_apriltag_debug* d);
+
+/* ------------------------------------------------------------------------------------------
+ * Between the halves: initial poses.  EZCalibrator::computeP3PRansac
+ * (/root/reference/src/ezcalibrator.cpp:560-628) for every view of a batch, one warp per view:
+ * pixels inside the image (float isPointInImage, calib_models.hpp:107-115) are normalised with K^-1 of the PRIOR
+ * intrinsics (:580) and, with the model points cast to float (:582), go through
+ * cv::solvePnPRansac(identity K, no distortion, max_iterations = 1000, reproj_threshold = 4 / mean focal,
+ * confidence = 0.999, SOLVEPNP_AP3P) (:592-606): RANSAC over 4-point samples with cv::RNG's own sequence, then EPnP on
+ * the inliers; a view fails with fewer than min_points (32) in-image points or inliers when the target has that many
+ * (:586-590, :610).  The result is converted like :616-625 (Rodrigues -> float -> Sophus::SO3d::fitToSO3).
+ * corners: HOST float [n_views][n_pts][2]; target: HOST double [n_pts][3]; focal[n_focal = 1|2], pp[2]: prior intrinsics.
+ * ok_out: HOST [n_views]; poses7_out: HOST [n_views][7] = qx qy qz qw tx ty tz (zeros when !ok);
+ * optional (may be NULL): n_inliers_out [n_views], inlier_mask_out [n_views][n_pts] (per TARGET point),
+ * rvec_tvec_out [n_views][6] = what cv::solvePnPRansac itself returns, n_iterations_out [n_views] RANSAC iterations run. */
+ezc_status ezc_p3p_ransac_batch(ezc_context* ctx, const float* corners, const double* target, int32_t n_views, int32_t n_pts,
+                                int32_t n_target_pts, const double* focal, int32_t n_focal, const double* pp, int32_t width,
+                                int32_t height, int32_t max_iterations, double reproj_threshold, double confidence,
+                                int32_t min_points, uint8_t* ok_out, double* poses7_out, int32_t* n_inliers_out,
+                                uint8_t* inlier_mask_out, double* rvec_tvec_out, int32_t* n_iterations_out);
 
 /* ------------------------------------------------------------------------------------------
  * Half (b): Levenberg-Marquardt calibration solve.

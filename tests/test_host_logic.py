@@ -54,38 +54,28 @@ def test_prior_intrinsics_rule():
     assert cx == 640 and cy == 512 and abs(f - 640 / np.tan(np.radians(35.0))) < 1e-9
 
 
-def test_initial_calibration_and_p3p_glue():
-    """Camera::setupInitialCalibration (camera.cpp:102-120) and EZCalibrator::computeP3PRansac (ezcalibrator.cpp:560-628)
-    as the host mirror restates them: prior focal from the field of view, poses from cv2.solvePnPRansac on pixels
-    normalised with the PRIOR intrinsics; the pose must reproject the target close to the observations."""
-    cv2 = pytest.importorskip("cv2")
-    from ezcalib_b200 import ezcalibrator as E, synth
+def test_initial_calibration():
+    """Camera::setupInitialCalibration (camera.cpp:102-120) as the host mirror restates it: prior focal from the field of
+    view, principal point at the image centre.  (computeP3PRansac is a GPU entry point now: tests/test_p3p_cpu.py checks
+    its mathematics against cv2 on the CPU, tests/test_p3p_gpu.py the kernel.)"""
+    from ezcalib_b200 import ezcalibrator as E
     W, H = 1280, 1024
     f0, pp0 = E.setup_initial_calibration(W, H, 70.0, True)
     assert f0.shape == (1,) and abs(f0[0] - max(W / 2, H / 2) / np.tan(np.deg2rad(35.0))) < 1e-9
     assert np.array_equal(pp0, [W / 2, H / 2])
     f2, _ = E.setup_initial_calibration(W, H, 70.0, False)
     assert f2.shape == (2,) and f2[0] == f2[1] == f0[0]
-    R = E.fit_to_so3(np.eye(3) + 1e-3 * np.arange(9).reshape(3, 3))
-    assert abs(np.linalg.det(R) - 1) < 1e-12 and np.allclose(R @ R.T, np.eye(3), atol=1e-12)
-    model = "radtan5"
-    d = synth.GT_DIST[model]
-    tgt = synth.chessboard_target(7, 10, 0.05)
-    rng = np.random.Generator(np.random.Philox(key=3))
-    poses = synth.sample_poses(rng, 4, tgt, model, 900.0, 645.0, 505.0, d, W, H, margin=90, tilt_sigma=0.3)
-    for pose in poses:
-        px = synth.project(model, 900.0, 900.0, 645.0, 505.0, d, pose, tgt).astype(np.float32)
-        ok, p7, n_inl = E.compute_p3p_ransac(px, tgt, f0, pp0, W, H)
-        assert ok and n_inl >= 32 and abs(np.linalg.norm(p7[:4]) - 1) < 1e-9
-        # pinhole reprojection with the prior intrinsics (the returned pose is EPnP on the inliers, the lens distortion is
-        # not modelled at this stage): a sane initial pose, not a fit
-        rep = synth.project("rad1", f0[0], f0[0], pp0[0], pp0[1], [0.0], p7, tgt)
-        err = np.linalg.norm(rep - px, axis=1)
-        assert np.median(err) < 15.0
-    # too few points in the image: the frame is skipped like the reference does (>= 32 required for a >= 32-point target)
-    px = np.full((54, 2), -1.0, np.float32)
-    px[:10] = 100.0 + np.arange(20).reshape(10, 2)
-    assert E.compute_p3p_ransac(px, tgt, f0, pp0, W, H)[0] is False
+
+
+def test_product_package_does_not_import_the_oracles():
+    """The product path must not route through cv2 or oracle/ (VERDICT round 1, N1)."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ezcalib_b200")
+    for name in os.listdir(root):
+        if name.endswith(".py"):
+            text = open(os.path.join(root, name)).read()
+            assert not re.search(r"^\s*(import|from)\s+(cv2|oracle)\b", text, re.M), name
 
 
 def test_result_yaml_matches_the_reference_writer(tmp_path):

@@ -1,10 +1,16 @@
 """GPU: the whole reference flow for one camera -- images -> detectTarget -> P3P-RANSAC -> computeCalibration -- through
 ezcalib_b200.ezcalibrator.run_calibration, against the same flow assembled from the reference's own building blocks
 (cv2.findChessboardCorners + cv2.cornerSubPix, cv2.solvePnPRansac, the restated-Ceres oracle)."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
 from oracle import lm_oracle as O
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "p3p_harness"))
+import p3p_cv2_ref as PR  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -48,14 +54,14 @@ def test_chessboard_images_to_calibration(ctx):
             continue
         ok, c = cv2.findChessboardCorners(host[i], (9, 6), flags=flags)
         c = cv2.cornerSubPix(host[i], c, (5, 5), (-1, -1), crit).reshape(-1, 2)
-        okp, pose, _ = E.compute_p3p_ransac(c, target, focal0, pp0, W, H)
+        okp, pose, _, _ = PR.compute_p3p_ransac_cv2(c, target, focal0, pp0, W, H)
         if okp:
             obs.append(c.astype(np.float32)); poses0.append(pose)
     assert len(obs) == len(cam.frames)
     f_ref, pp_ref, d_ref, poses_ref, rmse_ref, _ = O.solve_mono(mid, mono, np.stack(obs), target, W, H, focal0, pp0, np.zeros(len(d)),
                                                              np.stack(poses0))
     # detection differs by <= 1.2e-4 px, the P3P poses accordingly; both solves end in the same minimum
-    assert abs(cam.focal[0] - f_ref[0]) / f_ref[0] <= 1e-5
+    assert abs(cam.focal[0] - f_ref[0]) / f_ref[0] <= 1e-6
     assert np.max(np.abs(cam.pp - pp_ref)) <= 1e-2
     assert np.max(np.abs(cam.dist - d_ref)) <= 1e-4
     assert np.max(np.abs(np.array([fr.rmse_err for fr in cam.frames]) - rmse_ref)) <= 1e-3
