@@ -1349,6 +1349,26 @@ ezc_status ezc_lm_mono(ezc_context* ctx, const ezc_lm_problem* problem, double* 
   return st;
 }
 
+ezc_status ezc_lm_multicam(ezc_context* ctx, const ezc_lm_problem* problem, const double* focal, const double* pp, const double* dist,
+                           double* extrinsics, ezc_lm_summary* summary) {
+  EZC_CHECK(ctx && problem && focal && pp && dist && summary, EZC_ERR_INVALID, "ezc_lm_multicam: null argument");
+  EZC_CHECK(problem->cams_per_block != 0, EZC_ERR_INVALID, "ezc_lm_multicam: the problem must carry one constant camera per block");
+  EZC_CHECK(extrinsics || problem->n_blocks == 0, EZC_ERR_INVALID, "ezc_lm_multicam: null extrinsics");
+  ezc_lm_solver* s = nullptr;
+  ezc_status st = ezc_lm_create(ctx, problem, &s);
+  if (st != EZC_OK) return st;
+  st = ezc_lm_set_params(s, focal, pp, dist, extrinsics);
+  ezc_lm_options o;
+  ezc_lm_default_options(&o);
+  // every intrinsic block is SetParameterBlockConstant (/root/reference/src/ezcalibrator.cpp:664-670); one trust region for all
+  // extrinsic blocks, like the single ceres::Problem of the reference (:787-822)
+  o.opt_focal = o.opt_pp = o.opt_dist = 0;
+  if (st == EZC_OK) st = ezc_lm_solve(s, &o, summary);
+  if (st == EZC_OK) st = ezc_lm_get_params(s, nullptr, nullptr, nullptr, extrinsics);
+  ezc_lm_destroy(s);
+  return st;
+}
+
 ezc_status ezc_lm_residual_jacobian(ezc_context* ctx, int32_t model, int32_t mono, const double* focal, const double* pp,
                                     const double* dist, const double* pose7, const double* wpt3, double u, double v,
                                     double* r, double* J) {

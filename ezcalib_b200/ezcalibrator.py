@@ -31,6 +31,7 @@ class Camera:
     dist: np.ndarray
     frames: list = field(default_factory=list)
     T_cam0_2_cam: np.ndarray | None = None
+    stds: tuple | None = None       # (focal_std, pp_std, dist_std) after compute_calibration
 
 
 def replay_skip_rule(found_flags) -> list[int]:
@@ -53,18 +54,54 @@ def replay_skip_rule(found_flags) -> list[int]:
     return out
 
 
-def compute_calibration(ctx: lm.Context, cam: Camera, target: np.ndarray):
-    """EZCalibrator::computeCalibration's optimisation (ezcalibrator.cpp:105-291): 3 staged solves, parameters written
-    back into the camera / frames, rmse_err filled."""
-    obs = np.stack([f.corners_px for f in cam.frames]).astype(np.float32)
-    poses = np.stack([f.T_world_2_cam for f in cam.frames])
-    f, pp, d, poses, rmse, summ = lm.lm_mono(ctx, synth.MODEL_ID[cam.model], cam.use_mono_focal, obs, target, cam.width,
-                                              cam.height, cam.focal, cam.pp, cam.dist, poses)
+def _stds_from_covariance(solver: lm.LmSolver, cam: Camera):
+    """ceres::Covariance over (focal, pp, dist) -> setFocalStd / setPPStd / setDistParamsStd (ezcalibrator.cpp:293-331).
+    A rank-deficient system is not fatal: the reference prints 'Covariance Estimation Failed' and keeps the calibration."""
+    from ._lib import EzcError
+    try:
+        cov = solver.covariance()
+    except EzcError:
+        cam.stds = None
+        return
+    sd = np.sqrt(np.diag(cov))
+    nf = 1 if cam.use_mono_focal else 2
+    cam.stds = (sd[:nf].copy(), sd[nf:nf + 2].copy(), sd[nf + 2:].copy())
+
+
+def _solve_frames(ctx: lm.Context, cam: Camera, target: np.ndarray, frames: list, stages):
+    obs = np.stack([f.corners_px for f in frames]).astype(np.float32)
+    poses = np.stack([f.T_world_2_cam for f in frames])
+    solver = lm.LmSolver(ctx, synth.MODEL_ID[cam.model], cam.use_mono_focal, obs, target, cam.width, cam.height)
+    try:
+        solver.set_params(cam.focal, cam.pp, cam.dist, poses)
+        summ = [solver.solve(*mask)[0] for mask in stages]
+        rmse = solver.frame_rmse()
+        f, pp, d, poses = solver.get_params()
+        _stds_from_covariance(solver, cam)
+    finally:
+        solver.close()
     cam.focal, cam.pp, cam.dist = f, pp, d
-    for fr, p, r in zip(cam.frames, poses, rmse):
+    for fr, p, r in zip(frames, poses, rmse):
         fr.T_world_2_cam = p
         fr.rmse_err = float(r)
     return summ
+
+
+def compute_calibration(ctx: lm.Context, cam: Camera, target: np.ndarray):
+    """EZCalibrator::computeCalibration (ezcalibrator.cpp:105-339): 3 staged solves (focal + poses; + distortion; + principal
+    point; opt_focal, opt_pp, opt_dist masks), parameters written back into the camera / frames, rmse_err filled, standard
+    deviations from the covariance in cam.stds."""
+    return _solve_frames(ctx, cam, target, cam.frames, [(True, False, False), (True, False, True), (True, True, True)])
+
+
+def refine_calibration(ctx: lm.Context, cam: Camera, target: np.ndarray):
+    """EZCalibrator::refineCalibration (ezcalibrator.cpp:342-557; dormant in the reference, its call at :63 is commented
+    out): ONE solve with every block variable over the frames whose rmse_err <= 1; their rmse_err is recomputed, the
+    others keep theirs.  It drops the views stuck in the mirror pose of the planar target."""
+    good = [f for f in cam.frames if not f.rmse_err > 1.0]
+    if not good:
+        raise RuntimeError("refine_calibration: no frame with rmse_err <= 1")
+    return _solve_frames(ctx, cam, target, good, [(True, True, True)])[0]
 
 
 def build_multicam_problem(cameras: list[Camera], target: np.ndarray):
@@ -125,14 +162,10 @@ def run_multicam_calib(ctx: lm.Context, cameras: list[Camera], target: np.ndarra
         raise NotImplementedError("mixed distortion models across cameras are not supported yet")
     obs, pts, init, n_good = build_multicam_problem(cameras, target)
     cam1 = cameras[1]
-    solver = lm.LmSolver(ctx, synth.MODEL_ID[m0], mono0, obs, pts, cam1.width, cam1.height, pts_period=pts.shape[0], cams_per_block=True)
     focal = np.concatenate([c.focal for c in cameras[1:]])
     pp = np.concatenate([c.pp for c in cameras[1:]])
     dist = np.concatenate([c.dist for c in cameras[1:]])
-    solver.set_params(focal, pp, dist, init)
-    summ, _ = solver.solve(False, False, False)
-    _, _, _, ext = solver.get_params()
-    solver.close()
+    ext, summ = lm.lm_multicam(ctx, synth.MODEL_ID[m0], mono0, obs, pts, cam1.width, cam1.height, focal, pp, dist, init)
     for c, e in zip(cameras[1:], ext):
         c.T_cam0_2_cam = e
     return dict(summary=summ, n_good_pairs=n_good, init=init, extrinsics=ext, obs=obs, pts=pts)

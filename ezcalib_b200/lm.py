@@ -203,6 +203,28 @@ def lm_mono(ctx: Context, model_id: int, mono: bool, obs, pts, width, height, fo
     return focal, pp, dist, poses, rmse, [s.as_dict() for s in ss]
 
 
+def lm_multicam(ctx: Context, model_id: int, mono: bool, obs, pts, width, height, focal, pp, dist, extrinsics,
+                n_blocks_global: int | None = None):
+    """EZCalibrator::runMultiCameraCalib's optimisation through the one-shot C entry point (ezc_lm_multicam): block b =
+    extrinsic of camera b+1 with its own constant intrinsics; obs [n_blocks, n_frames0 * n_pts, 2], pts [n_frames0 * n_pts, 3].
+    Returns (extrinsics [n_blocks, 7], summary dict)."""
+    obs = np.ascontiguousarray(obs, dtype=np.float32)
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    p = LmProblemC()
+    p.model, p.use_mono_focal = int(model_id), int(bool(mono))
+    p.n_blocks, p.obs_per_block, p.pts_period, p.cams_per_block = obs.shape[0], obs.shape[1], pts.shape[0], 1
+    p.img_w, p.img_h = float(width), float(height)
+    p.pts, p.obs = _p(pts), _p(obs)
+    p.n_blocks_global = int(n_blocks_global if n_blocks_global is not None else p.n_blocks)
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (focal, pp, dist)]
+    ext = np.array(extrinsics, dtype=np.float64, copy=True).reshape(-1, 7)
+    s = LmSummaryC()
+    check(_lib.lib().ezc_lm_multicam(ctx.handle, C.byref(p), _p(a[0]), _p(a[1]), _p(a[2]), _p(ext), C.byref(s)), "ezc_lm_multicam")
+    d = s.as_dict()
+    d["termination_name"] = TERMINATION[d["termination"]]
+    return ext, d
+
+
 def residual_jacobian(ctx: Context, model_id: int, mono: bool, focal, pp, dist, pose, wpt, u, v):
     nf = 1 if mono else 2
     nd = _lib.lib().ezc_num_dist(int(model_id))

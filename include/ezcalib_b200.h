@@ -243,6 +243,15 @@ ezc_status ezc_lm_covariance(ezc_lm_solver* s, double* cov_out);
 ezc_status ezc_lm_mono(ezc_context* ctx, const ezc_lm_problem* problem, double* focal, double* pp, double* dist,
                        double* poses, double* frame_rmse_out, ezc_lm_summary summaries[3]);
 
+/* The optimisation of EZCalibrator::runMultiCameraCalib (/root/reference/src/ezcalibrator.cpp:631-844): block b is the
+ * extrinsic T_c(b+1)_c0 of camera b+1 with its own CONSTANT intrinsics (problem->cams_per_block = 1;
+ * focal [n_blocks][1|2], pp [n_blocks][2], dist [n_blocks][nd]); problem->pts are cam0's target points T_c0_w * p_w of
+ * every usable cam0 frame (:731-736), problem->obs the matching corners of camera b+1 ((-1,-1) where there is no pair).
+ * One ceres::Solve over all blocks (one radius, one termination).  extrinsics: HOST [n_blocks][7] in/out.
+ * View-sharded multi-GPU: each rank passes the blocks (cameras) it owns, n_blocks_global = all of them. */
+ezc_status ezc_lm_multicam(ezc_context* ctx, const ezc_lm_problem* problem, const double* focal, const double* pp, const double* dist,
+                           double* extrinsics, ezc_lm_summary* summary);
+
 /* Debug / test entry: raw residual r[2] and Jacobian J[2][nf+2+nd+6] (columns focal|pp|dist|pose6) of one
  * observation, evaluated by the same device code the solver uses. */
 ezc_status ezc_lm_residual_jacobian(ezc_context* ctx, int32_t model, int32_t use_mono_focal, const double* focal,

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <string>
 
 #include "ezcalib_b200.hpp"
 
@@ -19,8 +20,103 @@ template <class T> static void rd(std::ifstream& f, T* p, size_t n) {
   if (!f) { std::fprintf(stderr, "short read\n"); std::exit(2); }
 }
 
+// CPU-only: the DistParam / IntrinsicsParam / Camera mirrors (no CUDA context).  One line per quantity; the Python test
+// compares them with the reference's own headers compiled into oracle/_ref/liblm_ref.so.
+static int cpu_mirror() {
+  const char* names[7] = {"rad1", "rad2", "rad3", "radtan4", "radtan5", "radtan8", "kannalabrandt"};
+  const double coefs[8] = {-0.21, 0.06, -0.012, 0.004, 0.0011, -0.0007, 0.0009, -0.0005};
+  for (int m = 0; m < 7; ++m) {
+    auto d = makeDistParam(names[m], m % 2 == 0);
+    const int nd = d->getNumberOfParameters();
+    if ((int)d->model() != m || nd != ezc_num_dist(m)) { std::printf("model-table FAILED\n"); return 1; }
+    std::vector<double> v(coefs, coefs + nd);
+    d->resetParameters(v);
+    const auto back = d->getDistParameters();
+    const auto o = d->distortCamPoint(0.31, -0.17);
+    const auto o3 = d->distortCamPoint(Vector3d{0.62, -0.34, 2.0});
+    const auto u = d->undistortCamPoint(o[0], o[1]);
+    std::vector<double> cov((size_t)nd * nd, 0.);
+    for (int i = 0; i < nd; ++i) cov[(size_t)nd * i + i] = (i + 1.0) * (i + 1.0);
+    d->setDistParamsStd(cov);
+    const auto sd = d->getDistParamsStd();
+    std::printf("dist %s %d %.17g %.17g %.17g %.17g %.17g %.17g %zu", names[m], nd, o[0], o[1], o3[0], o3[1], u[0], u[1], sd.size());
+    for (double x : sd) std::printf(" %.17g", x);
+    for (double x : back) std::printf(" %.17g", x);
+    std::printf("\n");
+  }
+  try { makeDistParam("fisheye62", true); std::printf("unknown-model FAILED\n"); } catch (const std::invalid_argument&) { std::printf("unknown-model ok\n"); }
+  Camera cam("/data/cam0/", true, "radtan5", 70.0);
+  cam.setupInitialCalibration(1280, 1024);
+  const IntrinsicsParam& K = *cam.m_pcalib_params;
+  const Vector3d c = K.projImageToCam(100.25, 700.5);
+  const auto px = K.projCamToImage(Vector3d{0.2, -0.1, 2.0});
+  std::printf("camera %.17g %.17g %.17g %zu %.17g %.17g %.17g %.17g %d %d %d\n", K.getFocal()[0], K.getPrincipalPoint()[0], K.getPrincipalPoint()[1],
+              K.getFocal().size(), c.x, c.y, px[0], px[1], (int)K.isPointInImage(1279.4f, 10.f), (int)K.isPointInImage(1279.5f, 10.f),
+              (int)K.isPointInImage(-0.5, 3.0));
+  const SE3d T = se3::exp({0.1, -0.2, 0.3, 0.2, -0.1, 0.4});
+  const auto lg = se3::log(se3::mul(T, se3::inverse(se3::exp({0.0, 0.0, 0.0, 0.0, 0.0, 1e-12}))));
+  std::printf("se3 %.17g %.17g %.17g %.17g %.17g %.17g %.17g", T.q[0], T.q[1], T.q[2], T.q[3], T.t[0], T.t[1], T.t[2]);
+  for (double x : lg) std::printf(" %.17g", x);
+  std::printf("\n");
+  return 0;
+}
+
+// A 2-camera calibration through the mirror classes: Camera -> setupInitialCalibration -> computeP3PRansac ->
+// computeCalibration(cam) per camera -> runMultiCameraCalib.  argv[2] = binary file:
+//   int32 n_cams, n_frames, n_pts, width, height, mono ; double prior_fov ; char model[32]
+//   double target[n_pts][3] ; float corners[n_cams][n_frames][n_pts][2]
+static int rig(const char* path) {
+  std::ifstream f(path, std::ios::binary);
+  int32_t h[6];
+  rd(f, h, 6);
+  double fov;
+  rd(f, &fov, 1);
+  char model[32];
+  rd(f, model, 32);
+  const int n_cams = h[0], n_frames = h[1], n_pts = h[2];
+  std::vector<Vector3d> target(n_pts);
+  rd(f, &target[0].x, (size_t)n_pts * 3);
+  Context ctx(0);
+  std::vector<Camera> cams;
+  for (int c = 0; c < n_cams; ++c) {
+    cams.emplace_back("/data/cam" + std::to_string(c) + "/", h[5] != 0, std::string(model), fov);
+    Camera& cam = cams.back();
+    cam.m_id = c;
+    cam.setupInitialCalibration(h[3], h[4]);
+    std::vector<std::vector<Point2f>> corners(n_frames, std::vector<Point2f>(n_pts));
+    for (auto& v : corners) rd(f, &v[0].x, (size_t)n_pts * 2);
+    std::vector<SE3d> poses;
+    std::vector<int32_t> ninl;
+    const std::vector<uint8_t> ok = computeP3PRansac(ctx, corners, target, *cam.m_pcalib_params, poses, &ninl);
+    for (int i = 0; i < n_frames; ++i)
+      if (ok[i]) {
+        char name[32];
+        std::snprintf(name, sizeof(name), "%06d.png", i);
+        cam.m_v_calib_frames.emplace_back(name, (double)i, corners[i], poses[i]);
+      }
+    const CalibResult r = computeCalibration(ctx, cam, target);
+    std::printf("rig cam %d frames %zu focal %.17g pp %.17g %.17g dist", c, cam.m_v_calib_frames.size(), cam.m_pcalib_params->getFocal()[0],
+                cam.m_pcalib_params->getPrincipalPoint()[0], cam.m_pcalib_params->getPrincipalPoint()[1]);
+    for (double v : cam.m_pdist_params->getDistParameters()) std::printf(" %.17g", v);
+    std::printf(" cov %d nstd %zu\n", (int)r.covariance_ok, cam.m_pdist_params->getDistParamsStd().size());
+  }
+  const MultiCamResult mr = runMultiCameraCalib(ctx, cams, target);
+  std::printf("rig pairs %zu iterations %d", mr.nb_good_pairs, mr.summary.iterations);
+  for (int c = 1; c < n_cams; ++c) {
+    const SE3d& T = cams[c].m_T_cam0_2_cam;
+    std::printf(" ext %.17g %.17g %.17g %.17g %.17g %.17g %.17g", T.q[0], T.q[1], T.q[2], T.q[3], T.t[0], T.t[1], T.t[2]);
+  }
+  std::printf("\n");
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) return 2;
+  if (std::string(argv[1]) == "--cpu-mirror") return cpu_mirror();
+  if (std::string(argv[1]) == "--rig") {
+    if (argc < 3) return 2;
+    try { return rig(argv[2]); } catch (const std::exception& e) { std::fprintf(stderr, "exception: %s\n", e.what()); return 1; }
+  }
   std::ifstream f(argv[1], std::ios::binary);
   try {
     Context ctx(0);

@@ -96,3 +96,94 @@ def test_cpp_mirror_matches_python_api(ctx, tmp_path):
     std = [ln.split() for ln in lines if ln.startswith("calib std")][0]
     assert len(std) == 2 + 1 + 2 + 5 and all(float(v) > 0 for v in std[2:])
     assert "error-check ok" in lines
+
+
+def test_cpp_param_mirrors_match_the_compiled_reference():
+    """DistParam (7 models: distortCamPoint x3, undistortCamPoint, resetParameters / getDistParameters, the 2*nd std-dev
+    quirk), makeDistParam's config strings, IntrinsicsParam and Camera::setupInitialCalibration of include/ezcalib_b200.hpp
+    against the reference's own headers compiled into oracle/_ref/liblm_ref.so (CPU only, no CUDA context)."""
+    from ezcalib_b200 import ezcalibrator as E, synth
+    from oracle import lm_ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref/liblm_ref.so not built and /root/reference absent")
+    exe = _build()
+    r = subprocess.run([exe, "--cpu-mirror"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    coefs = [-0.21, 0.06, -0.012, 0.004, 0.0011, -0.0007, 0.0009, -0.0005]
+    dl = [ln.split() for ln in lines if ln.startswith("dist ")]
+    assert [d[1] for d in dl] == list(synth.MODELS)
+    for mid, d in enumerate(dl):
+        nd = int(d[2])
+        assert nd == R.num_dist(mid)
+        v = [float(x) for x in d[3:9]]
+        ref = R.distort(mid, coefs[:nd], 0.31, -0.17)
+        assert np.max(np.abs(np.array(v[0:2]) - ref)) <= 1e-15 and np.max(np.abs(np.array(v[2:4]) - ref)) <= 1e-15
+        und = R.undistort(mid, coefs[:nd], ref[0], ref[1])
+        assert np.max(np.abs(np.array(v[4:6]) - und)) <= 1e-12 and np.max(np.abs(und - [0.31, -0.17])) < 2e-5
+        nstd = int(d[9])
+        sd = np.array(d[10:10 + nstd], float)
+        assert np.array_equal(sd, R.dist_std_quirk(mid, np.diag(np.arange(1.0, nd + 1.0) ** 2)))
+        assert np.array_equal(np.array(d[10 + nstd:], float), coefs[:nd])
+    assert "unknown-model ok" in lines
+    cam = [ln.split() for ln in lines if ln.startswith("camera ")][0]
+    f0, pp0 = E.setup_initial_calibration(1280, 1024, 70.0, True)
+    assert float(cam[1]) == f0[0] and [float(cam[2]), float(cam[3])] == list(pp0) and int(cam[4]) == 1
+    assert abs(float(cam[5]) - (100.25 - 640) / f0[0]) < 1e-15 and abs(float(cam[6]) - (700.5 - 512) / f0[0]) < 1e-15
+    assert abs(float(cam[7]) - (f0[0] * 0.1 + 640)) < 1e-12 and abs(float(cam[8]) - (f0[0] * -0.05 + 512)) < 1e-12
+    assert [int(v) for v in cam[9:12]] == [1, 0, 0]
+    se = np.array([ln.split() for ln in lines if ln.startswith("se3 ")][0][1:], float)
+    T = R.se3_plus(np.array([0, 0, 0, 1.0, 0, 0, 0]), np.array([0.1, -0.2, 0.3, 0.2, -0.1, 0.4]))
+    assert np.max(np.abs(se[:7] - T)) <= 1e-15
+    assert np.max(np.abs(se[7:] - R.se3_minus(T, R.se3_plus(np.array([0, 0, 0, 1.0, 0, 0, 0]), np.array([0, 0, 0, 0, 0, 1e-12]))))) <= 1e-14
+
+
+@pytest.mark.gpu
+def test_cpp_rig_calibration_matches_python_api(ctx, tmp_path):
+    """Two cameras through the C++ mirror classes (Camera, IntrinsicsParam, DistParam, computeP3PRansac, computeCalibration,
+    runMultiCameraCalib) == the same flow through the Python host mirror."""
+    from ezcalib_b200 import ezcalibrator as E, synth
+    exe = _build()
+    model, mono, W, H, n_frames, fov = "radtan5", True, 1280, 1024, 16, 70.0
+    tgt = synth.chessboard_target(7, 10, 0.05)
+    rng = np.random.Generator(np.random.Philox(key=91))
+    d = synth.GT_DIST[model]
+    poses0 = synth.sample_poses(rng, n_frames, tgt, model, 900.0, 645.0, 505.0, d, W, H, margin=140, tilt_sigma=0.25)
+    T10 = np.concatenate([synth.quat_from_rotvec(np.array([0.01, -0.03, 0.005])), [-0.06, 0.002, 0.004]])
+    corners = np.zeros((2, n_frames, len(tgt), 2), np.float32)
+    for i, p in enumerate(poses0):
+        corners[0, i] = synth.project(model, 900.0, 900.0, 645.0, 505.0, d, p, tgt) + rng.normal(0, 0.05, (len(tgt), 2))
+        corners[1, i] = synth.project(model, 880.0, 880.0, 630.0, 515.0, d, synth.se3_mul(T10, p), tgt) + rng.normal(0, 0.05, (len(tgt), 2))
+    corners[1, 3] = -1.0   # one view camera 1 does not see
+    path = tmp_path / "rig.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("6i", 2, n_frames, len(tgt), W, H, int(mono)))
+        f.write(struct.pack("d", fov))
+        f.write(model.encode().ljust(32, b"\0"))
+        f.write(np.ascontiguousarray(tgt, np.float64).tobytes())
+        f.write(np.ascontiguousarray(corners, np.float32).tobytes())
+    r = subprocess.run([exe, "--rig", str(path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    cams = []
+    for c in range(2):
+        focal, pp = E.setup_initial_calibration(W, H, fov, mono)
+        cam = E.Camera(model, mono, W, H, focal, pp, np.zeros(len(d)))
+        ok, poses, _ = E.compute_p3p_ransac_batch(ctx, corners[c], tgt, focal, pp, W, H)
+        for i in range(n_frames):
+            if ok[i]:
+                cam.frames.append(E.CalibFrame("%06d.png" % i, corners[c, i], poses[i]))
+        E.compute_calibration(ctx, cam, tgt)
+        cams.append(cam)
+        ln = [x.split() for x in lines if x.startswith(f"rig cam {c} ")][0]
+        assert int(ln[4]) == len(cam.frames)
+        assert float(ln[6]) == cam.focal[0] and [float(ln[8]), float(ln[9])] == list(cam.pp)
+        i_d = ln.index("dist")
+        assert np.array_equal(np.array(ln[i_d + 1:i_d + 1 + len(d)], float), cam.dist)
+        assert int(ln[ln.index("cov") + 1]) == 1 and int(ln[ln.index("nstd") + 1]) == 2 * len(d)
+    out = E.run_multicam_calib(ctx, cams, tgt)
+    ln = [x.split() for x in lines if x.startswith("rig pairs")][0]
+    assert int(ln[2]) == out["n_good_pairs"] and int(ln[4]) == out["summary"]["iterations"]
+    ext = np.array(ln[ln.index("ext") + 1:ln.index("ext") + 8], float)
+    assert np.max(np.abs(ext - cams[1].T_cam0_2_cam)) <= 1e-9
+    assert np.max(np.abs(ext[4:] - T10[4:])) < 2e-3   # and it is the rig's baseline

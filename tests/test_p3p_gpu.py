@@ -72,13 +72,21 @@ def test_failures_and_dual_focal(ctx):
 
 
 def test_4k_rig_sized_batch_is_deterministic(ctx):
-    """cfg4 size: 2000 views x 144 points; run twice -> bit-identical; every clean view succeeds with all its points."""
+    """cfg4 size: 2000 views x 144 points at 3840x2160 (prior focal 15 % off, so the pinhole hypotheses do not explain
+    every point): run twice -> bit-identical; a sample of the views equals cv2 (inlier sets, poses <= 1e-6)."""
+    pytest.importorskip("cv2")
     from ezcalib_b200 import ezcalibrator as E
     target = synth.aprilgrid_target(6, 6, 0.06, 0.3)
     views, focal, pp, W, H = _views(target, 2000, seed=25, W=3840, H=2160, f=2800.0)
     corners = np.stack(views)
-    a = E.compute_p3p_ransac_batch(ctx, corners, target, focal, pp, W, H)
-    b = E.compute_p3p_ransac_batch(ctx, corners, target, focal, pp, W, H)
-    assert a[0].all() and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
-    inside = ((corners[..., 0] > -0.5) & (corners[..., 1] > -0.5) & (corners[..., 0] < W - 0.5) & (corners[..., 1] < H - 0.5)).sum(1)
-    assert np.array_equal(a[2], inside)
+    a = E.compute_p3p_ransac_batch(ctx, corners, target, focal, pp, W, H, want_debug=True)
+    b = E.compute_p3p_ransac_batch(ctx, corners, target, focal, pp, W, H, want_debug=True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    worst = 0.0
+    for k in range(0, 2000, 50):
+        ok0, pose0, inl0, rt0 = PR.compute_p3p_ransac_cv2(views[k], target, focal, pp, W, H)
+        assert bool(a[0][k]) == ok0 and np.array_equal(np.nonzero(a[3][k])[0], inl0)
+        if ok0:
+            worst = max(worst, float(np.max(np.abs(a[1][k] - pose0))))
+    assert worst <= 1e-6, worst

@@ -65,3 +65,38 @@ def test_chessboard_images_to_calibration(ctx):
     assert np.max(np.abs(cam.pp - pp_ref)) <= 1e-2
     assert np.max(np.abs(cam.dist - d_ref)) <= 1e-4
     assert np.max(np.abs(np.array([fr.rmse_err for fr in cam.frames]) - rmse_ref)) <= 1e-3
+
+
+def test_refine_calibration_drops_bad_views_and_equals_oracle(ctx):
+    """EZCalibrator::refineCalibration (ezcalibrator.cpp:342-557): one all-variable solve over the frames with rmse_err <= 1,
+    against the oracle's single solve on the same subset; frames above 1 px keep their pose and rmse_err."""
+    from ezcalib_b200 import ezcalibrator as E, synth
+    model, mono, W, H = "radtan5", True, 1280, 1024
+    mid = synth.MODEL_ID[model]
+    tgt = synth.chessboard_target(7, 10, 0.05)
+    P = synth.make_lm_problem(model, mono, 14, tgt, W, H, seed=31)
+    cam = E.Camera(model, mono, W, H, P.focal_init, P.pp_init, P.dist_init)
+    for i in range(14):
+        cam.frames.append(E.CalibFrame(str(i), P.obs[i], P.poses_init[i]))
+    # two views with grossly wrong observations: they end above 1 px after the staged solve
+    rng = np.random.default_rng(5)
+    for i in (4, 9):
+        cam.frames[i].corners_px = (P.obs[i] + rng.normal(0, 6.0, P.obs[i].shape)).astype(np.float32)
+    E.compute_calibration(ctx, cam, tgt)
+    assert cam.stds is not None and len(cam.stds[2]) == 5 and all(v > 0 for v in cam.stds[0])
+    bad = [i for i, f in enumerate(cam.frames) if f.rmse_err > 1.0]
+    assert bad == [4, 9]
+    keep_pose = {i: cam.frames[i].T_world_2_cam.copy() for i in bad}
+    keep_rmse = {i: cam.frames[i].rmse_err for i in bad}
+    good = [i for i in range(14) if i not in bad]
+    obs = np.stack([cam.frames[i].corners_px for i in good])
+    poses = np.stack([cam.frames[i].T_world_2_cam for i in good])
+    f_ref, pp_ref, d_ref, poses_ref, s_ref, _ = O.solve(mid, mono, obs, tgt, W, H, cam.focal, cam.pp, cam.dist, poses)
+    rm_ref = O.frame_rmse(mid, mono, obs, tgt, W, H, f_ref, pp_ref, d_ref, poses_ref)
+    summ = E.refine_calibration(ctx, cam, tgt)
+    assert summ["iterations"] == s_ref["iterations"] and summ["termination"] == s_ref["termination"]
+    assert abs(cam.focal[0] - f_ref[0]) / f_ref[0] <= 1e-6 and np.max(np.abs(cam.pp - pp_ref) / pp_ref) <= 1e-6
+    assert np.max(np.abs(cam.dist - d_ref)) <= 1e-6 * max(1.0, np.max(np.abs(d_ref)))
+    assert np.max(np.abs(np.array([cam.frames[i].rmse_err for i in good]) - rm_ref)) <= 1e-6
+    for i in bad:
+        assert np.array_equal(cam.frames[i].T_world_2_cam, keep_pose[i]) and cam.frames[i].rmse_err == keep_rmse[i]
