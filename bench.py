@@ -208,6 +208,15 @@ def run_gpu(args):
     if world > 1:
         ctx.set_allreduce(allreduce, rank, world)
 
+    if args.only_rig:
+        rig = run_cfg4(ctx, args, rank, world, stream)
+        if rank == 0:
+            emit({"metric": "cfg4 only (development run)", "cfg4": rig})
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        ctx.close()
+        return
     models = BENCH_MODELS if not args.models else tuple(args.models.split(","))
     n_views = args.views
     K, W = args.steps, args.warmup
@@ -325,14 +334,26 @@ def run_gpu(args):
     if not args.no_detect:
         line["detect"] = run_detect(ctx, args, rank, world, stream)
         line["gpu_launches"] += line["detect"]["gpu_launches"]
-        if world == 1:
-            line["detect_chessboard"] = run_detect_chessboard(ctx, args, rank, world, stream, "cfg1")
-            line["detect_chessboard_stereo"] = run_detect_chessboard(ctx, args, rank, world, stream, "cfg2")
-            line["gpu_launches"] += line["detect_chessboard"]["gpu_launches"] + line["detect_chessboard_stereo"]["gpu_launches"]
+        line["detect_chessboard"] = run_detect_chessboard(ctx, args, rank, world, stream, "cfg1")
+        line["detect_chessboard_stereo"] = run_detect_chessboard(ctx, args, rank, world, stream, "cfg2")
+        line["gpu_launches"] += line["detect_chessboard"]["gpu_launches"] + line["detect_chessboard_stereo"]["gpu_launches"]
+    if not args.no_rig:
+        rig = run_cfg4(ctx, args, rank, world, stream)
+        if rank == 0:
+            line["cfg4"] = rig
+            line["gpu_launches"] += rig["gpu_launches"]
     if rank == 0:
         if not args.no_cpu and world >= 1:
             v, ms_cpu, cb = run_cpu(argparse.Namespace(steps=min(K, 10), warmup=1), ("radtan5",), args.cpu_views, False)
             line["cpu_baseline"] = cb
+        # compact recap LAST: whoever keeps only the tail of a long line still sees every per-N number
+        head = {"n_gpus": world, "lm_iters_s": line["value"], "lm_e2e_iters_s": line["e2e"]["value"], "lm_roofline_frac": line["roofline"]["frac"]}
+        if "detect" in line:
+            head.update(aprilgrid_img_s=line["detect"]["value"], aprilgrid_e2e_img_s=line["detect"]["e2e"]["value"],
+                        chessboard_cfg1_img_s=line["detect_chessboard"]["value"], chessboard_cfg2_img_s=line["detect_chessboard_stereo"]["value"])
+        if line.get("cfg4"):
+            head.update(cfg4_wall_s=line["cfg4"]["value"], cfg4_frames=line["cfg4"]["frames_total"], cfg4_speedup_vs_cpu=line["cfg4"].get("speedup_vs_cpu"))
+        line["headline"] = head
         emit(line)
     if world > 1:
         dist.barrier()
@@ -445,6 +466,173 @@ def run_detect(ctx, args, rank, world, stream):
     return out
 
 
+# ------------------------------------------------------------------------------------------- cfg4: the 8-camera rig
+RIG_W, RIG_H, RIG_CAMS = 3840, 2160, 8
+
+
+def rig_ground_truth():
+    """8 cameras around cam0 (all overlap cam0): per-camera intrinsics, radtan8 distortion, T_cj_c0."""
+    from ezcalib_b200 import synth
+    rng = np.random.Generator(np.random.Philox(key=synth.MASTER_SEED + 4000))
+    d0 = np.array(synth.GT_DIST["radtan8"])
+    cams, ext = [], []
+    for c in range(RIG_CAMS):
+        f = 2750.0 * (1 + 0.01 * rng.standard_normal())
+        cams.append(dict(f=f, cx=RIG_W / 2 + 6 * rng.standard_normal(), cy=RIG_H / 2 + 6 * rng.standard_normal(),
+                         d=d0 * (1 + 0.05 * rng.standard_normal(len(d0)))))
+        if c == 0:
+            ext.append(np.array([0, 0, 0, 1.0, 0, 0, 0]))
+        else:
+            ext.append(np.concatenate([synth.quat_from_rotvec(np.deg2rad(1.5) * rng.standard_normal(3)),
+                                       np.array([0.06, 0.04, 0.01]) * rng.standard_normal(3)]))
+    return cams, ext
+
+
+def run_cfg4(ctx, args, rank, world, stream):
+    """BASELINE.json configs[3]: 8 cameras x n synchronised 3840x2160 frames (6x6 AprilGrid, radtan8), camera c on GPU c % N:
+    detect -> P3P-RANSAC -> 3-stage solve per camera, cam0's poses broadcast, joint extrinsic solve with scalar all-reduces
+    (apps/ezcalib.cpp:205-218, src/ezcalibrator.cpp:20-67, :631-844).  Frames are rendered into HBM in chunks outside the
+    timed regions (they stand for cv::imread, which SURVEY 8d excludes on both sides)."""
+    import torch
+    import torch.distributed as dist
+
+    from ezcalib_b200 import detect, ezcalibrator as E, synth
+    from ezcalib_b200 import dist as ezdist
+    n = args.rig_frames
+    model, mono, fov = "radtan8", True, 70.0
+    mid = synth.MODEL_ID[model]
+    tgt = synth.aprilgrid_target(DET_ROWS, DET_COLS, 0.06, 0.3)
+    gt_cams, gt_ext = rig_ground_truth()
+    rng = np.random.Generator(np.random.Philox(key=synth.MASTER_SEED + 4001))
+    c0 = gt_cams[0]
+    poses0 = synth.sample_poses(rng, n, tgt, model, c0["f"], c0["cx"], c0["cy"], c0["d"], RIG_W, RIG_H, margin=260, tilt_sigma=0.3)
+    names = ["%06d.png" % i for i in range(n)]
+    mine = [c for c in range(RIG_CAMS) if c % world == rank]
+    comm = ezdist.TorchComm() if world > 1 else E.SingleProcessComm()
+    chunk = max(1, min(n, args.rig_chunk))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    det_ms, n_imgs, launches0 = 0.0, 0, ctx.kernel_launches()
+    timings, local, sample = {}, {}, None
+    for c in mine:
+        g = gt_cams[c]
+        poses_c = np.stack([synth.se3_mul(gt_ext[c], p) for p in poses0])
+        cam12 = np.array([g["f"], g["f"], g["cx"], g["cy"]] + list(g["d"]))
+        found = np.zeros(n, bool)
+        corners = np.zeros((n, len(tgt), 2), np.float32)
+        for b in range(0, n, chunk):
+            m = min(chunk, n - b)
+            imgs = detect.render_targets(ctx, "aprilgrid", DET_ROWS, DET_COLS, 0.06, 0.3, mid, RIG_W, RIG_H, np.tile(cam12, (m, 1)),
+                                         poses_c[b:b + m], seed=synth.MASTER_SEED + 100 * c + b)
+            if c == mine[0] and b == 0:
+                detect.detect_aprilgrid(ctx, imgs, DET_ROWS, DET_COLS)   # warm-up (pools, first-launch costs), untimed
+                if rank == 0 and not args.no_cpu:
+                    k = min(m, args.rig_cpu_frames)
+                    sample = dict(images=imgs.download(0, k), cam=c)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            f_, c_, _ = detect.detect_aprilgrid(ctx, imgs, DET_ROWS, DET_COLS)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            det_ms += e0.elapsed_time(e1)
+            n_imgs += m
+            found[b:b + m] = f_
+            corners[b:b + m] = c_
+            imgs.close()
+        cam, processed, _ = E.calibrate_camera_from_corners(ctx, found, corners, names, tgt, model, mono, fov, RIG_W, RIG_H, timings)
+        local[c] = cam
+        if sample is not None and sample["cam"] == c:
+            sample.update(found=found[:len(sample["images"])].copy(), corners=corners[:len(sample["images"])].copy())
+    if world > 1:
+        dist.barrier()
+    ext, msum = E.run_rig_extrinsics(ctx, local, RIG_CAMS, tgt, comm, timings)
+    torch.cuda.synchronize()
+    launches = ctx.kernel_launches() - launches0
+    stage = np.array([det_ms * 1e-3, timings.get("p3p_s", 0.0), timings.get("solve_s", 0.0),
+                      timings.get("multicam_setup_s", 0.0) + timings.get("multicam_solve_s", 0.0)])
+    wall = float(stage.sum())
+    if world > 1:
+        t = torch.tensor(list(stage) + [wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stage, wall = t[:4].cpu().numpy(), float(t[4].item())
+    # sanity against the ground truth of the renders (calibration quality, not parity)
+    stats = []
+    for c in mine:
+        cam, g = local[c], gt_cams[c]
+        rm = np.array([f.rmse_err for f in cam.frames])
+        e = dict(cam=c, frames=len(cam.frames), focal_rel_err=abs(cam.focal[0] - g["f"]) / g["f"], median_rmse_px=float(np.median(rm)),
+                 frames_rmse_gt_1px=int((rm > 1.0).sum()))
+        if c >= 1:
+            e["baseline_err_mm"] = float(1e3 * np.linalg.norm(ext[c][4:] - gt_ext[c][4:]))
+        stats.append(e)
+    allstats = comm.allgather(stats)
+    out = None
+    if rank == 0:
+        flat = sorted((e for part in allstats for e in part), key=lambda e: e["cam"])
+        total_frames = RIG_CAMS * n
+        out = {"metric": "calibration wall-time, 8-camera rig", "value": round(wall, 4), "unit": "s", "higher_is_better": False,
+               "config": {"workload": "cfg4: %d cameras x %d synchronised %dx%d frames, 6x6 AprilGrid 36h11, radtan8 mono focal; camera c on GPU c %% %d; "
+                                      "frames rendered into HBM in chunks of %d outside the timed regions" % (RIG_CAMS, n, RIG_W, RIG_H, world, chunk)},
+               "n_gpus": world, "frames_total": total_frames,
+               "stage_s": {"detect": round(float(stage[0]), 4), "p3p": round(float(stage[1]), 4), "mono_solve": round(float(stage[2]), 4),
+                           "multicam": round(float(stage[3]), 4)},
+               "detect_images_per_s": round(n_imgs * world / max(float(stage[0]), 1e-9), 1),
+               "multicam": {"iterations": msum["iterations"], "termination": msum["termination_name"], "n_good_pairs": msum["n_good_pairs"]},
+               "per_camera": flat, "gpu_launches": int(launches),
+               "sane": bool(all(e["focal_rel_err"] < 5e-3 and e["median_rmse_px"] < 0.5 for e in flat) and
+                            all(e.get("baseline_err_mm", 0.0) < 5.0 for e in flat))}
+        if sample is not None:
+            out["cpu_baseline"] = cfg4_cpu_baseline(sample, tgt, model, mono, fov, n, local[sample["cam"]])
+            if out["cpu_baseline"].get("wall_s_extrapolated"):
+                out["speedup_vs_cpu"] = round(out["cpu_baseline"]["wall_s_extrapolated"] / wall, 1)
+    return out
+
+
+def cfg4_cpu_baseline(sample, tgt, model, mono, fov, n_frames, cam_gpu):
+    """The reference's serial flow (ezcalibrator.cpp:40-59, apps/ezcalib.cpp:205-218) timed on a stated sample of the same
+    frames and extrapolated linearly to the whole rig: extractTags (the reference's own sources, oracle/_ref, OpenMP) +
+    cv2.cornerSubPix per frame, cv2.solvePnPRansac per frame, the restated-Ceres 3-stage solve on the sampled views."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "p3p_harness"))
+    import p3p_cv2_ref as PR
+    from ezcalib_b200 import ezcalibrator as E, synth
+    from oracle import apriltag_oracle as A
+    from oracle import lm_oracle as O
+    imgs = sample["images"]
+    k = len(imgs)
+    focal0, pp0 = E.setup_initial_calibration(RIG_W, RIG_H, fov, mono)
+    A.detect_target(imgs[0], DET_ROWS, DET_COLS)
+    t0 = time.perf_counter()
+    det_same, obs, poses = True, [], []
+    for i in range(k):
+        ok, c, nd, _ = A.detect_target(imgs[i], DET_ROWS, DET_COLS)
+        det_same = det_same and bool(ok) == bool(sample["found"][i]) and np.array_equal(c[:, 0] < 0, sample["corners"][i][:, 0] < 0) \
+            and float(np.abs(c - sample["corners"][i]).max()) <= 0.01
+        if ok:
+            obs.append(c.astype(np.float32))
+    t1 = time.perf_counter()
+    p3p_same = True
+    by_name = {f.img_name: f for f in cam_gpu.frames}
+    for c in obs:
+        okp, pose, _, _ = PR.compute_p3p_ransac_cv2(c, tgt, focal0, pp0, RIG_W, RIG_H)
+        if okp:
+            poses.append(pose)
+    t2 = time.perf_counter()
+    n_lm = len(poses)
+    lm_s = 0.0
+    if n_lm >= 4:
+        O.solve_mono(synth.MODEL_ID[model], mono, np.stack(obs[:n_lm]), tgt, RIG_W, RIG_H, focal0, pp0, np.zeros(8), np.stack(poses), threads=host_cores())
+        lm_s = time.perf_counter() - t2
+    per_frame = (t2 - t0) / k + (lm_s / n_lm if n_lm else 0.0)
+    del by_name, p3p_same
+    return {"value": round(k / (t2 - t0 + lm_s), 4), "unit": "frames/s (detect + P3P + solve)", "cores": host_cores(), "kind": "reference",
+            "sample": "%d frames of camera %d: the reference's own extractTags (oracle/_ref, OpenMP) + cv2.cornerSubPix, cv2.solvePnPRansac, "
+                      "restated-Ceres 3-stage solve on those views; serial frame loop like ezcalibrator.cpp:40-59" % (k, sample["cam"]),
+            "detect_s_per_frame": round((t1 - t0) / k, 4), "p3p_s_per_frame": round((t2 - t1) / max(len(obs), 1), 6),
+            "solve_s_per_view": round(lm_s / n_lm, 6) if n_lm else None,
+            "wall_s_extrapolated": round(per_frame * RIG_CAMS * n_frames, 1),
+            "extrapolation": "per-frame cost x %d frames (the multi-camera extrinsic solve is not included on the CPU side)" % (RIG_CAMS * n_frames),
+            "detect_parity_on_sample": bool(det_same)}
+
+
 CB_CONFIGS = {
     # BASELINE.json configs[0]: calib_chessboard_mono_config.yaml geometry (more views than the reference's 50 so that
     # the batch exceeds L2 and the timing is not launch noise)
@@ -481,7 +669,6 @@ def run_detect_chessboard(ctx, args, rank, world, stream, cfg="cfg1"):
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    value = n * reps / (ms * 1e-3)
     # e2e: pinned host images -> (async) upload -> detect -> corners on the host
     host_all = imgs.download(0, n)
     pin = torch.from_numpy(host_all).pin_memory()
@@ -498,15 +685,21 @@ def run_detect_chessboard(ctx, args, rank, world, stream, cfg="cfg1"):
         im2.close()
         assert np.array_equal(f2, found) and np.array_equal(c2, corners)
     ms2 = float(np.median(runs))
+    if world > 1:   # weak scaling: n views per rank, slowest rank decides
+        import torch.distributed as dist
+        t = torch.tensor([ms, ms2], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms2 = float(t[0].item()), float(t[1].item())
+    value = n * reps * world / (ms * 1e-3)
     alg_bytes = W * H + 8 * 54
     peak = measured_peaks().get("hbm_gbs", 6650.0)
     out = {"metric": "images/s detect+subpix (chessboard)", "value": round(value, 2), "unit": "images/s",
            "config": {"workload": "%s: %d views %dx%d, 9x6 inner corners, rendered into HBM (inputs %.2f GB > L2)" % (C["label"], n, W, H, n * W * H / 1e9),
                       "found": int(found.sum())},
-           "e2e": {"value": round(n / (ms2 * 1e-3), 2), "unit": "images/s", "h2d_bytes_per_step": int(W * H), "d2h_bytes_per_step": 8 * 54 + 1},
+           "e2e": {"value": round(n * world / (ms2 * 1e-3), 2), "unit": "images/s", "h2d_bytes_per_step": int(W * H), "d2h_bytes_per_step": 8 * 54 + 1},
            "gpu_launches": int(ctx.kernel_launches() - l0),
-           "roofline": {"bound": "hbm", "achieved": round(value * alg_bytes / 1e9, 3), "peak": peak, "unit": "GB/s",
-                        "frac": round(value * alg_bytes / 1e9 / peak, 6), "traffic": None}}
+           "roofline": {"bound": "hbm", "achieved": round(value / world * alg_bytes / 1e9, 3), "peak": peak, "unit": "GB/s",
+                        "frac": round(value / world * alg_bytes / 1e9 / peak, 6), "traffic": None}}
     if rank == 0 and not args.no_cpu:
         import cv2
         flags = cv2.CALIB_CB_ADAPTIVE_THRESH + cv2.CALIB_CB_NORMALIZE_IMAGE + cv2.CALIB_CB_FILTER_QUADS + cv2.CALIB_CB_FAST_CHECK
@@ -609,6 +802,11 @@ def main():
     ap.add_argument("--det-reps", type=int, default=2)
     ap.add_argument("--cb-images", type=int, default=400)
     ap.add_argument("--det-cpu-images", type=int, default=24)
+    ap.add_argument("--no-rig", action="store_true")
+    ap.add_argument("--rig-frames", type=int, default=2000)
+    ap.add_argument("--rig-chunk", type=int, default=500)
+    ap.add_argument("--rig-cpu-frames", type=int, default=6)
+    ap.add_argument("--only-rig", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))

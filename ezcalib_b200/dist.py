@@ -45,3 +45,22 @@ def make_allreduce(device: str = "cuda", group=None):
         dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM, group=group)
 
     return fn
+
+
+class TorchComm:
+    """The communicator ezcalibrator.run_rig_extrinsics takes, over torch.distributed (host objects: NCCL or gloo group)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def bcast(self, obj, src: int):
+        box = [obj]
+        self._dist.broadcast_object_list(box, src=src, group=self.group)
+        return box[0]
+
+    def allgather(self, obj):
+        out = [None] * self.world
+        self._dist.all_gather_object(out, obj, group=self.group)
+        return out

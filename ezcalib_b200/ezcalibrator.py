@@ -104,51 +104,51 @@ def refine_calibration(ctx: lm.Context, cam: Camera, target: np.ndarray):
     return _solve_frames(ctx, cam, target, good, [(True, True, True)])[0]
 
 
+def multicam_block(cam0_frames: list, camj: Camera, cam_index: int, target: np.ndarray):
+    """One camera's share of EZCalibrator::runMultiCameraCalib's problem (ezcalibrator.cpp:654-785): the initial T_cj_c0 and
+    the observation rows against cam0's frames.  cam0_frames: objects with img_name / T_world_2_cam / rmse_err (cam0's
+    CalibFrames, or what the rank that owns cam0 broadcast).  Returns (obs [n_frames0 * n_pts, 2], init [7], n_good_pairs).
+    Reproduces the reference's initialisation quirk Q3: the 'median' for camera i is taken over copies of the relative pose
+    of cam0's frame #i (indexed with the CAMERA index, :680).  Frame lists are sorted by image name (the reference's linear
+    scans with their early `break` rely on it, :688-704), so a name lookup finds the same partner."""
+    n_pts = target.shape[0]
+    n0 = len(cam0_frames)
+    by_name = {f.img_name: f for f in camj.frames}
+    if cam_index >= n0:
+        raise IndexError("reference indexes cam0.m_v_calib_frames[camera index] out of range (quirk Q3)")
+    f0 = cam0_frames[cam_index]
+    logs = []
+    n_good = 0
+    if not f0.rmse_err > 1.0:
+        fj = by_name.get(f0.img_name)
+        if fj is not None:
+            lg = synth.se3_log(synth.se3_mul(fj.T_world_2_cam, synth.se3_inverse(f0.T_world_2_cam)))
+            logs = [lg] * n0          # the reference pushes the same value once per cam0 frame (loop variable j unused, :678-680)
+            n_good = n0
+    if not logs:
+        raise IndexError("no usable frame pair for the extrinsic initialisation (the reference reads out of bounds here, :707-713)")
+    logs = np.sort(np.asarray(logs), axis=0)
+    med = logs[len(logs) // 2]
+    init = synth.se3_exp_left(med, np.array([0, 0, 0, 1.0, 0, 0, 0]))
+    obs = np.full((n0 * n_pts, 2), -1.0, np.float32)
+    for a_, f0 in enumerate(cam0_frames):
+        if f0.rmse_err > 1.0:
+            continue
+        fj = by_name.get(f0.img_name)
+        if fj is not None and not fj.rmse_err > 1.0:
+            obs[a_ * n_pts:(a_ + 1) * n_pts] = fj.corners_px
+    return obs, init, n_good
+
+
 def build_multicam_problem(cameras: list[Camera], target: np.ndarray):
     """Problem set-up of EZCalibrator::runMultiCameraCalib (ezcalibrator.cpp:631-785): returns
-    (obs [n_cams-1, n_frames0*n_pts, 2], pts [n_frames0*n_pts, 3], init extrinsics [n_cams-1, 7], n_good_pairs).
-    Reproduces the reference's initialisation quirk Q3: the 'median' for camera i is taken over copies of the relative
-    pose of cam0's frame #i (indexed with the CAMERA index, :680)."""
+    (obs [n_cams-1, n_frames0*n_pts, 2], pts [n_frames0*n_pts, 3], init extrinsics [n_cams-1, 7], n_good_pairs)."""
     cam0 = cameras[0]
-    n_pts = target.shape[0]
-    n0 = len(cam0.frames)
     pts = np.concatenate([synth.transform(f.T_world_2_cam, target) for f in cam0.frames], axis=0)
-    obs = np.full((len(cameras) - 1, n0 * n_pts, 2), -1.0, np.float32)
-    init = np.zeros((len(cameras) - 1, 7))
-    n_good = 0
-    for i in range(1, len(cameras)):
-        camj = cameras[i]
-        logs = []
-        for _ in range(n0):
-            if i >= n0:
-                raise IndexError("reference indexes cam0.m_v_calib_frames[camera index] out of range (quirk Q3)")
-            f0 = cam0.frames[i]
-            if f0.rmse_err > 1.0:
-                continue
-            for fj in camj.frames:
-                if f0.img_name == fj.img_name:
-                    n_good += 1
-                    logs.append(synth.se3_log(synth.se3_mul(fj.T_world_2_cam, synth.se3_inverse(f0.T_world_2_cam))))
-                    break
-                elif fj.img_name > f0.img_name:
-                    break
-        if not logs:
-            raise IndexError("no usable frame pair for the extrinsic initialisation (the reference reads out of bounds here, :707-713)")
-        logs = np.sort(np.asarray(logs), axis=0)
-        med = logs[len(logs) // 2]
-        init[i - 1] = synth.se3_exp_left(med, np.array([0, 0, 0, 1.0, 0, 0, 0]))
-        for a, f0 in enumerate(cam0.frames):
-            if f0.rmse_err > 1.0:
-                continue
-            for fj in camj.frames:
-                if fj.rmse_err > 1.0:
-                    continue
-                if f0.img_name == fj.img_name:
-                    obs[i - 1, a * n_pts:(a + 1) * n_pts] = fj.corners_px
-                    break
-                elif fj.img_name > f0.img_name:
-                    break
-    return obs, pts, init, n_good
+    blocks = [multicam_block(cam0.frames, cameras[i], i, target) for i in range(1, len(cameras))]
+    obs = np.stack([b[0] for b in blocks])
+    init = np.stack([b[1] for b in blocks])
+    return obs, pts, init, int(sum(b[2] for b in blocks))
 
 
 def run_multicam_calib(ctx: lm.Context, cameras: list[Camera], target: np.ndarray):
@@ -253,6 +253,103 @@ def run_calibration(ctx: lm.Context, images: np.ndarray, target_kind: str, nb_ro
         raise RuntimeError("no frame with a detected target and a P3P pose")
     compute_calibration(ctx, cam, target)
     return cam, target, processed
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The whole application flow for a camera rig (apps/ezcalib.cpp:205-218: runCalibration per camera, then
+# runMultiCameraCalib), camera-per-GPU: rank r owns the cameras c with c % world == r.
+class SingleProcessComm:
+    """The communicator interface run_rig_calibration needs; one process, no exchange."""
+    rank, world = 0, 1
+
+    def bcast(self, obj, src: int):
+        return obj
+
+    def allgather(self, obj):
+        return [obj]
+
+
+class _FrameInfo:
+    __slots__ = ("img_name", "T_world_2_cam", "rmse_err")
+
+    def __init__(self, img_name, T, rmse):
+        self.img_name, self.T_world_2_cam, self.rmse_err = img_name, T, rmse
+
+
+def calibrate_camera_from_corners(ctx: lm.Context, found, corners, names, target, model, use_mono_focal, prior_fov_deg, W, H, timings=None):
+    """EZCalibrator::runCalibration after detection (ezcalibrator.cpp:39-67): skip-rule replay, P3P-RANSAC, 3-stage solve."""
+    import time
+    focal, pp = setup_initial_calibration(W, H, prior_fov_deg, use_mono_focal)
+    cam = Camera(model, use_mono_focal, W, H, focal, pp, np.zeros(synth.NUM_DIST[synth.MODEL_ID[model]]))
+    processed = replay_skip_rule([bool(f) for f in found])
+    cand = [i for i in processed if found[i]]
+    t0 = time.perf_counter()
+    if cand:
+        ok, poses, _ = compute_p3p_ransac_batch(ctx, np.asarray(corners)[cand], target, focal, pp, W, H)
+        for k, i in enumerate(cand):
+            if ok[k]:
+                cam.frames.append(CalibFrame(names[i], np.asarray(corners[i], np.float32), poses[k]))
+    t1 = time.perf_counter()
+    if not cam.frames:
+        raise RuntimeError("no frame with a detected target and a P3P pose")
+    summ = compute_calibration(ctx, cam, target)
+    t2 = time.perf_counter()
+    if timings is not None:
+        timings["p3p_s"] = timings.get("p3p_s", 0.0) + (t1 - t0)
+        timings["solve_s"] = timings.get("solve_s", 0.0) + (t2 - t1)
+    return cam, processed, summ
+
+
+def run_rig_extrinsics(ctx: lm.Context, local_cameras: dict, n_cams: int, target: np.ndarray, comm=None, timings=None):
+    """EZCalibrator::runMultiCameraCalib over ranks: local_cameras {camera index: calibrated Camera} holds the cameras this
+    rank owns.  The owner of cam0 broadcasts cam0's frame names, poses and rmse_err (the only data the other cameras' residual
+    blocks need, ezcalibrator.cpp:727-767); every rank builds the blocks of its own cameras; ONE joint solve -- the J^T J
+    is block diagonal per camera, Ceres still uses one trust region and one termination test for all of them, which is what the
+    per-iteration scalar all-reduce of the view-sharded solver provides (install it with ctx.set_allreduce before calling).
+    Returns {camera index: T_cam0_2_cam} for ALL cameras 1..n_cams-1 on every rank, and the summary."""
+    import time
+    comm = comm or SingleProcessComm()
+    t0 = time.perf_counter()
+    owner0 = 0 % comm.world
+    info = None
+    if 0 in local_cameras:
+        info = [(f.img_name, f.T_world_2_cam, f.rmse_err) for f in local_cameras[0].frames]
+    info = comm.bcast(info, owner0)
+    cam0_frames = [_FrameInfo(*x) for x in info]
+    n_pts = target.shape[0]
+    pts = np.concatenate([synth.transform(f.T_world_2_cam, target) for f in cam0_frames], axis=0)
+    mine = sorted(c for c in local_cameras if c >= 1)
+    blocks = [multicam_block(cam0_frames, local_cameras[c], c, target) for c in mine]
+    ref = comm.bcast((local_cameras[mine[0]].model, local_cameras[mine[0]].use_mono_focal, local_cameras[mine[0]].width,
+                      local_cameras[mine[0]].height) if (comm.rank == (1 % comm.world) and mine) else None, 1 % comm.world)
+    m0, mono0, W, H = ref
+    if any(local_cameras[c].model != m0 or local_cameras[c].use_mono_focal != mono0 for c in mine):
+        raise NotImplementedError("mixed distortion models across cameras are not supported yet")
+    nd = synth.NUM_DIST[synth.MODEL_ID[m0]]
+    if mine:
+        obs = np.stack([b[0] for b in blocks])
+        init = np.stack([b[1] for b in blocks])
+        focal = np.concatenate([local_cameras[c].focal for c in mine])
+        pp = np.concatenate([local_cameras[c].pp for c in mine])
+        dist = np.concatenate([local_cameras[c].dist for c in mine])
+    else:
+        obs = np.zeros((0, len(cam0_frames) * n_pts, 2), np.float32)
+        init = np.zeros((0, 7))
+        focal, pp, dist = np.zeros(1 if mono0 else 2), np.zeros(2), np.zeros(nd)
+    t1 = time.perf_counter()
+    ext, summ = lm.lm_multicam(ctx, synth.MODEL_ID[m0], mono0, obs, pts, W, H, focal, pp, dist, init, n_blocks_global=n_cams - 1)
+    t2 = time.perf_counter()
+    parts = comm.allgather({c: ext[k] for k, c in enumerate(mine)})
+    out = {}
+    for p_ in parts:
+        out.update(p_)
+    for c in mine:
+        local_cameras[c].T_cam0_2_cam = out[c]
+    summ["n_good_pairs"] = int(sum(comm.allgather(int(sum(b[2] for b in blocks)))))
+    if timings is not None:
+        timings["multicam_setup_s"] = t1 - t0
+        timings["multicam_solve_s"] = t2 - t1
+    return out, summ
 
 
 # ------------------------------------------------------------------------------------------------------------------
