@@ -151,11 +151,52 @@ constexpr int kHW = kTX + 2, kHH = kTY + 4;     // blur_h tile: cols x-1..x+TX, 
 constexpr int kSW = kTX + 2, kSH = kTY + 2;     // blurred tile: halo 1
 __device__ __constant__ float c_u8f[256];       // (float)((double)v / 255.)   (FloatImage from cv::Mat, TagDetector.cc:131-139)
 
+// Stage D of at_pre (shared by both tile flavours): gradient, activity mask, lazy theta.  Warp w owns rows 4w..4w+3, two
+// 32-pixel words per row.
+template <bool INTERIOR>
+__device__ __forceinline__ void at_pre_gradient(const float (*sb)[kSW], int tid, int im, int x0, int y0, int W, int H, int wpr,
+                                                uint32_t* __restrict__ amask, int* __restrict__ acount, float* __restrict__ theta,
+                                                float* __restrict__ mag) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const long long N = (long long)W * H;
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    const int r = warp * 4 + (k >> 1), cw = (k & 1) * 32;
+    const int y = y0 + r, xw = x0 + cw;
+    if (!INTERIOR && (y >= H || xw >= W)) continue;  // warp-uniform
+    const int x = xw + lane, c = cw + lane;
+    float mg = 0.f, Ix = 0.f, Iy = 0.f;
+    if (INTERIOR || (x >= 1 && x < W - 1 && y >= 1 && y < H - 1)) {
+      Ix = sb[r + 1][c + 2] - sb[r + 1][c];
+      Iy = sb[r + 2][c + 1] - sb[r][c + 1];
+      mg = Ix * Ix + Iy * Iy;
+    }
+    const bool act = mg >= kMinMag;
+    const unsigned m = __ballot_sync(0xffffffffu, act);
+    if (lane == 0) {
+      const long long wi = ((long long)im * H + y) * wpr + (xw >> 5);
+      amask[wi] = m;
+      acount[wi] = __popc(m);
+    }
+    if (act) {
+      const long long g = (long long)im * N + (long long)y * W + x;
+      theta[g] = fd_atan2f(Iy, Ix);
+      mag[g] = mg;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) at_pre_kernel(const uint8_t* __restrict__ img, long long pitch, long long istride, int W, int H,
                                                       int tiles_x, int tiles_y, int wpr, uint32_t* __restrict__ amask,
                                                       int* __restrict__ acount, float* __restrict__ theta, float* __restrict__ mag) {
-  __shared__ float lut[256];
-  __shared__ float u[kUH][kUW];
+  // The blur accumulates three float products in a double and rounds once to float.  Round 1's ncu showed this kernel issue
+  // bound at 252 thread-instructions per pixel: border tests, clamps and 2-D index arithmetic around ~40 instructions of
+  // real work.  Tiles that do not touch the image border (92 % at 2448x2048) now run a branch-free path: aligned 32-bit
+  // pixel loads, flat constant-trip loops, and the horizontal pass -- whose inputs are BYTES -- takes its addends from
+  // tables of the already widened products (double)(lut[v] * f_k) (no f32 -> f64 conversion).  The addends span < 2^11, so
+  // the sum of three is exact in a double and the rounded float is the same for any summation order.
+  __shared__ double lutd[3][256];
+  __shared__ __align__(16) uint32_t uw[kUH][18];   // u8 tile as words: byte b of row r = pixel x0 - 4 + b
   __shared__ float hb[kHH][kHW];
   __shared__ float sb[kSH][kSW];
   const int tid = threadIdx.x;
@@ -165,19 +206,55 @@ __global__ void __launch_bounds__(256) at_pre_kernel(const uint8_t* __restrict__
   const int im = t / tiles_y;
   const int x0 = tx * kTX, y0 = ty * kTY;
   const uint8_t* I = img + (long long)im * istride;
-  lut[tid] = c_u8f[tid];
-  __syncthreads();
-  // thread (lx, ly) = (tid & 63, tid >> 6) walks rows ly, ly+4, ... and columns tx (+64 for the halo columns): no
-  // division per element, column-dependent quantities are computed once
-  const int lx = tid & 63, ly = tid >> 6;
   const float f0 = c_filt[0], f1 = c_filt[1], f2 = c_filt[2];
-  // A. pixels (clamped coordinates: out-of-image entries are never consumed)
+  {
+    const float v = c_u8f[tid];
+    lutd[0][tid] = (double)(v * f0);
+    lutd[1][tid] = (double)(v * f1);
+    lutd[2][tid] = (double)(v * f2);
+  }
+  const uint8_t (*u)[72] = reinterpret_cast<const uint8_t (*)[72]>(uw);
+  const bool interior = x0 >= 4 && x0 + kTX + 4 <= W - 2 && y0 >= 2 && y0 + kTY + 2 <= H - 1 &&
+                        ((reinterpret_cast<uintptr_t>(I) | (uintptr_t)pitch) & 3) == 0;
+  if (interior) {
+    // A. pixels: 36 rows x 18 aligned words (columns x0-4 .. x0+67)
+    for (int i = tid; i < kUH * 18; i += 256) {
+      const int r = i / 18, w = i - r * 18;
+      uw[r][w] = *reinterpret_cast<const uint32_t*>(I + (long long)(y0 - 2 + r) * pitch + (x0 - 4) + 4 * w);
+    }
+    __syncthreads();
+    // B. horizontal pass: h(r, c) at x = x0 - 1 + c  <-  bytes c+4 (x+1), c+3 (x), c+2 (x-1)
+    for (int i = tid; i < kHH * kHW; i += 256) {
+      const int r = i / kHW, c = i - r * kHW;
+      double acc = lutd[0][u[r][c + 4]];
+      acc += lutd[1][u[r][c + 3]];
+      acc += lutd[2][u[r][c + 2]];
+      hb[r][c] = (float)acc;
+    }
+    __syncthreads();
+    // C. vertical pass: s(r, c) at y = y0 - 1 + r  <-  h rows r+2 (y+1), r+1 (y), r (y-1)
+    for (int i = tid; i < kSH * kSW; i += 256) {
+      const int r = i / kSW, c = i - r * kSW;
+      double acc = 0;
+      acc += (double)(hb[r + 2][c] * f0);
+      acc += (double)(hb[r + 1][c] * f1);
+      acc += (double)(hb[r][c] * f2);
+      sb[r][c] = (float)acc;
+    }
+    __syncthreads();
+    at_pre_gradient<true>(sb, tid, im, x0, y0, W, H, wpr, amask, acount, theta, mag);
+    return;
+  }
+  // ---- border tiles: clamped coordinates and the reference's border rules
+  uint8_t (*ub)[72] = reinterpret_cast<uint8_t (*)[72]>(uw);   // byte b of row r = pixel x0 - 2 + b here
+  // thread (lx, ly) = (tid & 63, tid >> 6) walks rows ly, ly+4, ... and columns tx (+64 for the halo columns)
+  const int lx = tid & 63, ly = tid >> 6;
   {
     const int xa = min(max(x0 - 2 + lx, 0), W - 1), xb = min(max(x0 - 2 + 64 + lx, 0), W - 1);
     for (int r = ly; r < kUH; r += 4) {
       const uint8_t* row = I + (long long)min(max(y0 - 2 + r, 0), H - 1) * pitch;
-      u[r][lx] = lut[row[xa]];
-      if (lx < kUW - 64) u[r][64 + lx] = lut[row[xb]];
+      ub[r][lx] = row[xa];
+      if (lx < kUW - 64) ub[r][64 + lx] = row[xb];
     }
   }
   __syncthreads();
@@ -188,18 +265,18 @@ __global__ void __launch_bounds__(256) at_pre_kernel(const uint8_t* __restrict__
       if (x < 0 || x >= W || y < 0 || y >= H) return 0.f;
       double acc = 0;
       if (x >= 2 && x <= W - 2) {
-        acc += (double)(u[r][c + 2] * f0); acc += (double)(u[r][c + 1] * f1); acc += (double)(u[r][c] * f2);
+        acc += lutd[0][ub[r][c + 2]]; acc += lutd[1][ub[r][c + 1]]; acc += lutd[2][ub[r][c]];
       } else {
-        auto px = [&](int xx, int yy) -> float { return lut[I[(long long)yy * pitch + xx]]; };
+        auto px = [&](int xx, int yy) -> int { return I[(long long)yy * pitch + xx]; };
         if (y == 0) {
-          if (x == 0) { acc += (double)(px(1, 0) * f0); acc += (double)(px(0, 0) * f1); acc += (double)(px(0, 0) * f2); }
-          else if (x == 1) { acc += (double)(px(2, 0) * f0); acc += (double)(px(1, 0) * f1); acc += (double)(px(0, 0) * f2); }
-          else { acc += (double)(px(W - 1, 0) * f0); acc += (double)(px(W - 1, 0) * f1); acc += (double)(px(W - 2, 0) * f2); }
+          if (x == 0) { acc += lutd[0][px(1, 0)]; acc += lutd[1][px(0, 0)]; acc += lutd[2][px(0, 0)]; }
+          else if (x == 1) { acc += lutd[0][px(2, 0)]; acc += lutd[1][px(1, 0)]; acc += lutd[2][px(0, 0)]; }
+          else { acc += lutd[0][px(W - 1, 0)]; acc += lutd[1][px(W - 1, 0)]; acc += lutd[2][px(W - 2, 0)]; }
         } else if (y == 1 && x == 0) {
-          acc += (double)(px(0, 1) * f0); acc += (double)(px(0, 1) * f1); acc += (double)(px(W - 1, 0) * f2);
+          acc += lutd[0][px(0, 1)]; acc += lutd[1][px(0, 1)]; acc += lutd[2][px(W - 1, 0)];
         } else {
-          const float a = (x == W - 1) ? px(W - 1, y) : px(0, y);
-          acc += (double)(a * f0); acc += (double)(a * f1); acc += (double)(a * f2);
+          const int a = (x == W - 1) ? px(W - 1, y) : px(0, y);
+          acc += lutd[0][a]; acc += lutd[1][a]; acc += lutd[2][a];
         }
       }
       return (float)acc;
@@ -228,34 +305,7 @@ __global__ void __launch_bounds__(256) at_pre_kernel(const uint8_t* __restrict__
     }
   }
   __syncthreads();
-  // D. gradient, activity mask, lazy theta: warp w owns rows 4w..4w+3, two 32-pixel words per row
-  const int warp = tid >> 5, lane = tid & 31;
-  const long long N = (long long)W * H;
-#pragma unroll 1
-  for (int k = 0; k < 8; ++k) {
-    const int r = warp * 4 + (k >> 1), cw = (k & 1) * 32;
-    const int y = y0 + r, xw = x0 + cw;
-    if (y >= H || xw >= W) continue;  // warp-uniform
-    const int x = xw + lane, c = cw + lane;
-    float mg = 0.f, Ix = 0.f, Iy = 0.f;
-    if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
-      Ix = sb[r + 1][c + 2] - sb[r + 1][c];
-      Iy = sb[r + 2][c + 1] - sb[r][c + 1];
-      mg = Ix * Ix + Iy * Iy;
-    }
-    const bool act = mg >= kMinMag;
-    const unsigned m = __ballot_sync(0xffffffffu, act);
-    if (lane == 0) {
-      const long long wi = ((long long)im * H + y) * wpr + (xw >> 5);
-      amask[wi] = m;
-      acount[wi] = __popc(m);
-    }
-    if (act) {
-      const long long g = (long long)im * N + (long long)y * W + x;
-      theta[g] = fd_atan2f(Iy, Ix);
-      mag[g] = mg;
-    }
-  }
+  at_pre_gradient<false>(sb, tid, im, x0, y0, W, H, wpr, amask, acount, theta, mag);
 }
 
 // compact id of an ACTIVE pixel from the scanned word counts
