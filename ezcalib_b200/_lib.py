@@ -48,7 +48,7 @@ class LmSummaryC(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p)
 
 _lib = None
 

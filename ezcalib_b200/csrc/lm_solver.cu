@@ -51,6 +51,32 @@ constexpr int kMaxSlotRanks = 64;
 __host__ __device__ inline int tile_index(int ti, int tj, int NT) { return ti * NT - ti * (ti - 1) / 2 + (tj - ti); }
 
 // -------------------------------------------------------------------------------------------
+// State of one ceres::Solve, resident in device memory: the trust-region loop (reduced-system solve, accept / reject,
+// radius, termination tests) runs in two one-thread kernels, so the host only enqueues iterations and looks at `done`
+// once per group of iterations instead of synchronising twice per iteration.
+struct LmDevState {
+  int cur, sb;               // which pose buffer / strip buffer holds the current point
+  int done, termination, failed_start;
+  int iter, n_success, n_invalid, n_jac, n_lin;
+  int first, reuse_diagonal, last_successful, fresh, solver_ok, trace_pending;
+  int n_residual_blocks;
+  double radius, decrease_factor, x_cost, x_norm, initial_cost;
+  double scale_c[kMaxK], diag_c[kMaxK], Hcc[kMaxK * kMaxK], gc[kMaxK], uc[kMaxK], dc[kMaxK];
+  CamParams cam, cam_cand;
+};
+
+struct LmDevOpts {
+  int max_num_iterations, max_invalid, trace_capacity;
+  double function_tolerance, gradient_tolerance, parameter_tolerance;
+  double max_radius, min_radius, min_relative_decrease, min_diag, max_diag;
+  double* trace_cost;
+  double* trace_radius;
+  int* trace_flag;
+  int k, nf, n_slots;
+  int cols[kMaxK];
+};
+
+// -------------------------------------------------------------------------------------------
 struct AccumArgs {
   const float2* obs;
   const double* pts;
@@ -65,6 +91,12 @@ struct AccumArgs {
   double* strips;         // [n_segs][8*DA]
   double* part;           // [n_warps][16][32]  persistent tiles
   double* cost_part;      // [n_warps]
+  // device-driven solve: st != nullptr -> poses / strips / camera come from the state (which = 0: current point,
+  // 1: candidate); the launch is a no-op once the solve is done or when the linear solve of this iteration failed
+  const LmDevState* st;
+  int which;
+  const double* poses2[2];
+  double* strips2[2];
 };
 
 // FP64 tensor-core MMA (DMMA): D(8x8) += A(8x4, row) * B(4x8, col).  Fragments: a = A[lane>>2][lane&3],
@@ -87,6 +119,15 @@ lm_accumulate_kernel(const AccumArgs a) {
   const int gw = blockIdx.x * kWarpsPerBlock + warp;
   const int nW = gridDim.x * kWarpsPerBlock;
 
+  const double* poses = a.poses;
+  double* strips_out = a.strips;
+  CamParams cam_shared = a.cam;
+  if (a.st) {
+    if (a.st->done || (a.which && !a.st->solver_ok)) return;
+    poses = a.poses2[a.which ? 1 - a.st->cur : a.st->cur];
+    strips_out = a.strips2[a.which ? 1 - a.st->sb : a.st->sb];
+    cam_shared = a.which ? a.st->cam_cand : a.st->cam;
+  }
   for (int i = lane; i < DA * kCS; i += 32) J[i] = 0.0;
 
   // fragment addressing: column (8g + lane>>2), row (row0 + lane&3)
@@ -102,9 +143,9 @@ lm_accumulate_kernel(const AccumArgs a) {
     const int l1 = min(l0 + a.seg_len, a.M);
     double pose[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) pose[i] = a.poses[(size_t)blk * 7 + i];
+    for (int i = 0; i < 7; ++i) pose[i] = poses[(size_t)blk * 7 + i];
     CamParams cam;
-    if constexpr (PER_BLOCK_CAM) cam = a.cams[blk]; else cam = a.cam;
+    if constexpr (PER_BLOCK_CAM) cam = a.cams[blk]; else cam = cam_shared;
     int nvalid = 0;
 
     for (int c0 = l0; c0 < l1; c0 += 32) {
@@ -166,7 +207,7 @@ lm_accumulate_kernel(const AccumArgs a) {
     }
     // ---- per-view tiles (tile row 0: pose rows, residual row 6, count row 7) -> strip of this segment
     for (int m = 16; m >= 1; m >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, m);
-    double* strip = a.strips + (size_t)seg * (8 * DA);
+    double* strip = strips_out + (size_t)seg * (8 * DA);
 #pragma unroll
     for (int gj = 0; gj < CG; ++gj) {
       double2 v = make_double2(acc[gj][0], acc[gj][1]);
@@ -184,8 +225,20 @@ lm_accumulate_kernel(const AccumArgs a) {
 }
 
 // Sum the per-segment strips of a block (only when a block is split into several segments).
+struct StripSel {   // device-driven solve: buffer pair + which point (see AccumArgs)
+  const LmDevState* st;
+  int which;
+  const double* seg2[2];
+  double* blk2[2];
+};
 __global__ void lm_strip_reduce_kernel(const double* __restrict__ seg_strips, int segs_per_block, int strip_len,
-                                       double* __restrict__ blk_strips) {
+                                       double* __restrict__ blk_strips, const StripSel sel) {
+  if (sel.st) {
+    if (sel.st->done || (sel.which && !sel.st->solver_ok)) return;
+    const int si = sel.which ? 1 - sel.st->sb : sel.st->sb;
+    seg_strips = sel.seg2[si];
+    blk_strips = sel.blk2[si];
+  }
   const int blk = blockIdx.x;
   for (int e = threadIdx.x; e < strip_len; e += blockDim.x) {
     double v = 0.0;
@@ -198,8 +251,9 @@ __global__ void lm_strip_reduce_kernel(const double* __restrict__ seg_strips, in
 // Fixed-order reduction of the persistent H_cc tiles and the cost over all warps of lm_accumulate.
 // grid = k(k+1)/2 + 1 blocks of 256 threads.
 __global__ void lm_hcc_reduce_kernel(const double* __restrict__ part, const double* __restrict__ cost_part, int n_warps,
-                                     int CG, int k, double* __restrict__ red1) {
+                                     int CG, int k, double* __restrict__ red1, const LmDevState* st, int which) {
   __shared__ double sh[256];
+  if (st && (st->done || (which && !st->solver_ok))) return;
   const int nent = k * (k + 1) / 2;
   double v = 0.0;
   int out = R1_COST;
@@ -227,8 +281,9 @@ __global__ void lm_hcc_reduce_kernel(const double* __restrict__ part, const doub
 // Generic fixed-order reduction of partial rows: in[nparts][nv] -> out[nv]; values with index >=
 // max_from are max-reduced.  grid = nv blocks of 256 threads.
 __global__ void lm_reduce_rows_kernel(const double* __restrict__ in, int nparts, int nv, int max_from,
-                                      double* __restrict__ out) {
+                                      double* __restrict__ out, const LmDevState* st) {
   __shared__ double sh[256];
+  if (st && (st->done || !st->solver_ok)) return;
   const int v = blockIdx.x;
   const bool is_max = v >= max_from;
   double acc = 0.0;
@@ -274,6 +329,9 @@ struct SchurArgs {
   double* lyz;            // [n_blocks][kLYZ]
   double* part;           // [grid][nv]
   int nv;                 // nS + 2k + 4 (+1 max)
+  const LmDevState* st;   // device-driven solve: radius / first / reuse_diag and the current buffers come from the state
+  const double* strips2[2];
+  const double* poses2[2];
 };
 
 constexpr int kXS = 36;            // staging stride (32 rows + 4): == 4 mod 16 -> conflict-free MMA fragment loads
@@ -295,6 +353,16 @@ __global__ void __launch_bounds__(128) lm_schur_kernel(const SchurArgs a) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int k = a.k, DA = a.DA;
   const bool live = b < a.n_blocks;
+  const double* strips_in = a.strips;
+  const double* poses_in = a.poses;
+  double radius = a.radius;
+  int first = a.first, reuse_diag = a.reuse_diag;
+  if (a.st) {
+    if (a.st->done) return;
+    strips_in = a.strips2[a.st->sb];
+    poses_in = a.poses2[a.st->cur];
+    radius = a.st->radius; first = a.st->first; reuse_diag = a.st->reuse_diagonal;
+  }
   for (int i = lane; i < 8 * KG * kXS; i += 32) xs[i] = 0.0;
 
   double Wm[6][KC];   // W rows, overwritten in place by Y rows
@@ -312,7 +380,7 @@ __global__ void __launch_bounds__(128) lm_schur_kernel(const SchurArgs a) {
 #pragma unroll
   for (int c = 0; c < KC; ++c) gc[c] = 0.0;
   if (live) {
-    const double* st = a.strips + (size_t)b * 8 * DA;
+    const double* st = strips_in + (size_t)b * 8 * DA;
     // 16-byte loads: every 32-byte sector of the strip rows is consumed by two back-to-back loads of the same lane
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -346,7 +414,7 @@ __global__ void __launch_bounds__(128) lm_schur_kernel(const SchurArgs a) {
     cnt = st[7 * DA + 7];
     if (a.undamped) {
       // sc = 1, lm2 = 0
-    } else if (a.first) {
+    } else if (first) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) { sc[i] = 1.0 / (1.0 + sqrt(H[i][i])); a.scale_p[(size_t)b * 6 + i] = sc[i]; }
     } else {
@@ -354,16 +422,16 @@ __global__ void __launch_bounds__(128) lm_schur_kernel(const SchurArgs a) {
       for (int i = 0; i < 6; ++i) sc[i] = a.scale_p[(size_t)b * 6 + i];
     }
     if (!a.undamped) {
-      if (!a.reuse_diag) {
+      if (!reuse_diag) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           const double d = fmin(fmax(sc[i] * sc[i] * H[i][i], a.min_diag), a.max_diag);
           a.diag_p[(size_t)b * 6 + i] = d;
-          lm2[i] = d / a.radius;
+          lm2[i] = d / radius;
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) lm2[i] = a.diag_p[(size_t)b * 6 + i] / a.radius;
+        for (int i = 0; i < 6; ++i) lm2[i] = a.diag_p[(size_t)b * 6 + i] / radius;
       }
     }
   }
@@ -445,7 +513,7 @@ __global__ void __launch_bounds__(128) lm_schur_kernel(const SchurArgs a) {
         if (2 * j < k) *reinterpret_cast<double2*>(rec + 28 + i * kMaxK + 2 * j) = make_double2(Wm[i][2 * j], (2 * j + 1 < KC) ? Wm[i][2 * j + 1] : 0.0);
     if (cnt > 0.0) {
       nres = cnt; nused = 1.0;
-      const double* x = a.poses + (size_t)b * 7;
+      const double* x = poses_in + (size_t)b * 7;
       double ng[6], out[7];
 #pragma unroll
       for (int i = 0; i < 6; ++i) ng[i] = -g[i];
@@ -482,8 +550,9 @@ __global__ void __launch_bounds__(128) lm_schur_kernel(const SchurArgs a) {
 //   [S upper triangle (k(k+1)/2) | Y^T z (k) | g_c (k) | |x|^2, n_res, n_used, fail | gmax(max)].
 // grid = nv blocks of 256 threads.
 __global__ void lm_schur_reduce_kernel(const double* __restrict__ part, int n_warps, int k, int KG, double* __restrict__ out, int rank,
-                                       int n_slots) {
+                                       int n_slots, const LmDevState* st) {
   __shared__ double sh[256];
+  if (st && st->done) return;
   const int nS = k * (k + 1) / 2;
   const int q = blockIdx.x;
   const int ZC = 8 * KG - 1;
@@ -537,6 +606,9 @@ struct BacksubArgs {
   double uc[kMaxK];      // s_c * yhat_c  (delta_c = -uc)
   double* step_p;        // [n_blocks][6] tangent step actually applied
   double* part;          // [grid][4]
+  const LmDevState* st;  // device-driven solve: uc and the buffers come from the state
+  const double* strips2[2];
+  double* poses2[2];
 };
 
 __global__ void __launch_bounds__(128) lm_backsub_kernel(const BacksubArgs a) {
@@ -544,11 +616,22 @@ __global__ void __launch_bounds__(128) lm_backsub_kernel(const BacksubArgs a) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int k = a.k, DA = a.DA;
   double gd = 0.0, dHd = 0.0, step2 = 0.0, cn2 = 0.0;
+  const double* strips_in = a.strips;
+  const double* poses_in = a.poses;
+  double* cand_out = a.cand_poses;
+  const double* ucp = a.uc;
+  if (a.st) {
+    if (a.st->done || !a.st->solver_ok) return;
+    strips_in = a.strips2[a.st->sb];
+    poses_in = a.poses2[a.st->cur];
+    cand_out = a.poses2[1 - a.st->cur];
+    ucp = a.st->uc;
+  }
   if (b < a.n_blocks) {
-    const double* st = a.strips + (size_t)b * 8 * DA;
+    const double* st = strips_in + (size_t)b * 8 * DA;
     const double* rec = a.lyz + (size_t)b * kLYZ;
-    const double* x = a.poses + (size_t)b * 7;
-    double* xc = a.cand_poses + (size_t)b * 7;
+    const double* x = poses_in + (size_t)b * 7;
+    double* xc = cand_out + (size_t)b * 7;
     const double cnt = st[7 * DA + 7];
     if (cnt > 0.0) {
       double L[6][6], tt[6], y[6], d[6];
@@ -574,8 +657,8 @@ __global__ void __launch_bounds__(128) lm_backsub_kernel(const BacksubArgs a) {
         for (int j = 0; j < kMaxK / 2; ++j) {
           if (2 * j < k) {
             const double2 v = y2[j];
-            sacc -= v.x * a.uc[2 * j];
-            if (2 * j + 1 < k) sacc -= v.y * a.uc[2 * j + 1];
+            sacc -= v.x * ucp[2 * j];
+            if (2 * j + 1 < k) sacc -= v.y * ucp[2 * j + 1];
           }
         }
         tt[i] = sacc;
@@ -601,7 +684,7 @@ __global__ void __launch_bounds__(128) lm_backsub_kernel(const BacksubArgs a) {
 #pragma unroll
         for (int j = 0; j < 6; ++j) hrow += ((i <= j) ? st[i * DA + j] : st[j * DA + i]) * d[j];
         double wrow = 0.0;
-        for (int c = 0; c < k; ++c) wrow += st[i * DA + 8 + c] * (-a.uc[c]);
+        for (int c = 0; c < k; ++c) wrow += st[i * DA + 8 + c] * (-ucp[c]);
         dHd += d[i] * (hrow + 2.0 * wrow);
       }
     } else {
@@ -616,6 +699,188 @@ __global__ void __launch_bounds__(128) lm_backsub_kernel(const BacksubArgs a) {
   v = block_reduce(dHd, false, sh);          if (threadIdx.x == 0) pout[1] = v;
   v = block_reduce(step2, false, sh);        if (threadIdx.x == 0) pout[2] = v;
   v = block_reduce(cn2, false, sh);          if (threadIdx.x == 0) pout[3] = v;
+}
+
+// -------------------------------------------------------------------------------------------
+// The trust-region loop of ceres::Solve on the device (one thread; k <= 12).  Same rules, same order of evaluation as the
+// host loop they replace (kept below as lm_solve_host_loop for A/B runs, EZC_LM_HOST_LOOP=1).
+__device__ __forceinline__ double* dev_shared_param(CamParams& c, int nf, int j) {
+  if (j < nf) return &c.focal[j];
+  if (j < nf + 2) return &c.pp[j - nf];
+  return &c.dist[j - nf - 2];
+}
+__device__ __forceinline__ void dev_record(const LmDevState* st, const LmDevOpts& o, int it, double cost, int flag) {
+  if (it < o.trace_capacity) {
+    if (o.trace_cost) o.trace_cost[it] = cost;
+    if (o.trace_radius) o.trace_radius[it] = st->radius;
+    if (o.trace_flag) o.trace_flag[it] = flag;
+  }
+}
+__device__ __forceinline__ void dev_take_hcc(LmDevState* st, const double* x2, int k) {
+  st->x_cost = x2[R1_COST];
+  for (int a = 0; a < k; ++a)
+    for (int b = a; b < k; ++b) st->Hcc[a * k + b] = st->Hcc[b * k + a] = x2[R1_HCC + a * kMaxK + b];
+}
+__device__ __forceinline__ void dev_loop_top(LmDevState* st, const LmDevOpts& o) {
+  // TrustRegionMinimizer::FinalizeIterationAndCheckIfMinimizerCanContinue: max iterations, then (in lm_step, once the
+  // gradient of this point is known) the gradient tolerance, then the minimum radius
+  if (st->iter >= o.max_num_iterations) { st->termination = 3; st->done = 1; }
+  else if (st->radius <= o.min_radius) { st->termination = 4; st->done = 1; }
+}
+
+// after the first Jacobian evaluation (H_cc + cost of the starting point, all-reduced, in x2)
+__global__ void lm_init_kernel(LmDevState* st, const double* __restrict__ x2, const LmDevOpts o) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  dev_take_hcc(st, x2, o.k);
+  st->n_jac = 1;
+  st->initial_cost = st->x_cost;
+  if (!isfinite(st->x_cost)) { st->failed_start = 1; st->termination = 5; st->done = 1; return; }
+  dev_loop_top(st, o);
+}
+
+// after lm_schur + reduction (packet x1, all-reduced): gradient test, reduced system, candidate shared parameters
+__global__ void lm_step_kernel(LmDevState* st, const double* __restrict__ x1, const LmDevOpts o) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || st->done) return;
+  const int k = o.k, nf = o.nf, nS = k * (k + 1) / 2;
+  const double* Ssum = x1;
+  const double* bsum = x1 + nS;
+  const double* gcs = x1 + nS + k;
+  const double xn2_p = x1[nS + 2 * k + 0], nres = x1[nS + 2 * k + 1], fail = x1[nS + 2 * k + 3];
+  double gmax = 0.0;
+  for (int r = 0; r < o.n_slots; ++r) gmax = fmax(gmax, x1[nS + 2 * k + 4 + r]);
+  ++st->n_lin;
+  if (st->fresh) {
+    for (int c = 0; c < k; ++c) st->gc[c] = gcs[c];
+    if (st->first) {
+      st->n_residual_blocks = (int)nres;
+      for (int c = 0; c < k; ++c) st->scale_c[c] = 1.0 / (1.0 + sqrt(st->Hcc[c * k + c]));
+      double xs = xn2_p;
+      for (int c = 0; c < k; ++c) { const double v = *dev_shared_param(st->cam, nf, o.cols[c]); xs += v * v; }
+      st->x_norm = sqrt(xs);
+      dev_record(st, o, 0, st->x_cost, 0);
+    } else if (st->trace_pending >= 0) {
+      dev_record(st, o, st->trace_pending, st->x_cost, 1);
+    }
+    st->trace_pending = -1;
+    st->fresh = 0;
+  }
+  st->first = 0;
+  for (int c = 0; c < k; ++c) gmax = fmax(gmax, fabs(st->gc[c]));
+  if (st->last_successful && gmax <= o.gradient_tolerance) { st->termination = 2; st->done = 1; return; }
+  ++st->iter;
+  if (!st->reuse_diagonal)
+    for (int c = 0; c < k; ++c)
+      st->diag_c[c] = fmin(fmax(st->scale_c[c] * st->scale_c[c] * st->Hcc[c * k + c], o.min_diag), o.max_diag);
+  st->reuse_diagonal = 1;
+  bool ok = (fail == 0.0);
+  for (int c = 0; c < kMaxK; ++c) { st->uc[c] = 0.0; st->dc[c] = 0.0; }
+  if (ok && k > 0) {
+    double S[kMaxK * kMaxK], rhs[kMaxK];
+    int q = 0;
+    for (int a = 0; a < k; ++a)
+      for (int b = a; b < k; ++b) {
+        const double v = st->scale_c[a] * st->scale_c[b] * (st->Hcc[a * k + b] - Ssum[q]);
+        S[a * k + b] = S[b * k + a] = v;
+        ++q;
+      }
+    for (int c = 0; c < k; ++c) {
+      S[c * k + c] += st->diag_c[c] / st->radius;
+      rhs[c] = st->scale_c[c] * (st->gc[c] - bsum[c]);
+    }
+    // in-place Cholesky (lower) + solve, same operation order as host_cholesky / host_chol_solve
+    for (int j = 0; j < k && ok; ++j) {
+      double d = S[j * k + j];
+      for (int m = 0; m < j; ++m) d -= S[j * k + m] * S[j * k + m];
+      if (!(d > 0.0)) { ok = false; break; }
+      d = sqrt(d);
+      S[j * k + j] = d;
+      for (int i = j + 1; i < k; ++i) {
+        double v = S[i * k + j];
+        for (int m = 0; m < j; ++m) v -= S[i * k + m] * S[j * k + m];
+        S[i * k + j] = v / d;
+      }
+    }
+    if (ok) {
+      for (int i = 0; i < k; ++i) { double v = rhs[i]; for (int m = 0; m < i; ++m) v -= S[i * k + m] * rhs[m]; rhs[i] = v / S[i * k + i]; }
+      for (int i = k - 1; i >= 0; --i) { double v = rhs[i]; for (int m = i + 1; m < k; ++m) v -= S[m * k + i] * rhs[m]; rhs[i] = v / S[i * k + i]; }
+      for (int c = 0; c < k; ++c) {
+        st->uc[c] = st->scale_c[c] * rhs[c];
+        st->dc[c] = -st->uc[c];
+        if (!isfinite(st->uc[c])) ok = false;
+      }
+    }
+  }
+  st->solver_ok = ok ? 1 : 0;
+  if (ok) {
+    st->cam_cand = st->cam;
+    for (int c = 0; c < k; ++c) *dev_shared_param(st->cam_cand, nf, o.cols[c]) += st->dc[c];
+    if (nf == 1) st->cam_cand.focal[1] = st->cam_cand.focal[0];
+  }
+}
+
+// after the speculative evaluation at the candidate (packet x2: H_cc, cost, model-cost sums; all-reduced)
+__global__ void lm_decide_kernel(LmDevState* st, const double* __restrict__ x2, const LmDevOpts o) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || st->done) return;
+  const int k = o.k, nf = o.nf;
+  bool step_valid = false;
+  double model_cost_change = 0.0, cand_cost = 0.0, step2 = 0.0, cn2 = 0.0;
+  if (st->solver_ok) {
+    ++st->n_jac;
+    cand_cost = x2[R1_COST];
+    double gd = x2[R1_SCHUR + 0], dHd = x2[R1_SCHUR + 1];
+    step2 = x2[R1_SCHUR + 2]; cn2 = x2[R1_SCHUR + 3];
+    for (int a = 0; a < k; ++a) {
+      gd += st->gc[a] * st->dc[a];
+      double row = 0.0;
+      for (int b = 0; b < k; ++b) row += st->Hcc[a * k + b] * st->dc[b];
+      dHd += st->dc[a] * row;
+      step2 += st->dc[a] * st->dc[a];
+      const double v = *dev_shared_param(st->cam_cand, nf, o.cols[a]);
+      cn2 += v * v;
+    }
+    model_cost_change = -gd - 0.5 * dHd;
+    step_valid = model_cost_change > 0.0;
+    if (!isfinite(cand_cost)) cand_cost = DBL_MAX;
+  }
+  if (!step_valid) {
+    ++st->n_invalid;
+    if (st->n_invalid >= o.max_invalid) { dev_record(st, o, st->iter, st->x_cost, 3); st->termination = 5; st->done = 1; return; }
+    st->radius = st->radius / st->decrease_factor; st->decrease_factor *= 2.0; st->reuse_diagonal = 1;
+    dev_record(st, o, st->iter, st->x_cost, 3);
+    st->last_successful = 0;
+    dev_loop_top(st, o);
+    return;
+  }
+  st->n_invalid = 0;
+  const double step_norm = sqrt(step2);
+  if (step_norm <= o.parameter_tolerance * (st->x_norm + o.parameter_tolerance)) {
+    dev_record(st, o, st->iter, st->x_cost, 2); st->termination = 1; st->done = 1; return;
+  }
+  const double cost_change = st->x_cost - cand_cost;
+  if (fabs(cost_change) <= o.function_tolerance * st->x_cost) {
+    dev_record(st, o, st->iter, st->x_cost, 2); st->termination = 0; st->done = 1; return;
+  }
+  const double rel = (cand_cost >= DBL_MAX) ? -DBL_MAX : cost_change / model_cost_change;
+  if (rel > o.min_relative_decrease) {
+    st->cam = st->cam_cand;
+    st->cur = 1 - st->cur;
+    st->sb = 1 - st->sb;
+    st->x_norm = sqrt(cn2);
+    st->radius = st->radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0));
+    st->radius = fmin(o.max_radius, st->radius);
+    st->decrease_factor = 2.0; st->reuse_diagonal = 0;
+    ++st->n_success;
+    st->last_successful = 1;
+    dev_take_hcc(st, x2, k);   // x_cost = cand_cost (non-finite was excluded above), H_cc of the new point
+    dev_record(st, o, st->iter, st->x_cost, 1);
+    st->trace_pending = st->iter;
+    st->fresh = 1;
+  } else {
+    st->radius = st->radius / st->decrease_factor; st->decrease_factor *= 2.0; st->reuse_diagonal = 1;
+    st->last_successful = 0;
+    dev_record(st, o, st->iter, st->x_cost, 2);
+  }
+  dev_loop_top(st, o);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -772,6 +1037,10 @@ struct ezc_lm_solver {
   DevBuf part2, part3, red2, gmaxbuf, rmse, dbg;
   HostPinned h_red;
   HostPinned h_stage;   // pose download staging for pageable destinations
+  // device-driven solve: state, the two fixed exchange buffers (Schur packet | candidate H_cc + cost + model terms; these are
+  // what the collectives reduce), device-side trace
+  DevBuf dstate, xchg, trace_c, trace_r, trace_f;
+  HostPinned h_state;
   // state of the current variable pattern
   int k = 0, NT = 2, DA = 8;
   int cols[kMaxK];
@@ -844,6 +1113,10 @@ ezc_status alloc_state(ezc_lm_solver* s) {
   EZC_CUDA(s->rmse.reserve(sizeof(double) * std::max(nb, 1)));
   EZC_CUDA(s->dbg.reserve(sizeof(double) * 64));
   EZC_CUDA(s->h_red.reserve(sizeof(double) * (R1_SIZE + 16)));
+  EZC_CUDA(s->dstate.reserve(sizeof(LmDevState)));
+  EZC_CUDA(s->xchg.reserve(sizeof(double) * 512));
+  EZC_CUDA(cudaMemsetAsync(s->xchg.p, 0, sizeof(double) * 512, ctx->stream));
+  EZC_CUDA(s->h_state.reserve(sizeof(LmDevState)));
   if (s->per_block_cam) {
     EZC_CUDA(s->cams[0].reserve(sizeof(CamParams) * std::max(nb, 1)));
     EZC_CUDA(s->cams[1].reserve(sizeof(CamParams) * std::max(nb, 1)));
@@ -891,9 +1164,16 @@ ezc_status create_common(ezc_context* ctx, const ezc_lm_problem* p, bool device_
 }
 
 // lm_accumulate (+ strip reduce + H_cc reduce) at the parameters (poses[pose_idx], cam) into strip / red1 buffer `buf`.
-ezc_status run_accumulate(ezc_lm_solver* s, int pose_idx, const CamParams& cam, int buf) {
+constexpr int kX1 = 0, kX2 = 256;   // offsets of the two exchange packets inside ezc_lm_solver::xchg
+
+// dev_which < 0: host-driven (explicit pose buffer / camera / strip buffer, result in red1[buf]);
+// dev_which = 0 | 1: device-driven at the current point | the candidate, result in xchg + kX2.
+ezc_status run_accumulate(ezc_lm_solver* s, int pose_idx, const CamParams& cam, int buf, int dev_which = -1) {
   ezc_context* ctx = s->ctx;
   AccumArgs a{};
+  const LmDevState* dst = dev_which >= 0 ? s->dstate.as<LmDevState>() : nullptr;
+  a.st = dst; a.which = dev_which < 0 ? 0 : dev_which;
+  for (int b = 0; b < 2; ++b) { a.poses2[b] = s->poses[b].as<double>(); a.strips2[b] = s->seg_strips[b].as<double>(); }
   a.obs = s->d_obs; a.pts = s->d_pts; a.poses = s->poses[pose_idx].as<double>();
   a.cams = s->per_block_cam ? s->cams[0].as<CamParams>() : nullptr;
   a.cam = cam;
@@ -913,16 +1193,20 @@ ezc_status run_accumulate(ezc_lm_solver* s, int pose_idx, const CamParams& cam, 
     fn<<<s->acc_grid, kWarpsPerBlock * 32, smem, ctx->stream>>>(a);
     if (ezc_status st = launch_check(ctx, "lm_accumulate")) return st;
     if (s->segs_per_block > 1) {
+      StripSel sel{};
+      sel.st = dst; sel.which = a.which;
+      for (int b = 0; b < 2; ++b) { sel.seg2[b] = s->seg_strips[b].as<double>(); sel.blk2[b] = s->blk_strips[b].as<double>(); }
       lm_strip_reduce_kernel<<<s->prob.n_blocks, 192, 0, ctx->stream>>>(s->seg_strips[buf].as<double>(), s->segs_per_block,
-                                                                         8 * s->DA, s->blk_strips[buf].as<double>());
+                                                                         8 * s->DA, s->blk_strips[buf].as<double>(), sel);
       if (ezc_status st = launch_check(ctx, "lm_strip_reduce")) return st;
     }
   } else {
     EZC_CUDA(cudaMemsetAsync(s->part.p, 0, sizeof(double) * 384 * s->acc_warps, ctx->stream));
     EZC_CUDA(cudaMemsetAsync(s->cost_part.p, 0, sizeof(double) * s->acc_warps, ctx->stream));
   }
+  double* hcc_out = dst ? s->xchg.as<double>() + kX2 : s->red1[buf].as<double>();
   lm_hcc_reduce_kernel<<<s->k * (s->k + 1) / 2 + 1, 256, 0, ctx->stream>>>(s->part.as<double>(), s->cost_part.as<double>(),
-                                                                           s->acc_warps, s->NT, s->k, s->red1[buf].as<double>());
+                                                                           s->acc_warps, s->NT, s->k, hcc_out, dst, a.which);
   return launch_check(ctx, "lm_hcc_reduce");
 }
 
@@ -930,7 +1214,8 @@ const double* block_strips(const ezc_lm_solver* s) {
   return s->segs_per_block > 1 ? s->blk_strips[s->sb].as<double>() : s->seg_strips[s->sb].as<double>();
 }
 
-ezc_status run_schur(ezc_lm_solver* s, double radius, bool first, bool reuse, bool undamped, double min_diag, double max_diag) {
+ezc_status run_schur(ezc_lm_solver* s, double radius, bool first, bool reuse, bool undamped, double min_diag, double max_diag,
+                     bool dev = false) {
   ezc_context* ctx = s->ctx;
   const int nb = s->prob.n_blocks;
   const int k = s->k;
@@ -943,20 +1228,30 @@ ezc_status run_schur(ezc_lm_solver* s, double radius, bool first, bool reuse, bo
   a.first = first; a.reuse_diag = reuse; a.undamped = undamped;
   a.scale_p = s->scale_p.as<double>(); a.diag_p = s->diag_p.as<double>(); a.lyz = s->lyz.as<double>();
   a.part = s->part2.as<double>(); a.nv = nv;
+  const LmDevState* dst = dev ? s->dstate.as<LmDevState>() : nullptr;
+  a.st = dst;
+  for (int b = 0; b < 2; ++b) {
+    a.strips2[b] = s->segs_per_block > 1 ? s->blk_strips[b].as<double>() : s->seg_strips[b].as<double>();
+    a.poses2[b] = s->poses[b].as<double>();
+  }
   const int grid = std::max(1, (nb + 127) / 128);
   if (k <= 7) lm_schur_kernel<7><<<grid, 128, 0, ctx->stream>>>(a);
   else lm_schur_kernel<12><<<grid, 128, 0, ctx->stream>>>(a);
   if (ezc_status st = launch_check(ctx, "lm_schur")) return st;
   // per-warp partials -> red1[R1_SCHUR ..] in fixed order (last value, the gradient max-norm, is max-reduced)
   const bool slots = ctx->world <= kMaxSlotRanks;
-  lm_schur_reduce_kernel<<<nv, 256, 0, ctx->stream>>>(s->part2.as<double>(), grid * 4, k, k <= 7 ? 1 : 2, s->red1[s->sb].as<double>() + R1_SCHUR,
-                                                      slots ? ctx->rank : 0, slots ? std::max(ctx->world, 1) : 1);
+  double* sr_out = dev ? s->xchg.as<double>() + kX1 : s->red1[s->sb].as<double>() + R1_SCHUR;
+  lm_schur_reduce_kernel<<<nv, 256, 0, ctx->stream>>>(s->part2.as<double>(), grid * 4, k, k <= 7 ? 1 : 2, sr_out,
+                                                      slots ? ctx->rank : 0, slots ? std::max(ctx->world, 1) : 1, dst);
   return launch_check(ctx, "lm_schur_reduce");
 }
 
 ezc_status allreduce(ezc_lm_solver* s, double* dev, int count, int op) {
   ezc_context* ctx = s->ctx;
-  if (ctx->world > 1 && ctx->allreduce) ctx->allreduce(ctx->allreduce_user, dev, count, op, ctx->stream);
+  if (ctx->world > 1 && ctx->allreduce) {
+    const int32_t rc = ctx->allreduce(ctx->allreduce_user, dev, count, op, ctx->stream);
+    EZC_CHECK(rc == 0, EZC_ERR_COLLECTIVE, "all-reduce callback failed (%d); abort the process group", (int)rc);
+  }
   return EZC_OK;
 }
 
@@ -1075,9 +1370,117 @@ ezc_status ezc_lm_get_params(ezc_lm_solver* s, double* focal, double* pp, double
   return EZC_OK;
 }
 
+static ezc_status lm_solve_device(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summary* summary);
+static ezc_status lm_solve_host_loop(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summary* summary);
+
 ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summary* summary) {
   EZC_CHECK(s && opt && summary, EZC_ERR_INVALID, "ezc_lm_solve: null argument");
   EZC_CHECK(s->have_params, EZC_ERR_INVALID, "ezc_lm_solve: call ezc_lm_set_params first");
+  static const bool host_loop = getenv("EZC_LM_HOST_LOOP") != nullptr;   // round-1 driver, kept for A/B runs
+  if (host_loop || s->ctx->world > kMaxSlotRanks) return lm_solve_host_loop(s, opt, summary);
+  return lm_solve_device(s, opt, summary);
+}
+
+// The solve with the trust-region loop on the device: per iteration the host enqueues
+//   lm_schur -> lm_schur_reduce -> [all-reduce] -> lm_step -> lm_backsub -> lm_reduce_rows -> lm_accumulate(candidate)
+//   -> (lm_strip_reduce) -> lm_hcc_reduce -> [all-reduce] -> lm_decide
+// and reads the state back once per group of iterations; launches after `done` return immediately.
+static ezc_status lm_solve_device(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summary* summary) {
+  ezc_context* ctx = s->ctx;
+  EZC_CUDA(cudaSetDevice(ctx->device));
+  std::memset(summary, 0, sizeof(*summary));
+  setup_pattern(s, opt->opt_focal, opt->opt_pp, opt->opt_dist);
+  const int k = s->k, nb = s->prob.n_blocks;
+  const int nS = k * (k + 1) / 2;
+  const int n_slots = std::max(ctx->world, 1);
+  LmDevOpts o{};
+  o.max_num_iterations = opt->max_num_iterations; o.max_invalid = opt->max_num_consecutive_invalid_steps;
+  o.function_tolerance = opt->function_tolerance; o.gradient_tolerance = opt->gradient_tolerance;
+  o.parameter_tolerance = opt->parameter_tolerance; o.max_radius = opt->max_trust_region_radius;
+  o.min_radius = opt->min_trust_region_radius; o.min_relative_decrease = opt->min_relative_decrease;
+  o.min_diag = opt->min_lm_diagonal; o.max_diag = opt->max_lm_diagonal;
+  o.k = k; o.nf = s->nf; o.n_slots = n_slots;
+  for (int c = 0; c < kMaxK; ++c) o.cols[c] = c < k ? s->cols[c] : 0;
+  const int cap = std::max(0, opt->trace_capacity);
+  o.trace_capacity = cap;
+  if (cap > 0) {
+    if (opt->trace_cost) { EZC_CUDA(s->trace_c.reserve(sizeof(double) * cap)); o.trace_cost = s->trace_c.as<double>(); }
+    if (opt->trace_radius) { EZC_CUDA(s->trace_r.reserve(sizeof(double) * cap)); o.trace_radius = s->trace_r.as<double>(); }
+    if (opt->trace_flag) { EZC_CUDA(s->trace_f.reserve(sizeof(int) * cap)); o.trace_flag = s->trace_f.as<int>(); }
+  }
+  LmDevState* hs = s->h_state.as<LmDevState>();
+  std::memset(hs, 0, sizeof(*hs));
+  hs->cur = s->cur; hs->sb = s->sb;
+  hs->n_success = 1; hs->termination = 3;
+  hs->first = 1; hs->fresh = 1; hs->trace_pending = -1;
+  hs->radius = opt->initial_trust_region_radius; hs->decrease_factor = 2.0;
+  hs->cam = s->cam; hs->cam_cand = s->cam;
+  LmDevState* ds = s->dstate.as<LmDevState>();
+  EZC_CUDA(cudaMemcpyAsync(ds, hs, sizeof(*hs), cudaMemcpyHostToDevice, ctx->stream));
+  double* x1 = s->xchg.as<double>() + kX1;
+  double* x2 = s->xchg.as<double>() + kX2;
+
+  if (ezc_status st = run_accumulate(s, 0, s->cam, 0, 0)) return st;
+  if (ezc_status st = allreduce(s, x2, R1_SCHUR, 0)) return st;   // H_cc + cost of this rank's views
+  lm_init_kernel<<<1, 32, 0, ctx->stream>>>(ds, x2, o);
+  if (ezc_status st = launch_check(ctx, "lm_init")) return st;
+
+  const int group = opt->max_num_iterations < 4 ? std::max(1, opt->max_num_iterations) : 4;
+  const int grid_b = std::max(1, (nb + 127) / 128);
+  for (;;) {
+    for (int g = 0; g < group; ++g) {
+      if (ezc_status st = run_schur(s, 0.0, false, false, false, opt->min_lm_diagonal, opt->max_lm_diagonal, true)) return st;
+      if (ezc_status st = allreduce(s, x1, nS + 2 * k + 4 + n_slots, 0)) return st;
+      lm_step_kernel<<<1, 32, 0, ctx->stream>>>(ds, x1, o);
+      if (ezc_status st = launch_check(ctx, "lm_step")) return st;
+      BacksubArgs ba{};
+      ba.scale_p = s->scale_p.as<double>(); ba.lyz = s->lyz.as<double>();
+      ba.n_blocks = nb; ba.DA = s->DA; ba.k = k;
+      ba.step_p = s->step_p.as<double>(); ba.part = s->part3.as<double>();
+      ba.st = ds;
+      for (int b = 0; b < 2; ++b) {
+        ba.strips2[b] = s->segs_per_block > 1 ? s->blk_strips[b].as<double>() : s->seg_strips[b].as<double>();
+        ba.poses2[b] = s->poses[b].as<double>();
+      }
+      lm_backsub_kernel<<<grid_b, 128, 0, ctx->stream>>>(ba);
+      if (ezc_status st = launch_check(ctx, "lm_backsub")) return st;
+      lm_reduce_rows_kernel<<<4, 256, 0, ctx->stream>>>(s->part3.as<double>(), grid_b, 4, 4, x2 + R1_SCHUR, ds);
+      if (ezc_status st = launch_check(ctx, "lm_reduce_rows")) return st;
+      if (ezc_status st = run_accumulate(s, 0, s->cam, 0, 1)) return st;
+      if (ezc_status st = allreduce(s, x2, R1_SCHUR + 4, 0)) return st;
+      lm_decide_kernel<<<1, 32, 0, ctx->stream>>>(ds, x2, o);
+      if (ezc_status st = launch_check(ctx, "lm_decide")) return st;
+    }
+    EZC_CUDA(cudaMemcpyAsync(hs, ds, sizeof(*hs), cudaMemcpyDeviceToHost, ctx->stream));
+    EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hs->done) break;
+  }
+  s->cam = hs->cam; s->cam_cand = hs->cam_cand;
+  s->cur = hs->cur; s->sb = hs->sb;
+  summary->initial_cost = hs->initial_cost;
+  summary->n_residual_blocks = hs->n_residual_blocks;
+  summary->jacobian_evaluations = hs->n_jac;
+  summary->linear_solves = hs->n_lin;
+  summary->final_cost = hs->x_cost;
+  summary->termination = hs->termination;
+  if (hs->failed_start) {
+    summary->iterations = 0; summary->num_successful = 0;
+    set_error("ezc_lm_solve: non-finite cost at the starting point");
+    return EZC_ERR_NUMERIC;
+  }
+  summary->iterations = hs->iter + 1;
+  summary->num_successful = hs->n_success;
+  const int nrec = std::min(cap, hs->iter + 1);
+  if (nrec > 0) {
+    if (opt->trace_cost) EZC_CUDA(cudaMemcpyAsync(opt->trace_cost, s->trace_c.p, sizeof(double) * nrec, cudaMemcpyDeviceToHost, ctx->stream));
+    if (opt->trace_radius) EZC_CUDA(cudaMemcpyAsync(opt->trace_radius, s->trace_r.p, sizeof(double) * nrec, cudaMemcpyDeviceToHost, ctx->stream));
+    if (opt->trace_flag) EZC_CUDA(cudaMemcpyAsync(opt->trace_flag, s->trace_f.p, sizeof(int) * nrec, cudaMemcpyDeviceToHost, ctx->stream));
+    EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return EZC_OK;
+}
+
+static ezc_status lm_solve_host_loop(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summary* summary) {
   ezc_context* ctx = s->ctx;
   EZC_CUDA(cudaSetDevice(ctx->device));
   std::memset(summary, 0, sizeof(*summary));
@@ -1103,7 +1506,7 @@ ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summ
   };
 
   if (ezc_status st = run_accumulate(s, s->cur, s->cam, s->sb)) return st;
-  allreduce(s, s->red1[s->sb].as<double>(), R1_SCHUR, 0);  // H_cc + cost of this rank's views
+  if (ezc_status st_ar = allreduce(s, s->red1[s->sb].as<double>(), R1_SCHUR, 0)) return st_ar;  // H_cc + cost of this rank's views
   ++n_jac;
   bool fresh_jacobian = true;
 
@@ -1118,10 +1521,10 @@ ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summ
     const bool slots = ctx->world <= kMaxSlotRanks;
     const int n_slots = slots ? std::max(ctx->world, 1) : 1;
     if (slots) {
-      allreduce(s, s->red1[s->sb].as<double>() + R1_SCHUR, n1 - R1_SCHUR + n_slots, 0);
+      if (ezc_status st_ar = allreduce(s, s->red1[s->sb].as<double>() + R1_SCHUR, n1 - R1_SCHUR + n_slots, 0)) return st_ar;
     } else {
-      allreduce(s, s->red1[s->sb].as<double>() + R1_SCHUR, n1 - R1_SCHUR, 0);
-      allreduce(s, s->red1[s->sb].as<double>() + n1, 1, 1);
+      if (ezc_status st_ar = allreduce(s, s->red1[s->sb].as<double>() + R1_SCHUR, n1 - R1_SCHUR, 0)) return st_ar;
+      if (ezc_status st_ar = allreduce(s, s->red1[s->sb].as<double>() + n1, 1, 1)) return st_ar;
     }
     EZC_CUDA(cudaMemcpyAsync(h, s->red1[s->sb].p, sizeof(double) * (n1 + n_slots), cudaMemcpyDeviceToHost, ctx->stream));
     EZC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1205,7 +1608,7 @@ ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summ
       if (ezc_status st = launch_check(ctx, "lm_backsub")) return st;
       // model-cost sums land right behind the candidate's H_cc / cost block (the Schur section of the alternate buffer is
       // free until that buffer becomes current): one all-reduce and one copy cover both
-      lm_reduce_rows_kernel<<<4, 256, 0, ctx->stream>>>(s->part3.as<double>(), grid, 4, 4, s->red1[1 - s->sb].as<double>() + R1_SCHUR);
+      lm_reduce_rows_kernel<<<4, 256, 0, ctx->stream>>>(s->part3.as<double>(), grid, 4, 4, s->red1[1 - s->sb].as<double>() + R1_SCHUR, nullptr);
       if (ezc_status st = launch_check(ctx, "lm_reduce_rows")) return st;
       // candidate shared parameters
       s->cam_cand = s->cam;
@@ -1216,7 +1619,7 @@ ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summ
       const int alt = 1 - s->sb;
       if (ezc_status st = run_accumulate(s, 1 - s->cur, s->cam_cand, alt)) return st;
       ++n_jac;
-      allreduce(s, s->red1[alt].as<double>(), R1_SCHUR + 4, 0);
+      if (ezc_status st_ar = allreduce(s, s->red1[alt].as<double>(), R1_SCHUR + 4, 0)) return st_ar;
       EZC_CUDA(cudaMemcpyAsync(h, s->red1[alt].as<double>() + R1_COST, sizeof(double) * 5, cudaMemcpyDeviceToHost, ctx->stream));
       EZC_CUDA(cudaStreamSynchronize(ctx->stream));
       double gd = h[1], dHd = h[2];
@@ -1309,7 +1712,7 @@ ezc_status ezc_lm_covariance(ezc_lm_solver* s, double* cov_out) {
   if (ezc_status st = run_accumulate(s, s->cur, s->cam, s->sb)) return st;
   if (ezc_status st = run_schur(s, 1.0, false, false, true, 0.0, 0.0)) return st;
   const int n1 = R1_SCHUR + nS + 2 * k + 4;
-  allreduce(s, s->red1[s->sb].as<double>(), n1, 0);
+  if (ezc_status st_ar = allreduce(s, s->red1[s->sb].as<double>(), n1, 0)) return st_ar;
   double* h = s->h_red.as<double>();
   EZC_CUDA(cudaMemcpyAsync(h, s->red1[s->sb].p, sizeof(double) * n1, cudaMemcpyDeviceToHost, ctx->stream));
   EZC_CUDA(cudaStreamSynchronize(ctx->stream));

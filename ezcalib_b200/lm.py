@@ -40,7 +40,14 @@ class Context:
     def set_allreduce(self, fn, rank: int, world: int):
         """fn(device_ptr:int, count:int, op:int, stream:int) all-reduces `count` doubles in place."""
         def _tramp(user, buf, count, op, stream):
-            fn(int(buf or 0), int(count), int(op), int(stream or 0))
+            # an exception inside a ctypes callback would be printed and swallowed: turn it into a status the C side returns
+            try:
+                fn(int(buf or 0), int(count), int(op), int(stream or 0))
+                return 0
+            except Exception as e:  # noqa: BLE001
+                import sys
+                print(f"ezcalib_b200: all-reduce callback failed: {e!r}", file=sys.stderr)
+                return 1
         self._cb = _lib.ALLREDUCE_FN(_tramp)
         check(_lib.lib().ezc_set_allreduce(self._h, self._cb, None, int(rank), int(world)), "ezc_set_allreduce")
 

@@ -25,14 +25,18 @@ typedef enum {
   EZC_ERR_INVALID = 1,   /* bad argument */
   EZC_ERR_CUDA = 2,      /* CUDA runtime failure (incl. no device) */
   EZC_ERR_NUMERIC = 3,   /* non-finite cost at the starting point (Ceres: FAILURE) */
-  EZC_ERR_CAPACITY = 4   /* an internal per-image capacity was exceeded */
+  EZC_ERR_CAPACITY = 4,  /* an internal per-image capacity was exceeded */
+  EZC_ERR_COLLECTIVE = 5 /* the multi-GPU exchange failed (callback returned non-zero) */
 } ezc_status;
 
 typedef struct ezc_context ezc_context;
 
-/* Collective hook: all-reduce `count` doubles IN PLACE in DEVICE memory, enqueued on `stream`.
- * op: 0 = sum, 1 = max.  Production: torch.distributed (NCCL over NVLink); tests: gloo. */
-typedef void (*ezc_allreduce_fn)(void* user, void* device_buf, int32_t count, int32_t op, void* stream);
+/* Collective hook: all-reduce `count` doubles IN PLACE in DEVICE memory, enqueued on `stream` (it must not block: the
+ * solver enqueues whole groups of LM iterations without synchronising).  op: 0 = sum, 1 = max.  Returns 0 on success; any
+ * other value makes the running ezc_lm_* call fail with EZC_ERR_COLLECTIVE -- the caller must then abort the process group
+ * (its peers are blocked in the same collective).  Production: ezc_comm_init's own exchange (see below) or
+ * torch.distributed (NCCL over NVLink); tests: gloo. */
+typedef int32_t (*ezc_allreduce_fn)(void* user, void* device_buf, int32_t count, int32_t op, void* stream);
 
 ezc_status ezc_create(int32_t device, ezc_context** out);
 void ezc_destroy(ezc_context* ctx);
