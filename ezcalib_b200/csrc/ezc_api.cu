@@ -64,6 +64,7 @@ void ezc_destroy(ezc_context* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);  // cached device blocks are handed to other contexts unsynchronised
+  if (ctx->comm && ctx->comm_free) ctx->comm_free(ctx->comm);
   if (ctx->at_pools && ctx->at_pools_free) ctx->at_pools_free(ctx->at_pools);
   if (ctx->cb_pools && ctx->cb_pools_free) ctx->cb_pools_free(ctx->cb_pools);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }

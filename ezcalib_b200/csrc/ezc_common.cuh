@@ -222,4 +222,7 @@ struct ezc_context {
   void (*cb_pools_free)(void*) = nullptr;
   // second stream for ezc_images_upload_async: H2D copies overlap the detection kernels of earlier sub-batches
   cudaStream_t copy_stream = nullptr;
+  // library-owned peer-memory exchange (csrc/comm.cu)
+  void* comm = nullptr;
+  void (*comm_free)(void*) = nullptr;
 };

@@ -54,7 +54,7 @@ __host__ __device__ inline int tile_index(int ti, int tj, int NT) { return ti * 
 // State of one ceres::Solve, resident in device memory: the trust-region loop (reduced-system solve, accept / reject,
 // radius, termination tests) runs in two one-thread kernels, so the host only enqueues iterations and looks at `done`
 // once per group of iterations instead of synchronising twice per iteration.
-struct LmDevState {
+struct alignas(8) LmDevState {
   int cur, sb;               // which pose buffer / strip buffer holds the current point
   int done, termination, failed_start;
   int iter, n_success, n_invalid, n_jac, n_lin;
@@ -729,8 +729,7 @@ __device__ __forceinline__ void dev_loop_top(LmDevState* st, const LmDevOpts& o)
 }
 
 // after the first Jacobian evaluation (H_cc + cost of the starting point, all-reduced, in x2)
-__global__ void lm_init_kernel(LmDevState* st, const double* __restrict__ x2, const LmDevOpts o) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void lm_init_compute(LmDevState* st, const double* x2, const LmDevOpts& o) {
   dev_take_hcc(st, x2, o.k);
   st->n_jac = 1;
   st->initial_cost = st->x_cost;
@@ -739,8 +738,8 @@ __global__ void lm_init_kernel(LmDevState* st, const double* __restrict__ x2, co
 }
 
 // after lm_schur + reduction (packet x1, all-reduced): gradient test, reduced system, candidate shared parameters
-__global__ void lm_step_kernel(LmDevState* st, const double* __restrict__ x1, const LmDevOpts o) {
-  if (threadIdx.x != 0 || blockIdx.x != 0 || st->done) return;
+__device__ void lm_step_compute(LmDevState* st, const double* x1, const LmDevOpts& o) {
+  if (st->done) return;
   const int k = o.k, nf = o.nf, nS = k * (k + 1) / 2;
   const double* Ssum = x1;
   const double* bsum = x1 + nS;
@@ -819,8 +818,8 @@ __global__ void lm_step_kernel(LmDevState* st, const double* __restrict__ x1, co
 }
 
 // after the speculative evaluation at the candidate (packet x2: H_cc, cost, model-cost sums; all-reduced)
-__global__ void lm_decide_kernel(LmDevState* st, const double* __restrict__ x2, const LmDevOpts o) {
-  if (threadIdx.x != 0 || blockIdx.x != 0 || st->done) return;
+__device__ void lm_decide_compute(LmDevState* st, const double* x2, const LmDevOpts& o) {
+  if (st->done) return;
   const int k = o.k, nf = o.nf;
   bool step_valid = false;
   double model_cost_change = 0.0, cand_cost = 0.0, step2 = 0.0, cn2 = 0.0;
@@ -881,6 +880,29 @@ __global__ void lm_decide_kernel(LmDevState* st, const double* __restrict__ x2, 
     dev_record(st, o, st->iter, st->x_cost, 2);
   }
   dev_loop_top(st, o);
+}
+
+// One warp stages the state and the packet in shared memory (coalesced), lane 0 runs the control code there (a chain of
+// dependent global loads / stores costs ~0.5 us each; in shared memory the whole step is a few microseconds), the warp
+// writes the state back.
+template <int WHICH>
+__global__ void __launch_bounds__(32) lm_control_kernel(LmDevState* st, const double* __restrict__ packet, int packet_len, const LmDevOpts o) {
+  __shared__ LmDevState sh;
+  __shared__ double px[512];
+  static_assert(sizeof(LmDevState) % 8 == 0, "state is copied as doubles");
+  constexpr int NW = sizeof(LmDevState) / 8;
+  const int lane = threadIdx.x;
+  if (WHICH != 0 && st->done) return;
+  for (int i = lane; i < NW; i += 32) reinterpret_cast<double*>(&sh)[i] = reinterpret_cast<const double*>(st)[i];
+  for (int i = lane; i < packet_len; i += 32) px[i] = packet[i];
+  __syncwarp();
+  if (lane == 0) {
+    if (WHICH == 0) lm_init_compute(&sh, px, o);
+    else if (WHICH == 1) lm_step_compute(&sh, px, o);
+    else lm_decide_compute(&sh, px, o);
+  }
+  __syncwarp();
+  for (int i = lane; i < NW; i += 32) reinterpret_cast<double*>(st)[i] = reinterpret_cast<const double*>(&sh)[i];
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1422,7 +1444,7 @@ static ezc_status lm_solve_device(ezc_lm_solver* s, const ezc_lm_options* opt, e
 
   if (ezc_status st = run_accumulate(s, 0, s->cam, 0, 0)) return st;
   if (ezc_status st = allreduce(s, x2, R1_SCHUR, 0)) return st;   // H_cc + cost of this rank's views
-  lm_init_kernel<<<1, 32, 0, ctx->stream>>>(ds, x2, o);
+  lm_control_kernel<0><<<1, 32, 0, ctx->stream>>>(ds, x2, R1_SCHUR, o);
   if (ezc_status st = launch_check(ctx, "lm_init")) return st;
 
   const int group = opt->max_num_iterations < 4 ? std::max(1, opt->max_num_iterations) : 4;
@@ -1431,7 +1453,7 @@ static ezc_status lm_solve_device(ezc_lm_solver* s, const ezc_lm_options* opt, e
     for (int g = 0; g < group; ++g) {
       if (ezc_status st = run_schur(s, 0.0, false, false, false, opt->min_lm_diagonal, opt->max_lm_diagonal, true)) return st;
       if (ezc_status st = allreduce(s, x1, nS + 2 * k + 4 + n_slots, 0)) return st;
-      lm_step_kernel<<<1, 32, 0, ctx->stream>>>(ds, x1, o);
+      lm_control_kernel<1><<<1, 32, 0, ctx->stream>>>(ds, x1, nS + 2 * k + 4 + n_slots, o);
       if (ezc_status st = launch_check(ctx, "lm_step")) return st;
       BacksubArgs ba{};
       ba.scale_p = s->scale_p.as<double>(); ba.lyz = s->lyz.as<double>();
@@ -1448,7 +1470,7 @@ static ezc_status lm_solve_device(ezc_lm_solver* s, const ezc_lm_options* opt, e
       if (ezc_status st = launch_check(ctx, "lm_reduce_rows")) return st;
       if (ezc_status st = run_accumulate(s, 0, s->cam, 0, 1)) return st;
       if (ezc_status st = allreduce(s, x2, R1_SCHUR + 4, 0)) return st;
-      lm_decide_kernel<<<1, 32, 0, ctx->stream>>>(ds, x2, o);
+      lm_control_kernel<2><<<1, 32, 0, ctx->stream>>>(ds, x2, R1_SCHUR + 4, o);
       if (ezc_status st = launch_check(ctx, "lm_decide")) return st;
     }
     EZC_CUDA(cudaMemcpyAsync(hs, ds, sizeof(*hs), cudaMemcpyDeviceToHost, ctx->stream));

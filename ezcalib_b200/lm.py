@@ -51,6 +51,25 @@ class Context:
         self._cb = _lib.ALLREDUCE_FN(_tramp)
         check(_lib.lib().ezc_set_allreduce(self._h, self._cb, None, int(rank), int(world)), "ezc_set_allreduce")
 
+    def comm_mailbox(self, world: int):
+        """Allocate this context's mailbox of the library-owned exchange; returns (device pointer, 64-byte CUDA IPC handle)."""
+        ptr = C.c_void_p()
+        h = (C.c_uint8 * 64)()
+        check(_lib.lib().ezc_comm_mailbox(self._h, int(world), C.byref(ptr), h), "ezc_comm_mailbox")
+        return int(ptr.value), bytes(h)
+
+    def comm_init(self, rank: int, world: int, handles):
+        """handles: the `world` IPC handles (bytes, 64 each) in rank order, all-gathered by the caller."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        check(_lib.lib().ezc_comm_init(self._h, int(rank), int(world), buf), "ezc_comm_init")
+
+    def comm_attach(self, rank: int, world: int, mailboxes):
+        """Same-process variant: mailboxes = device pointers (ints) of every rank's mailbox."""
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(m)) for m in mailboxes])
+        check(_lib.lib().ezc_comm_attach(self._h, int(rank), int(world), arr), "ezc_comm_attach")
+
     def kernel_launches(self) -> int:
         return int(_lib.lib().ezc_kernel_launches(self._h))
 

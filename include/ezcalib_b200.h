@@ -46,6 +46,17 @@ const char* ezc_last_error(void);
 ezc_status ezc_set_stream(ezc_context* ctx, void* cuda_stream);
 /* View-sharded multi-GPU: each rank owns a contiguous slice of the pose blocks. */
 ezc_status ezc_set_allreduce(ezc_context* ctx, ezc_allreduce_fn fn, void* user, int32_t rank, int32_t world);
+/* The library's own exchange for the view-sharded solve (one process per GPU on one NVLink / NVSwitch node): a one-shot
+ * all-reduce through peer memory -- every rank stores its <= 256-double packet into a mailbox slot of every peer, publishes a
+ * sequence flag, waits for the world's flags in its own mailbox and sums the slots in FIXED RANK ORDER (bit-identical on all
+ * ranks, independent of arrival order).  It replaces the two NCCL launches per LM iteration behind ezc_set_allreduce.
+ *   1. every rank: ezc_comm_mailbox(ctx, world, NULL, handle)     allocates the mailbox, returns its 64-byte CUDA IPC handle
+ *   2. the caller all-gathers the handles with whatever it has (MPI, torch.distributed, a socket)
+ *   3. every rank: ezc_comm_init(ctx, rank, world, handles)       maps the peers' mailboxes and installs the exchange
+ * ezc_comm_attach is the same for mailboxes that are plain device pointers in THIS process (several contexts in one process). */
+ezc_status ezc_comm_mailbox(ezc_context* ctx, int32_t world, void** mailbox_out, uint8_t* ipc_handle_out /*[64] or NULL*/);
+ezc_status ezc_comm_init(ezc_context* ctx, int32_t rank, int32_t world, const uint8_t* all_ipc_handles /*[world][64]*/);
+ezc_status ezc_comm_attach(ezc_context* ctx, int32_t rank, int32_t world, void* const* mailboxes /*[world]*/);
 /* Number of kernels of this library launched on the context so far (bench.py "gpu_launches"). */
 uint64_t ezc_kernel_launches(const ezc_context* ctx);
 /* Give the cached device blocks of `device` (-1: every device) back to the driver.  The cache is per device and is

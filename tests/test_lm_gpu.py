@@ -270,3 +270,62 @@ def test_multicam_extrinsics_match_oracle(ctx):
     assert np.max(np.abs(out["extrinsics"] - res[3])) <= 1e-9
     for j in range(2):  # recovered extrinsics close to the rig's ground truth
         assert np.max(np.abs(cams[j + 1].T_cam0_2_cam - rel[j])) < 2e-2  # poses of cam0 carry noise
+
+
+def test_peer_memory_exchange_two_contexts(ctx):
+    """The library-owned exchange (csrc/comm.cu: mailbox all-reduce through peer memory, fixed rank order) between two
+    contexts of this process (ezc_comm_attach; across processes ezc_comm_init maps the same mailboxes through CUDA IPC):
+    the view-sharded solve equals the 1-rank solve, both ranks end with bit-identical shared parameters, and a second run
+    reproduces the first bit for bit."""
+    import threading
+
+    from ezcalib_b200 import dist as ezdist, lm
+    model, mono = "radtan8", False
+    mid = synth.MODEL_ID[model]
+    tgt = synth.aprilgrid_target(6, 6, 0.06, 0.3)
+    P = synth.make_lm_problem(model, mono, 57, tgt, 2448, 2048, seed=29, drop_fraction=0.1)
+    ref = lm.lm_mono(ctx, mid, mono, P.obs, P.target, P.width, P.height, P.focal_init, P.pp_init, P.dist_init, P.poses_init)
+    world = 2
+
+    def run_once():
+        ctxs = [lm.Context(0) for _ in range(world)]
+        boxes = [c.comm_mailbox(world)[0] for c in ctxs]
+        for r, c in enumerate(ctxs):
+            c.comm_attach(r, world, boxes)
+        results, errors = [None] * world, []
+
+        def rank_main(rank):
+            try:
+                c = ctxs[rank]
+                b, e = ezdist.shard_range(P.obs.shape[0], rank, world)
+                s = lm.LmSolver(c, mid, mono, P.obs[b:e], P.target, P.width, P.height, n_blocks_global=P.obs.shape[0])
+                s.set_params(P.focal_init, P.pp_init, P.dist_init, P.poses_init[b:e])
+                summ = [s.solve(*mask)[0] for mask in ((1, 0, 0), (1, 0, 1), (1, 1, 1))]
+                f, pp, d, poses = s.get_params()
+                results[rank] = (f, pp, d, poses, s.frame_rmse(), summ)
+                s.close()
+            except Exception as ex:  # pragma: no cover
+                errors.append(ex)
+
+        ths = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+        for t in ths: t.start()
+        for t in ths: t.join(timeout=300)
+        assert not errors, errors
+        assert all(not t.is_alive() for t in ths), "exchange hung"
+        for c in ctxs:
+            c.close()
+        return results
+
+    res = run_once()
+    for r in range(world):
+        f, pp, d, poses, rmse, summ = res[r]
+        assert [s_["iterations"] for s_ in summ] == [s_["iterations"] for s_ in ref[5]]
+        assert _rel(f, ref[0]) <= 1e-9 and _rel(pp, ref[1]) <= 1e-9 and np.max(np.abs(d - ref[2])) <= 1e-9
+        b, e = ezdist.shard_range(P.obs.shape[0], r, world)
+        assert np.max(np.abs(poses - ref[3][b:e])) <= 1e-9 and np.max(np.abs(rmse - ref[4][b:e])) <= 1e-9
+    # fixed rank order: both ranks hold the same bits, and so does a second run
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+    res2 = run_once()
+    for r in range(world):
+        for a, b_ in zip(res[r][:5], res2[r][:5]):
+            assert np.array_equal(a, b_)
