@@ -203,10 +203,16 @@ def run_gpu(args):
     ctx = lm.Context(local_rank, stream=stream.cuda_stream)
 
     from ezcalib_b200 import dist as ezdist
-    allreduce = ezdist.make_allreduce(f"cuda:{local_rank}") if world > 1 else None
-
+    exchange = "none"
     if world > 1:
-        ctx.set_allreduce(allreduce, rank, world)
+        if os.environ.get("EZC_BENCH_NCCL"):
+            # round-1 path: the packets go through torch.distributed's NCCL all-reduce via a Python callback
+            ctx.set_allreduce(ezdist.make_allreduce(f"cuda:{local_rank}"), rank, world)
+            exchange = "torch.distributed all_reduce (NCCL) through the ezc_set_allreduce callback"
+        else:
+            # the library's own exchange: mailboxes in peer memory, IPC handles all-gathered once through torch.distributed
+            ezdist.init_peer_exchange(ctx, rank, world)
+            exchange = "ezc_comm: one-shot peer-memory all-reduce over NVLink, fixed rank order (csrc/comm.cu)"
 
     if args.only_rig:
         rig = run_cfg4(ctx, args, rank, world, stream)
@@ -322,6 +328,9 @@ def run_gpu(args):
         "e2e": {"value": round(e2e_value, 3), "unit": "LM iters/s (10M obs)",
                 "h2d_bytes_per_step": int(h2d_bytes / total_steps), "d2h_bytes_per_step": int(d2h_bytes / total_steps)},
         "gpu_launches": int(launches),
+        "exchange": exchange,
+        "parity_note": "B8 (ceres::Solve rules) is checked against a RESTATED Ceres (oracle/lm_oracle.cpp); the 14 residual functors and the "
+                       "SE3 manifold are pinned to the reference's own headers compiled unmodified (oracle/lm_ref)",
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": round(achieved, 3), "peak": round(peak_fp64, 3), "unit": "TFLOP/s",
                      "frac": round(achieved / peak_fp64, 4) if peak_fp64 else None,

@@ -64,3 +64,15 @@ class TorchComm:
         out = [None] * self.world
         self._dist.all_gather_object(out, obj, group=self.group)
         return out
+
+
+def init_peer_exchange(ctx, rank: int, world: int, group=None):
+    """Install the library-owned peer-memory all-reduce (csrc/comm.cu) on `ctx`: every rank allocates its mailbox, the
+    64-byte CUDA IPC handles are all-gathered through torch.distributed (any host transport would do), every rank maps its
+    peers' mailboxes.  One process per GPU on one NVLink / NVSwitch node."""
+    import torch.distributed as dist
+    _, handle = ctx.comm_mailbox(world)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    ctx.comm_init(rank, world, handles)
+    dist.barrier(group=group)
