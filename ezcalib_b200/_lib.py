@@ -100,6 +100,7 @@ def lib():
         L.ezc_lm_accumulate_only.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         L.ezc_lm_default_options.argtypes = [C.POINTER(LmOptionsC)]
         L.ezc_trim_cache.argtypes = [C.c_int32]
+        L.ezc_debug_libm.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.ezc_comm_mailbox.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]
         L.ezc_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.ezc_comm_attach.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
@@ -123,5 +124,5 @@ EXPORTED_SYMBOLS = [
     "ezc_apriltag_debug_get", "ezc_apriltag_debug_free", "ezc_measure_fp64_peak", "ezc_measure_dmma_peak", "ezc_num_dist", "ezc_lm_default_options", "ezc_lm_create", "ezc_lm_create_device",
     "ezc_lm_destroy", "ezc_lm_set_params", "ezc_lm_get_params", "ezc_lm_solve", "ezc_lm_frame_rmse",
     "ezc_lm_covariance", "ezc_lm_mono", "ezc_lm_residual_jacobian", "ezc_lm_normal_equations", "ezc_lm_accumulate_only",
-    "ezc_trim_cache", "ezc_p3p_ransac_batch", "ezc_lm_multicam", "ezc_comm_mailbox", "ezc_comm_init", "ezc_comm_attach",
+    "ezc_trim_cache", "ezc_p3p_ransac_batch", "ezc_lm_multicam", "ezc_comm_mailbox", "ezc_comm_init", "ezc_comm_attach", "ezc_debug_libm",
 ]

@@ -137,6 +137,12 @@ __global__ void at_gradient_kernel(const float* __restrict__ seg, int W, int H, 
   flag[gid] = (x + 1 < W && y + 1 < H && mg >= kMinMag) ? 1 : 0;
 }
 
+// test hook: the bit-exact libm restatements (libm_exact.cuh) on arbitrary arguments (tests/test_libm_exact.py)
+__global__ void at_libm_kernel(int which, const float* __restrict__ a, const float* __restrict__ b, long long n, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = which == 0 ? fd_atan2f(a[i], b[i]) : which == 1 ? gl_sinf(a[i]) : gl_cosf(a[i]);
+}
+
 // ---- stage 1, fused (production path) ------------------------------------------------------------
 // One tile-based kernel does u8 -> float, both blur passes (incl. the border quirk), the gradient, the activity test and
 // -- only for active pixels (~5 %) -- the bit-exact atan2f.  Same expressions, same evaluation order as the three
@@ -1518,5 +1524,26 @@ ezc_status ezc_apriltag_debug_get(const ezc_apriltag_debug* d, float* theta, flo
   return EZC_OK;
 }
 void ezc_apriltag_debug_free(ezc_apriltag_debug* d) { delete d; }
+
+ezc_status ezc_debug_libm(ezc_context* ctx, int32_t which, const float* a, const float* b, int64_t n, float* out) {
+  EZC_CHECK(ctx && a && out && n >= 0 && which >= 0 && which <= 2 && (which != 0 || b), EZC_ERR_INVALID, "ezc_debug_libm: bad argument");
+  EZC_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return EZC_OK;
+  ezc::DevBuf da, db, dout;
+  ezc::SyncOnExit sync_on_exit(ctx->stream);
+  EZC_CUDA(da.reserve(sizeof(float) * n)); EZC_CUDA(dout.reserve(sizeof(float) * n));
+  EZC_CUDA(cudaMemcpyAsync(da.p, a, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+  if (which == 0) {
+    EZC_CUDA(db.reserve(sizeof(float) * n));
+    EZC_CUDA(cudaMemcpyAsync(db.p, b, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ezc::at_libm_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 32), 256, 0, ctx->stream>>>(which, da.as<float>(), db.as<float>(), n,
+                                                                                                    dout.as<float>());
+  EZC_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  EZC_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return EZC_OK;
+}
 
 }  // extern "C"

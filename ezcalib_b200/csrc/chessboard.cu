@@ -1736,6 +1736,7 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
           CB_LAUNCH_PIX(cb_copy_active_kernel, N, no, tmp, prevb, N, no, P.refresh.as<int>());
         }
         const int n_act = (int)list.size();
+        if (getenv("EZC_CB_TIMING")) fprintf(stderr, "[cb] phase 2 k %d dil %d: %d of %d views\n", k, dil, n_act, nb);
         CB_LAUNCH_PIX(cb_copy_active_kernel, N, n_act, prevb, th, N, n_act, P.active.as<int>());
         CB_LAUNCH_FRAME(th, n_act, P.active.as<int>());
         // no edge-length compensation in the fallback (empirically what cv2 4.13 does: exact on all phase-2 fixtures)

@@ -2,7 +2,7 @@
 // relies on for DISCRETE decisions (edge costs, merge predicates): glibc 2.39's atan2f (fdlibm e_atan2f.c /
 // s_atanf.c) and sinf/cosf (ARM optimized routines, s_sincosf_data.c).  CUDA's own atan2f/sinf/cosf differ in
 // the last ulp, which flips integer edge costs (Edge.cc:22-23).  Verified bit-identical to the host glibc on
-// 4e7 random arguments each (tests/test_libm_exact.py does the same through the C ABI on the GPU box).
+// 4e7 random arguments each when written; tests/test_libm_exact.py repeats the check (8e5 arguments per function) through the C ABI on the GPU box.
 // Compile the including translation unit with -fmad=false.
 #pragma once
 #include <cuda_runtime.h>

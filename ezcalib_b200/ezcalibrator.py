@@ -126,7 +126,9 @@ def multicam_block(cam0_frames: list, camj: Camera, cam_index: int, target: np.n
             logs = [lg] * n0          # the reference pushes the same value once per cam0 frame (loop variable j unused, :678-680)
             n_good = n0
     if not logs:
-        raise IndexError("no usable frame pair for the extrinsic initialisation (the reference reads out of bounds here, :707-713)")
+        raise IndexError(f"no usable frame pair for the extrinsic initialisation of camera {cam_index}: cam0 frame #{cam_index} "
+                         f"({f0.img_name!r}, rmse_err {f0.rmse_err:.3f}) {'has rmse_err > 1' if f0.rmse_err > 1.0 else 'has no partner frame in this camera'}"
+                         f" ({len(camj.frames)} frames) -- the reference reads out of bounds here (ezcalibrator.cpp:707-713)")
     logs = np.sort(np.asarray(logs), axis=0)
     med = logs[len(logs) // 2]
     init = synth.se3_exp_left(med, np.array([0, 0, 0, 1.0, 0, 0, 0]))

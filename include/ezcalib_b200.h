@@ -149,6 +149,10 @@ ezc_status ezc_apriltag_debug_get(const ezc_apriltag_debug* d, float* theta, flo
                                   int32_t* rep, int32_t* size, float* segments /*[n][6]*/, float* quads /*[n][9]*/);
 void ezc_apriltag_debug_free(ezc_apriltag_debug* d);
 
+/* Test hook: the device restatements of the host libm functions the AprilTag path needs bit for bit (csrc/libm_exact.cuh):
+ * which = 0: atan2f(a[i], b[i]) (glibc / fdlibm), 1: sinf(a[i]), 2: cosf(a[i]) (glibc's ARM optimised routines).  HOST pointers. */
+ezc_status ezc_debug_libm(ezc_context* ctx, int32_t which, const float* a, const float* b, int64_t n, float* out);
+
 /* ------------------------------------------------------------------------------------------
  * Between the halves: initial poses.  EZCalibrator::computeP3PRansac
  * (/root/reference/src/ezcalibrator.cpp:560-628) for every view of a batch, one warp per view:
