@@ -25,7 +25,7 @@ class LmProblemC(C.Structure):
     _fields_ = [("model", C.c_int32), ("use_mono_focal", C.c_int32), ("n_blocks", C.c_int32),
                 ("obs_per_block", C.c_int32), ("pts_period", C.c_int32), ("cams_per_block", C.c_int32),
                 ("img_w", C.c_double), ("img_h", C.c_double), ("pts", C.c_void_p), ("obs", C.c_void_p),
-                ("n_blocks_global", C.c_int32)]
+                ("n_blocks_global", C.c_int32), ("collective", C.c_int32)]
 
 
 class LmOptionsC(C.Structure):

@@ -1041,6 +1041,8 @@ struct ezc_lm_solver {
   ezc_lm_problem prob{};
   int nf = 1, nd = 1, kfull = 4;
   bool per_block_cam = false;
+  bool collective = false;   // this solve exchanges its packets with the other ranks of the context
+  int world = 1, rank = 0;   // effective world / rank of THIS solve (1 / 0 when it is local)
   const float2* d_obs = nullptr;
   const double* d_pts = nullptr;
   DevBuf obs_buf, pts_buf;
@@ -1161,6 +1163,9 @@ ezc_status create_common(ezc_context* ctx, const ezc_lm_problem* p, bool device_
   s->nd = num_dist(p->model);
   s->kfull = s->nf + 2 + s->nd;
   s->per_block_cam = p->cams_per_block != 0;
+  s->collective = ctx->world > 1 && ctx->allreduce && (p->collective > 0 || (p->collective == 0 && p->n_blocks_global != p->n_blocks));
+  s->world = s->collective ? ctx->world : 1;
+  s->rank = s->collective ? ctx->rank : 0;
   const bool timing = getenv("EZC_LM_TIMING") != nullptr;
   const auto tc0 = std::chrono::steady_clock::now();
   ezc_status st = alloc_state(s);
@@ -1261,16 +1266,16 @@ ezc_status run_schur(ezc_lm_solver* s, double radius, bool first, bool reuse, bo
   else lm_schur_kernel<12><<<grid, 128, 0, ctx->stream>>>(a);
   if (ezc_status st = launch_check(ctx, "lm_schur")) return st;
   // per-warp partials -> red1[R1_SCHUR ..] in fixed order (last value, the gradient max-norm, is max-reduced)
-  const bool slots = ctx->world <= kMaxSlotRanks;
+  const bool slots = s->world <= kMaxSlotRanks;
   double* sr_out = dev ? s->xchg.as<double>() + kX1 : s->red1[s->sb].as<double>() + R1_SCHUR;
   lm_schur_reduce_kernel<<<nv, 256, 0, ctx->stream>>>(s->part2.as<double>(), grid * 4, k, k <= 7 ? 1 : 2, sr_out,
-                                                      slots ? ctx->rank : 0, slots ? std::max(ctx->world, 1) : 1, dst);
+                                                      slots ? s->rank : 0, slots ? std::max(s->world, 1) : 1, dst);
   return launch_check(ctx, "lm_schur_reduce");
 }
 
 ezc_status allreduce(ezc_lm_solver* s, double* dev, int count, int op) {
   ezc_context* ctx = s->ctx;
-  if (ctx->world > 1 && ctx->allreduce) {
+  if (s->collective) {
     const int32_t rc = ctx->allreduce(ctx->allreduce_user, dev, count, op, ctx->stream);
     EZC_CHECK(rc == 0, EZC_ERR_COLLECTIVE, "all-reduce callback failed (%d); abort the process group", (int)rc);
   }
@@ -1399,7 +1404,7 @@ ezc_status ezc_lm_solve(ezc_lm_solver* s, const ezc_lm_options* opt, ezc_lm_summ
   EZC_CHECK(s && opt && summary, EZC_ERR_INVALID, "ezc_lm_solve: null argument");
   EZC_CHECK(s->have_params, EZC_ERR_INVALID, "ezc_lm_solve: call ezc_lm_set_params first");
   static const bool host_loop = getenv("EZC_LM_HOST_LOOP") != nullptr;   // round-1 driver, kept for A/B runs
-  if (host_loop || s->ctx->world > kMaxSlotRanks) return lm_solve_host_loop(s, opt, summary);
+  if (host_loop || s->world > kMaxSlotRanks) return lm_solve_host_loop(s, opt, summary);
   return lm_solve_device(s, opt, summary);
 }
 
@@ -1414,7 +1419,7 @@ static ezc_status lm_solve_device(ezc_lm_solver* s, const ezc_lm_options* opt, e
   setup_pattern(s, opt->opt_focal, opt->opt_pp, opt->opt_dist);
   const int k = s->k, nb = s->prob.n_blocks;
   const int nS = k * (k + 1) / 2;
-  const int n_slots = std::max(ctx->world, 1);
+  const int n_slots = std::max(s->world, 1);
   LmDevOpts o{};
   o.max_num_iterations = opt->max_num_iterations; o.max_invalid = opt->max_num_consecutive_invalid_steps;
   o.function_tolerance = opt->function_tolerance; o.gradient_tolerance = opt->gradient_tolerance;
@@ -1540,8 +1545,8 @@ static ezc_status lm_solve_host_loop(ezc_lm_solver* s, const ezc_lm_options* opt
     ++n_lin;
     const int n1 = R1_SCHUR + nS + 2 * k + 4;
     // ONE collective per synchronisation point: the gradient max-norm rides in per-rank slots of the summed buffer
-    const bool slots = ctx->world <= kMaxSlotRanks;
-    const int n_slots = slots ? std::max(ctx->world, 1) : 1;
+    const bool slots = s->world <= kMaxSlotRanks;
+    const int n_slots = slots ? std::max(s->world, 1) : 1;
     if (slots) {
       if (ezc_status st_ar = allreduce(s, s->red1[s->sb].as<double>() + R1_SCHUR, n1 - R1_SCHUR + n_slots, 0)) return st_ar;
     } else {

@@ -339,7 +339,8 @@ def run_rig_extrinsics(ctx: lm.Context, local_cameras: dict, n_cams: int, target
         init = np.zeros((0, 7))
         focal, pp, dist = np.zeros(1 if mono0 else 2), np.zeros(2), np.zeros(nd)
     t1 = time.perf_counter()
-    ext, summ = lm.lm_multicam(ctx, synth.MODEL_ID[m0], mono0, obs, pts, W, H, focal, pp, dist, init, n_blocks_global=n_cams - 1)
+    ext, summ = lm.lm_multicam(ctx, synth.MODEL_ID[m0], mono0, obs, pts, W, H, focal, pp, dist, init, n_blocks_global=n_cams - 1,
+                               collective=1 if comm.world > 1 else -1)
     t2 = time.perf_counter()
     parts = comm.allgather({c: ext[k] for k, c in enumerate(mine)})
     out = {}

@@ -111,7 +111,8 @@ class LmSolver:
 
     def __init__(self, ctx: Context, model_id: int, mono: bool, obs, pts, width: float, height: float,
                  pts_period: int | None = None, cams_per_block: bool = False, device_ptrs: bool = False,
-                 n_blocks: int | None = None, obs_per_block: int | None = None, n_blocks_global: int | None = None):
+                 n_blocks: int | None = None, obs_per_block: int | None = None, n_blocks_global: int | None = None,
+                 collective: int = 0):
         self.ctx = ctx
         p = LmProblemC()
         p.model, p.use_mono_focal = int(model_id), int(bool(mono))
@@ -131,6 +132,7 @@ class LmSolver:
         p.cams_per_block = int(bool(cams_per_block))
         p.img_w, p.img_h = float(width), float(height)
         p.n_blocks_global = int(n_blocks_global if n_blocks_global is not None else p.n_blocks)
+        p.collective = int(collective)
         self.n_blocks = p.n_blocks
         self.mono = bool(mono)
         self.nf = 1 if mono else 2
@@ -230,7 +232,7 @@ def lm_mono(ctx: Context, model_id: int, mono: bool, obs, pts, width, height, fo
 
 
 def lm_multicam(ctx: Context, model_id: int, mono: bool, obs, pts, width, height, focal, pp, dist, extrinsics,
-                n_blocks_global: int | None = None):
+                n_blocks_global: int | None = None, collective: int = 0):
     """EZCalibrator::runMultiCameraCalib's optimisation through the one-shot C entry point (ezc_lm_multicam): block b =
     extrinsic of camera b+1 with its own constant intrinsics; obs [n_blocks, n_frames0 * n_pts, 2], pts [n_frames0 * n_pts, 3].
     Returns (extrinsics [n_blocks, 7], summary dict)."""
@@ -242,6 +244,7 @@ def lm_multicam(ctx: Context, model_id: int, mono: bool, obs, pts, width, height
     p.img_w, p.img_h = float(width), float(height)
     p.pts, p.obs = _p(pts), _p(obs)
     p.n_blocks_global = int(n_blocks_global if n_blocks_global is not None else p.n_blocks)
+    p.collective = int(collective)
     a = [np.ascontiguousarray(x, dtype=np.float64) for x in (focal, pp, dist)]
     ext = np.array(extrinsics, dtype=np.float64, copy=True).reshape(-1, 7)
     s = LmSummaryC()

@@ -198,6 +198,9 @@ typedef struct {
   const double* pts;         /* [pts_period][3] */
   const float* obs;          /* [n_blocks][obs_per_block][2]; cv::Point2f; (-1,-1) = missing */
   int32_t n_blocks_global;   /* total blocks over all ranks (== n_blocks when world == 1) */
+  int32_t collective;        /* on a context with an exchange installed (world > 1): 1 = this solve is view-sharded over the
+                                ranks (every rank must make the same calls), -1 = local to this rank (e.g. the per-camera mono
+                                calibrations of a rig), 0 = decide from n_blocks_global != n_blocks */
 } ezc_lm_problem;
 
 typedef struct {
