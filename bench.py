@@ -822,15 +822,16 @@ def main():
         if rank != 0:
             return
         models = BENCH_MODELS if not args.models else tuple(args.models.split(","))
-        a2 = argparse.Namespace(steps=args.steps, warmup=args.warmup)
-        # bounded sample: the default (20000 views, K + W = 13 iterations per model) takes ~50 s on 16-24 cores; more
-        # iterations get proportionally fewer views so that the run still ends within a few minutes
-        views = max(2000, int(args.cpu_views * min(1.0, 13.0 / max(args.steps + args.warmup, 1))))
+        # SAME configuration as our arm: every model on the full 69,445-view / 10,000,080-observation problem.  A CPU iteration
+        # of that size takes ~1.3 s per model on 16 cores, so a step budget bounds the run: at most 2 timed iterations (and 1
+        # warm-up iteration) per model however large --steps is -- ~1 minute in total.
+        a2 = argparse.Namespace(steps=max(1, min(args.steps, 2)), warmup=1)
+        views = args.views if args.cpu_views == 20000 else args.cpu_views
         value, ms, cb = run_cpu(a2, models, views, True)
         line = {"impl": "reference", "metric": "LM iters/s (10M obs)", "value": round(value, 6), "unit": "LM iters/s (10M obs)",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "cfg5 LM-only sweep (bounded CPU sample, scaled to 10M observations): " + cb["sample"],
+                "config": {"workload": "cfg5 LM-only sweep, same problem as the GPU arm (bounded in iterations, not in size): " + cb["sample"],
                            "note": "Ceres 2.2.0 is not installable here (no source, no network): this is the restated-Ceres oracle port with all host threads"},
                 "cpu_baseline": cb,
                 "e2e": {"value": round(value, 6), "unit": "LM iters/s (10M obs)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -786,22 +786,26 @@ __device__ void lm_step_compute(LmDevState* st, const double* x1, const LmDevOpt
       S[c * k + c] += st->diag_c[c] / st->radius;
       rhs[c] = st->scale_c[c] * (st->gc[c] - bsum[c]);
     }
-    // in-place Cholesky (lower) + solve, same operation order as host_cholesky / host_chol_solve
+    // in-place Cholesky (lower) + solve.  One thread: the FP64 divisions / square roots are ~400-cycle dependent chains, so
+    // each column takes ONE reciprocal (the host loop divided every entry) -- last-bit differences only.
+    double inv[kMaxK];
     for (int j = 0; j < k && ok; ++j) {
       double d = S[j * k + j];
       for (int m = 0; m < j; ++m) d -= S[j * k + m] * S[j * k + m];
       if (!(d > 0.0)) { ok = false; break; }
       d = sqrt(d);
       S[j * k + j] = d;
+      const double id = 1.0 / d;
+      inv[j] = id;
       for (int i = j + 1; i < k; ++i) {
         double v = S[i * k + j];
         for (int m = 0; m < j; ++m) v -= S[i * k + m] * S[j * k + m];
-        S[i * k + j] = v / d;
+        S[i * k + j] = v * id;
       }
     }
     if (ok) {
-      for (int i = 0; i < k; ++i) { double v = rhs[i]; for (int m = 0; m < i; ++m) v -= S[i * k + m] * rhs[m]; rhs[i] = v / S[i * k + i]; }
-      for (int i = k - 1; i >= 0; --i) { double v = rhs[i]; for (int m = i + 1; m < k; ++m) v -= S[m * k + i] * rhs[m]; rhs[i] = v / S[i * k + i]; }
+      for (int i = 0; i < k; ++i) { double v = rhs[i]; for (int m = 0; m < i; ++m) v -= S[i * k + m] * rhs[m]; rhs[i] = v * inv[i]; }
+      for (int i = k - 1; i >= 0; --i) { double v = rhs[i]; for (int m = i + 1; m < k; ++m) v -= S[m * k + i] * rhs[m]; rhs[i] = v * inv[i]; }
       for (int c = 0; c < k; ++c) {
         st->uc[c] = st->scale_c[c] * rhs[c];
         st->dc[c] = -st->uc[c];
@@ -865,7 +869,8 @@ __device__ void lm_decide_compute(LmDevState* st, const double* x2, const LmDevO
     st->cur = 1 - st->cur;
     st->sb = 1 - st->sb;
     st->x_norm = sqrt(cn2);
-    st->radius = st->radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0));
+    const double t21 = 2.0 * rel - 1.0;
+    st->radius = st->radius / fmax(1.0 / 3.0, 1.0 - t21 * t21 * t21);
     st->radius = fmin(o.max_radius, st->radius);
     st->decrease_factor = 2.0; st->reuse_diagonal = 0;
     ++st->n_success;
