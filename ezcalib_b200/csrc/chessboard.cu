@@ -1739,8 +1739,10 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
         if (getenv("EZC_CB_TIMING")) fprintf(stderr, "[cb] phase 2 k %d dil %d: %d of %d views\n", k, dil, n_act, nb);
         CB_LAUNCH_PIX(cb_copy_active_kernel, N, n_act, prevb, th, N, n_act, P.active.as<int>());
         CB_LAUNCH_FRAME(th, n_act, P.active.as<int>());
-        // no edge-length compensation in the fallback (empirically what cv2 4.13 does: exact on all phase-2 fixtures)
-        if (ezc_status st = run_attempt(ctx, P, th, W, H, n_act, pw, ph, 0)) return st;
+        // generateQuads gets the dilation count in the fallback too (edge_len compensation (sqrt(e) + 2 dil)^2), as OpenCV's
+        // source reads.  Round 1 ran the fallback without it -- indistinguishable on every fixture it had; the randomised
+        // degradations of tests/cb_fuzz.py separate the two: cv2 finds strongly blurred boards at 6-7 dilations only with it.
+        if (ezc_status st = run_attempt(ctx, P, th, W, H, n_act, pw, ph, dil)) return st;
         if (ezc_status st = sync_state(ctx, P, nb, h_state, list)) return st;
       }
     }

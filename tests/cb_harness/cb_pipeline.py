@@ -182,7 +182,7 @@ def find_chessboard_corners(img: np.ndarray, pattern_size, refine=True, info=Non
                         th = cv2.dilate(th, None, iterations=1)
                 prev_block = block
                 cv2.rectangle(th, (0, 0), (W - 1, H - 1), 255, 3, cv2.LINE_8)
-                ok, c, prev, nq = detect_from_binary(th, pw, ph, 0)  # no edge compensation in the fallback (matches cv2 4.13 exactly on all phase-2 fixtures)
+                ok, c, prev, nq = detect_from_binary(th, pw, ph, dilations if os.environ.get('CB_PHASE2_COMP', '1') == '1' else 0)
                 if prev:
                     prev_sqr_size = prev
                 if ok:
