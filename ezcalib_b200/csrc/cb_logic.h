@@ -329,7 +329,9 @@ CB_HD inline void find_quad_neighbors(Work& w, const Par& par) {
             // discriminating views: a 0.3-scale board needs the candidate-side test (two squares of one row
             // 9 px apart pass the one-sided test and scramble the corner order); noisy views at 5-7 dilations need it
             // NOT to apply when a large blob looks at its small side neighbour (cv2 links them and finds no board).
+#ifndef CB_NO_CANDIDATE_SIDE_TEST
             if (qk.edge_len >= cur_edge && !diagonal_neighbour(w, qk, j, pt, w.corners[cur.corners[(i + 2) & 3]].pt)) continue;
+#endif
             code = k * 4 + j; min_dist = dist;
           }
         }
