@@ -325,13 +325,16 @@ CB_HD inline void find_quad_neighbors(Work& w, const Par& par) {
             // edges that differ by more than 1:4 in length (16 in squared length) are incompatible
             if (qk.edge_len > 16 * cur_edge || cur_edge > 16 * qk.edge_len) continue;
             if (!diagonal_neighbour(w, cur, i, o, w.corners[qk.corners[(j + 2) & 3]].pt)) continue;
-            // ... and also from the candidate quad's side when that quad is at least as large as this one.  Pinned on
-            // discriminating views: a 0.3-scale board needs the candidate-side test (two squares of one row
-            // 9 px apart pass the one-sided test and scramble the corner order); noisy views at 5-7 dilations need it
-            // NOT to apply when a large blob looks at its small side neighbour (cv2 links them and finds no board).
-#ifndef CB_NO_CANDIDATE_SIDE_TEST
-            if (qk.edge_len >= cur_edge && !diagonal_neighbour(w, qk, j, pt, w.corners[cur.corners[(i + 2) & 3]].pt)) continue;
-#endif
+            // ... and also from the candidate quad's side unless the candidate is much smaller than this quad (squared edge
+            // ratio below 1 : kNbSqrScale).  Empirical, like everything around it (OpenCV's source is not in the image):
+            //   * a 0.3-scale board needs the candidate-side test (two squares of one row 9 px apart pass the one-sided
+            //     test and scramble the corner order);
+            //   * noisy views at 5-7 dilations need it NOT to apply when a large blob looks at its small side neighbour (cv2
+            //     links them and finds no board);
+            //   * round 2's randomised degradations (tests/cb_fuzz.py) showed that "candidate at least as large" was too
+            //     narrow once the fallback passes the dilation count to generateQuads: candidates up to sqrt(2) smaller are
+            //     tested too -- 26 of 35 residual views then agree with cv2 (15 before), every older fixture still does.
+            if (qk.edge_len * kNbSqrScale >= cur_edge && !diagonal_neighbour(w, qk, j, pt, w.corners[cur.corners[(i + 2) & 3]].pt)) continue;
             code = k * 4 + j; min_dist = dist;
           }
         }

@@ -107,17 +107,17 @@ def hole_contours(binary: np.ndarray):
     return out
 
 
-def detect_from_binary(binary: np.ndarray, pw: int, ph: int, dilations: int = 0):
+def detect_from_binary(binary: np.ndarray, pw: int, ph: int, dilations: int = 0, prev_in: int = 0):
     holes = hole_contours(binary)
     if not holes:
-        return False, np.zeros((0, 2), np.float32), 0, 0
+        return False, np.zeros((0, 2), np.float32), int(prev_in), 0
     pts = np.ascontiguousarray(np.concatenate([c for c, _ in holes]), np.int32)
     lengths = np.array([len(c) for c, _ in holes], np.int32)
     # remap parent ids to small ints
     ids = {}
     parent = np.array([ids.setdefault(p, len(ids)) for _, p in holes], np.int32)
     out = np.zeros((pw * ph, 2), np.float32)
-    n_out = C.c_int32(0); prev = C.c_int32(0); nq = C.c_int32(0)
+    n_out = C.c_int32(0); prev = C.c_int32(int(prev_in)); nq = C.c_int32(0)
     found = lib().cbh_detect_from_contours(pts.ctypes.data_as(C.c_void_p), lengths.ctypes.data_as(C.c_void_p),
                                            parent.ctypes.data_as(C.c_void_p), len(holes), pw, ph, int(dilations), out.ctypes.data_as(C.c_void_p),
                                            C.byref(n_out), C.byref(prev), C.byref(nq))
@@ -143,9 +143,7 @@ def find_chessboard_corners(img: np.ndarray, pattern_size, refine=True, info=Non
         if dilations > 0:
             thresh = cv2.dilate(thresh, None, iterations=1)
         cv2.rectangle(thresh, (0, 0), (W - 1, H - 1), 255, 3, cv2.LINE_8)
-        ok, c, prev, nq = detect_from_binary(thresh, pw, ph, dilations)
-        if prev:
-            prev_sqr_size = prev
+        ok, c, prev_sqr_size, nq = detect_from_binary(thresh, pw, ph, dilations, prev_sqr_size)   # in/out like cv2 (a group can reset it to 0)
         if ok:
             found, corners = True, c
             if info is not None:
@@ -182,9 +180,7 @@ def find_chessboard_corners(img: np.ndarray, pattern_size, refine=True, info=Non
                         th = cv2.dilate(th, None, iterations=1)
                 prev_block = block
                 cv2.rectangle(th, (0, 0), (W - 1, H - 1), 255, 3, cv2.LINE_8)
-                ok, c, prev, nq = detect_from_binary(th, pw, ph, dilations if os.environ.get('CB_PHASE2_COMP', '1') == '1' else 0)
-                if prev:
-                    prev_sqr_size = prev
+                ok, c, prev_sqr_size, nq = detect_from_binary(th, pw, ph, dilations if os.environ.get('CB_PHASE2_COMP', '1') == '1' else 0, prev_sqr_size)
                 if ok:
                     found, corners = True, c
                     if info is not None:
