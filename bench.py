@@ -134,6 +134,18 @@ def measured_peaks() -> dict:
     return {}
 
 
+def measured_traffic() -> dict:
+    """DRAM traffic measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum), written by tools/ncu_traffic.py into
+    profiles/ncu_traffic_r02.json -- measurements, not literals; absent file => traffic is reported as null."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            pass
+    return {}
+
+
 # ------------------------------------------------------------------------------------------- CPU arm
 def run_cpu(args, models, n_views_sample: int, as_reference: bool):
     from ezcalib_b200 import synth
@@ -336,7 +348,8 @@ def run_gpu(args):
                      "frac": round(achieved / peak_fp64, 4) if peak_fp64 else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of ONE radtan5 launch (10,000,080 obs), ncu --set full:
                      # profiles/ncu_lm_r01_final.txt; algorithmic: 80.0 MB obs + 3.9 MB poses read, 35.6 MB strips written
-                     "traffic": 118.9e6, "traffic_launch": "lm_accumulate_kernel<radtan5,mono> on 10,000,080 observations",
+                     "traffic": measured_traffic().get("lm_accumulate_radtan5_dram_bytes_per_launch"),
+                     "traffic_launch": "lm_accumulate_kernel<radtan5,mono> on 10,000,080 observations; " + str(measured_traffic().get("source", "no ncu capture in profiles/")),
                      "kernel": "lm_accumulate_kernel", "dmma_peak_tflops": round(peak_dmma, 3), "peak_source": "DFMA microbenchmark measured in this run "
                      "(MEASURED_PEAKS.json has no FP64 figure; hbm_gbs there = %s)" % measured_peaks().get("hbm_gbs")},
     }
@@ -453,9 +466,10 @@ def run_detect(ctx, args, rank, world, stream):
                    "h2d_link_gbs": round(h2d_gbs, 2), "h2d_bound_images_per_s": round(h2d_gbs * 1e9 / (DET_W * DET_H) * world, 1)},
            "gpu_launches": int(launches),
            "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
-                        "traffic": None, "kernel": "whole detection pipeline (largest shares: at_merge_kernel 24 %, at_pre_kernel 19 %; profiles/launch_shares_r01.txt)",
-                        "top_kernel_traffic": {"kernel": "at_merge_kernel", "dram_bytes_per_image": 137.5e6, "algorithmic_bytes_per_image": alg_bytes,
-                                               "source": "profiles/ncu_detect_r01_final.txt (ncu --set full, 214 views per launch)"},
+                        "traffic": measured_traffic().get("aprilgrid_pipeline_dram_bytes_per_image"),
+                        "kernel": "whole detection pipeline (per-kernel shares: profiles/launch_shares_r02.txt)",
+                        "top_kernel_traffic": {"kernel": "at_merge_kernel", "dram_bytes_per_image": measured_traffic().get("at_merge_dram_bytes_per_image"),
+                                               "algorithmic_bytes_per_image": alg_bytes, "source": measured_traffic().get("source")},
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if measured_peaks().get("hbm_gbs") else "fallback 6650"}}
     if rank == 0 and not args.no_cpu:
         from oracle import apriltag_oracle as A

@@ -1053,7 +1053,7 @@ __device__ void find_quad_neighbors_grid(cb::Work& w, const NbShared& S, const N
           if ((dist < min_dist || (dist == min_dist && sl < code)) && dist <= cur_edge * cb::kNbSqrScale && dist <= ek * cb::kNbSqrScale) {
             if (ek > 16 * cur_edge || cur_edge > 16 * ek) return;
             if (!diagonal_neighbour_s(S, idx, i, o, S.pt[4 * k + (((sl & 3) + 2) & 3)])) return;
-            if (ek >= cur_edge && !diagonal_neighbour_s(S, k, sl & 3, pt, S.pt[4 * idx + ((i + 2) & 3)])) return;   // see cb_logic.h
+            if (ek * cb::kNbSqrScale >= cur_edge && !diagonal_neighbour_s(S, k, sl & 3, pt, S.pt[4 * idx + ((i + 2) & 3)])) return;   // see cb_logic.h
             code = sl; min_dist = dist;
           }
         });
