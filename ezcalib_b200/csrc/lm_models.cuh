@@ -168,9 +168,12 @@ __device__ __forceinline__ void residual_jacobian_w(const CamParams& c, const do
   double w = 1.0;
   if constexpr (WEIGHTED) {
     // ceres::CauchyLoss(1): rho = log(1+s), rho' = 1/(1+s), rho'' < 0 -> Corrector alpha = 0 -> scale by sqrt(rho')
+    // The cost term 0.5 log(1+s) is NOT taken here: a double-precision log is ~80 instructions per observation on the
+    // pipe this kernel is bound by.  The caller multiplies the (1+s) of its observations (exponent peeled off with frexp)
+    // and takes one log per lane at the end: sum log = log prod.  `half_rho` carries 1+s.
     const double ss = rx * rx + ry * ry;
-    w = sqrt(1.0 / (1.0 + ss));
-    half_rho = 0.5 * log(1.0 + ss);
+    w = rsqrt(1.0 + ss);
+    half_rho = 1.0 + ss;
   }
   wgt = w;
   const double wfx = w * fx, wfy = w * fy;

@@ -135,7 +135,8 @@ lm_accumulate_kernel(const AccumArgs a) {
   double acc[NTILE][2];
 #pragma unroll
   for (int t = 0; t < NTILE; ++t) acc[t][0] = acc[t][1] = 0.0;
-  double cost = 0.0;
+  double cost_prod = 1.0;
+  int cost_exp = 0;
 
   for (int seg = gw; seg < a.n_segs; seg += nW) {
     const int blk = seg / a.segs_per_block;
@@ -165,7 +166,9 @@ lm_accumulate_kernel(const AccumArgs a) {
           double rx, ry, w, half_rho, Jpx[6], Jpy[6], Jcx[12], Jcy[12];
           residual_jacobian_w<MODEL, MONO, true>(cam, pose, P[0], P[1], P[2], (double)o.x, (double)o.y, rx, ry, w, half_rho, Jpx, Jpy,
                                                  Jcx, Jcy);
-          cost += half_rho;
+          // running product of (1+s) with the exponent kept apart: cost = 0.5 (log(prod) + e ln 2) at the end
+          cost_prod *= half_rho;
+          { int e2; cost_prod = frexp(cost_prod, &e2); cost_exp += e2; }
 #pragma unroll
           for (int j = 0; j < 6; ++j) {
             J[j * kCS + lane] = Jpx[j];
@@ -220,6 +223,7 @@ lm_accumulate_kernel(const AccumArgs a) {
   double* pw = a.part + (size_t)gw * 384;
 #pragma unroll
   for (int t = 0; t < NTILE; ++t) *reinterpret_cast<double2*>(pw + t * 64 + lane * 2) = make_double2(acc[t][0], acc[t][1]);
+  double cost = 0.5 * (log(cost_prod) + (double)cost_exp * 0.693147180559945309417232121458);
   for (int m = 16; m >= 1; m >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, m);
   if (lane == 0) a.cost_part[gw] = cost;
 }
