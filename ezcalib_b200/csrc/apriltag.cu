@@ -202,9 +202,13 @@ __global__ void __launch_bounds__(256) at_pre_kernel(const uint8_t* __restrict__
   // tables of the already widened products (double)(lut[v] * f_k) (no f32 -> f64 conversion).  The addends span < 2^11, so
   // the sum of three is exact in a double and the rounded float is the same for any summation order.
   __shared__ double lutd[3][256];
-  __shared__ __align__(16) uint32_t uw[kUH][18];   // u8 tile as words: byte b of row r = pixel x0 - 4 + b
-  __shared__ float hb[kHH][kHW];
+  __shared__ __align__(16) uint32_t uw_store[kUH * 19];   // u8 tile as words
+  __shared__ float hb_store[kHH * (kHW + 1)];
   __shared__ float sb[kSH][kSW];
+  uint32_t (*uw)[18] = reinterpret_cast<uint32_t (*)[18]>(uw_store);        // border tiles: byte b of row r = pixel x0 - 2 + b
+  uint32_t (*uwi)[19] = reinterpret_cast<uint32_t (*)[19]>(uw_store);       // interior tiles: byte b of row r = pixel x0 - 4 + b
+  float (*hb)[kHW] = reinterpret_cast<float (*)[kHW]>(hb_store);
+  float (*hbi)[kHW + 1] = reinterpret_cast<float (*)[kHW + 1]>(hb_store);   // odd row stride for the row-per-lane pass B
   const int tid = threadIdx.x;
   int t = blockIdx.x;
   const int tx = t % tiles_x; t /= tiles_x;
@@ -219,33 +223,55 @@ __global__ void __launch_bounds__(256) at_pre_kernel(const uint8_t* __restrict__
     lutd[1][tid] = (double)(v * f1);
     lutd[2][tid] = (double)(v * f2);
   }
-  const uint8_t (*u)[72] = reinterpret_cast<const uint8_t (*)[72]>(uw);
   const bool interior = x0 >= 4 && x0 + kTX + 4 <= W - 2 && y0 >= 2 && y0 + kTY + 2 <= H - 1 &&
                         ((reinterpret_cast<uintptr_t>(I) | (uintptr_t)pitch) & 3) == 0;
   if (interior) {
-    // A. pixels: 36 rows x 18 aligned words (columns x0-4 .. x0+67)
+    // A. pixels: 36 rows x 18 aligned words (columns x0-4 .. x0+67), row stride 19 words (odd: lanes that differ in the row
+    //    hit different banks in pass B)
     for (int i = tid; i < kUH * 18; i += 256) {
       const int r = i / 18, w = i - r * 18;
-      uw[r][w] = *reinterpret_cast<const uint32_t*>(I + (long long)(y0 - 2 + r) * pitch + (x0 - 4) + 4 * w);
+      uwi[r][w] = *reinterpret_cast<const uint32_t*>(I + (long long)(y0 - 2 + r) * pitch + (x0 - 4) + 4 * w);
     }
     __syncthreads();
-    // B. horizontal pass: h(r, c) at x = x0 - 1 + c  <-  bytes c+4 (x+1), c+3 (x), c+2 (x-1)
-    for (int i = tid; i < kHH * kHW; i += 256) {
-      const int r = i / kHW, c = i - r * kHW;
-      double acc = lutd[0][u[r][c + 4]];
-      acc += lutd[1][u[r][c + 3]];
-      acc += lutd[2][u[r][c + 2]];
-      hb[r][c] = (float)acc;
+    // B. horizontal pass, sliding window: task = (row r, segment of 11 outputs); the widened products of every input pixel are
+    //    looked up once and reused by the outputs they feed.  h(r, c) at x = x0 - 1 + c  <-  bytes c+4 (x+1), c+3 (x), c+2 (x-1).
+    if (tid < kHH * 6) {
+      const int seg = tid / kHH, r = tid - seg * kHH;      // consecutive lanes = consecutive rows
+      const int c0 = seg * 11;
+      const uint8_t* urow = reinterpret_cast<const uint8_t*>(uwi[r]);
+      double dm = lutd[2][urow[c0 + 2]];                    // f2 * p(x-1)
+      int vc = urow[c0 + 3];
+#pragma unroll
+      for (int k = 0; k < 11; ++k) {
+        const int vp = urow[c0 + k + 4];
+        double acc = lutd[0][vp];                           // f0 * p(x+1)
+        acc += lutd[1][vc];                                 // f1 * p(x)
+        acc += dm;
+        hbi[r][c0 + k] = (float)acc;
+        dm = lutd[2][vc];
+        vc = vp;
+      }
     }
     __syncthreads();
-    // C. vertical pass: s(r, c) at y = y0 - 1 + r  <-  h rows r+2 (y+1), r+1 (y), r (y-1)
-    for (int i = tid; i < kSH * kSW; i += 256) {
-      const int r = i / kSW, c = i - r * kSW;
-      double acc = 0;
-      acc += (double)(hb[r + 2][c] * f0);
-      acc += (double)(hb[r + 1][c] * f1);
-      acc += (double)(hb[r][c] * f2);
-      sb[r][c] = (float)acc;
+    // C. vertical pass, sliding window: task = (column c, segment of rows); each h value is multiplied and widened once per
+    //    tap instead of once per use.  s(r, c) at y = y0 - 1 + r  <-  h rows r+2 (y+1, f0), r+1 (y, f1), r (y-1, f2).
+    for (int task = tid; task < kSW * 4; task += 256) {
+      const int seg = task / kSW, c = task - seg * kSW;    // consecutive lanes = consecutive columns
+      const int r0 = seg * 9, r1 = min(r0 + 9, kSH);
+      float hm = hbi[r0][c], hc = hbi[r0 + 1][c];
+      double q2 = (double)(hm * f2);                        // f2 * h(y-1)
+      double q1 = (double)(hc * f1);                        // f1 * h(y)
+      for (int r = r0; r < r1; ++r) {
+        const float hp = hbi[r + 2][c];
+        double acc = 0;
+        acc += (double)(hp * f0);
+        acc += q1;
+        acc += q2;
+        sb[r][c] = (float)acc;
+        q2 = (double)(hc * f2);
+        q1 = (double)(hp * f1);
+        hc = hp;
+      }
     }
     __syncthreads();
     at_pre_gradient<true>(sb, tid, im, x0, y0, W, H, wpr, amask, acount, theta, mag);
@@ -436,6 +462,16 @@ struct DigitArray {
   const int* key; int shift;
   __device__ int operator()(uint32_t v) const { return (key[v] >> shift) & 255; }
 };
+// key of an edge = label of its component (root compact id); materialised once for the key-value sort
+__global__ void at_edge_keys_kernel(const int* __restrict__ label, const int* __restrict__ eA, int n, uint32_t* __restrict__ keys) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) keys[e] = (uint32_t)label[eA[e]];
+}
+// flag[i] = 1 where the sorted key sequence starts a new component
+__global__ void at_boundary_keys_kernel(const uint32_t* __restrict__ keys, int n, int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
 __global__ void at_iota_kernel(uint32_t* v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = (uint32_t)i;
@@ -1149,7 +1185,7 @@ namespace {
 struct Pools {
   DevBuf fr, seg, theta, mag, cidx, scan_tmp, total, amask, acount, dbg_theta, dbg_mag;
   DevBuf apix, a_theta, a_mag, nodes, parent, setsize, ecount, label;
-  DevBuf eA, eB, ecost, order0, order1, flags, starts;
+  DevBuf eA, eB, ecost, order0, order1, keys0, keys1, flags, starts;
   DevBuf rep, keep, plist0, plist1, cstart, segs_raw, seg_valid, segs, img_count, seg_start;
   DevBuf cell_of, cell_count, cell_start, cell_fill, cell_items, ccount, children;
   DevBuf qcount, quads, dets, qimg_count, qstart, ngood, corners, cimg, refine_flag;
@@ -1252,17 +1288,21 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
   // ---- 5: stable sort of the edges by (component, cost)
   uint32_t* o0 = P.order0.as<uint32_t>();
   uint32_t* o1 = P.order1.as<uint32_t>();
-  AT_LAUNCH(at_iota_kernel, nE, o0, nE);
-  if (ezc_status st = radix_pass(ctx, o0, o1, nE, DigitCost{P.ecost.as<uint8_t>()}, P.sort)) return st;
-  std::swap(o0, o1);
-  for (int shift = 0; shift < bits_for(std::max(nA, 2)); shift += 8) {
-    if (ezc_status st = radix_pass(ctx, o0, o1, nE, DigitLabelOfEdge{P.label.as<int>(), P.eA.as<int>(), shift}, P.sort)) return st;
-    std::swap(o0, o1);
+  // key-value LSD radix: one pass over the cost byte of the unsorted sequence, then ceil(bits/9) passes over the label
+  EZC_CUDA(P.keys0.reserve(sizeof(uint32_t) * ecap)); EZC_CUDA(P.keys1.reserve(sizeof(uint32_t) * ecap));
+  uint32_t* k0 = P.keys0.as<uint32_t>();
+  uint32_t* k1 = P.keys1.as<uint32_t>();
+  AT_LAUNCH(at_edge_keys_kernel, nE, P.label.as<int>(), P.eA.as<int>(), nE, k0);
+  if (ezc_status st = radix_pass_kv<8, true>(ctx, k0, nullptr, P.ecost.as<uint8_t>(), k1, o1, nE, 0, P.sort)) return st;
+  std::swap(o0, o1); std::swap(k0, k1);
+  for (int shift = 0; shift < bits_for(std::max(nA, 2)); shift += 9) {
+    if (ezc_status st = radix_pass_kv<9, false>(ctx, k0, o0, nullptr, k1, o1, nE, shift, P.sort)) return st;
+    std::swap(o0, o1); std::swap(k0, k1);
   }
   // component boundaries -> starts
   int nComp = 0;
   if (nE > 0) {
-    AT_LAUNCH(at_boundary_kernel, nE, o0, nE, P.label.as<int>(), P.eA.as<int>(), P.flags.as<int>());
+    AT_LAUNCH(at_boundary_keys_kernel, nE, k0, nE, P.flags.as<int>());
     if (ezc_status st = exclusive_scan_i32(ctx, P.flags.as<int>(), P.flags.as<int>(), nE, P.scan_tmp, d_tot)) return st;
     if (ezc_status st = read_int(ctx, d_tot, &nComp, P)) return st;
     EZC_CUDA(P.starts.reserve(sizeof(int) * ((size_t)nComp + 2)));

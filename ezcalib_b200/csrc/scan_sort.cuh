@@ -148,9 +148,87 @@ __global__ void __launch_bounds__(kSortWarps * 32) radix_scatter_kernel(const ui
   }
 }
 
+// ---- key-value variant: the keys are materialised once and travel with the values, so a pass streams 4 B (histogram) and
+// 8 B in / 8 B out (scatter) per item instead of re-deriving the key of every item through two dependent gathers in every
+// pass (round-2 ncu: the four label passes moved 142 MB per image that way).  BITS-bit digits (9 -> 3 passes over 26 bits).
+// FIRST: the pass over the per-item byte `cost` of the still unsorted sequence (vals_in = iota, not materialised).
+template <int BITS, bool FIRST>
+__global__ void __launch_bounds__(kSortWarps * 32) radix_hist_kv_kernel(const uint32_t* __restrict__ keys, const uint8_t* __restrict__ cost,
+                                                                          int n, int n_warps, int shift, int* __restrict__ counts) {
+  constexpr int NB = 1 << BITS;
+  __shared__ int h[kSortWarps][NB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kSortWarps + warp;
+  for (int b = lane; b < NB; b += 32) h[warp][b] = 0;
+  __syncwarp();
+  if (gw < n_warps) {
+    const int beg = gw * kSortChunk, end = min(n, beg + kSortChunk);
+    for (int i = beg + lane; i < end; i += 32) atomicAdd(&h[warp][FIRST ? (int)cost[i] : (int)((keys[i] >> shift) & (NB - 1))], 1);
+    __syncwarp();
+    for (int b = lane; b < NB; b += 32) counts[(size_t)b * n_warps + gw] = h[warp][b];
+  }
+}
+
+template <int BITS, bool FIRST>
+__global__ void __launch_bounds__(kSortWarps * 32) radix_scatter_kv_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                                             const uint8_t* __restrict__ cost, uint32_t* __restrict__ keys_out,
+                                                                             uint32_t* __restrict__ vals_out, int n, int n_warps, int shift,
+                                                                             const int* __restrict__ offsets) {
+  constexpr int NB = 1 << BITS;
+  __shared__ int off[kSortWarps][NB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kSortWarps + warp;
+  if (gw >= n_warps) return;
+  for (int b = lane; b < NB; b += 32) off[warp][b] = offsets[(size_t)b * n_warps + gw];
+  __syncwarp();
+  const int beg = gw * kSortChunk, end = min(n, beg + kSortChunk);
+  for (int i0 = beg; i0 < end; i0 += 32) {
+    const int i = i0 + lane;
+    const bool act = i < end;
+    uint32_t k = 0, v = 0;
+    int d = NB + lane;  // inactive lanes get unique pseudo-digits
+    if (act) {
+      k = keys_in[i];
+      v = FIRST ? (uint32_t)i : vals_in[i];
+      d = FIRST ? (int)cost[i] : (int)((k >> shift) & (NB - 1));
+    }
+    const unsigned m = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(m & ((1u << lane) - 1u));
+    int base = 0;
+    if (act) base = off[warp][d];
+    __syncwarp();
+    if (act) {
+      keys_out[base + rank] = k;
+      vals_out[base + rank] = v;
+      if (rank == 0) off[warp][d] = base + __popc(m);
+    }
+    __syncwarp();
+  }
+}
+
 struct SortTemp {
   DevBuf counts, scan_tmp;
 };
+
+// One stable key-value pass (see above).
+template <int BITS, bool FIRST>
+inline ezc_status radix_pass_kv(ezc_context* ctx, const uint32_t* keys_in, const uint32_t* vals_in, const uint8_t* cost, uint32_t* keys_out,
+                                uint32_t* vals_out, int n, int shift, SortTemp& t) {
+  if (n <= 0) return EZC_OK;
+  constexpr int NB = 1 << BITS;
+  const int n_warps = (n + kSortChunk - 1) / kSortChunk;
+  const int grid = (n_warps + kSortWarps - 1) / kSortWarps;
+  EZC_CUDA(t.counts.reserve(sizeof(int) * NB * (size_t)n_warps));
+  radix_hist_kv_kernel<BITS, FIRST><<<grid, kSortWarps * 32, 0, ctx->stream>>>(keys_in, cost, n, n_warps, shift, t.counts.as<int>());
+  EZC_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  if (ezc_status st = exclusive_scan_i32(ctx, t.counts.as<int>(), t.counts.as<int>(), (long long)NB * n_warps, t.scan_tmp, nullptr)) return st;
+  radix_scatter_kv_kernel<BITS, FIRST><<<grid, kSortWarps * 32, 0, ctx->stream>>>(keys_in, vals_in, cost, keys_out, vals_out, n, n_warps, shift,
+                                                                                t.counts.as<int>());
+  EZC_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return EZC_OK;
+}
 
 // One stable pass: reorders vals[n] into out[n] by the 8-bit digit digit(v).
 template <class DigitFn>
