@@ -185,9 +185,12 @@ __device__ __forceinline__ void at_pre_gradient(const float (*sb)[kSW], int tid,
       acount[wi] = __popc(m);
     }
     if (act) {
+      // the gradient itself; theta = atan2f(Iy, Ix) and mag are taken per ACTIVE pixel in at_theta_kernel: evaluating the
+      // ~250-instruction bit-exact atan2f here costs the whole warp whenever one lane of the word is active (~5 % of the
+      // pixels, ~40 % of the words)
       const long long g = (long long)im * N + (long long)y * W + x;
-      theta[g] = fd_atan2f(Iy, Ix);
-      mag[g] = mg;
+      theta[g] = Ix;
+      mag[g] = Iy;
     }
   }
 }
@@ -370,12 +373,23 @@ __global__ void at_compact_words_kernel(const uint32_t* __restrict__ amask, cons
     const int b = __ffs(m) - 1;
     m &= m - 1;
     const long long g = g0 + b;
-    const float th = theta[g], mg = mag[g];
     apix[c] = (int)g;
-    a_theta[c] = th; a_mag[c] = mg;
-    nodes[c] = UfNode{c, 1, th, th, mg, mg, 0, 0};
+    a_theta[c] = theta[g];   // Ix  (see at_pre_gradient)
+    a_mag[c] = mag[g];       // Iy
     ++c;
   }
+}
+
+// theta / mag of the active pixels (TagDetector.cc:159-166) and the union-find nodes, one thread per active pixel: every lane
+// of a warp runs the bit-exact atan2f.  In: a_theta = Ix, a_mag = Iy; out: a_theta = atan2f(Iy, Ix), a_mag = Ix^2 + Iy^2.
+__global__ void at_theta_kernel(int n, float* __restrict__ a_theta, float* __restrict__ a_mag, UfNode* __restrict__ nodes) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const float Ix = a_theta[c], Iy = a_mag[c];
+  const float mg = Ix * Ix + Iy * Iy;
+  const float th = fd_atan2f(Iy, Ix);
+  a_theta[c] = th; a_mag[c] = mg;
+  nodes[c] = UfNode{c, 1, th, th, mg, mg, 0, 0};
 }
 
 // ---- stage 3: edges (Edge.cc:14-67) ------------------------------------------------------------------
@@ -1269,6 +1283,7 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
   EZC_CUDA(P.rep.reserve(sizeof(int) * cap)); EZC_CUDA(P.keep.reserve(sizeof(int) * (cap + 1)));
   AT_LAUNCH(at_compact_words_kernel, n_words, P.amask.as<uint32_t>(), P.acount.as<int>(), n_words, wpr, W, H, P.theta.as<float>(),
             P.mag.as<float>(), P.apix.as<int>(), P.a_theta.as<float>(), P.a_mag.as<float>(), P.nodes.as<UfNode>());
+  AT_LAUNCH(at_theta_kernel, nA, nA, P.a_theta.as<float>(), P.a_mag.as<float>(), P.nodes.as<UfNode>());
   // ---- 3: edges
   AT_LAUNCH(at_edges_words_kernel<false>, nA, P.apix.as<int>(), P.a_theta.as<float>(), P.amask.as<uint32_t>(), P.acount.as<int>(), wpr,
             nA, W, H, P.ecount.as<int>(), nullptr, nullptr, nullptr, nullptr);
