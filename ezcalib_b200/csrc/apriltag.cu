@@ -445,14 +445,29 @@ __global__ void at_ccl_init_kernel(int* L, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) L[i] = i;
 }
+// find with intermediate pointer jumping (as in ECL-CC): every visited node is re-pointed at its grandparent.  Parents only
+// ever decrease towards the minimum id of the component, so the unsynchronised stores are benign: a stale value is still an
+// ancestor.  Thin line-shaped components (what edge pixels form) otherwise grow chains as long as the line.
+__device__ __forceinline__ int ccl_find_compress(int* L, int v) {
+  int curr = L[v];
+  if (curr != v) {
+    int prev = v, next;
+    while (curr > (next = L[curr])) {
+      L[prev] = next;
+      prev = curr;
+      curr = next;
+    }
+  }
+  return curr;
+}
 __global__ void at_ccl_union_kernel(int* L, const int* __restrict__ eA, const int* __restrict__ eB, int n_edges) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
   int a = eA[e], b = eB[e];
   bool done = false;
   while (!done) {
-    a = ccl_find(L, a);
-    b = ccl_find(L, b);
+    a = ccl_find_compress(L, a);
+    b = ccl_find_compress(L, b);
     if (a < b) { const int old = atomicMin(&L[b], a); done = (old == b); b = old; }
     else if (b < a) { const int old = atomicMin(&L[a], b); done = (old == a); a = old; }
     else done = true;
