@@ -90,3 +90,19 @@ def test_4k_rig_sized_batch_is_deterministic(ctx):
         if ok0:
             worst = max(worst, float(np.max(np.abs(a[1][k] - pose0))))
     assert worst <= 1e-6, worst
+
+
+def test_capacity_error_is_reported_not_fatal(ctx):
+    """More points per view than the kernel's shared-memory working set: EZC_ERR_CAPACITY, and the context stays usable."""
+    from ezcalib_b200 import ezcalibrator as E
+    from ezcalib_b200._lib import EzcError
+    n_pts = 4000
+    tgt = np.concatenate([np.random.default_rng(0).uniform(-1, 1, (n_pts, 2)), np.ones((n_pts, 1))], 1)
+    corners = np.full((2, n_pts, 2), 100.0, np.float32)
+    with pytest.raises(EzcError) as ei:
+        E.compute_p3p_ransac_batch(ctx, corners, tgt, np.array([900.0]), np.array([640.0, 512.0]), 1280, 1024)
+    assert "status 4" in str(ei.value) and "shared-memory" in str(ei.value)
+    small = synth.chessboard_target(7, 10, 0.05)
+    views, focal, pp, W, H = _views(small, 4, seed=3)
+    ok, _, _ = E.compute_p3p_ransac_batch(ctx, np.stack(views), small, focal, pp, W, H)
+    assert ok.all()
