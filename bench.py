@@ -843,7 +843,8 @@ def main():
         views = args.views if args.cpu_views == 20000 else args.cpu_views
         value, ms, cb = run_cpu(a2, models, views, True)
         line = {"impl": "reference", "metric": "LM iters/s (10M obs)", "value": round(value, 6), "unit": "LM iters/s (10M obs)",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+                "n_gpus": args.gpus, "steps": a2.steps, "warmup": a2.warmup, "steps_requested": args.steps, "warmup_requested": args.warmup,
+                "ms_per_step": round(ms, 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "cfg5 LM-only sweep, same problem as the GPU arm (bounded in iterations, not in size): " + cb["sample"],
                            "note": "Ceres 2.2.0 is not installable here (no source, no network): this is the restated-Ceres oracle port with all host threads"},
