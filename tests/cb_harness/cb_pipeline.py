@@ -180,7 +180,7 @@ def find_chessboard_corners(img: np.ndarray, pattern_size, refine=True, info=Non
                         th = cv2.dilate(th, None, iterations=1)
                 prev_block = block
                 cv2.rectangle(th, (0, 0), (W - 1, H - 1), 255, 3, cv2.LINE_8)
-                ok, c, prev_sqr_size, nq = detect_from_binary(th, pw, ph, dilations if os.environ.get('CB_PHASE2_COMP', '1') == '1' else 0, prev_sqr_size)
+                ok, c, prev_sqr_size, nq = detect_from_binary(th, pw, ph, {'1': dilations, '0': 0, 'm1': max(dilations - 1, 0), 'h': dilations // 2, 'p1': dilations + 1}[os.environ.get('CB_PHASE2_COMP', '1')], prev_sqr_size)
                 if ok:
                     found, corners = True, c
                     if info is not None:
