@@ -108,11 +108,11 @@ __global__ void cb_fg16_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
 // Vertical pass on the chunk and on its two neighbour columns, then the horizontal pass with byte shifts across words.
 template <bool IS_MAX>
 __global__ void cb_morph16_kernel(const uint8_t* __restrict__ src, long long pitch, long long istride, bool vec_src, uint8_t* __restrict__ dst,
-                                  int W, int H, const int* __restrict__ active, bool vec_dst) {
+                                  int W, int H, const int* __restrict__ active, bool vec_dst, const int* __restrict__ src_of = nullptr) {
   const ChunkPos c = chunk_pos(W, H);
   if (!c.ok) return;
   const int im = active ? active[blockIdx.y] : (int)blockIdx.y;
-  const uint8_t* S = src + (long long)im * istride;
+  const uint8_t* S = src + (long long)(src_of ? src_of[im] : im) * istride;   // src_of: the slot reads another image's source
   const uint32_t idb = IS_MAX ? 0u : 0xffu;
   auto op = [](uint32_t a, uint32_t b) { return IS_MAX ? __vmaxu4(a, b) : __vminu4(a, b); };
   Chunk16 m;

@@ -18,6 +18,7 @@
 // lock-step; images that are done drop out.  CALIB_CB_FAST_CHECK (checkChessboardBinary + checkChessboard) is
 // evaluated first when the caller asks for it (fast_check_gate below).
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "cb_logic.h"
@@ -1112,14 +1113,15 @@ __device__ void find_quad_neighbors_grid(cb::Work& w, const NbShared& S, const N
 
 // one BLOCK per active image
 __global__ void __launch_bounds__(kProcThreads) cb_process_kernel(const HoleInfo* __restrict__ holes, ImageState* __restrict__ st,
-                                                                  const int* __restrict__ active, int n_img, int pw, int ph, int dilations,
-                                                                  cb::Work* __restrict__ works, int* __restrict__ scratch_all,
+                                                                  const int* __restrict__ active, int n_img, int pw, int ph,
+                                                                  const int* __restrict__ dil_of, cb::Work* __restrict__ works, int* __restrict__ scratch_all,
                                                                   cb::Ptf* __restrict__ corners_out, int W, int H) {
   extern __shared__ __align__(16) unsigned char cb_smem[];
   const int slot = blockIdx.x;
   const int tid = threadIdx.x;
   if (slot >= n_img) return;
   const int im = active[slot];
+  const int dilations = dil_of[im];   // generateQuads' edge_len compensation is per attempt
   cb::Work& w = works[im];
   ImageState& S = st[im];
   int* scratch = scratch_all + (size_t)im * cb::kMaxQuads * 4;
@@ -1254,54 +1256,110 @@ __global__ void cb_apply_lut_kernel(const uint8_t* __restrict__ img, long long p
   }
   st16(out + ((long long)im * H + c.y) * W, c.x0, W, vec_dst, v);
 }
-// cv::adaptiveThreshold(MEAN_C, BINARY): separable box sums with replicated border, per-image block size
-__global__ void cb_box_h_kernel(const uint8_t* __restrict__ src, int W, int H, int n_img, const int* __restrict__ list,
-                                const int* __restrict__ block, int* __restrict__ out) {
-  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
+// cv::adaptiveThreshold(MEAN_C, BINARY): separable box sums with replicated border, per-image block size (up to 0.2 x
+// the short image side: ~200 taps).  Horizontal pass: one block per row, inclusive prefix sums of the row in shared
+// memory, each output the difference of two of them plus the replicated end pixels.  Vertical pass: one thread per
+// column and 32-row segment, a running sum that adds the row entering the window and drops the one leaving it.
+// Integer sums, so the result does not depend on how they are formed.
+// `src_of` (optional) names the image each listed slot reads: a speculative attempt works in a slot of its own on the
+// equalised copy of the view it belongs to.
+constexpr int kBoxRowThreads = 256;
+__global__ void __launch_bounds__(kBoxRowThreads) cb_box_h_kernel(const uint8_t* __restrict__ src, int W, int H, const int* __restrict__ list,
+                                                                  const int* __restrict__ block, int* __restrict__ out,
+                                                                  const int* __restrict__ src_of) {
+  extern __shared__ int box_pre[];   // W + 1 prefix sums, then one partial per warp
+  const int y = blockIdx.x, im = list[blockIdx.y];
   const long long N = (long long)W * H;
-  if (pix_ >= N) return;
-  const int slot = blockIdx.y;
-  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
-  const int im = list[slot];
-  const int b = block[im];
-  const int p = (int)pix_;
-  const long long gid = (long long)im * N + p;
-  const int y = p / W, x = p - y * W;
-  const uint8_t* S = src + (long long)im * N + (long long)y * W;
-  const int r = b / 2;
-  int s = 0;
-  for (int d = -r; d <= r; ++d) s += S[min(W - 1, max(0, x + d))];
-  out[gid] = s;
+  const uint8_t* S = src + (long long)(src_of ? src_of[im] : im) * N + (long long)y * W;
+  const int r = block[im] / 2;
+  int* warp_tot = box_pre + W + 1;
+  __shared__ int carry;
+  if (threadIdx.x == 0) { carry = 0; box_pre[0] = 0; }
+  __syncthreads();
+  for (int x0 = 0; x0 < W; x0 += kBoxRowThreads) {
+    const int x = x0 + threadIdx.x;
+    int v = x < W ? (int)S[x] : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    int before = carry;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    if (x < W) box_pre[x + 1] = before + v;
+    __syncthreads();
+    if (threadIdx.x == kBoxRowThreads - 1) carry = before + v;
+    __syncthreads();
+  }
+  const int first = (int)S[0], last = (int)S[W - 1];
+  int* O = out + (long long)im * N + (long long)y * W;
+  for (int x = threadIdx.x; x < W; x += kBoxRowThreads) {
+    const int lo = max(0, x - r), hi = min(W - 1, x + r);
+    O[x] = box_pre[hi + 1] - box_pre[lo] + max(0, r - x) * first + max(0, x + r - (W - 1)) * last;
+  }
 }
-__global__ void cb_box_v_thresh_kernel(const uint8_t* __restrict__ src, const int* __restrict__ hs, int W, int H, int n_img,
+constexpr int kBoxSegRows = 32;
+__global__ void cb_box_v_thresh_kernel(const uint8_t* __restrict__ src, const int* __restrict__ hs, int W, int H,
                                        const int* __restrict__ list, const int* __restrict__ block, const int* __restrict__ delta,
-                                       uint8_t* __restrict__ out) {
-  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
+                                       uint8_t* __restrict__ out, const int* __restrict__ src_of) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  const int im = list[blockIdx.z];
+  const int y0 = blockIdx.y * kBoxSegRows, y1 = min(H, y0 + kBoxSegRows);
   const long long N = (long long)W * H;
-  if (pix_ >= N) return;
-  const int slot = blockIdx.y;
-  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
-  const int im = list[slot];
-  const int b = block[im];
-  const int p = (int)pix_;
-  const long long gid = (long long)im * N + p;
-  const int y = p / W, x = p - y * W;
-  const int* S = hs + (long long)im * N;
-  const int r = b / 2;
-  int s = 0;
-  for (int d = -r; d <= r; ++d) s += S[(long long)min(H - 1, max(0, y + d)) * W + x];
+  const int b = block[im], r = b / 2, dlt = delta[im];
+  const int* S = hs + (long long)im * N + x;
+  const uint8_t* I = src + (long long)(src_of ? src_of[im] : im) * N + x;
+  uint8_t* O = out + (long long)im * N + x;
   const float scale = (float)(1.0 / ((double)b * b));
-  int mean = __float2int_rn((float)s * scale);
-  mean = mean > 255 ? 255 : mean;
-  out[gid] = ((int)src[gid] - mean > -delta[im]) ? 255 : 0;
+  int s = 0;
+  for (int d = -r; d <= r; ++d) s += S[(long long)min(H - 1, max(0, y0 + d)) * W];
+  for (int y = y0; y < y1; ++y) {
+    int mean = __float2int_rn((float)s * scale);
+    mean = mean > 255 ? 255 : mean;
+    O[(long long)y * W] = ((int)I[(long long)y * W] - mean > -dlt) ? 255 : 0;
+    s += S[(long long)min(H - 1, y + 1 + r) * W] - S[(long long)max(0, y - r) * W];
+  }
 }
-__global__ void cb_copy_active_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long N, int n_img, const int* __restrict__ list) {
-  const long long pix_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel of image slot blockIdx.y
-  if (pix_ >= N) return;
-  const int slot = blockIdx.y;
-  [[maybe_unused]] const long long cg = (long long)slot * N + pix_;
-  const long long gid = (long long)list[slot] * N + pix_;
-  dst[gid] = src[gid];
+// (src and dst may be the same buffer when `src_of` moves whole images between slots: no slot is then both read and written)
+// 16 bytes per thread when the image size allows (every image then starts 16-byte aligned in the packed buffers).
+__global__ void cb_copy_active_kernel(const uint8_t* src, uint8_t* dst, long long N, int n_img, const int* __restrict__ list,
+                                      const int* __restrict__ src_of) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int im = list[blockIdx.y];
+  const long long so = (long long)(src_of ? src_of[im] : im) * N, dof = (long long)im * N;
+  if ((N & 15) == 0) {
+    if (i * 16 < N) reinterpret_cast<uint4*>(dst + dof)[i] = reinterpret_cast<const uint4*>(src + so)[i];
+  } else {
+    for (long long k = i * 16; k < min(N, i * 16 + 16); ++k) dst[dof + k] = src[so + k];
+  }
+}
+// Results of the views that finished, kept apart from the per-slot state while speculative attempts reuse the slots.
+__global__ void cb_save_results_kernel(const ImageState* __restrict__ st, const cb::Ptf* __restrict__ corners, int n_img, int npts,
+                                       int* __restrict__ res_found, cb::Ptf* __restrict__ res_corners) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * npts) return;
+  const int im = i / npts;
+  if (i == im * npts) res_found[im] = st[im].found;
+  res_corners[i] = corners[i];
+}
+// pairs[2 j] = slot whose attempt is the one the sequential search would have stopped at, pairs[2 j + 1] = its view
+__global__ void cb_accept_kernel(const int* __restrict__ pairs, int n_pairs, int npts, const cb::Ptf* __restrict__ corners,
+                                 int* __restrict__ res_found, cb::Ptf* __restrict__ res_corners) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs * npts) return;
+  const int j = i / npts, k = i - j * npts;
+  const int slot = pairs[2 * j], view = pairs[2 * j + 1];
+  if (k == 0) res_found[view] = 1;
+  res_corners[(size_t)view * npts + k] = corners[(size_t)slot * npts + k];
+}
+__global__ void cb_restore_results_kernel(ImageState* __restrict__ st, cb::Ptf* __restrict__ corners, int n_img, int npts,
+                                          const int* __restrict__ res_found, const cb::Ptf* __restrict__ res_corners) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * npts) return;
+  const int im = i / npts;
+  if (i == im * npts) st[im].found = res_found[im];
+  corners[i] = res_corners[i];
 }
 __global__ void cb_gather_corners_kernel(const cb::Ptf* __restrict__ corners, const uint8_t* __restrict__ found, int n_img, int npts,
                                          float2* __restrict__ out, int* __restrict__ img_index) {
@@ -1330,6 +1388,7 @@ struct CbPools {
   DevBuf works, scratch, state, active, corners, found, block, delta, hsum, sub_corners, sub_idx, refresh;
   DevBuf pcnt, plast;   // per-pixel-label quad counters (kept zero between attempts)
   DevBuf blk_cnt, blk_off;   // roots per block of the chunk grid and their exclusive scan
+  DevBuf dil, srcmap, res_found, res_corners, pairs;   // per-slot dilation counts / source views, results of finished views
   DevBuf qlist, qcount;      // work lists of the holes with long contours
   DevBuf fc_w0, fc_w1, fc_w2, fc_k0, fc_k1, fc_k2, fc_fg, fc_comps, fc_hyps, fc_count, fc_list;
   HostPinned fc_h;
@@ -1390,10 +1449,37 @@ ezc_status upload_list(ezc_context* ctx, DevBuf& buf, const std::vector<int>& li
   return EZC_OK;
 }
 
+// cv::adaptiveThreshold of the equalised images named by `list` (n entries) into `dst`, block sizes / deltas per slot
+ezc_status adaptive_threshold(ezc_context* ctx, CbPools& P, int W, int H, int n, const int* list, uint8_t* dst, const int* src_of) {
+  if (n <= 0) return EZC_OK;
+  const size_t smem = sizeof(int) * ((size_t)W + 1 + kBoxRowThreads / 32);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    EZC_CUDA(cudaFuncSetAttribute(cb_box_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  cb_box_h_kernel<<<dim3((unsigned)H, (unsigned)n), kBoxRowThreads, smem, ctx->stream>>>(P.eq.as<uint8_t>(), W, H, list, P.block.as<int>(), P.hsum.as<int>(), src_of);
+  EZC_CUDA(cudaGetLastError());
+  cb_box_v_thresh_kernel<<<dim3((unsigned)((W + 127) / 128), (unsigned)((H + kBoxSegRows - 1) / kBoxSegRows), (unsigned)n), 128, 0, ctx->stream>>>(
+      P.eq.as<uint8_t>(), P.hsum.as<int>(), W, H, list, P.block.as<int>(), P.delta.as<int>(), dst, src_of);
+  EZC_CUDA(cudaGetLastError());
+  ctx->kernel_launches += 2;
+  return EZC_OK;
+}
+
 // One attempt for the images in `list` (device copy in P.active, n_act entries): quads from `bin` (already dilated +
 // framed) -> processQuads.  Per-pixel buffers are indexed by the REAL image index; only the hole flags are compact.
-ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, int H, int n_act, int pw, int ph, int dilations) {
+ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, int H, int n_act, int pw, int ph, const int* d_dil) {
   if (n_act <= 0) return EZC_OK;
+  const bool timing = getenv("EZC_CB_TIMING") != nullptr && getenv("EZC_CB_TIMING")[0] == '2';
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(ctx->stream);
+    const auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[cb]   %-12s %.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+    t_prev = t;
+  };
   const long long N = (long long)W * H;
   const int* list = P.active.as<int>();
   int* d_tot = P.total.as<int>();
@@ -1407,6 +1493,7 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
   EZC_CUDA(cudaMemcpyAsync(P.h.p, d_tot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   EZC_CUDA(cudaStreamSynchronize(ctx->stream));
   const int nH = *P.h.as<int>();
+  lap("labels");
   ImageState* st = P.state.as<ImageState>();
   if (nH > 0) {
     EZC_CUDA(P.hole_start.reserve(sizeof(int) * (size_t)nH));
@@ -1420,6 +1507,8 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
     EZC_CUDA(cudaMemcpyAsync(P.h.p, d_tot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     EZC_CUDA(cudaStreamSynchronize(ctx->stream));
     const int nPts = *P.h.as<int>();
+    lap("trace count");
+    if (timing) fprintf(stderr, "[cb]   %d contours, %d points\n", nH, nPts);
     EZC_CUDA(P.pool.reserve(sizeof(cb::Pt) * ((size_t)nPts + 16)));
     EZC_CUDA(P.stack_pool.reserve(sizeof(int) * 2 * ((size_t)nPts + 16)));
     EZC_CUDA(P.qlist.reserve(sizeof(int) * 2 * (size_t)nH)); EZC_CUDA(P.qcount.reserve(64));
@@ -1428,7 +1517,9 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
     int* list_big = list_mid + nH;
     CB_LAUNCH(cb_hole_offset_kernel, nH, P.holes.as<HoleInfo>(), nH, P.need.as<int>(), list_mid, list_big, P.qcount.as<int>());
     CB_LAUNCH(cb_trace_kernel<true>, nH, bin, P.labels.as<int>(), W, H, nH, P.holes.as<HoleInfo>(), P.pool.as<cb::Pt>(), cb::kMaxContourPts);
+    lap("trace store");
     CB_LAUNCH(cb_quad_kernel, nH, P.holes.as<HoleInfo>(), nH, P.pool.as<cb::Pt>(), P.stack_pool.as<int>());
+    lap("quads small");
     {
       static bool qw_attr = false;
       if (!qw_attr) {
@@ -1445,6 +1536,7 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
       EZC_CUDA(cudaGetLastError());
       ctx->kernel_launches += 2;
     }
+    lap("quads warp");
     CB_LAUNCH(cb_hole_ranges_kernel, nH, P.holes.as<HoleInfo>(), nH, N, 0, st);
   }
   CB_LAUNCH(cb_state_reset_kernel, n_act, st, list, n_act);
@@ -1459,11 +1551,12 @@ ezc_status run_attempt(ezc_context* ctx, CbPools& P, const uint8_t* bin, int W, 
       EZC_CUDA(cudaFuncSetAttribute(cb_process_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kProcSmem));
       attr_set = true;
     }
-    cb_process_kernel<<<n_act, kProcThreads, kProcSmem, ctx->stream>>>(P.holes.as<HoleInfo>(), st, list, n_act, pw, ph, dilations,
+    cb_process_kernel<<<n_act, kProcThreads, kProcSmem, ctx->stream>>>(P.holes.as<HoleInfo>(), st, list, n_act, pw, ph, d_dil,
                                                                        P.works.as<cb::Work>(), P.scratch.as<int>(), P.corners.as<cb::Ptf>(), W, H);
     EZC_CUDA(cudaGetLastError());
     ctx->kernel_launches++;
   }
+  lap("process");
   return EZC_OK;
 }
 
@@ -1671,80 +1764,269 @@ ezc_status detect_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0, 
     if (ezc_status st = fast_check_gate(ctx, P, d_img, imgs->pitch, imgs->image_stride, b0, W, H, nb, pw, ph, list)) return st;
     if (ezc_status st = upload_list(ctx, P.active, list)) return st;
   }
-  // ---- phase 1: histogram-binarised image; attempt 0 runs on it undilated, attempts 1..7 add one dilation each (the
-  // frame of the previous pass is dilated too). cv2 4.13's first failing level on pre-dilated ideal boards pins this.
-  for (int dil = 0; dil <= 7 && !list.empty(); ++dil) {
-    const int n_act = (int)list.size();
-    if (getenv("EZC_CB_TIMING")) fprintf(stderr, "[cb] phase 1 attempt %d: %d of %d views\n", dil, n_act, nb);
-    if (dil > 0) {
-      CB_LAUNCH_CH(cb_morph16_kernel<true>, W, H, n_act, b0, (long long)W, N, vec, b1, W, H, P.active.as<int>(), vec);
-      std::swap(b0, b1);
-    }
-    CB_LAUNCH_FRAME(b0, n_act, P.active.as<int>());
-    if (ezc_status st = run_attempt(ctx, P, b0, W, H, n_act, pw, ph, dil)) return st;
-    if (ezc_status st = sync_state(ctx, P, nb, h_state, list)) return st;
-  }
-  // ---- phase 2: equalised image, 6 adaptive thresholds x 8 dilations, for the images still without a board
-  const bool phase2_ran = !list.empty();
+  std::vector<int> h_dil(nb, 0);
+  EZC_CUDA(P.dil.reserve(sizeof(int) * nb));
+  auto upload_dil = [&](int d) -> ezc_status {
+    std::fill(h_dil.begin(), h_dil.end(), d);
+    EZC_CUDA(cudaMemcpyAsync(P.dil.p, h_dil.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+    return EZC_OK;
+  };
+  bool phase2_ran = false;
   std::vector<int> h_phase2(nb, 0);
-  for (int im : list) h_phase2[im] = 1;
-  if (phase2_ran) {
-    EZC_CUDA(P.eq.reserve(total)); EZC_CUDA(P.lut.reserve(256 * nb)); EZC_CUDA(P.prevbin.reserve(total));
-    EZC_CUDA(P.block.reserve(sizeof(int) * nb)); EZC_CUDA(P.delta.reserve(sizeof(int) * nb)); EZC_CUDA(P.hsum.reserve(sizeof(int) * total));
-    CB_LAUNCH(cb_equalize_lut_kernel, nb, P.hist.as<int>(), nb, (int)N, P.lut.as<uint8_t>());
-    CB_LAUNCH_CH(cb_apply_lut_kernel, W, H, (int)list.size(), d_img, (long long)imgs->pitch, (long long)imgs->image_stride, vec_src, W, H, P.active.as<int>(),
-                 P.lut.as<uint8_t>(), P.eq.as<uint8_t>(), vec);   // only the images that enter the fallback
-    std::vector<int> h_block(nb, 0), h_delta(nb, 0), prev_block(nb, -1);
-    for (int i = 0; i < nb; ++i) h_state[i].prev_sqr_size = 0;  // prev_sqr_size restarts at 0 with the fallback
-    EZC_CUDA(cudaMemcpyAsync(P.state.p, h_state.data(), sizeof(ImageState) * nb, cudaMemcpyHostToDevice, ctx->stream));
-    uint8_t* th = P.bin0.as<uint8_t>();       // thresh_img (gets the frame)
-    uint8_t* tmp = P.bin1.as<uint8_t>();
-    uint8_t* prevb = P.prevbin.as<uint8_t>(); // prev_thresh_img (no frame)
-    for (int k = 0; k < 6 && !list.empty(); ++k) {
-      std::fill(prev_block.begin(), prev_block.end(), -1);
-      for (int dil = 0; dil <= 7 && !list.empty(); ++dil) {
-        std::vector<int> fresh, old;
-        for (int im : list) {
-          const int ps = h_state[im].prev_sqr_size;
-          int bs = (int)lrint(ps == 0 ? std::min(W, H) * (k % 2 == 0 ? 0.2 : 0.1) : ps * 2.0);
-          bs |= 1;
-          if (bs != prev_block[im]) fresh.push_back(im); else old.push_back(im);
-          h_block[im] = bs;
-          h_delta[im] = (k / 2) * 5;
-          prev_block[im] = bs;
-        }
-        EZC_CUDA(cudaMemcpyAsync(P.block.p, h_block.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
-        EZC_CUDA(cudaMemcpyAsync(P.delta.p, h_delta.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
-        if (!fresh.empty()) {
-          // new block size: adaptive threshold of the equalised image, then `dil` dilations -> prev_thresh_img
-          if (ezc_status st = upload_list(ctx, P.refresh, fresh)) return st;
-          const int nf = (int)fresh.size();
-          CB_LAUNCH_PIX(cb_box_h_kernel, N, nf, P.eq.as<uint8_t>(), W, H, nf, P.refresh.as<int>(), P.block.as<int>(), P.hsum.as<int>());
-          CB_LAUNCH_PIX(cb_box_v_thresh_kernel, N, nf, P.eq.as<uint8_t>(), P.hsum.as<int>(), W, H, nf, P.refresh.as<int>(), P.block.as<int>(),
-                    P.delta.as<int>(), tmp);
-          for (int d = 0; d < dil; ++d) {
-            CB_LAUNCH_CH(cb_morph16_kernel<true>, W, H, nf, tmp, (long long)W, N, vec, th, W, H, P.refresh.as<int>(), vec);
-            CB_LAUNCH_PIX(cb_copy_active_kernel, N, nf, th, tmp, N, nf, P.refresh.as<int>());
-          }
-          CB_LAUNCH_PIX(cb_copy_active_kernel, N, nf, tmp, prevb, N, nf, P.refresh.as<int>());
-        }
-        if (!old.empty() && dil > 0) {
-          // same block size as before: one more dilation of prev_thresh_img
-          if (ezc_status st = upload_list(ctx, P.refresh, old)) return st;
-          const int no = (int)old.size();
-          CB_LAUNCH_CH(cb_morph16_kernel<true>, W, H, no, prevb, (long long)W, N, vec, tmp, W, H, P.refresh.as<int>(), vec);
-          CB_LAUNCH_PIX(cb_copy_active_kernel, N, no, tmp, prevb, N, no, P.refresh.as<int>());
-        }
-        const int n_act = (int)list.size();
-        if (getenv("EZC_CB_TIMING")) fprintf(stderr, "[cb] phase 2 k %d dil %d: %d of %d views\n", k, dil, n_act, nb);
-        CB_LAUNCH_PIX(cb_copy_active_kernel, N, n_act, prevb, th, N, n_act, P.active.as<int>());
-        CB_LAUNCH_FRAME(th, n_act, P.active.as<int>());
-        // generateQuads gets the dilation count in the fallback too (edge_len compensation (sqrt(e) + 2 dil)^2), as OpenCV's
-        // source reads.  Round 1 ran the fallback without it -- indistinguishable on every fixture it had; the randomised
-        // degradations of tests/cb_fuzz.py separate the two: cv2 finds strongly blurred boards at 6-7 dilations only with it.
-        if (ezc_status st = run_attempt(ctx, P, th, W, H, n_act, pw, ph, dil)) return st;
-        if (ezc_status st = sync_state(ctx, P, nb, h_state, list)) return st;
+  // The search is a sequence of 8 + 48 attempts per view (threshold image x dilation count) that stops at the first
+  // success.  Most views stop at attempt 0; the few that go on used to walk the rest one attempt at a time -- a serial
+  // tail of up to 55 x ~2.7 ms with one view on the GPU.  The only state an attempt inherits is prev_sqr_size, and only
+  // through the adaptive-threshold block size, so the remaining attempts of the unfinished views run CONCURRENTLY in
+  // the slots the finished views left free, each on the block size its predecessors are expected to leave behind; the
+  // host then walks the attempts in order and keeps exactly what the one-at-a-time search would have kept: an attempt
+  // whose assumed block size turns out wrong ends the walk and is rerun in the next round.  EZC_CB_SEQUENTIAL=1 keeps
+  // the one-at-a-time search (A/B parity check in tests/test_chessboard_gpu.py).
+  if (getenv("EZC_CB_SEQUENTIAL")) {
+    // ---- phase 1: histogram-binarised image; attempt 0 runs on it undilated, attempts 1..7 add one dilation each (the
+    // frame of the previous pass is dilated too). cv2 4.13's first failing level on pre-dilated ideal boards pins this.
+    for (int dil = 0; dil <= 7 && !list.empty(); ++dil) {
+      const int n_act = (int)list.size();
+      if (getenv("EZC_CB_TIMING")) fprintf(stderr, "[cb] phase 1 attempt %d: %d of %d views\n", dil, n_act, nb);
+      if (dil > 0) {
+        CB_LAUNCH_CH(cb_morph16_kernel<true>, W, H, n_act, b0, (long long)W, N, vec, b1, W, H, P.active.as<int>(), vec);
+        std::swap(b0, b1);
       }
+      CB_LAUNCH_FRAME(b0, n_act, P.active.as<int>());
+      if (ezc_status st = upload_dil(dil)) return st;
+      if (ezc_status st = run_attempt(ctx, P, b0, W, H, n_act, pw, ph, P.dil.as<int>())) return st;
+      if (ezc_status st = sync_state(ctx, P, nb, h_state, list)) return st;
+    }
+    // ---- phase 2: equalised image, 6 adaptive thresholds x 8 dilations, for the images still without a board
+    phase2_ran = !list.empty();
+    for (int im : list) h_phase2[im] = 1;
+    if (phase2_ran) {
+      EZC_CUDA(P.eq.reserve(total)); EZC_CUDA(P.lut.reserve(256 * nb)); EZC_CUDA(P.prevbin.reserve(total));
+      EZC_CUDA(P.block.reserve(sizeof(int) * nb)); EZC_CUDA(P.delta.reserve(sizeof(int) * nb)); EZC_CUDA(P.hsum.reserve(sizeof(int) * total));
+      CB_LAUNCH(cb_equalize_lut_kernel, nb, P.hist.as<int>(), nb, (int)N, P.lut.as<uint8_t>());
+      CB_LAUNCH_CH(cb_apply_lut_kernel, W, H, (int)list.size(), d_img, (long long)imgs->pitch, (long long)imgs->image_stride, vec_src, W, H, P.active.as<int>(),
+                   P.lut.as<uint8_t>(), P.eq.as<uint8_t>(), vec);   // only the images that enter the fallback
+      std::vector<int> h_block(nb, 0), h_delta(nb, 0), prev_block(nb, -1);
+      for (int i = 0; i < nb; ++i) h_state[i].prev_sqr_size = 0;  // prev_sqr_size restarts at 0 with the fallback
+      EZC_CUDA(cudaMemcpyAsync(P.state.p, h_state.data(), sizeof(ImageState) * nb, cudaMemcpyHostToDevice, ctx->stream));
+      uint8_t* th = P.bin0.as<uint8_t>();       // thresh_img (gets the frame)
+      uint8_t* tmp = P.bin1.as<uint8_t>();
+      uint8_t* prevb = P.prevbin.as<uint8_t>(); // prev_thresh_img (no frame)
+      for (int k = 0; k < 6 && !list.empty(); ++k) {
+        std::fill(prev_block.begin(), prev_block.end(), -1);
+        for (int dil = 0; dil <= 7 && !list.empty(); ++dil) {
+          std::vector<int> fresh, old;
+          for (int im : list) {
+            const int ps = h_state[im].prev_sqr_size;
+            int bs = (int)lrint(ps == 0 ? std::min(W, H) * (k % 2 == 0 ? 0.2 : 0.1) : ps * 2.0);
+            bs |= 1;
+            if (bs != prev_block[im]) fresh.push_back(im); else old.push_back(im);
+            h_block[im] = bs;
+            h_delta[im] = (k / 2) * 5;
+            prev_block[im] = bs;
+          }
+          EZC_CUDA(cudaMemcpyAsync(P.block.p, h_block.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+          EZC_CUDA(cudaMemcpyAsync(P.delta.p, h_delta.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+          if (!fresh.empty()) {
+            // new block size: adaptive threshold of the equalised image, then `dil` dilations -> prev_thresh_img
+            if (ezc_status st = upload_list(ctx, P.refresh, fresh)) return st;
+            const int nf = (int)fresh.size();
+            if (ezc_status st = adaptive_threshold(ctx, P, W, H, nf, P.refresh.as<int>(), tmp, nullptr)) return st;
+            for (int d = 0; d < dil; ++d) {
+              CB_LAUNCH_CH(cb_morph16_kernel<true>, W, H, nf, tmp, (long long)W, N, vec, th, W, H, P.refresh.as<int>(), vec);
+              CB_LAUNCH_PIX(cb_copy_active_kernel, (N + 15) / 16, nf, th, tmp, N, nf, P.refresh.as<int>(), (const int*)nullptr);
+            }
+            CB_LAUNCH_PIX(cb_copy_active_kernel, (N + 15) / 16, nf, tmp, prevb, N, nf, P.refresh.as<int>(), (const int*)nullptr);
+          }
+          if (!old.empty() && dil > 0) {
+            // same block size as before: one more dilation of prev_thresh_img
+            if (ezc_status st = upload_list(ctx, P.refresh, old)) return st;
+            const int no = (int)old.size();
+            CB_LAUNCH_CH(cb_morph16_kernel<true>, W, H, no, prevb, (long long)W, N, vec, tmp, W, H, P.refresh.as<int>(), vec);
+            CB_LAUNCH_PIX(cb_copy_active_kernel, (N + 15) / 16, no, tmp, prevb, N, no, P.refresh.as<int>(), (const int*)nullptr);
+          }
+          const int n_act = (int)list.size();
+          if (getenv("EZC_CB_TIMING")) fprintf(stderr, "[cb] phase 2 k %d dil %d: %d of %d views\n", k, dil, n_act, nb);
+          CB_LAUNCH_PIX(cb_copy_active_kernel, (N + 15) / 16, n_act, prevb, th, N, n_act, P.active.as<int>(), (const int*)nullptr);
+          CB_LAUNCH_FRAME(th, n_act, P.active.as<int>());
+          // generateQuads gets the dilation count in the fallback too (edge_len compensation (sqrt(e) + 2 dil)^2), as OpenCV's
+          // source reads.  Round 1 ran the fallback without it -- indistinguishable on every fixture it had; the randomised
+          // degradations of tests/cb_fuzz.py separate the two: cv2 finds strongly blurred boards at 6-7 dilations only with it.
+          if (ezc_status st = upload_dil(dil)) return st;
+          if (ezc_status st = run_attempt(ctx, P, th, W, H, n_act, pw, ph, P.dil.as<int>())) return st;
+          if (ezc_status st = sync_state(ctx, P, nb, h_state, list)) return st;
+        }
+      }
+    }
+  } else {
+    // ---- attempt 0 for every view that passed the gate
+    if (!list.empty()) {
+      const int n_act = (int)list.size();
+      if (getenv("EZC_CB_TIMING")) fprintf(stderr, "[cb] attempt 0: %d of %d views\n", n_act, nb);
+      CB_LAUNCH_FRAME(b0, n_act, P.active.as<int>());
+      if (ezc_status st = upload_dil(0)) return st;
+      if (ezc_status st = run_attempt(ctx, P, b0, W, H, n_act, pw, ph, P.dil.as<int>())) return st;
+      if (ezc_status st = sync_state(ctx, P, nb, h_state, list)) return st;
+    }
+    if (!list.empty()) {
+      // ---- the other 7 + 48 attempts, concurrently
+      struct Att { int phase, k, dil; };
+      std::vector<Att> att;
+      for (int d = 1; d <= 7; ++d) att.push_back({1, 0, d});
+      const int kP2 = (int)att.size();   // index of the first attempt of the fallback
+      for (int k = 0; k < 6; ++k) for (int d = 0; d <= 7; ++d) att.push_back({2, k, d});
+      const int kAtt = (int)att.size();
+      auto block_size = [&](int k, int ps) { return (int)lrint(ps == 0 ? std::min(W, H) * (k % 2 == 0 ? 0.2 : 0.1) : ps * 2.0) | 1; };
+      struct Slot { int view, j, block, head; };
+      std::vector<Slot> slots;
+      std::vector<int> pos(nb, 0), ps(nb, 0), h_src(nb, 0), h_block(nb, 0), h_delta(nb, 0), pairs;
+      std::vector<int> l_p1, l_head, l_follow, l_all, l_step;
+      EZC_CUDA(P.eq.reserve(total)); EZC_CUDA(P.lut.reserve(256 * nb)); EZC_CUDA(P.prevbin.reserve(total));
+      EZC_CUDA(P.block.reserve(sizeof(int) * nb)); EZC_CUDA(P.delta.reserve(sizeof(int) * nb)); EZC_CUDA(P.hsum.reserve(sizeof(int) * total));
+      EZC_CUDA(P.srcmap.reserve(sizeof(int) * nb)); EZC_CUDA(P.refresh.reserve(sizeof(int) * nb)); EZC_CUDA(P.pairs.reserve(sizeof(int) * 2 * nb));
+      EZC_CUDA(P.res_found.reserve(sizeof(int) * nb)); EZC_CUDA(P.res_corners.reserve(sizeof(cb::Ptf) * (size_t)npts * nb));
+      CB_LAUNCH(cb_save_results_kernel, (long long)nb * npts, P.state.as<ImageState>(), P.corners.as<cb::Ptf>(), nb, npts, P.res_found.as<int>(),
+                P.res_corners.as<cb::Ptf>());
+      // equalised copies (CALIB_CB_NORMALIZE_IMAGE) are made when a view's first fallback attempt is scheduled
+      std::vector<char> has_eq(nb, 0);
+      std::vector<int> l_eq;
+      bool lut_ready = false;
+      const uint8_t* base1 = b0;                   // attempt 0's image with its frame: phase 1 dilates it d times
+      uint8_t* tmp = b1;
+      uint8_t* th = P.prevbin.as<uint8_t>();
+      while (!list.empty()) {
+        const int R = (int)list.size();
+        // Attempts per view and round.  A slot is a whole image of per-pixel and per-contour work, so what is run ahead
+        // should be likely to be needed: views that fail attempts 0 and 1 mostly succeed a dilation or two later (cheap,
+        // clean images: the rest of phase 1 goes in one round, never across the phase boundary), and a view that reaches
+        // the fallback mostly fails all 48 of its attempts (noise: its 6 undilated thresholds cost ~15 ms each, the rest
+        // ~1.5 ms -- side by side they cost one of the former).  EZC_CB_SLOTS caps the slots of a round.
+        const int slot_cap = std::min(nb, getenv("EZC_CB_SLOTS") ? std::max(1, atoi(getenv("EZC_CB_SLOTS"))) : 64);
+        int c = std::max(1, slot_cap / R);
+        slots.clear(); l_p1.clear(); l_head.clear(); l_follow.clear(); l_all.clear();
+        for (int v : list) {
+          int assumed = ps[v], head = -1, head_k = -1;
+          // phase 1: dilations 2-3 first (where most late successes are), then the rest up to the phase boundary
+          const int j_end = pos[v] < kP2 ? std::min(pos[v] + std::min(c, pos[v] < 3 ? 2 : kP2), kP2) : std::min(pos[v] + c, kAtt);
+          for (int j = pos[v]; j < j_end; ++j) {
+            const Att& a = att[j];
+            const int sl = (int)slots.size();
+            Slot S{v, j, 0, -1};
+            h_dil[sl] = a.dil;
+            if (a.phase == 1) {
+              h_src[sl] = v; h_block[sl] = 0; h_delta[sl] = 0;
+              l_p1.push_back(sl);
+            } else {
+              if (j == kP2) assumed = 0;   // prev_sqr_size restarts at 0 with the fallback
+              S.block = block_size(a.k, assumed);
+              h_block[sl] = S.block; h_delta[sl] = (a.k / 2) * 5;
+              if (head >= 0 && head_k == a.k) { S.head = head; h_src[sl] = head; l_follow.push_back(sl); }
+              else { head = sl; head_k = a.k; h_src[sl] = v; l_head.push_back(sl); }
+            }
+            l_all.push_back(sl);
+            slots.push_back(S);
+          }
+        }
+        const int n_slots = (int)slots.size();
+        l_eq.clear();
+        for (int sl : l_head) if (!has_eq[slots[sl].view]) { has_eq[slots[sl].view] = 1; l_eq.push_back(slots[sl].view); }
+        if (!l_eq.empty()) {
+          if (!lut_ready) { CB_LAUNCH(cb_equalize_lut_kernel, nb, P.hist.as<int>(), nb, (int)N, P.lut.as<uint8_t>()); lut_ready = true; }
+          if (ezc_status st = upload_list(ctx, P.refresh, l_eq)) return st;
+          CB_LAUNCH_CH(cb_apply_lut_kernel, W, H, (int)l_eq.size(), d_img, (long long)imgs->pitch, (long long)imgs->image_stride, vec_src, W, H,
+                       P.refresh.as<int>(), P.lut.as<uint8_t>(), P.eq.as<uint8_t>(), vec);
+        }
+        const bool timing = getenv("EZC_CB_TIMING") != nullptr;
+        const auto t_round = std::chrono::steady_clock::now();
+        auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+          cudaStreamSynchronize(ctx->stream);
+          return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        };
+        EZC_CUDA(cudaMemcpyAsync(P.srcmap.p, h_src.data(), sizeof(int) * n_slots, cudaMemcpyHostToDevice, ctx->stream));
+        EZC_CUDA(cudaMemcpyAsync(P.block.p, h_block.data(), sizeof(int) * n_slots, cudaMemcpyHostToDevice, ctx->stream));
+        EZC_CUDA(cudaMemcpyAsync(P.delta.p, h_delta.data(), sizeof(int) * n_slots, cudaMemcpyHostToDevice, ctx->stream));
+        EZC_CUDA(cudaMemcpyAsync(P.dil.p, h_dil.data(), sizeof(int) * n_slots, cudaMemcpyHostToDevice, ctx->stream));
+        const int* d_src = P.srcmap.as<int>();
+        // Slot images.  Fallback slots start from the adaptive threshold of their view (one per (view, k): the other
+        // dilation levels of that k copy it) in buffer A; phase-1 slots start from attempt 0's framed image.  Dilation
+        // step t takes every slot with >= t dilations from one buffer to the other (A -> B for odd t), so a slot ends in
+        // B when its dilation count is odd; the others are copied over once.  B then gets the frames.
+        uint8_t* A = tmp;
+        uint8_t* B = th;
+        if (!l_head.empty()) {
+          if (ezc_status st = upload_list(ctx, P.refresh, l_head)) return st;
+          if (ezc_status st = adaptive_threshold(ctx, P, W, H, (int)l_head.size(), P.refresh.as<int>(), A, d_src)) return st;
+          // a head that is not at dilation 0 (the walk resumed in the middle of a k) is dilated below like the others
+        }
+        if (!l_follow.empty()) {
+          if (ezc_status st = upload_list(ctx, P.refresh, l_follow)) return st;
+          CB_LAUNCH_PIX(cb_copy_active_kernel, (N + 15) / 16, (int)l_follow.size(), A, A, N, (int)l_follow.size(), P.refresh.as<int>(), d_src);
+        }
+        if (!l_p1.empty()) {   // every phase-1 slot has >= 1 dilation: its first step reads the view's image directly
+          if (ezc_status st = upload_list(ctx, P.refresh, l_p1)) return st;
+          CB_LAUNCH_CH(cb_morph16_kernel<true>, W, H, (int)l_p1.size(), base1, (long long)W, N, vec, B, W, H, P.refresh.as<int>(), vec, d_src);
+        }
+        for (int t = 1; t <= 7; ++t) {
+          l_step.clear();
+          for (int sl = 0; sl < n_slots; ++sl) if (h_dil[sl] >= t && !(t == 1 && att[slots[sl].j].phase == 1)) l_step.push_back(sl);
+          if (l_step.empty()) continue;
+          if (ezc_status st = upload_list(ctx, P.refresh, l_step)) return st;
+          const int ns = (int)l_step.size();
+          const uint8_t* from = (t & 1) ? A : B;
+          uint8_t* to = (t & 1) ? B : A;
+          CB_LAUNCH_CH(cb_morph16_kernel<true>, W, H, ns, from, (long long)W, N, vec, to, W, H, P.refresh.as<int>(), vec);
+        }
+        l_step.clear();
+        for (int sl = 0; sl < n_slots; ++sl) if ((h_dil[sl] & 1) == 0) l_step.push_back(sl);
+        if (!l_step.empty()) {
+          if (ezc_status st = upload_list(ctx, P.refresh, l_step)) return st;
+          CB_LAUNCH_PIX(cb_copy_active_kernel, (N + 15) / 16, (int)l_step.size(), A, B, N, (int)l_step.size(), P.refresh.as<int>(), (const int*)nullptr);
+        }
+        if (ezc_status st = upload_list(ctx, P.active, l_all)) return st;
+        CB_LAUNCH_FRAME(B, n_slots, P.active.as<int>());
+        for (int sl = 0; sl < n_slots; ++sl) { h_state[sl] = ImageState{0, 0, 0, 0, 0}; h_state[sl].prev_sqr_size = -1; }   // -1: not written by this attempt
+        EZC_CUDA(cudaMemcpyAsync(P.state.p, h_state.data(), sizeof(ImageState) * n_slots, cudaMemcpyHostToDevice, ctx->stream));
+        const double ms_prep = timing ? ms_since(t_round) : 0.0;
+        if (ezc_status st = run_attempt(ctx, P, B, W, H, n_slots, pw, ph, P.dil.as<int>())) return st;
+        EZC_CUDA(cudaMemcpyAsync(h_state.data(), P.state.p, sizeof(ImageState) * n_slots, cudaMemcpyDeviceToHost, ctx->stream));
+        EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (timing)
+          fprintf(stderr, "[cb] concurrent round: %d views x up to %d attempts = %d slots of %d: images %.2f ms, attempts %.2f ms\n", R, c, n_slots, nb,
+                  ms_prep, ms_since(t_round) - ms_prep);
+        // walk every view's attempts in order
+        std::vector<int> next;
+        pairs.clear();
+        for (int sl = 0; sl < n_slots;) {
+          const int v = slots[sl].view;
+          int cur = ps[v], j_next = pos[v];
+          bool done = false;
+          int e = sl;
+          for (; e < n_slots && slots[e].view == v; ++e) {
+            if (done) continue;
+            const Att& a = att[slots[e].j];
+            if (a.phase == 2) {
+              h_phase2[v] = 1;
+              if (slots[e].j == kP2) cur = 0;
+              if (block_size(a.k, cur) != slots[e].block) { done = true; continue; }   // ran on the wrong threshold image: rerun from here
+            }
+            if (h_state[e].found) { pairs.push_back(e); pairs.push_back(v); j_next = kAtt; done = true; continue; }
+            if (h_state[e].prev_sqr_size >= 0) cur = h_state[e].prev_sqr_size;
+            j_next = slots[e].j + 1;
+          }
+          // a walk that stops exactly at the phase boundary re-enters with the fallback's reset applied by the next round
+          pos[v] = j_next; ps[v] = cur;
+          if (j_next < kAtt) next.push_back(v);
+          sl = e;
+        }
+        if (!pairs.empty()) {
+          EZC_CUDA(cudaMemcpyAsync(P.pairs.p, pairs.data(), sizeof(int) * pairs.size(), cudaMemcpyHostToDevice, ctx->stream));
+          CB_LAUNCH(cb_accept_kernel, (long long)(pairs.size() / 2) * npts, P.pairs.as<int>(), (int)(pairs.size() / 2), npts, P.corners.as<cb::Ptf>(),
+                    P.res_found.as<int>(), P.res_corners.as<cb::Ptf>());
+        }
+        list.swap(next);
+      }
+      for (int i = 0; i < nb; ++i) phase2_ran = phase2_ran || h_phase2[i] != 0;
+      CB_LAUNCH(cb_restore_results_kernel, (long long)nb * npts, P.state.as<ImageState>(), P.corners.as<cb::Ptf>(), nb, npts, P.res_found.as<int>(),
+                P.res_corners.as<cb::Ptf>());
     }
   }
   // ---- final checks, internal (2,2) refinement on the image the search ended on, then the reference's (5,5) refinement

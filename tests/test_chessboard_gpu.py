@@ -204,3 +204,43 @@ def test_fast_check_gate_matches_cv2(ctx):
     assert changed >= 1           # the corpus contains boards only the gate rejects
     # identical attempt and quads on every view, incl. the 0.3-scale boards found in the fallback phase
     assert n_close == n_found, (n_close, n_found)
+
+
+def _detect_both_ways(ctx, stack, **kw):
+    """(found, corners) of the concurrent-attempt search and of the one-at-a-time search (EZC_CB_SEQUENTIAL=1)."""
+    from ezcalib_b200 import detect
+    out = []
+    for sequential in (False, True):
+        if sequential:
+            os.environ["EZC_CB_SEQUENTIAL"] = "1"
+        try:
+            imgs = detect.Images(ctx, stack)
+            out.append(detect.detect_chessboard(ctx, imgs, 7, 10, **kw))
+            imgs.close()
+        finally:
+            os.environ.pop("EZC_CB_SEQUENTIAL", None)
+    return out
+
+
+def test_concurrent_attempts_equal_the_sequential_search(ctx):
+    """The remaining attempts of unfinished views run concurrently in free slots (chessboard.cu, detect_sub_batch); the
+    walk over their results must keep exactly what the one-at-a-time search keeps: same flags, same corners bit for bit.
+    Golden fixtures (incl. the noise view that fails all 56 attempts), degraded fuzz views, and a batch small enough that
+    the free slots run out (several rounds, chunks that end in the middle of a threshold level)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import cb_fuzz
+    stacks = [np.stack([G[n + "_img"] for n in BIG]),
+              cb_fuzz.make_views(ctx, 1001, 64), cb_fuzz.make_views(ctx, 1002, 64),
+              cb_fuzz.make_views(ctx, 1003, 64)[:6], cb_fuzz.make_views(ctx, 1001, 64)[40:45]]
+    for stack in stacks:
+        (f_con, c_con), (f_seq, c_seq) = _detect_both_ways(ctx, stack)
+        assert np.array_equal(f_con, f_seq), np.flatnonzero(f_con != f_seq)
+        assert np.array_equal(c_con, c_seq), float(np.abs(c_con - c_seq).max())
+    # sub-batches of 1 and 3 views: no free slots at all / a few -- the per-view results do not depend on the slot count
+    stack = stacks[1][:9]
+    (f_ref, c_ref), _ = _detect_both_ways(ctx, stack)
+    for m in (1, 3):
+        (f_con, c_con), (f_seq, c_seq) = _detect_both_ways(ctx, stack, max_images_in_flight=m)
+        assert np.array_equal(f_con, f_seq) and np.array_equal(c_con, c_seq), m
+        assert np.array_equal(f_con, f_ref) and np.array_equal(c_con, c_ref), m
