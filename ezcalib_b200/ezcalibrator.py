@@ -146,7 +146,7 @@ def build_multicam_problem(cameras: list[Camera], target: np.ndarray):
     """Problem set-up of EZCalibrator::runMultiCameraCalib (ezcalibrator.cpp:631-785): returns
     (obs [n_cams-1, n_frames0*n_pts, 2], pts [n_frames0*n_pts, 3], init extrinsics [n_cams-1, 7], n_good_pairs)."""
     cam0 = cameras[0]
-    pts = np.concatenate([synth.transform(f.T_world_2_cam, target) for f in cam0.frames], axis=0)
+    pts = synth.transform(np.stack([f.T_world_2_cam for f in cam0.frames]), target).reshape(-1, 3)   # one batched call
     blocks = [multicam_block(cam0.frames, cameras[i], i, target) for i in range(1, len(cameras))]
     obs = np.stack([b[0] for b in blocks])
     init = np.stack([b[1] for b in blocks])
@@ -319,7 +319,7 @@ def run_rig_extrinsics(ctx: lm.Context, local_cameras: dict, n_cams: int, target
     info = comm.bcast(info, owner0)
     cam0_frames = [_FrameInfo(*x) for x in info]
     n_pts = target.shape[0]
-    pts = np.concatenate([synth.transform(f.T_world_2_cam, target) for f in cam0_frames], axis=0)
+    pts = synth.transform(np.stack([f.T_world_2_cam for f in cam0_frames]), target).reshape(-1, 3)   # one batched call
     mine = sorted(c for c in local_cameras if c >= 1)
     blocks = [multicam_block(cam0_frames, local_cameras[c], c, target) for c in mine]
     ref = comm.bcast((local_cameras[mine[0]].model, local_cameras[mine[0]].use_mono_focal, local_cameras[mine[0]].width,
