@@ -348,10 +348,14 @@ __device__ __forceinline__ int compact_id(const uint32_t* __restrict__ amask, co
   return aoff[wi] + __popc(amask[wi] & ((1u << bit) - 1u));
 }
 
-// One 32-byte record per union-find node (UnionFindSimple's parent/size + Edge.cc's theta/mag spans): the merge sweep
-// touches all six values of both roots of every candidate edge, i.e. two sectors instead of twelve scattered ones.
+// Union-find forest (UnionFindSimple's parent/size + Edge.cc's theta/mag spans).  The PARENT links live in an int array of
+// their own: the root look-ups of the merge sweep -- several hops per edge end, only the link of each hop is needed -- then
+// touch 4 bytes per node instead of a 32-byte record, and the links of a whole 214-view sub-batch (~120 MB) stay largely
+// L2-resident where the records (~950 MB) streamed from HBM (round 2: 29 GB of DRAM reads for 7.5 M edges, 390 B per edge).
+// One 32-byte record per node keeps the statistics: the sweep reads all five values of both ROOTS of a candidate edge, two
+// sectors instead of ten scattered ones.
 struct __align__(32) UfNode {
-  int parent, size;
+  int unused, size;
   float tmin, tmax, mmin, mmax;
   int pad0, pad1;
 };
@@ -382,14 +386,16 @@ __global__ void at_compact_words_kernel(const uint32_t* __restrict__ amask, cons
 
 // theta / mag of the active pixels (TagDetector.cc:159-166) and the union-find nodes, one thread per active pixel: every lane
 // of a warp runs the bit-exact atan2f.  In: a_theta = Ix, a_mag = Iy; out: a_theta = atan2f(Iy, Ix), a_mag = Ix^2 + Iy^2.
-__global__ void at_theta_kernel(int n, float* __restrict__ a_theta, float* __restrict__ a_mag, UfNode* __restrict__ nodes) {
+__global__ void at_theta_kernel(int n, float* __restrict__ a_theta, float* __restrict__ a_mag, UfNode* __restrict__ nodes,
+                                int* __restrict__ parent) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
   const float Ix = a_theta[c], Iy = a_mag[c];
   const float mg = Ix * Ix + Iy * Iy;
   const float th = fd_atan2f(Iy, Ix);
   a_theta[c] = th; a_mag[c] = mg;
-  nodes[c] = UfNode{c, 1, th, th, mg, mg, 0, 0};
+  nodes[c] = UfNode{0, 1, th, th, mg, mg, 0, 0};
+  parent[c] = c;
 }
 
 // ---- stage 3: edges (Edge.cc:14-67) ------------------------------------------------------------------
@@ -523,12 +529,13 @@ __device__ __forceinline__ int uf_find(int* parent, int x) {
 // One WARP per component.  The sweep order is strictly sequential in the reference; what a warp adds is
 // latency hiding that cannot change the result: (A) the 32 lanes look up the current roots of the next 32
 // edges in parallel -- an edge whose end points already share a root can never merge later (sets only grow),
-// so it is dropped; (B) the remaining candidates are replayed one by one, in order, by the whole warp
-// (uniform control flow, lane 0 writes), re-resolving their roots first because an earlier candidate of the
-// same batch may have merged them.
-__device__ __forceinline__ int uf_find_ro(const UfNode* nodes, int x) {
-  int p = nodes[x].parent;
-  while (p != x) { x = p; p = nodes[x].parent; }
+// so it is dropped -- and load the statistics of both roots; (B) the remaining candidates are replayed one by one, in
+// order, by the whole warp from REGISTERS (uniform control flow, lane 0 writes the forest): each lane tracks what the
+// earlier candidates of the batch did to its roots.  Before, every replayed candidate re-walked its roots and re-read both
+// records from memory -- ~1-2 us of dependent loads each, the whole kernel latency-bound on them.
+__device__ __forceinline__ int uf_find_ro(const int* parent, int x) {
+  int p = parent[x];
+  while (p != x) { x = p; p = parent[x]; }
   return x;
 }
 
@@ -537,7 +544,7 @@ __device__ __forceinline__ int uf_find_ro(const UfNode* nodes, int x) {
 // slots occupied, 1.3 ms for ONE image against 7.4 ms for 214).
 __global__ void __launch_bounds__(128) at_merge_kernel(const uint32_t* __restrict__ order, const int* __restrict__ starts, int n_comp,
                                                          const int* __restrict__ eA, const int* __restrict__ eB, UfNode* nodes,
-                                                         int* __restrict__ work_counter) {
+                                                         int* parent, int* __restrict__ work_counter) {
   const int lane = threadIdx.x & 31;
   for (;;) {
   int c = 0;
@@ -551,65 +558,75 @@ __global__ void __launch_bounds__(128) at_merge_kernel(const uint32_t* __restric
     if (i < end) {
       const uint32_t e = order[i];
       const int a = eA[e], b = eB[e];
-      ra = uf_find_ro(nodes, a);
-      rb = uf_find_ro(nodes, b);
+      ra = uf_find_ro(parent, a);
+      rb = uf_find_ro(parent, b);
       // path shortening (UnionFindSimple compresses too; it never changes a representative)
-      if (nodes[a].parent != ra) nodes[a].parent = ra;
-      if (nodes[b].parent != rb) nodes[b].parent = rb;
+      if (parent[a] != ra) parent[a] = ra;
+      if (parent[b] != rb) parent[b] = rb;
     }
-    unsigned cand = __ballot_sync(0xffffffffu, i < end && ra != rb);
-    __syncwarp();
+    // statistics of both roots, loaded by every candidate lane at once; from here on the batch needs no global loads:
+    // every merge of this component happens in this warp, so each lane keeps its roots and their statistics current from the
+    // broadcast winner / loser / merged record of the merges replayed before its turn.
+    int sza = 0, szb = 0;
+    float tmina = 0.f, tmaxa = 0.f, mmina = 0.f, mmaxa = 0.f, tminb = 0.f, tmaxb = 0.f, mminb = 0.f, mmaxb = 0.f;
+    const bool is_cand = i < end && ra != rb;
+    if (is_cand) {
+      const int4 a0 = *reinterpret_cast<const int4*>(&nodes[ra]);
+      const float2 a1 = *reinterpret_cast<const float2*>(&nodes[ra].mmin);
+      const int4 b0 = *reinterpret_cast<const int4*>(&nodes[rb]);
+      const float2 b1 = *reinterpret_cast<const float2*>(&nodes[rb].mmin);
+      sza = a0.y; tmina = __int_as_float(a0.z); tmaxa = __int_as_float(a0.w); mmina = a1.x; mmaxa = a1.y;
+      szb = b0.y; tminb = __int_as_float(b0.z); tmaxb = __int_as_float(b0.w); mminb = b1.x; mmaxb = b1.y;
+    }
+    unsigned cand = __ballot_sync(0xffffffffu, is_cand);
     while (cand) {
       const int l = __ffs(cand) - 1;
       cand &= cand - 1;
-      const int ida = uf_find_ro(nodes, __shfl_sync(0xffffffffu, ra, l));
-      const int idb = uf_find_ro(nodes, __shfl_sync(0xffffffffu, rb, l));
-      if (ida != idb) {
-        // the whole record of each root in two 16-byte loads
-        const int4 a0 = *reinterpret_cast<const int4*>(&nodes[ida]);
-        const float2 a1 = *reinterpret_cast<const float2*>(&nodes[ida].mmin);
-        const int4 b0 = *reinterpret_cast<const int4*>(&nodes[idb]);
-        const float2 b1 = *reinterpret_cast<const float2*>(&nodes[idb].mmin);
-        const int sza = a0.y, szb = b0.y;
-        const float tmina = __int_as_float(a0.z), tmaxa = __int_as_float(a0.w);
-        const float tminb = __int_as_float(b0.z), tmaxb = __int_as_float(b0.w);
-        const float mmina = a1.x, mmaxa = a1.y, mminb = b1.x, mmaxb = b1.y;
-        const float costa = (tmaxa - tmina);
-        const float costb = (tmaxb - tminb);
-        const float bshift = mod2pi_ref((tmina + tmaxa) / 2, (tminb + tmaxb) / 2) - (tminb + tmaxb) / 2;
-        const float tminab = fminr(tmina, tminb + bshift);
-        float tmaxab = fmaxr(tmaxa, tmaxb + bshift);
-        if (tmaxab - tminab > 2 * kPiF) tmaxab = tminab + 2 * kPiF;
-        const float mminab = fminr(mmina, mminb);
-        const float mmaxab = fmaxr(mmaxa, mmaxb);
-        const float costab = (tmaxab - tminab);
-        if (costab <= (fminr(costa, costb) + kThetaThresh / (sza + szb)) &&
-            (mmaxab - mminab) <= fminr(mmaxa - mmina, mmaxb - mminb) + kMagThresh / (sza + szb)) {
-          if (lane == 0) {
-            // UnionFindSimple::connectNodes (UnionFindSimple.cc:25-44)
-            if (sza > szb) { nodes[idb].parent = ida; nodes[ida] = UfNode{ida, sza + szb, tminab, tmaxab, mminab, mmaxab, 0, 0}; }
-            else { nodes[ida].parent = idb; nodes[idb] = UfNode{idb, szb + sza, tminab, tmaxab, mminab, mmaxab, 0, 0}; }
-          }
-        }
+      const int ida = __shfl_sync(0xffffffffu, ra, l), idb = __shfl_sync(0xffffffffu, rb, l);
+      if (ida == idb) continue;   // joined by an earlier candidate of this batch
+      const int c_sza = __shfl_sync(0xffffffffu, sza, l), c_szb = __shfl_sync(0xffffffffu, szb, l);
+      const float c_tmina = __shfl_sync(0xffffffffu, tmina, l), c_tmaxa = __shfl_sync(0xffffffffu, tmaxa, l);
+      const float c_tminb = __shfl_sync(0xffffffffu, tminb, l), c_tmaxb = __shfl_sync(0xffffffffu, tmaxb, l);
+      const float c_mmina = __shfl_sync(0xffffffffu, mmina, l), c_mmaxa = __shfl_sync(0xffffffffu, mmaxa, l);
+      const float c_mminb = __shfl_sync(0xffffffffu, mminb, l), c_mmaxb = __shfl_sync(0xffffffffu, mmaxb, l);
+      const float costa = (c_tmaxa - c_tmina);
+      const float costb = (c_tmaxb - c_tminb);
+      const float bshift = mod2pi_ref((c_tmina + c_tmaxa) / 2, (c_tminb + c_tmaxb) / 2) - (c_tminb + c_tmaxb) / 2;
+      const float tminab = fminr(c_tmina, c_tminb + bshift);
+      float tmaxab = fmaxr(c_tmaxa, c_tmaxb + bshift);
+      if (tmaxab - tminab > 2 * kPiF) tmaxab = tminab + 2 * kPiF;
+      const float mminab = fminr(c_mmina, c_mminb);
+      const float mmaxab = fmaxr(c_mmaxa, c_mmaxb);
+      const float costab = (tmaxab - tminab);
+      if (costab <= (fminr(costa, costb) + kThetaThresh / (c_sza + c_szb)) &&
+          (mmaxab - mminab) <= fminr(c_mmaxa - c_mmina, c_mmaxb - c_mminb) + kMagThresh / (c_sza + c_szb)) {
+        // UnionFindSimple::connectNodes (UnionFindSimple.cc:25-44): the smaller set hangs under the larger one
+        const int win = c_sza > c_szb ? ida : idb, lose = c_sza > c_szb ? idb : ida;
+        const int szab = c_sza + c_szb;
+        if (lane == 0) { parent[lose] = win; nodes[win] = UfNode{0, szab, tminab, tmaxab, mminab, mmaxab, 0, 0}; }
+        if (ra == lose) ra = win;
+        if (rb == lose) rb = win;
+        if (ra == win) { sza = szab; tmina = tminab; tmaxa = tmaxab; mmina = mminab; mmaxa = mmaxab; }
+        if (rb == win) { szb = szab; tminb = tminab; tmaxb = tmaxab; mminb = mminab; mmaxb = mmaxab; }
       }
-      __syncwarp();
     }
+    __syncwarp();
   }
   }   // next component
 }
 
-// parent / size arrays of the forest (debug export)
-__global__ void at_split_nodes_kernel(const UfNode* __restrict__ nodes, int n, int* __restrict__ parent, int* __restrict__ setsize) {
+// size array of the forest (debug export)
+__global__ void at_split_nodes_kernel(const UfNode* __restrict__ nodes, int n, int* __restrict__ setsize) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  parent[i] = nodes[i].parent; setsize[i] = nodes[i].size;
+  setsize[i] = nodes[i].size;
 }
 
-__global__ void at_rep_kernel(const UfNode* __restrict__ nodes, int n_active, int* __restrict__ rep, int* __restrict__ keep) {
+__global__ void at_rep_kernel(const UfNode* __restrict__ nodes, const int* __restrict__ parent, int n_active, int* __restrict__ rep,
+                              int* __restrict__ keep) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_active) return;
-  int r = i;
-  while (nodes[r].parent != r) r = nodes[r].parent;
+  const int r = uf_find_ro(parent, i);
   rep[i] = r;
   keep[i] = nodes[r].size >= kMinSegmentSize ? 1 : 0;  // TagDetector.cc:248
 }
@@ -1288,12 +1305,12 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
   if (ezc_status st = read_int(ctx, d_tot, &nA, P)) return st;
   const size_t cap = (size_t)std::max(nA, 1);
   EZC_CUDA(P.apix.reserve(sizeof(int) * cap)); EZC_CUDA(P.a_theta.reserve(sizeof(float) * cap)); EZC_CUDA(P.a_mag.reserve(sizeof(float) * cap));
-  EZC_CUDA(P.nodes.reserve(sizeof(UfNode) * cap));
+  EZC_CUDA(P.nodes.reserve(sizeof(UfNode) * cap)); EZC_CUDA(P.parent.reserve(sizeof(int) * cap));
   EZC_CUDA(P.ecount.reserve(sizeof(int) * (cap + 1))); EZC_CUDA(P.label.reserve(sizeof(int) * cap));
   EZC_CUDA(P.rep.reserve(sizeof(int) * cap)); EZC_CUDA(P.keep.reserve(sizeof(int) * (cap + 1)));
   AT_LAUNCH(at_compact_words_kernel, n_words, P.amask.as<uint32_t>(), P.acount.as<int>(), n_words, wpr, W, H, P.theta.as<float>(),
             P.mag.as<float>(), P.apix.as<int>(), P.a_theta.as<float>(), P.a_mag.as<float>(), P.nodes.as<UfNode>());
-  AT_LAUNCH(at_theta_kernel, nA, nA, P.a_theta.as<float>(), P.a_mag.as<float>(), P.nodes.as<UfNode>());
+  AT_LAUNCH(at_theta_kernel, nA, nA, P.a_theta.as<float>(), P.a_mag.as<float>(), P.nodes.as<UfNode>(), P.parent.as<int>());
   // ---- 3: edges
   AT_LAUNCH(at_edges_words_kernel<false>, nA, P.apix.as<int>(), P.a_theta.as<float>(), P.amask.as<uint32_t>(), P.acount.as<int>(), wpr,
             nA, W, H, P.ecount.as<int>(), nullptr, nullptr, nullptr, nullptr);
@@ -1332,6 +1349,18 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
     if (ezc_status st = read_int(ctx, d_tot, &nComp, P)) return st;
     EZC_CUDA(P.starts.reserve(sizeof(int) * ((size_t)nComp + 2)));
     AT_LAUNCH(at_starts_kernel, nE, P.flags.as<int>(), d_tot, nE, P.starts.as<int>());
+    if (getenv("EZC_AT_STATS")) {   // component size distribution (edges per component) of this sub-batch
+      std::vector<int> hs((size_t)nComp + 1);
+      EZC_CUDA(cudaMemcpyAsync(hs.data(), P.starts.p, sizeof(int) * ((size_t)nComp + 1), cudaMemcpyDeviceToHost, ctx->stream));
+      EZC_CUDA(cudaStreamSynchronize(ctx->stream));
+      std::vector<int> sz((size_t)nComp);
+      for (int c = 0; c < nComp; ++c) sz[c] = hs[c + 1] - hs[c];
+      std::sort(sz.begin(), sz.end());
+      long long tot = 0; for (int v : sz) tot += v;
+      long long top = 0; for (int c = std::max(0, nComp - 1000); c < nComp; ++c) top += sz[c];
+      fprintf(stderr, "[at] %d views: %d components, %lld edges; max %d, p99.9 %d, p99 %d, median %d; 1000 largest hold %.1f %% of the edges\n", nb, nComp, tot,
+              sz.back(), sz[(size_t)(nComp * 0.999)], sz[(size_t)(nComp * 0.99)], sz[nComp / 2], 100.0 * top / tot);
+    }
     // ---- 6: merge sweep
     {
       // persistent 4-warp blocks (16 per SM), components handed out through a global counter
@@ -1339,7 +1368,7 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
       EZC_CUDA(cudaMemsetAsync(P.work.p, 0, sizeof(int), ctx->stream));
       const int grid = (int)std::min<long long>(((long long)nComp + 3) / 4, (long long)ctx->sm_count * 16);
       at_merge_kernel<<<grid, 128, 0, ctx->stream>>>(o0, P.starts.as<int>(), nComp, P.eA.as<int>(), P.eB.as<int>(), P.nodes.as<UfNode>(),
-                                                     P.work.as<int>());
+                                                     P.parent.as<int>(), P.work.as<int>());
       EZC_CUDA(cudaGetLastError());
       ctx->kernel_launches++;
     }
@@ -1352,8 +1381,8 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
     std::vector<uint8_t> ec(nE);
     std::vector<uint32_t> ord(nE);
     if (nA) {
-      EZC_CUDA(P.parent.reserve(sizeof(int) * (size_t)nA)); EZC_CUDA(P.setsize.reserve(sizeof(int) * (size_t)nA));
-      AT_LAUNCH(at_split_nodes_kernel, nA, P.nodes.as<UfNode>(), nA, P.parent.as<int>(), P.setsize.as<int>());
+      EZC_CUDA(P.setsize.reserve(sizeof(int) * (size_t)nA));
+      AT_LAUNCH(at_split_nodes_kernel, nA, P.nodes.as<UfNode>(), nA, P.setsize.as<int>());
       EZC_CUDA(cudaMemcpyAsync(apix.data(), P.apix.p, sizeof(int) * nA, cudaMemcpyDeviceToHost, ctx->stream));
       EZC_CUDA(cudaMemcpyAsync(par.data(), P.parent.p, sizeof(int) * nA, cudaMemcpyDeviceToHost, ctx->stream));
       EZC_CUDA(cudaMemcpyAsync(ssz.data(), P.setsize.p, sizeof(int) * nA, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1371,7 +1400,7 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
     for (int i = 0; i < nA; ++i) { int r = i; while (par[r] != r) r = par[r]; dbg->rep[apix[i]] = apix[r]; dbg->size[apix[i]] = ssz[r]; }
   }
   // ---- 7: clusters = pixels grouped by representative (ascending), raster order inside
-  AT_LAUNCH(at_rep_kernel, nA, P.nodes.as<UfNode>(), nA, P.rep.as<int>(), P.keep.as<int>());
+  AT_LAUNCH(at_rep_kernel, nA, P.nodes.as<UfNode>(), P.parent.as<int>(), nA, P.rep.as<int>(), P.keep.as<int>());
   if (ezc_status st = exclusive_scan_i32(ctx, P.keep.as<int>(), P.keep.as<int>(), nA, P.scan_tmp, d_tot)) return st;
   int nK = 0;
   if (ezc_status st = read_int(ctx, d_tot, &nK, P)) return st;
