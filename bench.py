@@ -599,7 +599,8 @@ def run_cfg4(ctx, args, rank, world, stream):
                "stage_s": {"detect": round(float(stage[0]), 4), "p3p": round(float(stage[1]), 4), "mono_solve": round(float(stage[2]), 4),
                            "multicam": round(float(stage[3]), 4)},
                "detect_images_per_s": round(n_imgs * world / max(float(stage[0]), 1e-9), 1),
-               "multicam": {"iterations": msum["iterations"], "termination": msum["termination_name"], "n_good_pairs": msum["n_good_pairs"]},
+               "multicam": {"iterations": msum["iterations"], "termination": msum["termination_name"], "n_good_pairs": msum["n_good_pairs"],
+                            "setup_s_rank0": round(timings.get("multicam_setup_s", 0.0), 4), "solve_s_rank0": round(timings.get("multicam_solve_s", 0.0), 4)},
                "per_camera": flat, "gpu_launches": int(launches),
                "sane": bool(all(e["focal_rel_err"] < 5e-3 and e["median_rmse_px"] < 0.5 for e in flat) and
                             all(e.get("baseline_err_mm", 0.0) < 5.0 for e in flat))}

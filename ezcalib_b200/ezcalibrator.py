@@ -146,7 +146,7 @@ def build_multicam_problem(cameras: list[Camera], target: np.ndarray):
     """Problem set-up of EZCalibrator::runMultiCameraCalib (ezcalibrator.cpp:631-785): returns
     (obs [n_cams-1, n_frames0*n_pts, 2], pts [n_frames0*n_pts, 3], init extrinsics [n_cams-1, 7], n_good_pairs)."""
     cam0 = cameras[0]
-    pts = synth.transform(np.stack([f.T_world_2_cam for f in cam0.frames]), target).reshape(-1, 3)   # one batched call
+    pts = _transform_points(np.stack([f.T_world_2_cam for f in cam0.frames]), target).reshape(-1, 3)
     blocks = [multicam_block(cam0.frames, cameras[i], i, target) for i in range(1, len(cameras))]
     obs = np.stack([b[0] for b in blocks])
     init = np.stack([b[1] for b in blocks])
@@ -302,6 +302,19 @@ def calibrate_camera_from_corners(ctx: lm.Context, found, corners, names, target
     return cam, processed, summ
 
 
+def _transform_points(poses: np.ndarray, pts: np.ndarray) -> np.ndarray:
+    """synth.transform(poses [n,7], pts [m,3]) -> [n, m, 3] with the cross products written out (np.cross spends most of its
+    time in axis bookkeeping): the same multiplications and subtractions in the same order, so the result is bit-identical."""
+    qx, qy, qz, qw = (poses[:, None, i] for i in range(4))
+    px, py, pz = pts[None, :, 0], pts[None, :, 1], pts[None, :, 2]
+    ux, uy, uz = 2.0 * (qy * pz - qz * py), 2.0 * (qz * px - qx * pz), 2.0 * (qx * py - qy * px)
+    out = np.empty((poses.shape[0], pts.shape[0], 3))
+    out[..., 0] = px + qw * ux + (qy * uz - qz * uy) + poses[:, None, 4]
+    out[..., 1] = py + qw * uy + (qz * ux - qx * uz) + poses[:, None, 5]
+    out[..., 2] = pz + qw * uz + (qx * uy - qy * ux) + poses[:, None, 6]
+    return out
+
+
 def run_rig_extrinsics(ctx: lm.Context, local_cameras: dict, n_cams: int, target: np.ndarray, comm=None, timings=None):
     """EZCalibrator::runMultiCameraCalib over ranks: local_cameras {camera index: calibrated Camera} holds the cameras this
     rank owns.  The owner of cam0 broadcasts cam0's frame names, poses and rmse_err (the only data the other cameras' residual
@@ -314,13 +327,14 @@ def run_rig_extrinsics(ctx: lm.Context, local_cameras: dict, n_cams: int, target
     t0 = time.perf_counter()
     owner0 = 0 % comm.world
     info = None
-    if 0 in local_cameras:
-        info = [(f.img_name, f.T_world_2_cam, f.rmse_err) for f in local_cameras[0].frames]
-    info = comm.bcast(info, owner0)
-    cam0_frames = [_FrameInfo(*x) for x in info]
+    if 0 in local_cameras:   # three flat objects (names, poses, rmse) instead of one tuple per frame: cheap to pickle
+        fr0 = local_cameras[0].frames
+        info = ([f.img_name for f in fr0], np.stack([f.T_world_2_cam for f in fr0]), np.array([f.rmse_err for f in fr0]))
+    names0, poses0, rmse0 = comm.bcast(info, owner0)
+    cam0_frames = [_FrameInfo(nm, poses0[i], float(rmse0[i])) for i, nm in enumerate(names0)]
     n_pts = target.shape[0]
-    pts = synth.transform(np.stack([f.T_world_2_cam for f in cam0_frames]), target).reshape(-1, 3)   # one batched call
     mine = sorted(c for c in local_cameras if c >= 1)
+    pts = _transform_points(poses0, target).reshape(-1, 3)
     blocks = [multicam_block(cam0_frames, local_cameras[c], c, target) for c in mine]
     ref = comm.bcast((local_cameras[mine[0]].model, local_cameras[mine[0]].use_mono_focal, local_cameras[mine[0]].width,
                       local_cameras[mine[0]].height) if (comm.rank == (1 % comm.world) and mine) else None, 1 % comm.world)
