@@ -451,6 +451,21 @@ __global__ void at_ccl_init_kernel(int* L, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) L[i] = i;
 }
+// Initial forest = the horizontal runs: a pixel whose left neighbour has an edge to it (the 'right' edge is the first one a
+// pixel emits, and its target is then the next compact id) starts under the head of its run -- no atomics, and the union
+// pass that follows finds most end points one hop from a root.
+__global__ void at_ccl_init_runs_kernel(int* __restrict__ L, const int* __restrict__ eoff, const int* __restrict__ eB, int n, int n_edges) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int h = i;
+  // at most 16 steps back (a thread per pixel walking a 300-pixel run to its head would be quadratic work): a pixel deep
+  // inside a long run hangs under a pixel 16 places earlier, which hangs under ... the head
+  for (int step = 0; step < 16 && h > 0; ++step) {
+    const int e0 = eoff[h - 1], e1 = eoff[h];
+    if (e1 > e0 && eB[e0] == h) --h; else break;   // an edge (h-1 -> h): same run (any first edge to the next id links them)
+  }
+  L[i] = h;
+}
 // (pointer jumping inside the find, as in ECL-CC, was measured: 5.13 -> 5.83 ms for 214 views -- the extra stores cost more than
 // the shorter chains save on these thin components.)
 __global__ void at_ccl_union_kernel(int* L, const int* __restrict__ eA, const int* __restrict__ eB, int n_edges) {
@@ -489,10 +504,27 @@ __global__ void at_edge_keys_kernel(const int* __restrict__ label, const int* __
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n) keys[e] = (uint32_t)label[eA[e]];
 }
-// flag[i] = 1 where the sorted key sequence starts a new component
-__global__ void at_boundary_keys_kernel(const uint32_t* __restrict__ keys, int n, int* __restrict__ flag) {
+// Dense component numbers.  An edge always runs from a pixel to one LATER in raster order (right, down, both down
+// diagonals), and compact ids are raster ordered, so the root of a component (its smallest id) is the first end point of at
+// least one edge: the components that own edges are exactly the roots with a non-empty edge range.  Numbering those (scan)
+// gives sort keys of ~15 bits instead of the 25 bits of a compact id -- one 9-bit pass less -- and a key that IS the
+// component index, so the start of every component in the sorted sequence is written directly (no scan over the edges).
+__global__ void at_root_flag_kernel(const int* __restrict__ label, const int* __restrict__ eoff, int n_active, int n_edges, int* __restrict__ flag) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_active) return;
+  const int cnt = (c + 1 < n_active ? eoff[c + 1] : n_edges) - eoff[c];
+  flag[c] = (label[c] == c && cnt > 0) ? 1 : 0;
+}
+__global__ void at_dense_label_kernel(const int* __restrict__ label, const int* __restrict__ dense, int n_active, int* __restrict__ dlabel) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n_active) dlabel[c] = dense[label[c]];
+}
+__global__ void at_starts_dense_kernel(const uint32_t* __restrict__ keys, int n, int n_comp, int* __restrict__ starts) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+  if (i >= n) return;
+  const uint32_t k = keys[i];
+  if (i == 0 || keys[i - 1] != k) starts[k] = i;
+  if (i == n - 1) starts[n_comp] = n;
 }
 __global__ void at_iota_kernel(uint32_t* v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1324,31 +1356,46 @@ ezc_status process_sub_batch(ezc_context* ctx, const ezc_images* imgs, int img0,
   AT_LAUNCH(at_edges_words_kernel<true>, nA, P.apix.as<int>(), P.a_theta.as<float>(), P.amask.as<uint32_t>(), P.acount.as<int>(), wpr,
             nA, W, H, nullptr, P.ecount.as<int>(), P.eA.as<int>(), P.eB.as<int>(), P.ecost.as<uint8_t>());
   // ---- 4: connected components of the edge graph
-  AT_LAUNCH(at_ccl_init_kernel, nA, P.label.as<int>(), nA);
+  AT_LAUNCH(at_ccl_init_runs_kernel, nA, P.label.as<int>(), P.ecount.as<int>(), P.eB.as<int>(), nA, nE);
   AT_LAUNCH(at_ccl_union_kernel, nE, P.label.as<int>(), P.eA.as<int>(), P.eB.as<int>(), nE);
   AT_LAUNCH(at_ccl_flatten_kernel, nA, P.label.as<int>(), nA);
   // ---- 5: stable sort of the edges by (component, cost)
   uint32_t* o0 = P.order0.as<uint32_t>();
   uint32_t* o1 = P.order1.as<uint32_t>();
-  // key-value LSD radix: one pass over the cost byte of the unsorted sequence, then ceil(bits/9) passes over the label
+  // key-value LSD radix: one pass over the cost byte of the unsorted sequence, then the passes over the dense component
+  // number (two 8-bit passes up to 65,536 components per sub-batch, 9-bit passes beyond)
   EZC_CUDA(P.keys0.reserve(sizeof(uint32_t) * ecap)); EZC_CUDA(P.keys1.reserve(sizeof(uint32_t) * ecap));
   uint32_t* k0 = P.keys0.as<uint32_t>();
   uint32_t* k1 = P.keys1.as<uint32_t>();
-  AT_LAUNCH(at_edge_keys_kernel, nE, P.label.as<int>(), P.eA.as<int>(), nE, k0);
-  if (ezc_status st = radix_pass_kv<8, true>(ctx, k0, nullptr, P.ecost.as<uint8_t>(), k1, o1, nE, 0, P.sort)) return st;
-  std::swap(o0, o1); std::swap(k0, k1);
-  for (int shift = 0; shift < bits_for(std::max(nA, 2)); shift += 9) {
-    if (ezc_status st = radix_pass_kv<9, false>(ctx, k0, o0, nullptr, k1, o1, nE, shift, P.sort)) return st;
-    std::swap(o0, o1); std::swap(k0, k1);
-  }
-  // component boundaries -> starts
+  // dense component numbers (see at_root_flag_kernel); P.rep / P.keep are free until stage 7
   int nComp = 0;
   if (nE > 0) {
-    AT_LAUNCH(at_boundary_keys_kernel, nE, k0, nE, P.flags.as<int>());
-    if (ezc_status st = exclusive_scan_i32(ctx, P.flags.as<int>(), P.flags.as<int>(), nE, P.scan_tmp, d_tot)) return st;
+    AT_LAUNCH(at_root_flag_kernel, nA, P.label.as<int>(), P.ecount.as<int>(), nA, nE, P.flags.as<int>());
+    if (ezc_status st = exclusive_scan_i32(ctx, P.flags.as<int>(), P.rep.as<int>(), nA, P.scan_tmp, d_tot)) return st;
     if (ezc_status st = read_int(ctx, d_tot, &nComp, P)) return st;
+    AT_LAUNCH(at_dense_label_kernel, nA, P.label.as<int>(), P.rep.as<int>(), nA, P.keep.as<int>());
+  }
+  AT_LAUNCH(at_edge_keys_kernel, nE, P.keep.as<int>(), P.eA.as<int>(), nE, k0);
+  if (ezc_status st = radix_pass_kv<8, true>(ctx, k0, nullptr, P.ecost.as<uint8_t>(), k1, o1, nE, 0, P.sort)) return st;
+  std::swap(o0, o1); std::swap(k0, k1);
+  {
+    const int bits = bits_for(std::max(nComp, 2));
+    if (bits <= 16) {
+      for (int shift = 0; shift < bits; shift += 8) {
+        if (ezc_status st = radix_pass_kv<8, false>(ctx, k0, o0, nullptr, k1, o1, nE, shift, P.sort)) return st;
+        std::swap(o0, o1); std::swap(k0, k1);
+      }
+    } else {
+      for (int shift = 0; shift < bits; shift += 9) {
+        if (ezc_status st = radix_pass_kv<9, false>(ctx, k0, o0, nullptr, k1, o1, nE, shift, P.sort)) return st;
+        std::swap(o0, o1); std::swap(k0, k1);
+      }
+    }
+  }
+  // component starts, written directly: the sorted key is the component index and every index 0..nComp-1 occurs
+  if (nE > 0) {
     EZC_CUDA(P.starts.reserve(sizeof(int) * ((size_t)nComp + 2)));
-    AT_LAUNCH(at_starts_kernel, nE, P.flags.as<int>(), d_tot, nE, P.starts.as<int>());
+    AT_LAUNCH(at_starts_dense_kernel, nE, k0, nE, nComp, P.starts.as<int>());
     if (getenv("EZC_AT_STATS")) {   // component size distribution (edges per component) of this sub-batch
       std::vector<int> hs((size_t)nComp + 1);
       EZC_CUDA(cudaMemcpyAsync(hs.data(), P.starts.p, sizeof(int) * ((size_t)nComp + 1), cudaMemcpyDeviceToHost, ctx->stream));
