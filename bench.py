@@ -681,16 +681,20 @@ def run_detect_chessboard(ctx, args, rank, world, stream, cfg="cfg1"):
     poses = synth.sample_poses(rng, n, tgt, model, f, cx, cy, d, W, H, margin=C["margin"], tilt_sigma=0.3)
     cams = np.tile(np.array([f, f, cx, cy] + list(d) + [0.0] * (8 - len(d))), (n, 1))
     imgs = detect.render_targets(ctx, "chessboard", 7, 10, 0.05, 0.0, mid, W, H, cams, poses, seed=synth.MASTER_SEED + 7 + rank)
-    for _ in range(3):
+    t_warm = time.perf_counter()   # at least 3 calls and 0.5 s: the GPU has idled through the CPU baseline of the previous block
+    n_warm = 0
+    while n_warm < 3 or time.perf_counter() - t_warm < 0.5:
         found, corners = detect.detect_chessboard(ctx, imgs, 7, 10)
+        n_warm += 1
     l0 = ctx.kernel_launches()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # five timed calls, each bracketed by events; the MEDIAN call is reported (a call is 30-60 ms, and one in a few runs
-    # is hit by a hiccup of twice that -- the mean of three consecutive calls moved by 2x from run to run)
+    # seven timed calls, each bracketed by events; the MEDIAN call is reported (a call is 30-60 ms of many short launches
+    # and host round trips, and in a full bench run single calls take up to twice that -- the mean of three consecutive
+    # calls moved by 2x from run to run)
     reps = 1
     calls_ms = []
-    for _ in range(5):
+    for _ in range(7):
         torch.cuda.synchronize()
         e0.record(stream)
         found, corners = detect.detect_chessboard(ctx, imgs, 7, 10)

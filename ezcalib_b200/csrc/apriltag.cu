@@ -584,12 +584,15 @@ __global__ void __launch_bounds__(128) at_merge_kernel(const uint32_t* __restric
   c = __shfl_sync(0xffffffffu, c, 0);
   if (c >= n_comp) return;
   const int beg = starts[c], end = starts[c + 1];
+  // the end points of the NEXT 32 edges are fetched while this batch is processed: they do not depend on the merges
+  int a_nx = 0, b_nx = 0;
+  if (beg + lane < end) { const uint32_t e = order[beg + lane]; a_nx = eA[e]; b_nx = eB[e]; }
   for (int i0 = beg; i0 < end; i0 += 32) {
     const int i = i0 + lane;
     int ra = 0, rb = 0;
+    const int a = a_nx, b = b_nx;
+    if (i + 32 < end) { const uint32_t e = order[i + 32]; a_nx = eA[e]; b_nx = eB[e]; }
     if (i < end) {
-      const uint32_t e = order[i];
-      const int a = eA[e], b = eB[e];
       ra = uf_find_ro(parent, a);
       rb = uf_find_ro(parent, b);
       // path shortening (UnionFindSimple compresses too; it never changes a representative)
