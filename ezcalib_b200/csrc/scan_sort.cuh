@@ -192,7 +192,20 @@ __global__ void __launch_bounds__(kSortWarps * 32) radix_scatter_kv_kernel(const
       v = FIRST ? (uint32_t)i : vals_in[i];
       d = FIRST ? (int)cost[i] : (int)((k >> shift) & (NB - 1));
     }
-    const unsigned m = __match_any_sync(0xffffffffu, d);
+    unsigned m;
+    if (FIRST) {
+      // peers by ballots over the digit's bits: on the strongly skewed cost byte MATCH.ANY throttled the MIO pipe
+      // (ncu: mio_throttle 92 cycles per issue in this pass, 1 in the passes over the component number)
+      m = __ballot_sync(0xffffffffu, act);
+      if (!act) m = 1u << lane;
+#pragma unroll
+      for (int b = 0; b < BITS; ++b) {
+        const unsigned bal = __ballot_sync(0xffffffffu, act && ((d >> b) & 1));
+        if (act) m &= ((d >> b) & 1) ? bal : ~bal;
+      }
+    } else {
+      m = __match_any_sync(0xffffffffu, d);
+    }
     const int rank = __popc(m & ((1u << lane) - 1u));
     int base = 0;
     if (act) base = off[warp][d];
