@@ -317,28 +317,33 @@ def _transform_points(poses: np.ndarray, pts: np.ndarray) -> np.ndarray:
 
 def run_rig_extrinsics(ctx: lm.Context, local_cameras: dict, n_cams: int, target: np.ndarray, comm=None, timings=None):
     """EZCalibrator::runMultiCameraCalib over ranks: local_cameras {camera index: calibrated Camera} holds the cameras this
-    rank owns.  The owner of cam0 broadcasts cam0's frame names, poses and rmse_err (the only data the other cameras' residual
-    blocks need, ezcalibrator.cpp:727-767); every rank builds the blocks of its own cameras; ONE joint solve -- the J^T J
+    rank owns.  The owner of cam0 shares cam0's frame names, poses and rmse_err (the only data the other cameras' residual
+    blocks need, ezcalibrator.cpp:727-767) in one object all-gather; every rank builds the blocks of its own cameras; ONE joint solve -- the J^T J
     is block diagonal per camera, Ceres still uses one trust region and one termination test for all of them, which is what the
     per-iteration scalar all-reduce of the view-sharded solver provides (install it with ctx.set_allreduce before calling).
     Returns {camera index: T_cam0_2_cam} for ALL cameras 1..n_cams-1 on every rank, and the summary."""
     import time
     comm = comm or SingleProcessComm()
     t0 = time.perf_counter()
-    owner0 = 0 % comm.world
-    info = None
-    if 0 in local_cameras:   # three flat objects (names, poses, rmse) instead of one tuple per frame: cheap to pickle
+    # ONE object exchange up front (an object collective costs ~10 ms over NCCL, the joint solve itself ~2 ms): the owner of
+    # cam0 contributes cam0's frames as three flat objects (names, poses, rmse), the owner of cam1 the shared camera model
+    mine = sorted(c for c in local_cameras if c >= 1)
+    contrib = {}
+    if 0 in local_cameras:
         fr0 = local_cameras[0].frames
-        info = ([f.img_name for f in fr0], np.stack([f.T_world_2_cam for f in fr0]), np.array([f.rmse_err for f in fr0]))
-    names0, poses0, rmse0 = comm.bcast(info, owner0)
+        contrib["cam0"] = ([f.img_name for f in fr0], np.stack([f.T_world_2_cam for f in fr0]), np.array([f.rmse_err for f in fr0]))
+    if 1 in local_cameras:
+        c1 = local_cameras[1]
+        contrib["ref"] = (c1.model, c1.use_mono_focal, c1.width, c1.height)
+    merged = {}
+    for part in comm.allgather(contrib):
+        merged.update(part)
+    names0, poses0, rmse0 = merged["cam0"]
+    m0, mono0, W, H = merged["ref"]
     cam0_frames = [_FrameInfo(nm, poses0[i], float(rmse0[i])) for i, nm in enumerate(names0)]
     n_pts = target.shape[0]
-    mine = sorted(c for c in local_cameras if c >= 1)
     pts = _transform_points(poses0, target).reshape(-1, 3)
     blocks = [multicam_block(cam0_frames, local_cameras[c], c, target) for c in mine]
-    ref = comm.bcast((local_cameras[mine[0]].model, local_cameras[mine[0]].use_mono_focal, local_cameras[mine[0]].width,
-                      local_cameras[mine[0]].height) if (comm.rank == (1 % comm.world) and mine) else None, 1 % comm.world)
-    m0, mono0, W, H = ref
     if any(local_cameras[c].model != m0 or local_cameras[c].use_mono_focal != mono0 for c in mine):
         raise NotImplementedError("mixed distortion models across cameras are not supported yet")
     nd = synth.NUM_DIST[synth.MODEL_ID[m0]]
@@ -356,13 +361,13 @@ def run_rig_extrinsics(ctx: lm.Context, local_cameras: dict, n_cams: int, target
     ext, summ = lm.lm_multicam(ctx, synth.MODEL_ID[m0], mono0, obs, pts, W, H, focal, pp, dist, init, n_blocks_global=n_cams - 1,
                                collective=1 if comm.world > 1 else -1)
     t2 = time.perf_counter()
-    parts = comm.allgather({c: ext[k] for k, c in enumerate(mine)})
+    parts = comm.allgather(({c: ext[k] for k, c in enumerate(mine)}, int(sum(b[2] for b in blocks))))
     out = {}
-    for p_ in parts:
+    for p_, _ in parts:
         out.update(p_)
     for c in mine:
         local_cameras[c].T_cam0_2_cam = out[c]
-    summ["n_good_pairs"] = int(sum(comm.allgather(int(sum(b[2] for b in blocks)))))
+    summ["n_good_pairs"] = int(sum(g for _, g in parts))
     if timings is not None:
         timings["multicam_setup_s"] = t1 - t0
         timings["multicam_solve_s"] = t2 - t1
