@@ -237,6 +237,15 @@ def test_concurrent_attempts_equal_the_sequential_search(ctx):
         (f_con, c_con), (f_seq, c_seq) = _detect_both_ways(ctx, stack)
         assert np.array_equal(f_con, f_seq), np.flatnonzero(f_con != f_seq)
         assert np.array_equal(c_con, c_seq), float(np.abs(c_con - c_seq).max())
+    # other slot caps (EZC_CB_SLOTS): rounds that end in the middle of a threshold level / one round for everything
+    for slots in ("3", "400"):
+        os.environ["EZC_CB_SLOTS"] = slots
+        try:
+            (f_s, c_s), _ = _detect_both_ways(ctx, stacks[2])
+        finally:
+            os.environ.pop("EZC_CB_SLOTS", None)
+        (f_d, c_d), _ = _detect_both_ways(ctx, stacks[2])
+        assert np.array_equal(f_s, f_d) and np.array_equal(c_s, c_d), slots
     # sub-batches of 1 and 3 views: no free slots at all / a few -- the per-view results do not depend on the slot count
     stack = stacks[1][:9]
     (f_ref, c_ref), _ = _detect_both_ways(ctx, stack)
