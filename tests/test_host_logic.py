@@ -123,3 +123,17 @@ def test_config_reader_follows_the_reference_format(tmp_path):
     bad.write_text(cfg.read_text().replace("  - 70.0\n  - 120.0\n", "  - 70.0\n"))
     with pytest.raises(ValueError, match="prior_fov"):
         E.read_calib_config(str(bad))
+
+
+def test_rig_point_transform_is_bit_identical_to_synth_transform():
+    """run_rig_extrinsics / build_multicam_problem transform the target into cam0's frames with the cross products written
+    out (one batched call for 2000 frames); the result must equal synth.transform bit for bit -- the C++ mirror and the
+    oracle consume the same points."""
+    from ezcalib_b200 import ezcalibrator as E, synth
+    rng = np.random.default_rng(3)
+    poses = rng.normal(size=(257, 7))
+    poses[:, :4] /= np.linalg.norm(poses[:, :4], axis=1, keepdims=True)
+    tgt = synth.aprilgrid_target(6, 6, 0.06, 0.3)
+    assert np.array_equal(E._transform_points(poses, tgt), synth.transform(poses, tgt))
+    one = np.concatenate([synth.transform(p, tgt) for p in poses[:5]], axis=0)
+    assert np.array_equal(E._transform_points(poses[:5], tgt).reshape(-1, 3), one)
